@@ -1,0 +1,111 @@
+"""ctypes loader for libferreus_b200.so (the C ABI declared in include/ferreus_b200.h).
+
+The product path has no CPU fallback: if the shared library is missing this raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libferreus_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+FB_OK = 0
+FB_ERR_POINT_OUTSIDE_TREE = 1
+FB_ERR_NO_GRADIENTS = 2
+FB_ERR_INVALID_ARGUMENT = 3
+FB_ERR_CUDA = 4
+
+
+class FbKernelParams(C.Structure):
+    _fields_ = [("kernel_type", C.c_int32), ("base_range", C.c_double), ("total_sill", C.c_double)]
+
+
+class FbFmmParams(C.Structure):
+    _fields_ = [("max_points_per_cell", C.c_uint64), ("compression_type", C.c_int32),
+                ("epsilon", C.c_double), ("eval_chunk_size", C.c_uint64)]
+
+
+class FbTreeInfo(C.Structure):
+    _fields_ = [("n_points", C.c_uint64), ("n_cells", C.c_uint64), ("n_leaves", C.c_uint64),
+                ("depth", C.c_uint64), ("n_u", C.c_uint64), ("n_v", C.c_uint64), ("n_w", C.c_uint64),
+                ("n_x", C.c_uint64), ("dim", C.c_int32), ("order", C.c_int32), ("nrhs", C.c_int32),
+                ("radius", C.c_double), ("center", C.c_double * 3), ("p2p_pairs", C.c_uint64),
+                ("m2p_pairs", C.c_uint64), ("p2l_pairs", C.c_uint64)]
+
+
+def build(force=False, jobs=8):
+    """Compile the library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    if force:
+        subprocess.check_call(["make", "-C", CSRC, "clean"])
+    subprocess.check_call(["make", "-C", CSRC, f"-j{jobs}"])
+    return LIB_PATH
+
+
+_lib = None
+
+_dp = C.POINTER(C.c_double)
+_u64p = C.POINTER(C.c_uint64)
+_u8p = C.POINTER(C.c_uint8)
+_sz = C.c_size_t
+_pd = C.c_ssize_t
+
+# symbol -> (restype, argtypes); every symbol declared in include/ferreus_b200.h
+SIGNATURES = {
+    "fb_last_error": (C.c_char_p, []),
+    "fb_kernel_launch_count": (C.c_uint64, []),
+    "fb_set_device": (C.c_int, [C.c_int]),
+    "fb_tree_new": (C.c_int, [_dp, _sz, C.c_int, _pd, _pd, C.c_int, C.POINTER(FbKernelParams), C.c_int, C.c_int,
+                              _dp, C.POINTER(FbFmmParams), C.POINTER(C.c_void_p)]),
+    "fb_tree_free": (None, [C.c_void_p]),
+    "fb_tree_set_weights": (C.c_int, [C.c_void_p, _dp, _sz, _sz, _pd, _pd]),
+    "fb_tree_set_local_coefficients": (C.c_int, [C.c_void_p, _dp, _sz, _sz, _pd, _pd]),
+    "fb_tree_evaluate": (C.c_int, [C.c_void_p, _dp, _sz, _sz, _pd, _pd, _dp, _sz, _pd, _pd, _dp, _dp, _pd, _pd,
+                                   _u64p]),
+    "fb_tree_evaluate_leaves": (C.c_int, [C.c_void_p, _dp, _sz, _sz, _pd, _pd, _dp, _sz, _pd, _pd, _dp, _dp, _pd,
+                                          _pd, _u64p]),
+    "fb_tree_evaluate_at_sources": (C.c_int, [C.c_void_p, _dp, _sz, _sz, _pd, _pd, _u64p, _sz, _dp, _pd, _pd]),
+    "fb_tree_upload_weights": (C.c_int, [C.c_void_p, _dp, _sz, _sz, _pd, _pd]),
+    "fb_tree_matvec_resident": (C.c_int, [C.c_void_p]),
+    "fb_tree_download_result": (C.c_int, [C.c_void_p, _dp, _pd, _pd]),
+    "fb_tree_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "fb_tree_last_timing": (C.c_int, [C.c_void_p, _dp]),
+    "fb_tree_source_points": (C.c_int, [C.c_void_p, _dp, _pd, _pd]),
+    "fb_tree_get_info": (C.c_int, [C.c_void_p, C.POINTER(FbTreeInfo)]),
+    "fb_tree_dump_cells": (C.c_int, [C.c_void_p, _u64p, _u8p, _u64p, _u64p]),
+    "fb_tree_dump_list": (C.c_int, [C.c_void_p, C.c_int, _u64p, _u64p]),
+    "fb_tree_m2l_rank": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "fb_tree_m2l_operator": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp]),
+}
+
+
+def lib():
+    """Load the shared library (once).  Raises if it has not been built: there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C ferreus_rbf_rs_b200/csrc`). The CUDA library is the only implementation.")
+    l = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(l, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = l
+    return l
+
+
+def last_error():
+    msg = lib().fb_last_error()
+    return msg.decode() if msg else ""
+
+
+def dptr(a):
+    return a.ctypes.data_as(_dp)
+
+
+def strides_of(a):
+    """element strides (row, col) of a 2-D float64 array"""
+    return a.strides[0] // 8, a.strides[1] // 8

@@ -1,0 +1,959 @@
+// fb_tree: device-resident BBFMM evaluator (build, upward, downward, leaf pass) and its C ABI.
+#include "fmm.h"
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstring>
+#include <cub/cub.cuh>
+
+#include "fmm_kernels.cuh"
+
+namespace fb {
+
+std::atomic<uint64_t> g_launches{0};
+static thread_local std::string t_last_error;
+void set_last_error(const std::string &msg) { t_last_error = msg; }
+
+static inline unsigned nblocks(size_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+template <class K>
+static void set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024)
+    FB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+}  // namespace fb
+
+using namespace fb;
+
+fb_tree::~fb_tree() {
+  for (auto &e : ev)
+    if (e) cudaEventDestroy(e);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+// ------------------------------------------------------------------------------------------- build
+void fb_tree::build(const double *points, size_t n_, int dim_, ptrdiff_t rs, ptrdiff_t cs, int order_,
+                    const fb_kernel_params *k, int adaptive, int sparse, const double *extents,
+                    const fb_fmm_params *params) {
+  FB_REQUIRE(points && n_ > 0, "source_points must be a non-empty n x dim matrix");
+  FB_REQUIRE(dim_ >= 1 && dim_ <= 3, "Unsupported number of dimensions: " + std::to_string(dim_));
+  FB_REQUIRE(order_ >= 1 && order_ <= kMaxOrder, "interpolation_order must be in 1.." + std::to_string(kMaxOrder));
+  FB_REQUIRE(n_ < (1ull << 31), "at most 2^31-1 source points per tree");
+  FB_REQUIRE(k != nullptr, "kernel params required");
+  FB_REQUIRE(k->base_range > 0.0 && k->total_sill <= k->base_range,
+             "KernelParams: base_range > 0 and total_sill <= base_range required");  // kernel_helpers.rs:72-73
+  FB_REQUIRE(make_kparams(*k, kp), "unknown kernel_type");
+  kparams_c = *k;
+  n = n_;
+  dim = dim_;
+  order = order_;
+  P = 1;
+  for (int d = 0; d < dim; ++d) P *= order;
+  if (params) {
+    fparams = *params;
+  } else {  // FmmParams::new_defaults, bbfmm.rs:95-104
+    fparams.max_points_per_cell = 256;
+    fparams.compression_type = FB_COMPRESSION_ACA;
+    fparams.epsilon = std::pow(10.0, -(double)order);
+    fparams.eval_chunk_size = 1024;
+  }
+  FB_REQUIRE(fparams.compression_type >= 0 && fparams.compression_type <= 2, "unknown compression type");
+
+  FB_CUDA(cudaGetDevice(&device));
+  FB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  for (auto &e : ev) FB_CUDA(cudaEventCreate(&e));
+
+  host_points.resize(n * dim);
+  for (size_t i = 0; i < n; ++i)
+    for (int d = 0; d < dim; ++d) host_points[i * dim + d] = points[(ptrdiff_t)i * rs + (ptrdiff_t)d * cs];
+
+  // extents: given [mins..., maxs...] or from the data (bbfmm.rs:281-284, utils.rs:22-54)
+  double ext[6];
+  if (extents) {
+    for (int d = 0; d < 2 * dim; ++d) ext[d] = extents[d];
+  } else {
+    for (int d = 0; d < dim; ++d) ext[d] = ext[dim + d] = host_points[d];
+    for (size_t i = 0; i < n; ++i)
+      for (int d = 0; d < dim; ++d) {
+        const double v = host_points[i * dim + d];
+        if (v < ext[d]) ext[d] = v;
+        if (v > ext[dim + d]) ext[dim + d] = v;
+      }
+  }
+  // calculate_tree_center_and_radius, morton.rs:349-373
+  double center[3] = {0, 0, 0}, radius = -INFINITY;
+  for (int d = 0; d < dim; ++d) {
+    const double lo = std::floor(ext[d]), hi = std::ceil(ext[dim + d]);
+    center[d] = (lo + hi) / 2.0;
+    radius = std::max(radius, (hi - lo) / 2.0 + 1e-3);
+  }
+  FB_REQUIRE(std::isfinite(radius) && radius > 0, "invalid extents");
+
+  // ---- device radix sort of the level-16 Morton codes
+  DBuf<double> d_pts;
+  d_pts.reserve(n * dim);
+  FB_CUDA(cudaMemcpyAsync(d_pts.p, host_points.data(), n * dim * sizeof(double), cudaMemcpyHostToDevice, stream));
+  DBuf<unsigned long long> d_codes, d_codes2;
+  DBuf<uint32_t> d_idx;
+  d_codes.reserve(n);
+  d_codes2.reserve(n);
+  d_idx.reserve(n);
+  d_perm.reserve(n);
+  d_inv.reserve(n);
+  d_err.reserve(1);
+  FB_CUDA(cudaMemsetAsync(d_err.p, 0xFF, sizeof(unsigned long long), stream));
+  const double side16 = 2.0 * radius / 65536.0;  // morton.rs:29-32 at level 16
+  FB_LAUNCH(k_point_codes, nblocks(n, 256), 256, 0, stream, d_pts.p, n, dim, center[0] - radius, center[1] - radius,
+            center[2] - radius, side16, d_codes.p, d_idx.p, d_err.p);
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, d_codes.p, d_codes2.p, d_idx.p, d_perm.p, (int)n, 0, 16 * dim,
+                                  stream);
+  d_cub.reserve(cub_bytes);
+  FB_CUDA(cub::DeviceRadixSort::SortPairs(d_cub.p, cub_bytes, d_codes.p, d_codes2.p, d_idx.p, d_perm.p, (int)n, 0,
+                                          16 * dim, stream));
+  g_launches.fetch_add(4);
+  d_sx.reserve(n);
+  d_sy.reserve(n);
+  d_sz.reserve(n);
+  FB_LAUNCH(k_gather_sorted, nblocks(n, 256), 256, 0, stream, d_pts.p, d_perm.p, n, dim, d_sx.p, d_sy.p, d_sz.p,
+            d_inv.p);
+  std::vector<unsigned long long> h_codes(n);
+  unsigned long long h_err = 0;
+  FB_CUDA(cudaMemcpyAsync(h_codes.data(), d_codes2.p, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+  FB_CUDA(cudaMemcpyAsync(&h_err, d_err.p, sizeof(h_err), cudaMemcpyDeviceToHost, stream));
+  FB_CUDA(cudaStreamSynchronize(stream));
+  if (h_err != ~0ull)
+    throw Error(FB_ERR_INVALID_ARGUMENT,
+                "source point at row " + std::to_string(h_err) + " lies outside the given tree extents", h_err);
+
+  // ---- host: adaptive/uniform subdivision over the sorted codes + interaction lists
+  ht.build((const uint64_t *)h_codes.data(), n, dim, center, radius, (size_t)fparams.max_points_per_cell, !sparse,
+           adaptive != 0);
+  const size_t nc = ht.ncells();
+  const int nl = (int)ht.leaves.size();
+
+  // ---- host: operators
+  ops.build(order, dim, radius, ht.depth, kp, fparams.compression_type, fparams.epsilon);
+
+  // ---- upload cells
+  std::vector<double> ccx(nc), ccy(nc), ccz(nc), chalf(nc);
+  std::vector<int> slot(nc);
+  for (size_t c = 0; c < nc; ++c) {
+    double cc[3] = {0, 0, 0}, side;
+    ht.cell_center((int)c, cc, side);
+    ccx[c] = cc[0];
+    ccy[c] = dim > 1 ? cc[1] : 0.0;
+    ccz[c] = dim > 2 ? cc[2] : 0.0;
+    chalf[c] = side * 0.5;
+    slot[c] = (int)(ht.prefix[c] & ((1u << dim) - 1u));  // morton.rs:300-305
+  }
+  d_ccx.upload(ccx, stream);
+  d_ccy.upload(ccy, stream);
+  d_ccz.upload(ccz, stream);
+  d_chalf.upload(chalf, stream);
+  d_cell_slot.upload(slot, stream);
+  d_cell_parent.upload(ht.parent, stream);
+  d_cell_ptb.upload(ht.pt_begin, stream);
+  d_cell_pte.upload(ht.pt_end, stream);
+  d_child_ptr.upload(ht.child_ptr, stream);
+  d_child_idx.upload(ht.child_idx, stream);
+  std::vector<uint8_t> ones(nc, 1);
+  d_flag_all.upload(ones, stream);
+  d_flag.reserve(nc);
+
+  // leaves
+  std::vector<int> cell_to_leaf(nc, -1);
+  std::vector<unsigned long long> llo(nl), lhi(nl);
+  std::vector<int> src_leaves, tl_b(nl), tl_e(nl);
+  for (int l = 0; l < nl; ++l) {
+    const int c = ht.leaves[l];
+    cell_to_leaf[c] = l;
+    const int sh = dim * (16 - ht.level[c]);
+    llo[l] = ht.prefix[c] << sh;
+    lhi[l] = llo[l] + (1ull << sh);
+    tl_b[l] = ht.pt_begin[c];
+    tl_e[l] = ht.pt_end[c];
+    if (ht.pt_end[c] > ht.pt_begin[c]) src_leaves.push_back(c);
+  }
+  d_leaf_cell.upload(ht.leaves, stream);
+  d_leaf_lo.upload(llo, stream);
+  d_leaf_hi.upload(lhi, stream);
+  d_src_leaves.upload(src_leaves, stream);
+  n_src_leaves = (int)src_leaves.size();
+  d_src_tl_begin.upload(tl_b, stream);
+  d_src_tl_end.upload(tl_e, stream);
+  // non-leaf cells per level (M2M grids)
+  h_parents.assign(ht.depth + 1, {});
+  for (size_t c = 0; c < nc; ++c)
+    if (ht.child_ptr[c + 1] > ht.child_ptr[c]) h_parents[ht.level[c]].push_back((int)c);
+  {
+    std::vector<int> flat;
+    parents_off.assign(ht.depth + 2, 0);
+    for (int l = 0; l <= ht.depth; ++l) {
+      parents_off[l] = (int)flat.size();
+      flat.insert(flat.end(), h_parents[l].begin(), h_parents[l].end());
+    }
+    parents_off[ht.depth + 1] = (int)flat.size();
+    d_parents.upload(flat, stream);
+  }
+  // all-sources target set: tiles per leaf
+  {
+    std::vector<int> t_leaf, t_off;
+    for (int l = 0; l < nl; ++l)
+      for (int o = 0; o < tl_e[l] - tl_b[l]; o += kTile) {
+        t_leaf.push_back(l);
+        t_off.push_back(o);
+      }
+    src_tiles = (int)t_leaf.size();
+    d_src_tile_leaf.upload(t_leaf, stream);
+    d_src_tile_off.upload(t_off, stream);
+    std::vector<int> nt{src_tiles};
+    d_src_ntiles.upload(nt, stream);
+  }
+
+  // ---- leaf lists: U as merged contiguous source ranges, W as cells; X per cell as ranges
+  {
+    std::vector<long long> u_ptr(nl + 1, 0), w_ptr(nl + 1, 0);
+    std::vector<int> u_b, u_c, w_c;
+    p2p_pairs = m2p_pairs = p2l_pairs = 0;
+    std::vector<std::pair<int, int>> rng;
+    for (int l = 0; l < nl; ++l) {
+      const int c = ht.leaves[l];
+      rng.clear();
+      uint64_t nsrc = 0;
+      for (long long e = ht.u_ptr[c]; e < ht.u_ptr[c + 1]; ++e) {
+        const int u = ht.u_idx[e];
+        if (ht.pt_end[u] > ht.pt_begin[u]) {
+          rng.emplace_back(ht.pt_begin[u], ht.pt_end[u]);
+          nsrc += ht.pt_end[u] - ht.pt_begin[u];
+        }
+      }
+      std::sort(rng.begin(), rng.end());
+      for (size_t i = 0; i < rng.size(); ++i) {
+        if (!u_b.empty() && (long long)u_b.size() > u_ptr[l] && u_b.back() + u_c.back() == rng[i].first)
+          u_c.back() += rng[i].second - rng[i].first;
+        else {
+          u_b.push_back(rng[i].first);
+          u_c.push_back(rng[i].second - rng[i].first);
+        }
+      }
+      u_ptr[l + 1] = (long long)u_b.size();
+      const uint64_t nt = ht.pt_end[c] - ht.pt_begin[c];
+      p2p_pairs += nt * nsrc;
+      for (long long e = ht.w_ptr[c]; e < ht.w_ptr[c + 1]; ++e) w_c.push_back(ht.w_idx[e]);
+      w_ptr[l + 1] = (long long)w_c.size();
+      m2p_pairs += nt * (uint64_t)(ht.w_ptr[c + 1] - ht.w_ptr[c]);
+    }
+    d_u_ptr.upload(u_ptr, stream);
+    d_u_begin.upload(u_b, stream);
+    d_u_count.upload(u_c, stream);
+    d_w_ptr.upload(w_ptr, stream);
+    d_w_cell.upload(w_c, stream);
+    std::vector<int> x_cells, x_b, x_c;
+    std::vector<long long> x_ptr{0};
+    for (size_t c = 0; c < nc; ++c) {
+      if (ht.x_ptr[c + 1] == ht.x_ptr[c]) continue;
+      rng.clear();
+      for (long long e = ht.x_ptr[c]; e < ht.x_ptr[c + 1]; ++e) {
+        const int x = ht.x_idx[e];
+        if (ht.pt_end[x] > ht.pt_begin[x]) {
+          rng.emplace_back(ht.pt_begin[x], ht.pt_end[x]);
+          p2l_pairs += ht.pt_end[x] - ht.pt_begin[x];
+        }
+      }
+      if (rng.empty()) continue;
+      std::sort(rng.begin(), rng.end());
+      const size_t start = x_b.size();
+      for (auto &r : rng) {
+        if (x_b.size() > start && x_b.back() + x_c.back() == r.first)
+          x_c.back() += r.second - r.first;
+        else {
+          x_b.push_back(r.first);
+          x_c.push_back(r.second - r.first);
+        }
+      }
+      x_cells.push_back((int)c);
+      x_ptr.push_back((long long)x_b.size());
+    }
+    n_x_cells = (int)x_cells.size();
+    d_x_cells.upload(x_cells, stream);
+    d_x_ptr.upload(x_ptr, stream);
+    d_x_begin.upload(x_b, stream);
+    d_x_count.upload(x_c, stream);
+  }
+
+  // ---- operators to device
+  d_nodes.upload(ops.nodes, stream);
+  d_tnodes.upload(ops.tnodes, stream);
+  d_child_s.upload(ops.child_s, stream);
+  {
+    std::vector<int> pt(ops.perm.begin(), ops.perm.end());
+    d_perm_tab.upload(pt, stream);
+  }
+  // M2L groups: entries (target, source, permutation) per (level, reference vector), sorted by target
+  {
+    m2l_groups.clear();
+    std::vector<double> pool;
+    std::vector<int> e_tgt, e_src, e_perm;
+    const bool compressed = fparams.compression_type != FB_COMPRESSION_NONE;
+    for (int lvl = 2; lvl <= ht.depth; ++lvl) {
+      std::vector<std::vector<std::array<int, 3>>> per_ref(ops.n_ref);
+      for (int c = ht.level_ptr[lvl]; c < ht.level_ptr[lvl + 1]; ++c) {
+        uint32_t ac[3];
+        ht.anchor(c, ac);
+        for (long long e = ht.v_ptr[c]; e < ht.v_ptr[c + 1]; ++e) {
+          const int s = ht.v_idx[e];
+          uint32_t as[3];
+          ht.anchor(s, as);
+          int tix = 0;  // calculate_m2l_transfer_index, bbfmm.rs:989-998: t = round((c_target - c_source)/side)
+          for (int d = 0; d < dim; ++d) tix = tix * 7 + ((int)ac[d] - (int)as[d] + 3);
+          per_ref[ops.ref_lookup[tix]].push_back({c, s, ops.perm_lookup[tix]});
+        }
+      }
+      for (int r = 0; r < ops.n_ref; ++r) {
+        if (per_ref[r].empty()) continue;
+        const M2LOperator &op = ops.m2l[lvl - 2][r];
+        M2LGroup g;
+        g.level = lvl;
+        g.ref = r;
+        g.rank = op.rank;
+        g.rank_pad = compressed ? ((op.rank + 3) / 4) * 4 : P;
+        g.n_entries = per_ref[r].size();
+        g.entry_off = e_tgt.size();
+        for (auto &t : per_ref[r]) {
+          e_tgt.push_back(t[0]);
+          e_src.push_back(t[1]);
+          e_perm.push_back(t[2]);
+        }
+        if (compressed) {  // VtT [P][rank_pad], UT [rank_pad][P]
+          g.v_off = pool.size();
+          pool.resize(pool.size() + (size_t)P * g.rank_pad, 0.0);
+          for (int j = 0; j < P; ++j)
+            for (int k2 = 0; k2 < op.rank; ++k2) pool[g.v_off + (size_t)j * g.rank_pad + k2] = op.Vt(k2, j);
+          g.u_off = pool.size();
+          pool.resize(pool.size() + (size_t)g.rank_pad * P, 0.0);
+          for (int k2 = 0; k2 < op.rank; ++k2)
+            for (int m2 = 0; m2 < P; ++m2) pool[g.u_off + (size_t)k2 * P + m2] = op.U(m2, k2);
+        } else {  // UT[k][m] = K[m][k]
+          g.v_off = 0;
+          g.u_off = pool.size();
+          pool.resize(pool.size() + (size_t)P * P, 0.0);
+          for (int k2 = 0; k2 < P; ++k2)
+            for (int m2 = 0; m2 < P; ++m2) pool[g.u_off + (size_t)k2 * P + m2] = op.U(m2, k2);
+        }
+        if (pool.size() & 1) pool.push_back(0.0);
+        m2l_groups.push_back(g);
+      }
+    }
+    d_oppool.upload(pool, stream);
+    d_m2l_tgt.upload(e_tgt, stream);
+    d_m2l_src.upload(e_src, stream);
+    d_m2l_perm.upload(e_perm, stream);
+    // columns per CTA: as many as fit next to the Y tile in shared memory, multiple of 4, at most 64
+    int max_rp = 4;
+    for (auto &g : m2l_groups) max_rp = std::max(max_rp, compressed ? g.rank_pad : 0);
+    const size_t budget = 200 * 1024;
+    int ncol = (int)(budget / (sizeof(double) * (size_t)(P + (compressed ? max_rp : 0))));
+    ncol = std::min(64, (ncol / 4) * 4);
+    FB_REQUIRE(ncol >= 4, "interpolation order too large for the M2L shared-memory tile");
+    m2l_nc = ncol;
+  }
+  FB_CUDA(cudaStreamSynchronize(stream));
+  have_weights = have_locals = false;
+}
+
+// --------------------------------------------------------------------------------------- weights
+void fb_tree::upload_weights(const double *w, size_t n_rows, size_t nrhs_, ptrdiff_t rs, ptrdiff_t cs) {
+  FB_REQUIRE(w != nullptr, "weights required");
+  FB_REQUIRE(n_rows >= n, "weights must have at least one row per source point");
+  FB_REQUIRE(nrhs_ >= 1, "weights need at least one column");
+  const size_t cnt = n * nrhs_;
+  d_w_user.reserve(cnt);
+  if (cs == 1 && rs == (ptrdiff_t)nrhs_) {
+    FB_CUDA(cudaMemcpyAsync(d_w_user.p, w, cnt * sizeof(double), cudaMemcpyHostToDevice, stream));
+  } else {
+    h_stage.reserve(cnt);
+    for (size_t i = 0; i < n; ++i)
+      for (size_t r = 0; r < nrhs_; ++r) h_stage.p[i * nrhs_ + r] = w[(ptrdiff_t)i * rs + (ptrdiff_t)r * cs];
+    FB_CUDA(cudaMemcpyAsync(d_w_user.p, h_stage.p, cnt * sizeof(double), cudaMemcpyHostToDevice, stream));
+  }
+  nrhs = (int)nrhs_;
+  sort_weights();
+}
+
+void fb_tree::sort_weights() {
+  d_w.reserve(n * (size_t)nrhs);
+  FB_LAUNCH(k_sort_weights, nblocks(n, 256), 256, 0, stream, d_w_user.p, d_perm.p, n, nrhs, d_w.p);
+}
+
+// ---------------------------------------------------------------------------------------- upward
+void fb_tree::upward() {
+  const size_t nc = ht.ncells();
+  d_mult.zero(nc * (size_t)nrhs * P, stream);
+  const int p = order;
+  if (timing) FB_CUDA(cudaEventRecord(ev[0], stream));
+  const int nsl = n_src_leaves;
+  if (nsl > 0) {
+    const size_t smem = sizeof(double) * ((size_t)p * p + 3 * (size_t)kP2MChunk * p);
+    set_smem(k_p2m, smem);
+    FB_LAUNCH(k_p2m, nsl, 256, smem, stream, d_src_leaves.p, d_cell_ptb.p, d_cell_pte.p, d_sx.p, d_sy.p, d_sz.p,
+              d_w.p, n, d_ccx.p, d_ccy.p, d_ccz.p, d_chalf.p, d_tnodes.p, p, dim, P, nrhs, d_mult.p);
+  }
+  if (timing) FB_CUDA(cudaEventRecord(ev[1], stream));
+  const size_t smem = sizeof(double) * (2 * (size_t)p * p + 3 * (size_t)P);
+  set_smem(k_m2m, smem);
+  for (int lvl = ht.depth - 1; lvl >= 1; --lvl) {  // bbfmm.rs:675-687
+    const int np = parents_off[lvl + 1] - parents_off[lvl];
+    if (np <= 0) continue;
+    FB_LAUNCH(k_m2m, np, 128, smem, stream, d_parents.p + parents_off[lvl], d_child_ptr.p, d_child_idx.p,
+              d_cell_slot.p, d_child_s.p, p, dim, P, nrhs, d_mult.p);
+  }
+  if (timing) FB_CUDA(cudaEventRecord(ev[2], stream));
+  have_weights = true;
+}
+
+// -------------------------------------------------------------------------------------- downward
+void fb_tree::downward(const uint8_t *flags) {
+  const size_t nc = ht.ncells();
+  const int p = order;
+  d_loc.zero(nc * (size_t)nrhs * P, stream);
+  if (timing) FB_CUDA(cudaEventRecord(ev[3], stream));
+  // M2L (loop A of bbfmm.rs:781-832)
+  const bool compressed = fparams.compression_type != FB_COMPRESSION_NONE;
+  for (const M2LGroup &g : m2l_groups) {
+    const size_t ncols = g.n_entries * (size_t)nrhs;
+    const unsigned grid = (unsigned)((ncols + m2l_nc - 1) / m2l_nc);
+    const size_t smem = sizeof(double) * (size_t)m2l_nc * (size_t)(P + (compressed ? g.rank_pad : 0));
+    set_smem(k_m2l, 200 * 1024);
+    FB_LAUNCH(k_m2l, grid, 256, smem, stream, d_m2l_tgt.p + g.entry_off, d_m2l_src.p + g.entry_off,
+              d_m2l_perm.p + g.entry_off, g.n_entries, compressed ? d_oppool.p + g.v_off : nullptr,
+              d_oppool.p + g.u_off, g.rank, g.rank_pad, d_perm_tab.p, P, nrhs, m2l_nc, flags, d_mult.p, d_loc.p);
+  }
+  if (timing) FB_CUDA(cudaEventRecord(ev[4], stream));
+  // P2L (adaptive only)
+  if (ht.adaptive && n_x_cells > 0) {
+    P2LArgs a{};
+    a.cells = d_x_cells.p;
+    a.n_cells = n_x_cells;
+    a.x_ptr = d_x_ptr.p;
+    a.x_begin = d_x_begin.p;
+    a.x_count = d_x_count.p;
+    a.cell_flag = flags;
+    a.sx = d_sx.p;
+    a.sy = d_sy.p;
+    a.sz = d_sz.p;
+    a.w = d_w.p;
+    a.n = n;
+    a.loc = d_loc.p;
+    a.ccx = d_ccx.p;
+    a.ccy = d_ccy.p;
+    a.ccz = d_ccz.p;
+    a.chalf = d_chalf.p;
+    a.nodes = d_nodes.p;
+    a.p = p;
+    a.dim = dim;
+    a.P = P;
+    a.nrhs = nrhs;
+    a.rhs0 = 0;
+    a.kp = kp;
+    launch_p2l(a, stream);
+  }
+  if (timing) FB_CUDA(cudaEventRecord(ev[5], stream));
+  // L2L (loop B of bbfmm.rs:834-856): children at levels 2..depth
+  const size_t smem = sizeof(double) * (2 * (size_t)p * p + 2 * (size_t)P);
+  set_smem(k_l2l, smem);
+  for (int lvl = 2; lvl <= ht.depth; ++lvl) {
+    const int c0 = ht.level_ptr[lvl], cnt = ht.level_ptr[lvl + 1] - c0;
+    if (cnt <= 0) continue;
+    FB_LAUNCH(k_l2l, cnt, 128, smem, stream, c0, d_cell_parent.p, d_cell_slot.p, flags, d_child_s.p, p, dim, P, nrhs,
+              d_loc.p);
+  }
+  if (timing) FB_CUDA(cudaEventRecord(ev[6], stream));
+  have_locals = true;
+}
+
+// ------------------------------------------------------------------------------------- leaf pass
+void fb_tree::leaf_pass(const TargetSet &ts, bool grads) {
+  const int p = order;
+  d_out.zero(ts.m * (size_t)nrhs, stream);
+  if (grads) d_gout.zero(ts.m * (size_t)nrhs * dim, stream);
+  if (timing) FB_CUDA(cudaEventRecord(ev[7], stream));
+  if (ts.max_tiles > 0) {
+    const size_t smem = sizeof(double) * ((size_t)p * p + P + (size_t)kTile * dim * p * (grads ? 2 : 1));
+    set_smem(k_l2p, smem);
+    FB_LAUNCH(k_l2p, ts.max_tiles, kTile, smem, stream, ts, d_leaf_cell.p, d_loc.p, d_ccx.p, d_ccy.p, d_ccz.p,
+              d_chalf.p, d_tnodes.p, p, dim, P, nrhs, d_out.p, grads ? d_gout.p : nullptr);
+  }
+  if (timing) FB_CUDA(cudaEventRecord(ev[8], stream));
+  DirectArgs a{};
+  a.ts = ts;
+  a.u_ptr = d_u_ptr.p;
+  a.u_begin = d_u_begin.p;
+  a.u_count = d_u_count.p;
+  a.w_ptr = d_w_ptr.p;
+  a.w_cell = d_w_cell.p;
+  a.sx = d_sx.p;
+  a.sy = d_sy.p;
+  a.sz = d_sz.p;
+  a.w = d_w.p;
+  a.n = n;
+  a.mult = d_mult.p;
+  a.ccx = d_ccx.p;
+  a.ccy = d_ccy.p;
+  a.ccz = d_ccz.p;
+  a.chalf = d_chalf.p;
+  a.nodes = d_nodes.p;
+  a.p = p;
+  a.dim = dim;
+  a.P = P;
+  a.nrhs = nrhs;
+  a.rhs0 = 0;
+  a.out = d_out.p;
+  a.gout = grads ? d_gout.p : nullptr;
+  a.kp = kp;
+  launch_leaf_direct(a, stream);
+  if (timing) FB_CUDA(cudaEventRecord(ev[9], stream));
+}
+
+// ----------------------------------------------------------------------------------- target sets
+TargetSet fb_tree::source_target_set() {
+  if (d_src_out_row.cap < n) {  // out_row = source row of each sorted position
+    d_src_out_row.reserve(n);
+    FB_CUDA(cudaMemcpyAsync(d_src_out_row.p, d_perm.p, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
+  }
+  TargetSet ts;
+  ts.m = n;
+  ts.x = d_sx.p;
+  ts.y = d_sy.p;
+  ts.z = d_sz.p;
+  ts.out_row = d_src_out_row.p;
+  ts.leaf_begin = d_src_tl_begin.p;
+  ts.leaf_end = d_src_tl_end.p;
+  ts.tile_leaf = d_src_tile_leaf.p;
+  ts.tile_off = d_src_tile_off.p;
+  ts.n_tiles_dev = d_src_ntiles.p;
+  ts.max_tiles = src_tiles;
+  ts.cell_flag = d_flag_all.p;
+  return ts;
+}
+
+// shared tail of bin_targets / subset_target_set: keys (leaf slot or sorted source position) -> TargetSet
+static TargetSet finish_target_set(fb_tree &t, size_t m, int key_bits, bool keys_are_positions) {
+  const int nl = (int)t.ht.leaves.size();
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, t.d_t_key.p, t.d_t_key2.p, t.d_t_val.p, t.d_t_val2.p, (int)m, 0,
+                                  key_bits, t.stream);
+  size_t scan_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, t.d_tile_cnt.p, t.d_tile_cnt.p, nl, t.stream);
+  t.d_cub.reserve(std::max(cub_bytes, scan_bytes));
+  FB_CUDA(cub::DeviceRadixSort::SortPairs(t.d_cub.p, cub_bytes, t.d_t_key.p, t.d_t_key2.p, t.d_t_val.p, t.d_t_val2.p,
+                                          (int)m, 0, key_bits, t.stream));
+  g_launches.fetch_add(3);
+  t.d_tl_begin.reserve(nl);
+  t.d_tl_end.reserve(nl);
+  t.d_tile_cnt.reserve(2 * (size_t)nl);
+  FB_LAUNCH(k_leaf_ranges, nblocks(nl, 128), 128, 0, t.stream, t.d_t_key2.p, m,
+            keys_are_positions ? t.d_src_tl_begin.p : nullptr, keys_are_positions ? t.d_src_tl_end.p : nullptr, nl,
+            t.d_tl_begin.p, t.d_tl_end.p, t.d_tile_cnt.p);
+  int *scan_out = t.d_tile_cnt.p + nl;
+  FB_CUDA(cub::DeviceScan::ExclusiveSum(t.d_cub.p, scan_bytes, t.d_tile_cnt.p, scan_out, nl, t.stream));
+  g_launches.fetch_add(1);
+  const int max_tiles = (int)std::min<size_t>((m + kTile - 1) / kTile + (size_t)nl, m);
+  t.d_tile_leaf.reserve(max_tiles);
+  t.d_tile_off.reserve(max_tiles);
+  t.d_ntiles.reserve(1);
+  FB_LAUNCH(k_fill_tiles, nblocks(nl, 128), 128, 0, t.stream, scan_out, t.d_tile_cnt.p, nl, t.d_tile_leaf.p,
+            t.d_tile_off.p, t.d_ntiles.p);
+  FB_CUDA(cudaMemsetAsync(t.d_flag.p, 0, t.ht.ncells(), t.stream));
+  FB_LAUNCH(k_flag_cells, nblocks(nl, 128), 128, 0, t.stream, t.d_leaf_cell.p, t.d_tl_begin.p, t.d_tl_end.p, nl,
+            t.d_cell_parent.p, t.d_flag.p);
+  TargetSet ts;
+  ts.m = m;
+  ts.x = t.d_tx.p;
+  ts.y = t.d_ty.p;
+  ts.z = t.d_tz.p;
+  ts.out_row = t.d_t_val2.p;
+  ts.leaf_begin = t.d_tl_begin.p;
+  ts.leaf_end = t.d_tl_end.p;
+  ts.tile_leaf = t.d_tile_leaf.p;
+  ts.tile_off = t.d_tile_off.p;
+  ts.n_tiles_dev = t.d_ntiles.p;
+  ts.max_tiles = max_tiles;
+  ts.cell_flag = t.d_flag.p;
+  return ts;
+}
+
+static int bits_for(size_t v) {
+  int b = 1;
+  while (b < 32 && (1ull << b) <= v) ++b;
+  return b;
+}
+
+TargetSet fb_tree::bin_targets(const double *targets, size_t m, ptrdiff_t rs, ptrdiff_t cs, uint64_t *bad) {
+  FB_REQUIRE(targets != nullptr && m > 0, "target_points must be a non-empty m x dim matrix");
+  FB_REQUIRE(m < (1ull << 31), "at most 2^31-1 targets per call");
+  const int nl = (int)ht.leaves.size();
+  d_t_user.reserve(m * dim);
+  if (cs == 1 && rs == (ptrdiff_t)dim) {
+    FB_CUDA(cudaMemcpyAsync(d_t_user.p, targets, m * dim * sizeof(double), cudaMemcpyHostToDevice, stream));
+  } else {
+    h_stage.reserve(m * dim);
+    for (size_t i = 0; i < m; ++i)
+      for (int d = 0; d < dim; ++d) h_stage.p[i * dim + d] = targets[(ptrdiff_t)i * rs + (ptrdiff_t)d * cs];
+    FB_CUDA(cudaMemcpyAsync(d_t_user.p, h_stage.p, m * dim * sizeof(double), cudaMemcpyHostToDevice, stream));
+  }
+  d_t_key.reserve(m);
+  d_t_key2.reserve(m);
+  d_t_val.reserve(m);
+  d_t_val2.reserve(m);
+  d_tx.reserve(m);
+  d_ty.reserve(m);
+  d_tz.reserve(m);
+  d_err.reserve(1);
+  FB_CUDA(cudaMemsetAsync(d_err.p, 0xFF, sizeof(unsigned long long), stream));
+  const double side_depth = 2.0 * ht.radius / (double)(1ull << ht.depth);  // linear_tree.rs:495
+  FB_LAUNCH(k_target_leaf, nblocks(m, 256), 256, 0, stream, d_t_user.p, m, dim, ht.depth, ht.disp[0], ht.disp[1],
+            ht.disp[2], side_depth, d_leaf_lo.p, d_leaf_hi.p, nl, d_t_key.p, d_t_val.p, d_err.p);
+  unsigned long long h_err = 0;
+  FB_CUDA(cudaMemcpyAsync(&h_err, d_err.p, sizeof(h_err), cudaMemcpyDeviceToHost, stream));
+  FB_CUDA(cudaStreamSynchronize(stream));
+  if (h_err != ~0ull) {
+    if (bad) *bad = h_err;
+    throw Error(FB_ERR_POINT_OUTSIDE_TREE,
+                "FMM evaluation failed: target point at row " + std::to_string(h_err) +
+                    " lies outside the tree extents",
+                h_err);
+  }
+  TargetSet ts = finish_target_set(*this, m, bits_for((size_t)nl), false);
+  FB_LAUNCH(k_gather_targets, nblocks(m, 256), 256, 0, stream, d_t_user.p, d_t_val2.p, m, dim, d_tx.p, d_ty.p,
+            d_tz.p);
+  return ts;
+}
+
+TargetSet fb_tree::subset_target_set(const uint64_t *idx, size_t m) {
+  FB_REQUIRE(idx != nullptr && m > 0 && m < (1ull << 31), "index list must be non-empty");
+  d_idx64.reserve(m);
+  FB_CUDA(cudaMemcpyAsync(d_idx64.p, idx, m * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+  d_t_key.reserve(m);
+  d_t_key2.reserve(m);
+  d_t_val.reserve(m);
+  d_t_val2.reserve(m);
+  d_tx.reserve(m);
+  d_ty.reserve(m);
+  d_tz.reserve(m);
+  d_err.reserve(1);
+  FB_CUDA(cudaMemsetAsync(d_err.p, 0xFF, sizeof(unsigned long long), stream));
+  FB_LAUNCH(k_subset_positions, nblocks(m, 256), 256, 0, stream, d_idx64.p, d_inv.p, m, n, d_t_key.p, d_t_val.p,
+            d_err.p);
+  unsigned long long h_err = 0;
+  FB_CUDA(cudaMemcpyAsync(&h_err, d_err.p, sizeof(h_err), cudaMemcpyDeviceToHost, stream));
+  FB_CUDA(cudaStreamSynchronize(stream));
+  FB_REQUIRE(h_err == ~0ull, "source index out of range at position " + std::to_string(h_err));
+  TargetSet ts = finish_target_set(*this, m, bits_for(n), true);
+  FB_LAUNCH(k_gather_coords, nblocks(m, 256), 256, 0, stream, d_sx.p, d_sy.p, d_sz.p, d_t_key2.p, m, d_tx.p, d_ty.p,
+            d_tz.p);
+  return ts;
+}
+
+void fb_tree::fetch_output(size_t m, bool grads, double *out_vals, double *out_grads, ptrdiff_t o_rs,
+                           ptrdiff_t o_cs) {
+  auto fetch = [&](const double *dsrc, size_t cols, double *dst) {
+    const size_t cnt = m * cols;
+    if (o_cs == 1 && o_rs == (ptrdiff_t)cols) {
+      FB_CUDA(cudaMemcpyAsync(dst, dsrc, cnt * sizeof(double), cudaMemcpyDeviceToHost, stream));
+      FB_CUDA(cudaStreamSynchronize(stream));
+    } else {
+      h_stage.reserve(cnt);
+      FB_CUDA(cudaMemcpyAsync(h_stage.p, dsrc, cnt * sizeof(double), cudaMemcpyDeviceToHost, stream));
+      FB_CUDA(cudaStreamSynchronize(stream));
+      // strides describe the value matrix (m x nrhs); gradients use o_rs * dim, o_cs (same orientation)
+      const ptrdiff_t rs = (cols == (size_t)nrhs) ? o_rs : (o_cs == 1 ? (ptrdiff_t)cols : 1);
+      const ptrdiff_t cs2 = (cols == (size_t)nrhs) ? o_cs : (o_cs == 1 ? 1 : (ptrdiff_t)m);
+      for (size_t i = 0; i < m; ++i)
+        for (size_t c = 0; c < cols; ++c) dst[(ptrdiff_t)i * rs + (ptrdiff_t)c * cs2] = h_stage.p[i * cols + c];
+    }
+  };
+  fetch(d_out.p, (size_t)nrhs, out_vals);
+  if (grads && out_grads) {
+    if (o_cs == 1 && o_rs == (ptrdiff_t)nrhs) {  // row-major values => row-major gradients
+      FB_CUDA(cudaMemcpyAsync(out_grads, d_gout.p, m * (size_t)nrhs * dim * sizeof(double), cudaMemcpyDeviceToHost,
+                              stream));
+      FB_CUDA(cudaStreamSynchronize(stream));
+    } else {
+      fetch(d_gout.p, (size_t)nrhs * dim, out_grads);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ C ABI
+template <class F>
+static int guarded(F &&f, uint64_t *bad = nullptr) {
+  try {
+    f();
+    return FB_OK;
+  } catch (const fb::Error &e) {
+    set_last_error(e.what());
+    if (bad && e.code == FB_ERR_POINT_OUTSIDE_TREE) *bad = e.index;
+    return e.code;
+  } catch (const std::exception &e) {
+    set_last_error(e.what());
+    return FB_ERR_CUDA;
+  }
+}
+
+static void collect_timing(fb_tree *t) {
+  if (!t->timing) return;
+  auto ms = [&](int a, int b) {
+    float v = 0;
+    cudaEventElapsedTime(&v, t->ev[a], t->ev[b]);
+    return (double)v;
+  };
+  t->last_ms[0] = ms(0, 1);  // p2m
+  t->last_ms[1] = ms(1, 2);  // m2m
+  t->last_ms[2] = ms(3, 4);  // m2l
+  t->last_ms[3] = ms(4, 5);  // p2l
+  t->last_ms[4] = ms(5, 6);  // l2l
+  t->last_ms[5] = ms(7, 8);  // l2p
+  t->last_ms[6] = ms(8, 9);  // p2p + m2p
+  t->last_ms[7] = ms(0, 9);  // total
+}
+
+extern "C" {
+
+const char *fb_last_error(void) { return t_last_error.c_str(); }
+uint64_t fb_kernel_launch_count(void) { return g_launches.load(); }
+int fb_set_device(int device) {
+  return guarded([&] { FB_CUDA(cudaSetDevice(device)); });
+}
+
+int fb_tree_new(const double *points, size_t n, int dim, ptrdiff_t row_stride, ptrdiff_t col_stride,
+                int interpolation_order, const fb_kernel_params *kernel, int adaptive_tree, int sparse,
+                const double *extents_or_null, const fb_fmm_params *params_or_null, fb_tree **out) {
+  if (!out) return FB_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  fb_tree *t = nullptr;
+  const int rc = guarded([&] {
+    t = new fb_tree();
+    t->build(points, n, dim, row_stride, col_stride, interpolation_order, kernel, adaptive_tree, sparse,
+             extents_or_null, params_or_null);
+  });
+  if (rc != FB_OK) {
+    delete t;
+    return rc;
+  }
+  *out = t;
+  return FB_OK;
+}
+
+void fb_tree_free(fb_tree *t) {
+  if (!t) return;
+  cudaSetDevice(t->device);
+  delete t;
+}
+
+int fb_tree_set_weights(fb_tree *t, const double *w, size_t n_rows, size_t nrhs, ptrdiff_t rs, ptrdiff_t cs) {
+  return guarded([&] {
+    FB_REQUIRE(t, "null tree");
+    FB_CUDA(cudaSetDevice(t->device));
+    t->upload_weights(w, n_rows, nrhs, rs, cs);
+    t->upward();
+    FB_CUDA(cudaStreamSynchronize(t->stream));
+  });
+}
+
+int fb_tree_set_local_coefficients(fb_tree *t, const double *w, size_t n_rows, size_t nrhs, ptrdiff_t rs,
+                                   ptrdiff_t cs) {
+  return guarded([&] {
+    FB_REQUIRE(t, "null tree");
+    FB_CUDA(cudaSetDevice(t->device));
+    FB_REQUIRE(t->have_weights, "set_weights must be called before set_local_coefficients");
+    FB_REQUIRE((int)nrhs == t->nrhs, "weights must have the column count given to set_weights");
+    const int keep = t->nrhs;
+    t->upload_weights(w, n_rows, nrhs, rs, cs);
+    t->nrhs = keep;
+    t->downward(t->d_flag_all.p);
+    FB_CUDA(cudaStreamSynchronize(t->stream));
+  });
+}
+
+static int eval_common(fb_tree *t, const double *w, size_t n_rows, size_t nrhs, ptrdiff_t w_rs, ptrdiff_t w_cs,
+                       const double *targets, size_t m, ptrdiff_t t_rs, ptrdiff_t t_cs, double *out_vals,
+                       double *out_grads, ptrdiff_t o_rs, ptrdiff_t o_cs, uint64_t *bad, bool leaves_only) {
+  return guarded(
+      [&] {
+        FB_REQUIRE(t, "null tree");
+        FB_CUDA(cudaSetDevice(t->device));
+        FB_REQUIRE(out_vals, "output buffer required");
+        FB_REQUIRE(t->have_weights, "set_weights must be called before evaluate");
+        FB_REQUIRE((int)nrhs == t->nrhs, "weights must have the column count given to set_weights");
+        if (leaves_only) FB_REQUIRE(t->have_locals, "set_local_coefficients must be called before evaluate_leaves");
+        TargetSet ts = t->bin_targets(targets, m, t_rs, t_cs, bad);  // before touching weights: errors leave state intact
+        t->upload_weights(w, n_rows, nrhs, w_rs, w_cs);
+        if (!leaves_only) t->downward(ts.cell_flag);
+        t->leaf_pass(ts, out_grads != nullptr);
+        t->fetch_output(m, out_grads != nullptr, out_vals, out_grads, o_rs, o_cs);
+      },
+      bad);
+}
+
+int fb_tree_evaluate(fb_tree *t, const double *w, size_t n_rows, size_t nrhs, ptrdiff_t w_rs, ptrdiff_t w_cs,
+                     const double *targets, size_t m, ptrdiff_t t_rs, ptrdiff_t t_cs, double *out_vals,
+                     double *out_grads_or_null, ptrdiff_t o_rs, ptrdiff_t o_cs, uint64_t *bad_index) {
+  return eval_common(t, w, n_rows, nrhs, w_rs, w_cs, targets, m, t_rs, t_cs, out_vals, out_grads_or_null, o_rs, o_cs,
+                     bad_index, false);
+}
+
+int fb_tree_evaluate_leaves(fb_tree *t, const double *w, size_t n_rows, size_t nrhs, ptrdiff_t w_rs, ptrdiff_t w_cs,
+                            const double *targets, size_t m, ptrdiff_t t_rs, ptrdiff_t t_cs, double *out_vals,
+                            double *out_grads_or_null, ptrdiff_t o_rs, ptrdiff_t o_cs, uint64_t *bad_index) {
+  return eval_common(t, w, n_rows, nrhs, w_rs, w_cs, targets, m, t_rs, t_cs, out_vals, out_grads_or_null, o_rs, o_cs,
+                     bad_index, true);
+}
+
+int fb_tree_evaluate_at_sources(fb_tree *t, const double *w, size_t n_rows, size_t nrhs, ptrdiff_t w_rs,
+                                ptrdiff_t w_cs, const uint64_t *idx_or_null, size_t n_idx, double *out_vals,
+                                ptrdiff_t o_rs, ptrdiff_t o_cs) {
+  return guarded([&] {
+    FB_REQUIRE(t, "null tree");
+    FB_CUDA(cudaSetDevice(t->device));
+    FB_REQUIRE(out_vals, "output buffer required");
+    FB_REQUIRE(t->have_weights, "set_weights must be called before evaluate");
+    FB_REQUIRE((int)nrhs == t->nrhs, "weights must have the column count given to set_weights");
+    TargetSet ts = idx_or_null ? t->subset_target_set(idx_or_null, n_idx) : t->source_target_set();
+    t->upload_weights(w, n_rows, nrhs, w_rs, w_cs);
+    t->downward(ts.cell_flag);
+    t->leaf_pass(ts, false);
+    t->fetch_output(ts.m, false, out_vals, nullptr, o_rs, o_cs);
+  });
+}
+
+int fb_tree_upload_weights(fb_tree *t, const double *w, size_t n_rows, size_t nrhs, ptrdiff_t rs, ptrdiff_t cs) {
+  return guarded([&] {
+    FB_REQUIRE(t, "null tree");
+    FB_CUDA(cudaSetDevice(t->device));
+    t->upload_weights(w, n_rows, nrhs, rs, cs);
+    FB_CUDA(cudaStreamSynchronize(t->stream));
+  });
+}
+
+int fb_tree_matvec_resident(fb_tree *t) {
+  return guarded([&] {
+    FB_REQUIRE(t, "null tree");
+    FB_CUDA(cudaSetDevice(t->device));
+    FB_REQUIRE(t->d_w_user.cap >= t->n * (size_t)t->nrhs, "fb_tree_upload_weights must be called first");
+    t->sort_weights();
+    t->upward();
+    TargetSet ts = t->source_target_set();
+    t->downward(ts.cell_flag);
+    t->leaf_pass(ts, false);
+    FB_CUDA(cudaStreamSynchronize(t->stream));
+    collect_timing(t);
+  });
+}
+
+int fb_tree_download_result(fb_tree *t, double *out_vals, ptrdiff_t o_rs, ptrdiff_t o_cs) {
+  return guarded([&] {
+    FB_REQUIRE(t && out_vals, "null argument");
+    FB_CUDA(cudaSetDevice(t->device));
+    t->fetch_output(t->n, false, out_vals, nullptr, o_rs, o_cs);
+  });
+}
+
+int fb_tree_set_timing(fb_tree *t, int enabled) {
+  if (!t) return FB_ERR_INVALID_ARGUMENT;
+  t->timing = enabled != 0;
+  return FB_OK;
+}
+
+int fb_tree_last_timing(fb_tree *t, double *ms_out8) {
+  if (!t || !ms_out8) return FB_ERR_INVALID_ARGUMENT;
+  for (int i = 0; i < 8; ++i) ms_out8[i] = t->last_ms[i];
+  return FB_OK;
+}
+
+int fb_tree_source_points(const fb_tree *t, double *out, ptrdiff_t row_stride, ptrdiff_t col_stride) {
+  if (!t || !out) return FB_ERR_INVALID_ARGUMENT;
+  for (size_t i = 0; i < t->n; ++i)
+    for (int d = 0; d < t->dim; ++d)
+      out[(ptrdiff_t)i * row_stride + (ptrdiff_t)d * col_stride] = t->host_points[i * t->dim + d];
+  return FB_OK;
+}
+
+int fb_tree_get_info(const fb_tree *t, fb_tree_info *info) {
+  if (!t || !info) return FB_ERR_INVALID_ARGUMENT;
+  std::memset(info, 0, sizeof(*info));
+  info->n_points = t->n;
+  info->n_cells = t->ht.ncells();
+  info->n_leaves = t->ht.leaves.size();
+  info->depth = (uint64_t)t->ht.depth;
+  info->n_u = t->ht.u_idx.size();
+  info->n_v = t->ht.v_idx.size();
+  info->n_w = t->ht.w_idx.size();
+  info->n_x = t->ht.x_idx.size();
+  info->dim = t->dim;
+  info->order = t->order;
+  info->nrhs = t->nrhs;
+  info->radius = t->ht.radius;
+  for (int d = 0; d < 3; ++d) info->center[d] = t->ht.center[d];
+  info->p2p_pairs = t->p2p_pairs;
+  info->m2p_pairs = t->m2p_pairs;
+  info->p2l_pairs = t->p2l_pairs;
+  return FB_OK;
+}
+
+int fb_tree_dump_cells(const fb_tree *t, uint64_t *keys, uint8_t *leaf_flags, uint64_t *leaf_ptr,
+                       uint64_t *leaf_idx) {
+  if (!t) return FB_ERR_INVALID_ARGUMENT;
+  return guarded([&] {
+    const size_t nc = t->ht.ncells();
+    std::vector<uint32_t> perm;
+    if (leaf_idx) {
+      perm.resize(t->n);
+      FB_CUDA(cudaSetDevice(t->device));
+      FB_CUDA(cudaMemcpy(perm.data(), t->d_perm.p, t->n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    }
+    uint64_t off = 0;
+    for (size_t c = 0; c < nc; ++c) {
+      if (keys) keys[c] = t->ht.ref_key((int)c);
+      if (leaf_flags) leaf_flags[c] = t->ht.is_leaf[c];
+      if (leaf_ptr) leaf_ptr[c] = off;
+      if (t->ht.is_leaf[c]) {
+        const int b = t->ht.pt_begin[c], e = t->ht.pt_end[c];
+        if (leaf_idx) {
+          for (int i = b; i < e; ++i) leaf_idx[off + (i - b)] = perm[i];
+          std::sort(leaf_idx + off, leaf_idx + off + (e - b));
+        }
+        off += (uint64_t)(e - b);
+      }
+    }
+    if (leaf_ptr) leaf_ptr[nc] = off;
+  });
+}
+
+int fb_tree_dump_list(const fb_tree *t, int which, uint64_t *ptr, uint64_t *idx) {
+  if (!t || which < 0 || which > 3) return FB_ERR_INVALID_ARGUMENT;
+  const std::vector<int64_t> *p[4] = {&t->ht.u_ptr, &t->ht.v_ptr, &t->ht.w_ptr, &t->ht.x_ptr};
+  const std::vector<int32_t> *x[4] = {&t->ht.u_idx, &t->ht.v_idx, &t->ht.w_idx, &t->ht.x_idx};
+  if (ptr)
+    for (size_t i = 0; i < p[which]->size(); ++i) ptr[i] = (uint64_t)(*p[which])[i];
+  if (idx)
+    for (size_t i = 0; i < x[which]->size(); ++i) idx[i] = (uint64_t)(*x[which])[i];
+  return FB_OK;
+}
+
+int fb_tree_m2l_rank(const fb_tree *t, int level, int ref) {
+  if (!t || level < 2 || level > t->ht.depth || ref < 0 || ref >= t->ops.n_ref) return -1;
+  return t->ops.m2l[level - 2][ref].rank;
+}
+
+int fb_tree_m2l_operator(const fb_tree *t, int level, int ref, double *u_or_null, double *vt_or_null) {
+  if (!t || level < 2 || level > t->ht.depth || ref < 0 || ref >= t->ops.n_ref) return FB_ERR_INVALID_ARGUMENT;
+  const fb::M2LOperator &op = t->ops.m2l[level - 2][ref];
+  if (u_or_null) std::copy(op.U.a.begin(), op.U.a.end(), u_or_null);
+  if (vt_or_null) std::copy(op.Vt.a.begin(), op.Vt.a.end(), vt_or_null);
+  return FB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,149 @@
+// Internal declarations of the device-resident FMM evaluator (struct fb_tree) and its kernels.
+#pragma once
+#include <memory>
+
+#include "common.h"
+#include "host_ops.h"
+#include "host_tree.h"
+#include "kernel_functions.cuh"
+
+namespace fb {
+
+constexpr int kMaxOrder = 16;   // Chebyshev nodes per axis supported by the device kernels
+constexpr int kTile = 128;      // targets per CTA in the direct-sum / L2P kernels
+
+// ---- a target set binned into the leaves of a tree (sorted by leaf, Morton order) -------------
+struct TargetSet {
+  size_t m = 0;              // number of targets
+  const double *x = nullptr, *y = nullptr, *z = nullptr;  // sorted coordinates (unused dims are 0)
+  const uint32_t *out_row = nullptr;                       // output row of each sorted target
+  const int *leaf_begin = nullptr, *leaf_end = nullptr;    // per leaf slot: range in the sorted arrays
+  const int *tile_leaf = nullptr, *tile_off = nullptr;     // CTA tiles of <= kTile targets
+  const int *n_tiles_dev = nullptr;                        // device scalar: number of valid tiles
+  int max_tiles = 0;                                       // launch bound for the tile grid
+  const uint8_t *cell_flag = nullptr;                      // per cell: subtree contains targets
+};
+
+struct DirectArgs {  // leaf pass: P2P over U ranges + M2P over W cells (bbfmm.rs:1162-1355)
+  TargetSet ts;
+  const long long *u_ptr;
+  const int *u_begin, *u_count;  // merged contiguous source ranges
+  const long long *w_ptr;
+  const int *w_cell;
+  const double *sx, *sy, *sz, *w;  // sources (sorted) and weights [rhs][n]
+  size_t n;
+  const double *mult;  // multipoles [cell][rhs][P]
+  const double *ccx, *ccy, *ccz, *chalf;
+  const double *nodes;  // p Chebyshev nodes
+  int p, dim, P, nrhs, rhs0;
+  double *out;    // [m][nrhs]
+  double *gout;   // [m][nrhs*dim] or null
+  KParams kp;
+};
+
+struct P2LArgs {  // bbfmm.rs:1001-1048
+  const int *cells;  // cells that own a non-empty X list
+  int n_cells;
+  const long long *x_ptr;  // per entry of `cells`
+  const int *x_begin, *x_count;
+  const uint8_t *cell_flag;
+  const double *sx, *sy, *sz, *w;
+  size_t n;
+  double *loc;  // locals [cell][rhs][P]
+  const double *ccx, *ccy, *ccz, *chalf;
+  const double *nodes;
+  int p, dim, P, nrhs, rhs0;
+  KParams kp;
+};
+
+void launch_leaf_direct(const DirectArgs &a, cudaStream_t s);
+void launch_p2l(const P2LArgs &a, cudaStream_t s);
+
+// ---- M2L work lists, one group per (level, reference vector) -----------------------------------
+struct M2LGroup {
+  int level, ref, rank, rank_pad;
+  size_t n_entries;
+  size_t entry_off;     // offset into the entry arrays
+  size_t u_off, v_off;  // offsets (in doubles) into the operator pool
+};
+
+}  // namespace fb
+
+// The opaque C handle
+struct fb_tree {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int dim = 3, order = 0, P = 0;
+  size_t n = 0;
+  int nrhs = 1;
+  bool have_weights = false, have_locals = false;
+  fb_kernel_params kparams_c{};
+  fb::KParams kp{};
+  fb_fmm_params fparams{};
+  std::vector<double> host_points;  // n x dim row-major copy (source_points())
+  fb::HostTree ht;
+  fb::Operators ops;
+  uint64_t p2p_pairs = 0, m2p_pairs = 0, p2l_pairs = 0;
+
+  // --- device state
+  fb::DBuf<double> d_sx, d_sy, d_sz;          // sorted source coordinates
+  fb::DBuf<uint32_t> d_perm, d_inv;           // sorted position -> source row, and inverse
+  fb::DBuf<double> d_w;                       // weights, sorted, [rhs][n]
+  fb::DBuf<double> d_w_user;                  // weights as uploaded [n][nrhs] row-major
+  fb::DBuf<double> d_mult, d_loc;             // [cell][rhs][P]
+  fb::DBuf<double> d_ccx, d_ccy, d_ccz, d_chalf;
+  fb::DBuf<int> d_cell_parent, d_cell_slot, d_cell_ptb, d_cell_pte;
+  fb::DBuf<int> d_child_ptr, d_child_idx;
+  fb::DBuf<uint8_t> d_flag_all, d_flag;       // per-cell "has targets" flags
+  fb::DBuf<int> d_leaf_cell;                  // leaf slot -> cell
+  fb::DBuf<unsigned long long> d_leaf_lo, d_leaf_hi;  // level-16 code range of each leaf slot
+  fb::DBuf<int> d_src_leaves;                 // cells of leaves that hold sources (P2M grid)
+  std::vector<std::vector<int>> h_parents;    // per level: non-leaf cells
+  fb::DBuf<int> d_parents;                    // concatenated, offsets in parents_off
+  std::vector<int> parents_off;
+  fb::DBuf<int> d_level_cells;                // cells level-major == identity, kept for clarity
+  // lists
+  fb::DBuf<long long> d_u_ptr, d_w_ptr, d_x_ptr;
+  fb::DBuf<int> d_u_begin, d_u_count, d_w_cell, d_x_begin, d_x_count, d_x_cells;
+  int n_x_cells = 0;
+  int n_src_leaves = 0;
+  // all-sources target set
+  fb::DBuf<int> d_src_tl_begin, d_src_tl_end, d_src_tile_leaf, d_src_tile_off, d_src_ntiles;
+  fb::DBuf<uint32_t> d_src_out_row;
+  int src_tiles = 0;
+  // general target set scratch
+  fb::DBuf<double> d_t_user, d_tx, d_ty, d_tz;
+  fb::DBuf<uint32_t> d_t_key, d_t_key2, d_t_val, d_t_val2;
+  fb::DBuf<int> d_tl_begin, d_tl_end, d_tile_leaf, d_tile_off, d_ntiles, d_tile_cnt;
+  fb::DBuf<unsigned long long> d_err;
+  fb::DBuf<unsigned char> d_cub;
+  fb::DBuf<unsigned long long> d_idx64;
+  // outputs
+  fb::DBuf<double> d_out, d_gout;
+  fb::PinnedBuf<double> h_stage;
+  // operators
+  fb::DBuf<double> d_nodes, d_tnodes, d_child_s, d_oppool;
+  fb::DBuf<int> d_perm_tab, d_inv_tab;
+  // M2L
+  std::vector<fb::M2LGroup> m2l_groups;
+  fb::DBuf<int> d_m2l_tgt, d_m2l_src, d_m2l_perm;
+  int m2l_nc = 16;  // columns per CTA
+  // timing
+  bool timing = false;
+  double last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  cudaEvent_t ev[10] = {};
+
+  ~fb_tree();
+  void build(const double *points, size_t n_, int dim_, ptrdiff_t rs, ptrdiff_t cs, int order_,
+             const fb_kernel_params *k, int adaptive, int sparse, const double *extents,
+             const fb_fmm_params *params);
+  void upload_weights(const double *w, size_t n_rows, size_t nrhs_, ptrdiff_t rs, ptrdiff_t cs);
+  void sort_weights();
+  void upward();
+  void downward(const uint8_t *flags);
+  void leaf_pass(const fb::TargetSet &ts, bool grads);
+  fb::TargetSet source_target_set();
+  fb::TargetSet bin_targets(const double *targets, size_t m, ptrdiff_t rs, ptrdiff_t cs, uint64_t *bad);
+  fb::TargetSet subset_target_set(const uint64_t *idx, size_t n_idx);
+  void fetch_output(size_t m, bool grads, double *out_vals, double *out_grads, ptrdiff_t o_rs, ptrdiff_t o_cs);
+};

@@ -1,0 +1,535 @@
+// Device kernels of the FMM passes other than the direct sums (see direct.cu).
+//   tree:      k_point_codes, k_gather_sorted, k_target_leaf ...       (morton.rs:35-119, linear_tree.rs:487-534)
+//   upward:    k_p2m, k_m2m                                              (bbfmm.rs:666-772)
+//   downward:  k_m2l, k_l2l                                              (bbfmm.rs:778-1086)
+//   leaf:      k_l2p                                                     (bbfmm.rs:1358-1440)
+#pragma once
+#include "fmm.h"
+
+namespace fb {
+
+// ------------------------------------------------------------------------------------------ tree
+__device__ __forceinline__ unsigned long long interleave_bits(unsigned a0, unsigned a1, unsigned a2, int dim) {
+  unsigned long long code = 0;
+  for (int bit = 0; bit < 16; ++bit) {
+    code |= (unsigned long long)((a0 >> bit) & 1u) << (bit * dim);
+    if (dim > 1) code |= (unsigned long long)((a1 >> bit) & 1u) << (bit * dim + 1);
+    if (dim > 2) code |= (unsigned long long)((a2 >> bit) & 1u) << (bit * dim + 2);
+  }
+  return code;
+}
+
+// floor((x - disp) / side) as u64 with Rust `as` saturation (morton.rs:46): NaN/negative -> 0
+__device__ __forceinline__ unsigned long long anchor_sat(double x, double disp, double side) {
+  const double q = floor(__ddiv_rn(__dsub_rn(x, disp), side));
+  if (!(q >= 0.0)) return 0ull;
+  if (q >= 18446744073709551616.0) return 0xFFFFFFFFFFFFFFFFull;
+  return (unsigned long long)q;
+}
+
+// level-16 interleaved code of every source point; err = first row outside the root cube (high side)
+__global__ void k_point_codes(const double *pts, size_t n, int dim, double d0, double d1, double d2, double side16,
+                              unsigned long long *codes, uint32_t *idx, unsigned long long *err) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double disp[3] = {d0, d1, d2};
+  unsigned a[3] = {0, 0, 0};
+  for (int j = 0; j < dim; ++j) {
+    const unsigned long long v = anchor_sat(pts[i * dim + j], disp[j], side16);
+    if (v >= 65536ull) atomicMin(err, (unsigned long long)i);
+    a[j] = (unsigned)(v & 0xFFFFull);
+  }
+  codes[i] = interleave_bits(a[0], a[1], a[2], dim);
+  idx[i] = (uint32_t)i;
+}
+
+__global__ void k_gather_sorted(const double *pts, const uint32_t *perm, size_t n, int dim, double *sx, double *sy,
+                                double *sz, uint32_t *inv) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t s = perm[i];
+  sx[i] = pts[(size_t)s * dim];
+  sy[i] = dim > 1 ? pts[(size_t)s * dim + 1] : 0.0;
+  sz[i] = dim > 2 ? pts[(size_t)s * dim + 2] : 0.0;
+  if (inv) inv[s] = (uint32_t)i;
+}
+
+// weights [n][nrhs] row-major (user order) -> [rhs][n] sorted order
+__global__ void k_sort_weights(const double *wu, const uint32_t *perm, size_t n, int nrhs, double *ws) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t s = perm[i];
+  for (int r = 0; r < nrhs; ++r) ws[(size_t)r * n + i] = wu[s * nrhs + r];
+}
+
+// leaf slot of every target (linear_tree.rs:487-520): key at level `depth`, then the enclosing leaf
+__global__ void k_target_leaf(const double *tg, size_t m, int dim, int depth, double d0, double d1, double d2,
+                              double side_depth, const unsigned long long *leaf_lo, const unsigned long long *leaf_hi,
+                              int n_leaves, uint32_t *slot, uint32_t *idx, unsigned long long *err) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const double disp[3] = {d0, d1, d2};
+  unsigned a[3] = {0, 0, 0};
+  bool outside = false;
+  for (int j = 0; j < dim; ++j) {
+    const unsigned long long v = anchor_sat(tg[i * dim + j], disp[j], side_depth) & 0xFFFFull;  // 16-bit LUT masking
+    if (v >= (1ull << depth)) outside = true;
+    a[j] = (unsigned)v;
+  }
+  idx[i] = (uint32_t)i;
+  uint32_t s = 0;
+  if (!outside) {
+    const unsigned long long code = interleave_bits(a[0], a[1], a[2], dim) << (dim * (16 - depth));
+    int lo = 0, hi = n_leaves;  // last leaf with leaf_lo <= code
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (leaf_lo[mid] <= code)
+        lo = mid;
+      else
+        hi = mid;
+    }
+    if (n_leaves > 0 && leaf_lo[lo] <= code && code < leaf_hi[lo])
+      s = (uint32_t)lo;
+    else
+      outside = true;
+  }
+  if (outside) atomicMin(err, (unsigned long long)i);
+  slot[i] = s;
+}
+
+__global__ void k_subset_positions(const unsigned long long *idx, const uint32_t *inv, size_t m, size_t n,
+                                   uint32_t *pos, uint32_t *val, unsigned long long *err) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const unsigned long long s = idx[i];
+  if (s >= n) {
+    atomicMin(err, (unsigned long long)i);
+    pos[i] = 0;
+  } else {
+    pos[i] = inv[s];
+  }
+  val[i] = (uint32_t)i;
+}
+
+// per leaf slot: range of sorted targets whose key (leaf slot, or sorted source position) falls in the leaf
+__global__ void k_leaf_ranges(const uint32_t *keys, size_t m, const int *key_lo, const int *key_hi, int n_leaves,
+                              int *begin, int *end, int *tile_cnt) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= n_leaves) return;
+  const uint32_t klo = key_lo ? (uint32_t)key_lo[l] : (uint32_t)l;
+  const uint32_t khi = key_hi ? (uint32_t)key_hi[l] : (uint32_t)l + 1u;
+  size_t lo = 0, hi = m;
+  while (lo < hi) {
+    const size_t mid = (lo + hi) >> 1;
+    if (keys[mid] < klo) lo = mid + 1; else hi = mid;
+  }
+  const size_t b = lo;
+  hi = m;
+  while (lo < hi) {
+    const size_t mid = (lo + hi) >> 1;
+    if (keys[mid] < khi) lo = mid + 1; else hi = mid;
+  }
+  begin[l] = (int)b;
+  end[l] = (int)lo;
+  tile_cnt[l] = ((int)(lo - b) + kTile - 1) / kTile;
+}
+
+__global__ void k_fill_tiles(const int *tile_off_scan, const int *tile_cnt, int n_leaves, int *tile_leaf, int *tile_off,
+                             int *n_tiles) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= n_leaves) return;
+  const int base = tile_off_scan[l];
+  for (int t = 0; t < tile_cnt[l]; ++t) {
+    tile_leaf[base + t] = l;
+    tile_off[base + t] = t * kTile;
+  }
+  if (l == n_leaves - 1) *n_tiles = base + tile_cnt[l];
+}
+
+__global__ void k_gather_targets(const double *tg, const uint32_t *order, size_t m, int dim, double *tx, double *ty,
+                                 double *tz) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const size_t s = order[i];
+  tx[i] = tg[s * dim];
+  ty[i] = dim > 1 ? tg[s * dim + 1] : 0.0;
+  tz[i] = dim > 2 ? tg[s * dim + 2] : 0.0;
+}
+
+__global__ void k_gather_coords(const double *sx, const double *sy, const double *sz, const uint32_t *pos, size_t m,
+                                double *tx, double *ty, double *tz) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const size_t s = pos[i];
+  tx[i] = sx[s];
+  ty[i] = sy[s];
+  tz[i] = sz[s];
+}
+
+// cells_with_targets = union of ancestors of leaves that hold targets (bbfmm.rs:467-478)
+__global__ void k_flag_cells(const int *leaf_cell, const int *begin, const int *end, int n_leaves, const int *parent,
+                             uint8_t *flag) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= n_leaves || end[l] <= begin[l]) return;
+  int c = leaf_cell[l];
+  while (c >= 0) {
+    flag[c] = 1;
+    c = parent[c];
+  }
+}
+
+// --------------------------------------------------------------------------------------- Chebyshev
+// S_n(x)[m] = (2 sum_k T_k(x) T_k(x_m) - 1) / p  (chebyshev.rs:114-127); optionally dS/dx (chebyshev.rs:130-142)
+__device__ __forceinline__ void cheb_s(int p, double x, const double *tn, double *S, double *dS, double dscale) {
+  double T[kMaxOrder], dT[kMaxOrder];
+  T[0] = 1.0;
+  dT[0] = 0.0;
+  if (p > 1) {
+    T[1] = x;
+    dT[1] = 1.0;
+  }
+  for (int k = 2; k < p; ++k) {
+    T[k] = 2.0 * x * T[k - 1] - T[k - 2];
+    if (dS) dT[k] = 2.0 * T[k - 1] + 2.0 * x * dT[k - 1] - dT[k - 2];
+  }
+  const double pd = (double)p;
+  for (int m = 0; m < p; ++m) {
+    double s = 0.0, ds = 0.0;
+    for (int k = 0; k < p; ++k) {
+      const double t = tn[m * p + k];
+      s += T[k] * t;
+      if (dS) ds += dT[k] * t;
+    }
+    S[m] = (s * 2.0 - 1.0) / pd;
+    if (dS) dS[m] = ds * (2.0 / pd) * dscale;
+  }
+}
+
+// P2M: one CTA per source leaf (bbfmm.rs:691-739, chebyshev.rs:831-927)
+constexpr int kP2MChunk = 64;
+__global__ void __launch_bounds__(256) k_p2m(const int *leaves, const int *ptb, const int *pte, const double *sx,
+                                             const double *sy, const double *sz, const double *w, size_t n,
+                                             const double *ccx, const double *ccy, const double *ccz,
+                                             const double *chalf, const double *tnodes, int p, int dim, int P, int nrhs,
+                                             double *mult) {
+  extern __shared__ double sm[];
+  double *tn = sm;                       // p*p
+  double *S = tn + p * p;                // [3][chunk][p]
+  const int c = leaves[blockIdx.x];
+  const int b = ptb[c], e = pte[c];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < p * p; i += blockDim.x) tn[i] = tnodes[i];
+  const double cc[3] = {ccx[c], ccy[c], ccz[c]};
+  const double half = chalf[c];
+  const int p1 = dim > 1 ? p : 1, p2 = dim > 2 ? p : 1;
+  for (int c0 = b; c0 < e; c0 += kP2MChunk) {
+    const int m = min(kP2MChunk, e - c0);
+    __syncthreads();
+    for (int t = tid; t < m * dim; t += blockDim.x) {
+      const int pt = t / dim, d = t % dim;
+      const double coord = d == 0 ? sx[c0 + pt] : (d == 1 ? sy[c0 + pt] : sz[c0 + pt]);
+      const double x = (coord - cc[d]) / half;  // chebyshev.rs:841-845
+      cheb_s(p, x, tn, &S[(d * kP2MChunk + pt) * p], nullptr, 0.0);
+    }
+    __syncthreads();
+    for (int o = tid; o < P * nrhs; o += blockDim.x) {
+      const int node = o % P, r = o / P;
+      const int i2 = node % p2, i1 = (node / p2) % p1, i0 = node / (p1 * p2);
+      const double *wr = w + (size_t)r * n + c0;
+      double acc = 0.0;
+      for (int pt = 0; pt < m; ++pt) {
+        double s = S[(0 * kP2MChunk + pt) * p + i0];
+        if (dim > 1) s *= S[(1 * kP2MChunk + pt) * p + i1];
+        if (dim > 2) s *= S[(2 * kP2MChunk + pt) * p + i2];
+        acc += s * wr[pt];
+      }
+      mult[((size_t)c * nrhs + r) * P + node] += acc;
+    }
+  }
+}
+
+// One axis of the tensor-product transfer:  out[.. a ..] = sum_b A(a, b) in[.. b ..]
+//   up   (M2M): A(m, i) = child_s[h][i][m]      down (L2L): A(i, m) = child_s[h][i][m]
+__device__ __forceinline__ void tensor_axis(const double *in, double *out, const double *A, int p, int P, int stride,
+                                            bool up, int tid, int nthreads) {
+  for (int o = tid; o < P; o += nthreads) {
+    const int a = (o / stride) % p;
+    const int base = o - a * stride;
+    double s = 0.0;
+    for (int b = 0; b < p; ++b) s += (up ? A[b * p + a] : A[a * p + b]) * in[base + b * stride];
+    out[o] = s;
+  }
+}
+
+// M2M: one CTA per parent; M_parent += M2M[child_index] * M_child, sum-factorised over the axes
+// (bbfmm.rs:742-772; M2M[c] = (S_x (x) S_y (x) S_z)^T, chebyshev.rs:196-241)
+__global__ void __launch_bounds__(128) k_m2m(const int *parents, const int *child_ptr, const int *child_idx,
+                                             const int *cell_slot, const double *child_s, int p, int dim, int P,
+                                             int nrhs, double *mult) {
+  extern __shared__ double sm[];
+  double *A = sm;              // 2*p*p
+  double *b0 = A + 2 * p * p;  // P
+  double *b1 = b0 + P;         // P
+  double *accp = b1 + P;       // P
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int parent = parents[blockIdx.x];
+  for (int i = tid; i < 2 * p * p; i += nt) A[i] = child_s[i];
+  for (int r = 0; r < nrhs; ++r) {
+    for (int i = tid; i < P; i += nt) accp[i] = 0.0;
+    for (int k = child_ptr[parent]; k < child_ptr[parent + 1]; ++k) {
+      const int ch = child_idx[k];
+      const int slot = cell_slot[ch];
+      __syncthreads();
+      const double *src = mult + ((size_t)ch * nrhs + r) * P;
+      for (int i = tid; i < P; i += nt) b0[i] = src[i];
+      __syncthreads();
+      double *in = b0, *out = b1;
+      for (int d = 0; d < dim; ++d) {
+        int stride = 1;
+        for (int e = d + 1; e < dim; ++e) stride *= p;
+        const int h = (slot >> d) & 1;  // bit d of the child index = half along axis d (chebyshev.rs:183-192)
+        tensor_axis(in, out, A + h * p * p, p, P, stride, true, tid, nt);
+        __syncthreads();
+        double *t = in;
+        in = out;
+        out = t;
+      }
+      for (int i = tid; i < P; i += nt) accp[i] += in[i];
+    }
+    __syncthreads();
+    double *dst = mult + ((size_t)parent * nrhs + r) * P;
+    for (int i = tid; i < P; i += nt) dst[i] += accp[i];
+  }
+}
+
+// L2L: one CTA per child cell of the level; L_child += M2M[child_index]^T L_parent (bbfmm.rs:1051-1086)
+__global__ void __launch_bounds__(128) k_l2l(int cell0, const int *cell_parent, const int *cell_slot,
+                                             const uint8_t *flag, const double *child_s, int p, int dim, int P, int nrhs,
+                                             double *loc) {
+  extern __shared__ double sm[];
+  double *A = sm;
+  double *b0 = A + 2 * p * p;
+  double *b1 = b0 + P;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int c = cell0 + blockIdx.x;
+  if (!flag[c]) return;
+  const int parent = cell_parent[c];
+  const int slot = cell_slot[c];
+  for (int i = tid; i < 2 * p * p; i += nt) A[i] = child_s[i];
+  for (int r = 0; r < nrhs; ++r) {
+    __syncthreads();
+    const double *src = loc + ((size_t)parent * nrhs + r) * P;
+    for (int i = tid; i < P; i += nt) b0[i] = src[i];
+    __syncthreads();
+    double *in = b0, *out = b1;
+    for (int d = 0; d < dim; ++d) {
+      int stride = 1;
+      for (int e = d + 1; e < dim; ++e) stride *= p;
+      const int h = (slot >> d) & 1;
+      tensor_axis(in, out, A + h * p * p, p, P, stride, false, tid, nt);
+      __syncthreads();
+      double *t = in;
+      in = out;
+      out = t;
+    }
+    double *dst = loc + ((size_t)c * nrhs + r) * P;
+    for (int i = tid; i < P; i += nt) dst[i] += in[i];
+  }
+}
+
+// M2L for one (level, reference vector) group (bbfmm.rs:864-986).  A CTA owns NC (entry, rhs) columns:
+//   Xs[j][c] = M_src[perm[j]]  (symmetry permutation applied while staging into shared memory)
+//   Ys = Vt * Xs   (rank x NC)      Zs = U * Ys   (P x NC)      L_tgt[perm[m]] += Zs[m]   (atomic)
+// Operators are stored transposed for coalesced register-tile loads: VtT[j][k] (P x rank_pad), UT[k][m]
+// (rank_pad x P).  Uncompressed operators skip the first product (Ys aliases Xs, rank = P).
+__global__ void __launch_bounds__(256) k_m2l(const int *e_tgt, const int *e_src, const int *e_perm, size_t n_entries,
+                                             const double *VtT, const double *UT, int rank, int rank_pad,
+                                             const int *perm_tab, int P, int nrhs, int NC, const uint8_t *flag,
+                                             const double *mult, double *loc) {
+  extern __shared__ double sm[];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const size_t ncols = n_entries * (size_t)nrhs;
+  const size_t col0 = (size_t)blockIdx.x * NC;
+  const int nc = (int)min((size_t)NC, ncols - col0);
+  double *Xs = sm;                                   // P x NC  (row j, column c)
+  double *Ys = VtT ? Xs + (size_t)P * NC : Xs;       // rank_pad x NC
+  __shared__ int s_tgt[64], s_rhs[64], s_perm[64], s_src[64];
+  __shared__ int s_any;
+  if (tid == 0) s_any = 0;
+  __syncthreads();
+  if (tid < NC) {
+    int tg = -1, sr = -1, pm = 0, rh = 0;
+    if (tid < nc) {
+      const size_t col = col0 + tid;
+      const size_t e = col / nrhs;
+      rh = (int)(col % nrhs);
+      tg = e_tgt[e];
+      sr = e_src[e];
+      pm = e_perm[e];
+      if (!flag[tg]) tg = -1; else s_any = 1;
+    }
+    s_tgt[tid] = tg;
+    s_src[tid] = sr;
+    s_perm[tid] = pm;
+    s_rhs[tid] = rh;
+  }
+  __syncthreads();
+  if (!s_any) return;
+  // stage permuted multipoles
+  for (int c = 0; c < NC; ++c) {
+    if (s_tgt[c] >= 0) {
+      const double *src = mult + ((size_t)s_src[c] * nrhs + s_rhs[c]) * P;
+      const int *pm = perm_tab + (size_t)s_perm[c] * P;
+      for (int j = tid; j < P; j += nt) Xs[(size_t)j * NC + c] = src[pm[j]];
+    } else {
+      for (int j = tid; j < P; j += nt) Xs[(size_t)j * NC + c] = 0.0;
+    }
+  }
+  __syncthreads();
+  const int ctiles = NC / 4;
+  if (VtT) {  // Ys = Vt * Xs with 2 x 4 register tiles
+    const int ktiles = rank_pad / 2;
+    for (int tile = tid; tile < ktiles * ctiles; tile += nt) {
+      const int kt = tile % ktiles, ct = tile / ktiles;
+      double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+      const double *vp = VtT + kt * 2;
+      const double *xp = Xs + ct * 4;
+      for (int j = 0; j < P; ++j) {
+        const double2 v = *reinterpret_cast<const double2 *>(vp + (size_t)j * rank_pad);
+        const double2 x0 = *reinterpret_cast<const double2 *>(xp + (size_t)j * NC);
+        const double2 x1 = *reinterpret_cast<const double2 *>(xp + (size_t)j * NC + 2);
+        acc[0][0] += v.x * x0.x; acc[0][1] += v.x * x0.y; acc[0][2] += v.x * x1.x; acc[0][3] += v.x * x1.y;
+        acc[1][0] += v.y * x0.x; acc[1][1] += v.y * x0.y; acc[1][2] += v.y * x1.x; acc[1][3] += v.y * x1.y;
+      }
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 4; ++b) Ys[(size_t)(kt * 2 + a) * NC + ct * 4 + b] = acc[a][b];
+    }
+    __syncthreads();
+  }
+  // Zs = U * Ys with 4 x 4 register tiles, scattered through the inverse permutation
+  const int rk = VtT ? rank_pad : P;
+  const int mtiles = (P + 3) / 4;
+  for (int tile = tid; tile < mtiles * ctiles; tile += nt) {
+    const int mt = tile % mtiles, ct = tile / mtiles;
+    const int m0 = mt * 4;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    const double *yp = Ys + ct * 4;
+    if (m0 + 3 < P) {
+      for (int k = 0; k < rk; ++k) {
+        const double *up = UT + (size_t)k * P + m0;
+        const double u0 = up[0], u1 = up[1], u2 = up[2], u3 = up[3];
+        const double2 y0 = *reinterpret_cast<const double2 *>(yp + (size_t)k * NC);
+        const double2 y1 = *reinterpret_cast<const double2 *>(yp + (size_t)k * NC + 2);
+        acc[0][0] += u0 * y0.x; acc[0][1] += u0 * y0.y; acc[0][2] += u0 * y1.x; acc[0][3] += u0 * y1.y;
+        acc[1][0] += u1 * y0.x; acc[1][1] += u1 * y0.y; acc[1][2] += u1 * y1.x; acc[1][3] += u1 * y1.y;
+        acc[2][0] += u2 * y0.x; acc[2][1] += u2 * y0.y; acc[2][2] += u2 * y1.x; acc[2][3] += u2 * y1.y;
+        acc[3][0] += u3 * y0.x; acc[3][1] += u3 * y0.y; acc[3][2] += u3 * y1.x; acc[3][3] += u3 * y1.y;
+      }
+    } else {
+      for (int k = 0; k < rk; ++k) {
+        const double *up = UT + (size_t)k * P;
+        const double2 y0 = *reinterpret_cast<const double2 *>(yp + (size_t)k * NC);
+        const double2 y1 = *reinterpret_cast<const double2 *>(yp + (size_t)k * NC + 2);
+        for (int a = 0; a < 4; ++a) {
+          const double u = (m0 + a < P) ? up[m0 + a] : 0.0;
+          acc[a][0] += u * y0.x; acc[a][1] += u * y0.y; acc[a][2] += u * y1.x; acc[a][3] += u * y1.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int c = ct * 4 + b;
+      const int tg = s_tgt[c];
+      if (tg < 0) continue;
+      double *dst = loc + ((size_t)tg * nrhs + s_rhs[c]) * P;
+      const int *pm = perm_tab + (size_t)s_perm[c] * P;
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+        if (m0 + a < P) atomicAdd(dst + pm[m0 + a], acc[a][b]);  // L[i] += y[inv[i]]  <=>  L[perm[m]] += y[m]
+    }
+  }
+}
+
+// L2P: out[t] = S(x_t) . L_leaf (+ gradients); one CTA per target tile (bbfmm.rs:1358-1440)
+__global__ void __launch_bounds__(kTile) k_l2p(const TargetSet ts, const int *leaf_cell, const double *loc,
+                                               const double *ccx, const double *ccy, const double *ccz,
+                                               const double *chalf, const double *tnodes, int p, int dim, int P,
+                                               int nrhs, double *out, double *gout) {
+  extern __shared__ double sm[];
+  const int tile = blockIdx.x;
+  if (tile >= *ts.n_tiles_dev) return;
+  const int li = ts.tile_leaf[tile];
+  const int tb = ts.leaf_begin[li] + ts.tile_off[tile];
+  const int cnt = min(kTile, ts.leaf_end[li] - tb);
+  const int tid = threadIdx.x;
+  const int c = leaf_cell[li];
+  double *tn = sm;                 // p*p
+  double *L = tn + p * p;          // P (one rhs at a time)
+  double *S = L + P;               // [kTile][dim][p]
+  double *dS = S + kTile * dim * p;  // [kTile][dim][p] when gradients
+  for (int i = tid; i < p * p; i += kTile) tn[i] = tnodes[i];
+  __syncthreads();
+  const bool active = tid < cnt;
+  const double half = chalf[c];
+  if (active) {
+    const double cc[3] = {ccx[c], ccy[c], ccz[c]};
+    const double xs[3] = {ts.x[tb + tid], ts.y[tb + tid], ts.z[tb + tid]};
+    for (int d = 0; d < dim; ++d) {
+      const double x = (xs[d] - cc[d]) / half;
+      cheb_s(p, x, tn, &S[(tid * dim + d) * p], gout ? &dS[(tid * dim + d) * p] : nullptr, 1.0 / half);
+    }
+  }
+  const int p1 = dim > 1 ? p : 1, p2 = dim > 2 ? p : 1;
+  const size_t row = active ? ts.out_row[tb + tid] : 0;
+  for (int r = 0; r < nrhs; ++r) {
+    __syncthreads();
+    const double *src = loc + ((size_t)c * nrhs + r) * P;
+    for (int i = tid; i < P; i += kTile) L[i] = src[i];
+    __syncthreads();
+    if (!active) continue;
+    const double *S0 = &S[(tid * dim + 0) * p];
+    const double *S1 = dim > 1 ? &S[(tid * dim + 1) * p] : nullptr;
+    const double *S2 = dim > 2 ? &S[(tid * dim + 2) * p] : nullptr;
+    double v = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0;
+    for (int i0 = 0; i0 < p; ++i0) {
+      double a1 = 0.0, a1d1 = 0.0, a1d2 = 0.0;
+      for (int i1 = 0; i1 < p1; ++i1) {
+        double a2 = 0.0, a2d = 0.0;
+        const double *Lp = L + (i0 * p1 + i1) * p2;
+        if (dim > 2) {
+          for (int i2 = 0; i2 < p2; ++i2) {
+            a2 += S2[i2] * Lp[i2];
+            if (gout) a2d += dS[(tid * dim + 2) * p + i2] * Lp[i2];
+          }
+        } else {
+          a2 = Lp[0];
+        }
+        const double s1 = dim > 1 ? S1[i1] : 1.0;
+        a1 += s1 * a2;
+        if (gout) {
+          if (dim > 1) a1d1 += dS[(tid * dim + 1) * p + i1] * a2;
+          a1d2 += s1 * a2d;
+        }
+      }
+      v += S0[i0] * a1;
+      if (gout) {
+        g0 += dS[(tid * dim + 0) * p + i0] * a1;
+        g1 += S0[i0] * a1d1;
+        g2 += S0[i0] * a1d2;
+      }
+    }
+    out[row * nrhs + r] += v;
+    if (gout) {
+      double *gp = gout + row * (size_t)(nrhs * dim) + (size_t)r * dim;
+      gp[0] += g0;
+      if (dim > 1) gp[1] += g1;
+      if (dim > 2) gp[2] += g2;
+    }
+  }
+}
+
+}  // namespace fb

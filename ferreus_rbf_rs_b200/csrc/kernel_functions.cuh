@@ -1,0 +1,149 @@
+// The closed kernel registry of ferreus_rbf_utils (utils.rs:558-571) as host+device functors.
+// Math follows rbf_kernels.rs:25-317, non_rbf_kernels.rs:20-163, constants.rs:13-50.
+// Kernels are selected by template parameter (no function pointers on the device).
+#pragma once
+#include <cmath>
+
+#include "../../include/ferreus_b200.h"
+
+#ifdef __CUDACC__
+#define FB_HD __host__ __device__ __forceinline__
+#else
+#define FB_HD inline
+#endif
+
+namespace fb {
+
+// kernel families (the four spheroidal orders share one family with a runtime exponent)
+enum KFam { KF_LINEAR = 0, KF_TPS, KF_CUBIC, KF_SPH, KF_LAPLACE, KF_R2, KF_R4, KF_COUNT };
+
+struct KParams {
+  int fam;
+  int pw;             // spheroidal POW (1..4), rbf_kernels.rs:176-203
+  double s2;          // s^2, s = range_scaling / base_range
+  double ip2;         // inflexion_point^2
+  double near_slope;  // total_sill * linear_slope * s
+  double far_coef;    // total_sill * inv_y_intercept
+  double total_sill;
+};
+
+inline bool make_kparams(const fb_kernel_params &k, KParams &out) {
+  static const double C[4][4] = {// inflexion_point, linear_slope, range_scaling, inv_y_intercept (constants.rs:21-50)
+                                 {0.5000000000, 0.7500000000, 2.6798340586, 0.8734640537},
+                                 {0.4082482905, 1.0206207262, 1.5822795750, 0.8575980168},
+                                 {0.3535533906, 1.2374368671, 1.2008676644, 0.8494862533},
+                                 {0.3162277660, 1.4230249471, 1.0000000000, 0.8445585690}};
+  out = KParams{};
+  out.total_sill = k.total_sill;
+  switch (k.kernel_type) {
+    case FB_KERNEL_LINEAR: out.fam = KF_LINEAR; return true;
+    case FB_KERNEL_THIN_PLATE_SPLINE: out.fam = KF_TPS; return true;
+    case FB_KERNEL_CUBIC: out.fam = KF_CUBIC; return true;
+    case FB_KERNEL_LAPLACIAN: out.fam = KF_LAPLACE; return true;
+    case FB_KERNEL_ONE_OVER_R2: out.fam = KF_R2; return true;
+    case FB_KERNEL_ONE_OVER_R4: out.fam = KF_R4; return true;
+    case FB_KERNEL_SPHEROIDAL3:
+    case FB_KERNEL_SPHEROIDAL5:
+    case FB_KERNEL_SPHEROIDAL7:
+    case FB_KERNEL_SPHEROIDAL9: {
+      const int o = k.kernel_type - FB_KERNEL_SPHEROIDAL3;
+      const double s = C[o][2] / k.base_range;  // rbf_kernels.rs:229-238
+      out.fam = KF_SPH;
+      out.pw = o + 1;
+      out.s2 = s * s;
+      out.ip2 = C[o][0] * C[o][0];
+      out.near_slope = k.total_sill * C[o][1] * s;
+      out.far_coef = k.total_sill * C[o][3];
+      return true;
+    }
+    default: return false;
+  }
+}
+
+constexpr double kEps = 2.220446049250313e-16;  // f64::EPSILON
+
+// value from squared distance
+template <int FAM>
+FB_HD double kernel_value(double r2, const KParams &kp) {
+  if (FAM == KF_LINEAR) {
+    return -sqrt(r2);
+  } else if (FAM == KF_TPS) {  // r^2 ln r, 0 when r < eps (rbf_kernels.rs:77-83)
+    const double r = sqrt(r2);
+    return (r < kEps) ? 0.0 : (r * r) * log(r);
+  } else if (FAM == KF_CUBIC) {
+    const double r = sqrt(r2);
+    return r * r * r;
+  } else if (FAM == KF_SPH) {  // rbf_kernels.rs:243-256
+    const double sr2 = kp.s2 * r2;
+    if (sr2 <= kp.ip2) return kp.total_sill - kp.near_slope * sqrt(r2);
+    const double t = 1.0 + sr2;
+    double tp = t;
+    for (int i = 1; i < kp.pw; ++i) tp *= t;
+    return kp.far_coef / (tp * sqrt(t));
+  } else if (FAM == KF_LAPLACE) {
+    const double r = sqrt(r2);
+    return (r < kEps) ? 0.0 : 1.0 / r;
+  } else if (FAM == KF_R2) {
+    const double r = sqrt(r2);
+    return (r < kEps) ? 0.0 : 1.0 / (r * r);
+  } else {
+    const double r = sqrt(r2);
+    const double rr = r * r;
+    return (r < kEps) ? 0.0 : 1.0 / (rr * rr);
+  }
+}
+
+// value and gradient factor: grad = fac * (target - source); zero gradient when r2 <= eps
+template <int FAM>
+FB_HD void kernel_value_grad(double r2, const KParams &kp, double &val, double &fac) {
+  const bool small = r2 <= kEps;
+  const double r = sqrt(r2);
+  if (FAM == KF_LINEAR) {
+    val = -r;
+    fac = small ? 0.0 : -1.0 / r;
+  } else if (FAM == KF_TPS) {
+    const double lr = small ? 0.0 : log(r);
+    val = small ? 0.0 : r2 * lr;
+    fac = small ? 0.0 : 2.0 * lr + 1.0;
+  } else if (FAM == KF_CUBIC) {
+    val = small ? 0.0 : r2 * r;
+    fac = small ? 0.0 : 3.0 * r;
+  } else if (FAM == KF_SPH) {
+    val = kernel_value<KF_SPH>(r2, kp);
+    const double sr2 = kp.s2 * r2;
+    if (small) {
+      fac = 0.0;
+    } else if (sr2 <= kp.ip2) {
+      fac = -kp.near_slope * (1.0 / r);
+    } else {
+      const double t = 1.0 + sr2;
+      const double p = (double)kp.pw + 0.5;
+      fac = -2.0 * p * kp.s2 * kp.far_coef / pow(t, p + 1.0);
+    }
+  } else if (FAM == KF_LAPLACE) {
+    const double ir = small ? 0.0 : 1.0 / r;
+    val = ir;
+    fac = -(ir * ir * ir);
+  } else if (FAM == KF_R2) {
+    val = small ? 0.0 : 1.0 / r2;
+    fac = small ? 0.0 : -2.0 * (1.0 / (r2 * r2));
+  } else {
+    val = small ? 0.0 : 1.0 / (r2 * r2);
+    fac = small ? 0.0 : -4.0 * (1.0 / (r2 * r2 * r2));
+  }
+}
+
+// runtime-dispatched host evaluation (operator precompute, dense domain matrices)
+inline double kernel_value_rt(double r2, const KParams &kp) {
+  switch (kp.fam) {
+    case KF_LINEAR: return kernel_value<KF_LINEAR>(r2, kp);
+    case KF_TPS: return kernel_value<KF_TPS>(r2, kp);
+    case KF_CUBIC: return kernel_value<KF_CUBIC>(r2, kp);
+    case KF_SPH: return kernel_value<KF_SPH>(r2, kp);
+    case KF_LAPLACE: return kernel_value<KF_LAPLACE>(r2, kp);
+    case KF_R2: return kernel_value<KF_R2>(r2, kp);
+    default: return kernel_value<KF_R4>(r2, kp);
+  }
+}
+
+}  // namespace fb

@@ -1,0 +1,144 @@
+/*
+ * ferreus_b200.h — C ABI of libferreus_b200.so (B200 / sm_100a implementation of the
+ * ferreus_rbf_rs BBFMM matvec and the FGMRES + domain-decomposition RBF solve).
+ *
+ * Every entry point replaces one method of the reference's type-erased evaluator
+ * `ferreus_rbf_utils::FmmTree` (ferreus_rbf_utils/src/utils.rs:383-493) or of
+ * `ferreus_rbf::RBFInterpolator` (ferreus_rbf/src/rbf.rs:304-924).  Plain pointers and sizes
+ * only; matrices are passed with element strides so faer column-major (`row_stride = 1,
+ * col_stride = nrows`) and numpy row-major (`row_stride = ncols, col_stride = 1`) both pass
+ * zero-copy.  All host pointers; the library owns all device memory.
+ *
+ * A handle is NOT thread-safe (same contract as `&mut self` in the reference); distinct
+ * handles may be used concurrently.  No function aborts the process: errors are returned as
+ * codes and `fb_last_error()` gives the message of the last failure on the calling thread.
+ */
+#ifndef FERREUS_B200_H
+#define FERREUS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes (reference: FmmError, ferreus_bbfmm/src/bbfmm.rs:20-45) ------------------ */
+#define FB_OK 0
+#define FB_ERR_POINT_OUTSIDE_TREE 1   /* FmmError::PointOutsideTree{point_index} -> *bad_index */
+#define FB_ERR_NO_GRADIENTS 2         /* FmmError::KernelDoesNotSupportGradients (unreachable for built-ins) */
+#define FB_ERR_INVALID_ARGUMENT 3     /* reference panics (bbfmm.rs:297, kernel_helpers.rs:72-73) */
+#define FB_ERR_CUDA 4                 /* CUDA / NCCL failure, see fb_last_error() */
+
+/* ---- kernel registry (ferreus_rbf_utils/src/utils.rs:558-571, same order) ------------------- */
+enum fb_kernel_type {
+  FB_KERNEL_LINEAR = 0,
+  FB_KERNEL_THIN_PLATE_SPLINE = 1,
+  FB_KERNEL_CUBIC = 2,
+  FB_KERNEL_SPHEROIDAL3 = 3,
+  FB_KERNEL_SPHEROIDAL5 = 4,
+  FB_KERNEL_SPHEROIDAL7 = 5,
+  FB_KERNEL_SPHEROIDAL9 = 6,
+  FB_KERNEL_LAPLACIAN = 7,
+  FB_KERNEL_ONE_OVER_R2 = 8,
+  FB_KERNEL_ONE_OVER_R4 = 9
+};
+
+/* KernelParams (ferreus_rbf_utils/src/kernel_helpers.rs:17-36) */
+typedef struct fb_kernel_params {
+  int32_t kernel_type; /* enum fb_kernel_type */
+  double base_range;   /* > 0 */
+  double total_sill;   /* <= base_range */
+} fb_kernel_params;
+
+/* M2LCompressionType (ferreus_bbfmm/src/bbfmm.rs:62-73) */
+enum fb_compression_type { FB_COMPRESSION_NONE = 0, FB_COMPRESSION_SVD = 1, FB_COMPRESSION_ACA = 2 };
+
+/* FmmParams (ferreus_bbfmm/src/bbfmm.rs:77-104); NULL => new_defaults(order): 256, ACA, 10^-order, 1024 */
+typedef struct fb_fmm_params {
+  uint64_t max_points_per_cell;
+  int32_t compression_type; /* enum fb_compression_type */
+  double epsilon;
+  uint64_t eval_chunk_size; /* accepted for API compatibility; affects memory only in the reference */
+} fb_fmm_params;
+
+typedef struct fb_tree fb_tree; /* opaque: replaces ferreus_rbf_utils::FmmTree */
+
+const char *fb_last_error(void);
+/* number of CUDA kernels launched by this library on the calling process so far (bench accounting) */
+uint64_t fb_kernel_launch_count(void);
+/* CUDA device used by handles created afterwards on this thread (default: current device) */
+int fb_set_device(int device);
+
+/* FmmTree::new  (ferreus_rbf_utils/src/utils.rs:392-421 -> ferreus_bbfmm/src/bbfmm.rs:272-353).
+ * points: n x dim (dim 1..3).  extents: NULL or [mins..., maxs...] (2*dim doubles).            */
+int fb_tree_new(const double *points, size_t n, int dim, ptrdiff_t row_stride, ptrdiff_t col_stride,
+                int interpolation_order, const fb_kernel_params *kernel, int adaptive_tree, int sparse,
+                const double *extents_or_null, const fb_fmm_params *params_or_null, fb_tree **out);
+void fb_tree_free(fb_tree *t);
+
+/* FmmTree::set_weights (bbfmm.rs:383-401): upward pass P2M + M2M; only the first n rows are read. */
+int fb_tree_set_weights(fb_tree *t, const double *w, size_t n_rows, size_t nrhs, ptrdiff_t row_stride,
+                        ptrdiff_t col_stride);
+/* FmmTree::set_local_coefficients (bbfmm.rs:518-524): full downward pass. */
+int fb_tree_set_local_coefficients(fb_tree *t, const double *w, size_t n_rows, size_t nrhs,
+                                   ptrdiff_t row_stride, ptrdiff_t col_stride);
+
+/* FmmTree::evaluate / evaluate_with_gradients (bbfmm.rs:411-507).
+ * out_vals: m x nrhs, out_grads (NULL => values only): m x (nrhs*dim), columns
+ * [rhs0_dx, rhs0_dy, rhs0_dz, rhs1_dx, ...]; both with the given output strides.
+ * On FB_ERR_POINT_OUTSIDE_TREE *bad_index is the first offending target row.                  */
+int fb_tree_evaluate(fb_tree *t, const double *w, size_t n_rows, size_t nrhs, ptrdiff_t w_rs, ptrdiff_t w_cs,
+                     const double *targets, size_t m, ptrdiff_t t_rs, ptrdiff_t t_cs, double *out_vals,
+                     double *out_grads_or_null, ptrdiff_t o_rs, ptrdiff_t o_cs, uint64_t *bad_index);
+/* FmmTree::evaluate_leaves / evaluate_leaves_with_gradients (bbfmm.rs:537-616): leaf pass only. */
+int fb_tree_evaluate_leaves(fb_tree *t, const double *w, size_t n_rows, size_t nrhs, ptrdiff_t w_rs,
+                            ptrdiff_t w_cs, const double *targets, size_t m, ptrdiff_t t_rs, ptrdiff_t t_cs,
+                            double *out_vals, double *out_grads_or_null, ptrdiff_t o_rs, ptrdiff_t o_cs,
+                            uint64_t *bad_index);
+/* Extension used by the solver: identical to evaluate(w, source_points[idx]) (the call made by
+ * fast_matrix_vector_product, ferreus_rbf/src/rbf.rs:1357-1364) but skips re-binning targets that
+ * are source points.  idx NULL => all sources in order.  out: n_idx x nrhs.                   */
+int fb_tree_evaluate_at_sources(fb_tree *t, const double *w, size_t n_rows, size_t nrhs, ptrdiff_t w_rs,
+                                ptrdiff_t w_cs, const uint64_t *idx_or_null, size_t n_idx, double *out_vals,
+                                ptrdiff_t o_rs, ptrdiff_t o_cs);
+/* One matvec = set_weights + evaluate at all sources with w and the result kept resident in HBM
+ * (the timed region of the headline metric without host<->device copies).  Inputs must have been
+ * uploaded with fb_tree_upload_weights; result fetched with fb_tree_download_result.           */
+int fb_tree_upload_weights(fb_tree *t, const double *w, size_t n_rows, size_t nrhs, ptrdiff_t rs, ptrdiff_t cs);
+int fb_tree_matvec_resident(fb_tree *t);
+int fb_tree_download_result(fb_tree *t, double *out_vals, ptrdiff_t o_rs, ptrdiff_t o_cs);
+/* per-pass device time (ms, CUDA events) of the last fb_tree_matvec_resident call when timing is
+ * enabled with fb_tree_set_timing(t, 1).  names: p2m m2m m2l p2l l2l l2p p2p_m2p total          */
+int fb_tree_set_timing(fb_tree *t, int enabled);
+int fb_tree_last_timing(fb_tree *t, double *ms_out8);
+
+/* FmmTree::source_points (utils.rs:486-492): n x dim copy with the given strides. */
+int fb_tree_source_points(const fb_tree *t, double *out, ptrdiff_t row_stride, ptrdiff_t col_stride);
+
+/* ---- introspection for the bit-exact tree gate (not in the reference API) ------------------- */
+typedef struct fb_tree_info {
+  uint64_t n_points, n_cells, n_leaves, depth;
+  uint64_t n_u, n_v, n_w, n_x; /* total entries of each interaction list */
+  int32_t dim, order, nrhs;
+  double radius;
+  double center[3];
+  uint64_t p2p_pairs, m2p_pairs, p2l_pairs; /* sum n_t*n_s over U / n_t over (leaf,W) / n_s over (cell,X) */
+} fb_tree_info;
+int fb_tree_get_info(const fb_tree *t, fb_tree_info *info);
+/* keys: n_cells reference-format Morton keys ((interleave<<15)|level, morton.rs:58-119), level-major;
+ * leaf_flags: n_cells (1 = leaf); leaf_ptr: n_cells+1, leaf_idx: n_points (source rows of each cell in
+ * ascending order, non-leaf cells have empty ranges).  Any pointer may be NULL.                 */
+int fb_tree_dump_cells(const fb_tree *t, uint64_t *keys, uint8_t *leaf_flags, uint64_t *leaf_ptr,
+                       uint64_t *leaf_idx);
+/* which: 0=U 1=V 2=W 3=X.  ptr: n_cells+1, idx: total entries (cell indices into keys[]). */
+int fb_tree_dump_list(const fb_tree *t, int which, uint64_t *ptr, uint64_t *idx);
+/* rank of the compressed M2L operator for (level 2..depth, reference vector 0..n_ref-1); -1 if absent */
+int fb_tree_m2l_rank(const fb_tree *t, int level, int ref);
+/* dense copy of U (P x rank, column-major) / Vt (rank x P, column-major) */
+int fb_tree_m2l_operator(const fb_tree *t, int level, int ref, double *u_or_null, double *vt_or_null);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FERREUS_B200_H */

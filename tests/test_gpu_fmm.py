@@ -1,0 +1,207 @@
+"""GPU parity tests of the BBFMM path (call through the C ABI via the ferreus_bbfmm mirror).
+
+Bars (BASELINE.json north_star): tree / index construction bit-exact against the oracle restatement;
+FMM matvec relative L2 <= 1e-10 against the oracle at the same depth, order and compression; accuracy
+against exact dense summation reported against the expected Chebyshev error.
+"""
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+MATVEC_TOL = 1e-10  # north_star: relative L2 error vs the reference FMM matvec
+
+
+TREE_CASES = [
+    # n, dim, kind, adaptive, sparse, max_pts
+    (6000, 3, "uniform", True, True, 40),
+    (5000, 3, "clustered", True, True, 25),
+    (3000, 3, "clustered", True, False, 25),
+    (5000, 2, "clustered", True, True, 20),
+    (2000, 1, "uniform", True, True, 16),
+    (4000, 3, "clustered", False, True, 30),
+    (4000, 2, "uniform", False, False, 30),
+]
+
+
+@pytest.mark.parametrize("n,dim,kind,adaptive,sparse,max_pts", TREE_CASES)
+def test_tree_and_lists_bit_exact(n, dim, kind, adaptive, sparse, max_pts):
+    pts = H.make_points(n, dim, kind, seed=11)
+    ot = H.oracle_tree(pts, 4, 7, adaptive, sparse, max_pts, 0, 1e-4)
+    pt = H.product_tree(pts, 4, 7, adaptive, sparse, max_pts, 0, 1e-4)
+    info = pt.info()
+    assert info["depth"] == ot.depth
+    keys, flags, ptr, idx = pt.dump_cells()
+    order = np.argsort(keys)
+    okeys, oflags = H.oracle_cell_table(ot)
+    assert np.array_equal(keys[order], okeys), "cell key sets differ"
+    assert np.array_equal(flags[order], oflags), "leaf sets differ"
+    # leaf membership: same ascending source rows per leaf
+    for c in range(len(keys)):
+        if flags[c]:
+            mine = idx[int(ptr[c]):int(ptr[c + 1])]
+            ref = ot.lists.leaf_source_indices.get(int(keys[c]), np.zeros(0, dtype=np.int64))
+            assert np.array_equal(mine.astype(np.int64), np.asarray(ref, dtype=np.int64))
+    # interaction lists as sets of keys
+    for which, ref in enumerate([ot.lists.u_lists, ot.lists.v_lists, ot.lists.w_lists or {},
+                                 ot.lists.x_lists or {}]):
+        mine = H.product_lists_as_key_sets(pt, which, keys)
+        ref = {k: set(v) for k, v in ref.items() if len(v) > 0}
+        assert mine == ref, f"list {'UVWX'[which]} differs"
+
+
+MATVEC_CASES = [
+    # n, dim, kind, kernel, order, compression, nrhs, adaptive, sparse, max_pts
+    (6000, 3, "uniform", 0, 5, 0, 1, True, True, 40),
+    (5000, 3, "clustered", 0, 6, 2, 2, True, True, 25),
+    (5000, 3, "clustered", 0, 5, 1, 1, True, True, 25),
+    (4000, 3, "clustered", 2, 6, 2, 3, True, True, 30),
+    (4000, 3, "clustered", 3, 6, 2, 1, True, False, 30),
+    (6000, 2, "uniform", 1, 7, 2, 4, True, True, 30),
+    (3000, 2, "clustered", 7, 6, 0, 1, False, True, 30),
+    (2000, 1, "uniform", 7, 6, 2, 1, True, True, 16),
+    (3000, 3, "clustered", 5, 5, 2, 8, True, True, 30),
+    (3000, 3, "clustered", 8, 5, 0, 1, True, True, 30),
+    (3000, 3, "clustered", 9, 5, 2, 5, True, True, 30),
+]
+
+
+@pytest.mark.parametrize("n,dim,kind,kernel,order,comp,nrhs,adaptive,sparse,max_pts", MATVEC_CASES)
+def test_matvec_matches_oracle(n, dim, kind, kernel, order, comp, nrhs, adaptive, sparse, max_pts):
+    pts = H.make_points(n, dim, kind, seed=5)
+    w = np.random.default_rng(6).random((n, nrhs)) - 0.5
+    eps = 10.0 ** (-order)
+    ot = H.oracle_tree(pts, order, kernel, adaptive, sparse, max_pts, comp, eps)
+    pt = H.product_tree(pts, order, kernel, adaptive, sparse, max_pts, comp, eps)
+    if comp != 0:  # same truncation ranks, otherwise the two FMMs differ by O(eps) not round-off
+        nref = {1: 2, 2: 7, 3: 16}[dim]
+        for lvl in range(2, ot.depth + 1):
+            for r in range(nref):
+                assert pt.m2l_rank(lvl, r) == ot.ops.rank(lvl, r), f"rank mismatch level {lvl} ref {r}"
+    ot.set_weights(w)
+    ref = ot.evaluate(w, pts)
+    pt.set_weights(w)
+    got = np.asarray(pt.evaluate(w, pts)).reshape(n, nrhs)
+    assert H.rel_l2(got, ref) <= MATVEC_TOL
+    got2 = np.asarray(pt.evaluate_at_sources(w)).reshape(n, nrhs)
+    assert H.rel_l2(got2, ref) <= MATVEC_TOL
+    # resident path (bench `value` leg)
+    pt.upload_weights(w)
+    pt.matvec_resident()
+    got3 = np.asarray(pt.download_result()).reshape(n, nrhs)
+    assert H.rel_l2(got3, ref) <= MATVEC_TOL
+
+
+def test_accuracy_vs_dense_improves_with_order():
+    from oracle import kernels as okern
+    pts = H.make_points(4000, 3, "clustered", seed=3)
+    w = np.random.default_rng(4).random((4000, 1))
+    dense = okern.dense_matvec(okern.Kernel(0), pts, pts, w)
+    errs = []
+    for order in (4, 6, 8):
+        pt = H.product_tree(pts, order, 0, True, True, 30, 0, 1e-9)
+        pt.set_weights(w)
+        errs.append(H.rel_l2(np.asarray(pt.evaluate(w, pts)).reshape(-1, 1), dense))
+    assert errs[0] > errs[1] > errs[2]
+    assert errs[2] < 1e-7
+
+
+def test_targets_and_gradients_match_oracle():
+    n, m = 4000, 1500
+    pts = H.make_points(n, 3, "clustered", seed=21)
+    rng = np.random.default_rng(22)
+    targets = pts[rng.integers(0, n, m)] + 0.01 * rng.standard_normal((m, 3))
+    targets = np.clip(targets, pts.min(axis=0), pts.max(axis=0))
+    w = rng.random((n, 2)) - 0.5
+    ext = list(np.minimum(pts.min(0), targets.min(0))) + list(np.maximum(pts.max(0), targets.max(0)))
+    for kernel in (0, 2, 3, 1, 7):
+        ot = H.oracle_tree(pts, 5, kernel, True, False, 30, 2, 1e-5, extents=ext)
+        pt = H.product_tree(pts, 5, kernel, True, False, 30, 2, 1e-5, extents=np.array(ext))
+        ot.set_weights(w)
+        pt.set_weights(w)
+        rv, rg = ot.evaluate(w, targets, with_gradients=True)
+        gv, gg = pt.evaluate_with_gradients(w, targets)
+        assert H.rel_l2(gv, rv) <= MATVEC_TOL
+        assert H.rel_l2(gg, rg) <= 1e-9
+        gv2 = pt.evaluate(w, targets)
+        assert H.rel_l2(gv2, rv) <= MATVEC_TOL
+        # leaf-only path after a full downward pass (bbfmm.rs:518-616)
+        ot.set_local_coefficients(w)
+        pt.set_local_coefficients(w)
+        rl = ot.evaluate_leaves(w, targets[:200])
+        gl = pt.evaluate_leaves(w, targets[:200])
+        assert H.rel_l2(gl, rl) <= MATVEC_TOL
+        rlv, rlg = ot.evaluate_leaves(w, targets[:200], with_gradients=True)
+        glv, glg = pt.evaluate_leaves_with_gradients(w, targets[:200])
+        assert H.rel_l2(glv, rlv) <= MATVEC_TOL
+        assert H.rel_l2(glg, rlg) <= 1e-9
+
+
+def test_point_outside_tree_known_answer():
+    """Reference test bbfmm.rs:1464-1500: 1-D source 0.5 in extents [0,1]; target 10.0 -> PointOutsideTree{1}."""
+    import ferreus_rbf_rs_b200 as fb
+    pts = np.array([[0.5]])
+    tree = fb.FmmTree(pts, 3, fb.KernelParams(fb.FmmKernelType.LinearRbf), True, False,
+                      extents=np.array([0.0, 1.0]))
+    w = np.array([[1.0]])
+    tree.set_weights(w)
+    with pytest.raises(ValueError) as ei:
+        tree.evaluate(w, np.array([[0.5], [10.0]]))
+    assert str(ei.value) == "FMM evaluation failed: target point at row 1 lies outside the tree extents"
+    # the in-range target alone evaluates: k(0) = 0 for the linear kernel
+    v = tree.evaluate(w, np.array([[0.5]]))
+    assert abs(float(v[0])) < 1e-14
+    # low side saturates to anchor 0 (morton.rs:46) and is binned, not rejected
+    v = tree.evaluate(w, np.array([[-0.0005]]))
+    assert np.isfinite(v).all()
+
+
+def test_sparse_hole_is_outside_tree():
+    pts = np.array([[0.1, 0.1], [0.12, 0.1], [0.9, 0.9], [0.88, 0.9]])
+    ot = H.oracle_tree(pts, 4, 0, True, True, 1, 0, 1e-4)
+    pt = H.product_tree(pts, 4, 0, True, True, 1, 0, 1e-4)
+    w = np.ones((4, 1))
+    ot.set_weights(w)
+    pt.set_weights(w)
+    from oracle.linear_tree import PointOutsideTree
+    bad = np.array([[0.1, 0.1], [0.1, 0.9], [0.9, 0.1]])
+    with pytest.raises(PointOutsideTree) as oe:
+        ot.evaluate(w, bad)
+    with pytest.raises(ValueError) as pe:
+        pt.evaluate(w, bad)
+    assert f"row {oe.value.point_index} " in str(pe.value)
+
+
+def test_subset_of_sources_matches_full():
+    n = 5000
+    pts = H.make_points(n, 3, "clustered", seed=31)
+    w = np.random.default_rng(32).random((n, 2))
+    pt = H.product_tree(pts, 5, 0, True, True, 30, 2, 1e-5)
+    pt.set_weights(w)
+    full = np.asarray(pt.evaluate_at_sources(w))
+    idx = np.random.default_rng(33).permutation(n)[:700]
+    sub = np.asarray(pt.evaluate_at_sources(w, idx))
+    assert H.rel_l2(sub, full[idx]) <= 1e-13
+    ref = np.asarray(pt.evaluate(w, pts[idx]))
+    assert H.rel_l2(sub, ref) <= 1e-13
+
+
+def test_strided_inputs_and_single_column_shapes():
+    n = 3000
+    pts = np.asfortranarray(H.make_points(n, 3, "uniform", seed=41))  # column-major like faer
+    w = np.asfortranarray(np.random.default_rng(42).random((n, 2)))
+    a = H.product_tree(pts, 4, 0, True, True, 30, 2, 1e-4)
+    b = H.product_tree(np.ascontiguousarray(pts), 4, 0, True, True, 30, 2, 1e-4)
+    a.set_weights(w)
+    b.set_weights(np.ascontiguousarray(w))
+    va = a.evaluate(w, pts)
+    vb = b.evaluate(np.ascontiguousarray(w), np.ascontiguousarray(pts))
+    assert va.shape == (n, 2)
+    assert np.array_equal(va, vb)
+    w1 = np.random.default_rng(43).random(n)  # 1-D weights -> 1-D result (python_bindings.rs:39-51)
+    a.set_weights(w1)
+    assert a.evaluate(w1, pts).shape == (n,)
+    assert a.source_points().shape == (n, 3)
+    assert np.array_equal(a.source_points(), pts)
