@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""bench.py — headline metric of BASELINE.json: BBFMM matvec throughput (Mpts/s), 3-D N = 1M.
+
+One "step" = one matvec = set_weights(w) + evaluate(w, targets = sources) on a pre-built tree
+(exactly one solver matvec of the reference, ferreus_rbf/src/rbf.rs:1357-1364).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n POINTS]
+
+* `value`  : whole-job Mpts/s with inputs resident in HBM (fb_tree_matvec_resident), device time from CUDA
+             events on the library's launch stream, max over ranks.
+* `e2e`    : same metric through the reference-facing API with HOST buffers: FmmTree.set_weights(w) +
+             FmmTree.evaluate(w, points) (H2D of weights and targets, target binning, D2H of the result inside
+             the timed region).
+* `roofline`: dominant kernel (k_leaf_direct = P2P + M2P), algorithmic FLOPs / CUDA-event time against the
+             FP64 FMA peak measured in the same run (MEASURED_PEAKS.json has no FP64 entry).
+* `cpu_baseline`: the oracle port (oracle/fast.py + oracle/csrc/oracle_passes.c, OpenMP) on this host.
+N > 1: one process per GPU (torchrun), each rank owns an independent 1M-point tree (weak scaling, no
+data-path collective; see DESIGN.md "multi-GPU").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ORDER = 7
+KERNEL_FLOPS = {"linear": 1}  # c_k of SURVEY.md §8(d)
+
+
+def make_workload(n, seed):
+    rng = np.random.default_rng(seed)
+    pts = rng.random((n, 3))
+    w = rng.random((n, 1))
+    return pts, w
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.samples.append([s.strip() for s in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx.append(float(s[1]))
+                for nme, v in zip(names, s[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        # keep the samples taken under load (upper half of the clock distribution)
+        load = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(pts, w, leaf_fraction):
+    """Oracle port on the host cores (kind = "port": restatement of the reference algorithm, not the Rust
+    binary — no cargo/rustc on this image)."""
+    from oracle import bbfmm as obb
+    from oracle import fast
+    from oracle import kernels as okern
+    t0 = time.perf_counter()
+    ot = obb.FmmTree(pts, ORDER, okern.Kernel(okern.LINEAR), True, True, None,
+                     obb.FmmParams(256, 2, 10.0 ** -ORDER, 1024))
+    ff = fast.FastFmm(ot)
+    build_s = time.perf_counter() - t0
+    return ff, build_s, fast.lib().orc_num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port, all host threads) on the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pts, w = make_workload(args.n, 1000)
+    ff, build_s, cores = cpu_baseline(pts, w, args.cpu_leaf_fraction)
+    times = []
+    detail = None
+    for it in range(args.warmup + args.steps):
+        sec, detail = ff.timed_matvec_estimate(w, args.cpu_leaf_fraction, seed=it)
+        if it >= args.warmup:
+            times.append(sec)
+    ms = 1e3 * float(np.mean(times))
+    val = args.n / (ms * 1e-3) / 1e6
+    sample = (f"upward, M2L, P2L, L2L in full; leaf pass (P2P+M2P) on {detail['sample_leaves']} of "
+              f"{detail['leaves']} target leaves scaled by pair count x{detail['leaf_scale']:.1f}")
+    line = {"impl": "reference", "metric": "bbfmm_matvec_throughput", "value": val, "unit": "Mpts/s", "n_gpus": 0,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.n, 1),
+            "cpu_baseline": {"value": val, "unit": "Mpts/s", "cores": cores, "kind": "port", "sample": sample,
+                             "tree_build_s": build_s},
+            "e2e": {"value": val, "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n, n_gpus):
+    return {"workload": f"ferreus_bbfmm 3D LinearRbf matvec, N={n} uniform points in the unit cube per GPU, "
+                        f"Chebyshev order {ORDER}, 1 RHS, adaptive sparse tree, 256 pts/leaf, ACA eps=1e-{ORDER} "
+                        "(BASELINE.md headline H)",
+            "points_per_gpu": n, "order": ORDER, "nrhs": 1, "kernel": "LinearRbf", "compression": "ACA",
+            "l2_policy": "256 MiB buffer written between timed iterations (L2 flush)",
+            "parallelism": f"{n_gpus} independent trees (one per GPU), no data-path collective"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--cpu-leaf-fraction", type=float, default=0.02)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import ferreus_rbf_rs_b200 as fb
+    from ferreus_rbf_rs_b200 import _lib
+    L = _lib.lib()
+    L.fb_set_device(local_rank)
+
+    n = args.n
+    pts, w = make_workload(n, 1000 + rank)
+    t0 = time.perf_counter()
+    tree = fb.FmmTree(pts, ORDER, fb.KernelParams(fb.FmmKernelType.LinearRbf), True, True)
+    build_s = time.perf_counter() - t0
+    info = tree.info()
+    tree.set_timing(True)
+    tree.upload_weights(w)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    launches0 = L.fb_kernel_launch_count()
+    for _ in range(args.warmup):
+        tree.matvec_resident()
+    launches_per_step = (L.fb_kernel_launch_count() - launches0) // max(args.warmup, 1)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    # ---- timed: K resident matvecs, device time (CUDA events on the library stream) per step
+    barrier()
+    dev_ms, stage_ms = [], []
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        tree.matvec_resident()
+        dev_ms.append(tree.last_matvec_ms())
+        stage_ms.append(tree.last_timing())
+    barrier()
+    wall_s = time.perf_counter() - wall0
+    total_ms = float(np.sum(dev_ms))
+
+    # ---- e2e: reference-facing calls with host buffers (H2D + binning + D2H inside the timed region)
+    for _ in range(2):
+        tree.set_weights(w)
+        tree.evaluate(w, pts)
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        tree.set_weights(w)
+        out = tree.evaluate(w, pts)
+    barrier()
+    e2e_s = time.perf_counter() - e0
+    clocks = sampler.finish()
+
+    tms = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    total_ms_max, e2e_ms_max = [float(v) for v in tms.tolist()]
+
+    if rank == 0:
+        ms_per_step = total_ms_max / args.steps
+        value = world * n / (ms_per_step * 1e-3) / 1e6
+        e2e_val = world * n / (e2e_ms_max / args.steps * 1e-3) / 1e6
+        # ---- roofline of the dominant kernel
+        fp64_peak = np.zeros(1)
+        L.fb_measure_fp64_tflops(_lib.dptr(fp64_peak))
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        P = ORDER ** 3
+        f_pair = (3 * 3 - 1) + KERNEL_FLOPS["linear"] + 2 * 1          # (3d-1) + c_k + 2K
+        pairs_leaf = info["p2p_pairs"] + info["m2p_pairs"] * P
+        pairs_p2l = info["p2l_pairs"] * P
+        med = {k: float(np.median([s[k] for s in stage_ms])) for k in stage_ms[0]}
+        leaf_tf = pairs_leaf * f_pair / (med["p2p_m2p"] * 1e-3) / 1e12
+        p2l_tf = pairs_p2l * f_pair / max(med["p2l"] * 1e-3, 1e-9) / 1e12
+        roofline = {"kernel": "k_leaf_direct (P2P + M2P)", "bound": "fp64", "achieved": leaf_tf,
+                    "peak": float(fp64_peak[0]), "unit": "TFLOP/s", "frac": leaf_tf / float(fp64_peak[0]),
+                    "traffic": None,
+                    "peak_source": "in-run DFMA micro-benchmark (fb_measure_fp64_tflops); MEASURED_PEAKS.json has no "
+                                   "FP64 entry",
+                    "algorithmic_flops_per_launch": pairs_leaf * f_pair,
+                    "flops_per_pair": f_pair, "launch_ms": med["p2p_m2p"]}
+        stages = {"ms": med, "p2l_tflops": p2l_tf, "hbm_peak_gbs": hbm_peak,
+                  "hbm_peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                  "pairs": {"p2p": info["p2p_pairs"], "m2p_nodes": info["m2p_pairs"] * P, "p2l_nodes": pairs_p2l,
+                            "m2l_entries": info["n_v"]}}
+        line = {"metric": "bbfmm_matvec_throughput", "value": value, "unit": "Mpts/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(n, world),
+                "e2e": {"value": e2e_val, "unit": "Mpts/s", "h2d_bytes_per_step": int(2 * w.nbytes + pts.nbytes),
+                        "d2h_bytes_per_step": int(out.nbytes), "api": "FmmTree.set_weights + FmmTree.evaluate"},
+                "gpu_launches": int(launches_per_step * args.steps),
+                "clocks": clocks, "roofline": roofline, "stages": stages,
+                "tree": {"build_s": build_s, "cells": info["n_cells"], "leaves": info["n_leaves"],
+                         "depth": info["depth"]},
+                "wall_s_timed_region": wall_s}
+        if world == 1 and not args.no_cpu_baseline:
+            ff, cpu_build_s, cores = cpu_baseline(pts, w, args.cpu_leaf_fraction)
+            sec, detail = ff.timed_matvec_estimate(w, args.cpu_leaf_fraction)
+            # parity spot check of the timed GPU result against the oracle on the sampled leaves is in tests/
+            line["cpu_baseline"] = {
+                "value": n / sec / 1e6, "unit": "Mpts/s", "cores": cores, "kind": "port",
+                "sample": (f"oracle port (OpenMP): upward, M2L, P2L, L2L in full; leaf pass on {detail['sample_leaves']} "
+                           f"of {detail['leaves']} leaves scaled x{detail['leaf_scale']:.1f} by pair count"),
+                "seconds_per_matvec": sec, "tree_build_s": cpu_build_s}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

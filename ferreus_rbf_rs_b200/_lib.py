@@ -47,6 +47,7 @@ _lib = None
 _dp = C.POINTER(C.c_double)
 _u64p = C.POINTER(C.c_uint64)
 _u8p = C.POINTER(C.c_uint8)
+_i32p = C.POINTER(C.c_int32)
 _sz = C.c_size_t
 _pd = C.c_ssize_t
 
@@ -70,12 +71,20 @@ SIGNATURES = {
     "fb_tree_download_result": (C.c_int, [C.c_void_p, _dp, _pd, _pd]),
     "fb_tree_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "fb_tree_last_timing": (C.c_int, [C.c_void_p, _dp]),
+    "fb_tree_last_matvec_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "fb_measure_fp64_tflops": (C.c_int, [_dp]),
     "fb_tree_source_points": (C.c_int, [C.c_void_p, _dp, _pd, _pd]),
     "fb_tree_get_info": (C.c_int, [C.c_void_p, C.POINTER(FbTreeInfo)]),
     "fb_tree_dump_cells": (C.c_int, [C.c_void_p, _u64p, _u8p, _u64p, _u64p]),
     "fb_tree_dump_list": (C.c_int, [C.c_void_p, C.c_int, _u64p, _u64p]),
     "fb_tree_m2l_rank": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "fb_tree_m2l_operator": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp]),
+    "fb_ops_new": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(FbKernelParams), C.c_int, C.c_double,
+                             C.POINTER(C.c_void_p)]),
+    "fb_ops_free": (None, [C.c_void_p]),
+    "fb_ops_rank": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "fb_ops_get": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp]),
+    "fb_ops_tables": (C.c_int, [C.c_void_p, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _dp]),
 }
 
 

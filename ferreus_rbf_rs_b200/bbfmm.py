@@ -215,6 +215,11 @@ class FmmTree:
         self._check(self._lib.fb_tree_download_result(self._h, _lib.dptr(out), self._nrhs, 1))
         return _to_numpy(out)
 
+    def last_matvec_ms(self):
+        ms = C.c_double(0.0)
+        self._check(self._lib.fb_tree_last_matvec_ms(self._h, C.byref(ms)))
+        return ms.value
+
     def set_timing(self, enabled):
         self._check(self._lib.fb_tree_set_timing(self._h, int(bool(enabled))))
 

@@ -30,6 +30,8 @@ using namespace fb;
 fb_tree::~fb_tree() {
   for (auto &e : ev)
     if (e) cudaEventDestroy(e);
+  for (auto &e : ev_mv)
+    if (e) cudaEventDestroy(e);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -64,6 +66,7 @@ void fb_tree::build(const double *points, size_t n_, int dim_, ptrdiff_t rs, ptr
   FB_CUDA(cudaGetDevice(&device));
   FB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   for (auto &e : ev) FB_CUDA(cudaEventCreate(&e));
+  for (auto &e : ev_mv) FB_CUDA(cudaEventCreate(&e));
 
   host_points.resize(n * dim);
   for (size_t i = 0; i < n; ++i)
@@ -843,12 +846,17 @@ int fb_tree_matvec_resident(fb_tree *t) {
     FB_REQUIRE(t, "null tree");
     FB_CUDA(cudaSetDevice(t->device));
     FB_REQUIRE(t->d_w_user.cap >= t->n * (size_t)t->nrhs, "fb_tree_upload_weights must be called first");
+    FB_CUDA(cudaEventRecord(t->ev_mv[0], t->stream));
     t->sort_weights();
     t->upward();
     TargetSet ts = t->source_target_set();
     t->downward(ts.cell_flag);
     t->leaf_pass(ts, false);
+    FB_CUDA(cudaEventRecord(t->ev_mv[1], t->stream));
     FB_CUDA(cudaStreamSynchronize(t->stream));
+    float mv_ms = 0;
+    FB_CUDA(cudaEventElapsedTime(&mv_ms, t->ev_mv[0], t->ev_mv[1]));
+    t->last_matvec_ms = mv_ms;
     collect_timing(t);
   });
 }
@@ -858,6 +866,56 @@ int fb_tree_download_result(fb_tree *t, double *out_vals, ptrdiff_t o_rs, ptrdif
     FB_REQUIRE(t && out_vals, "null argument");
     FB_CUDA(cudaSetDevice(t->device));
     t->fetch_output(t->n, false, out_vals, nullptr, o_rs, o_cs);
+  });
+}
+
+int fb_tree_last_matvec_ms(fb_tree *t, double *ms_out) {
+  if (!t || !ms_out) return FB_ERR_INVALID_ARGUMENT;
+  *ms_out = t->last_matvec_ms;
+  return FB_OK;
+}
+
+// FP64 FMA-pipe peak of the current device: 16 independent DFMA chains per thread, CUDA-event timed
+__global__ void k_dfma_peak(double *out, int iters, double a, double b) {
+  double x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = (double)(threadIdx.x + i) * 1e-3;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = fma(x[i], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += x[i];
+  if (s == 12345.678) out[0] = s;
+}
+
+int fb_measure_fp64_tflops(double *tflops_out) {
+  return guarded([&] {
+    FB_REQUIRE(tflops_out, "null argument");
+    int dev = 0, sms = 0;
+    FB_CUDA(cudaGetDevice(&dev));
+    FB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    fb::DBuf<double> out;
+    out.reserve(1);
+    cudaEvent_t e0, e1;
+    FB_CUDA(cudaEventCreate(&e0));
+    FB_CUDA(cudaEventCreate(&e1));
+    const int iters = 8192, blocks = sms * 8, threads = 256;
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+      FB_CUDA(cudaEventRecord(e0, 0));
+      FB_LAUNCH(k_dfma_peak, blocks, threads, 0, 0, out.p, iters, 0.999999, 1e-9);
+      FB_CUDA(cudaEventRecord(e1, 0));
+      FB_CUDA(cudaEventSynchronize(e1));
+      float ms = 0;
+      FB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      const double fl = 2.0 * 16.0 * iters * (double)blocks * threads;
+      best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops_out = best;
   });
 }
 
@@ -953,6 +1011,45 @@ int fb_tree_m2l_operator(const fb_tree *t, int level, int ref, double *u_or_null
   const fb::M2LOperator &op = t->ops.m2l[level - 2][ref];
   if (u_or_null) std::copy(op.U.a.begin(), op.U.a.end(), u_or_null);
   if (vt_or_null) std::copy(op.Vt.a.begin(), op.Vt.a.end(), vt_or_null);
+  return FB_OK;
+}
+
+struct fb_ops {
+  fb::Operators ops;
+};
+
+int fb_ops_new(int interpolation_order, int dim, double radius, int depth, const fb_kernel_params *kernel,
+               int compression_type, double epsilon, fb_ops **out) {
+  if (!out || !kernel || dim < 1 || dim > 3 || interpolation_order < 1) return FB_ERR_INVALID_ARGUMENT;
+  fb::KParams kp;
+  if (!fb::make_kparams(*kernel, kp)) return FB_ERR_INVALID_ARGUMENT;
+  fb_ops *o = new fb_ops();
+  o->ops.build(interpolation_order, dim, radius, depth, kp, compression_type, epsilon);
+  *out = o;
+  return FB_OK;
+}
+void fb_ops_free(fb_ops *o) { delete o; }
+int fb_ops_rank(const fb_ops *o, int level, int ref) {
+  if (!o || level < 2 || level - 2 >= (int)o->ops.m2l.size() || ref < 0 || ref >= o->ops.n_ref) return -1;
+  return o->ops.m2l[level - 2][ref].rank;
+}
+int fb_ops_get(const fb_ops *o, int level, int ref, double *u_or_null, double *vt_or_null) {
+  if (fb_ops_rank(o, level, ref) < 0) return FB_ERR_INVALID_ARGUMENT;
+  const fb::M2LOperator &op = o->ops.m2l[level - 2][ref];
+  if (u_or_null) std::copy(op.U.a.begin(), op.U.a.end(), u_or_null);
+  if (vt_or_null) std::copy(op.Vt.a.begin(), op.Vt.a.end(), vt_or_null);
+  return FB_OK;
+}
+int fb_ops_tables(const fb_ops *o, int32_t *n_perm, int32_t *n_ref, int32_t *perm, int32_t *inv_perm,
+                  int32_t *perm_lookup, int32_t *ref_lookup, double *m2m_child_s) {
+  if (!o) return FB_ERR_INVALID_ARGUMENT;
+  if (n_perm) *n_perm = o->ops.n_perm;
+  if (n_ref) *n_ref = o->ops.n_ref;
+  if (perm) std::copy(o->ops.perm.begin(), o->ops.perm.end(), perm);
+  if (inv_perm) std::copy(o->ops.inv_perm.begin(), o->ops.inv_perm.end(), inv_perm);
+  if (perm_lookup) std::copy(o->ops.perm_lookup.begin(), o->ops.perm_lookup.end(), perm_lookup);
+  if (ref_lookup) std::copy(o->ops.ref_lookup.begin(), o->ops.ref_lookup.end(), ref_lookup);
+  if (m2m_child_s) std::copy(o->ops.child_s.begin(), o->ops.child_s.end(), m2m_child_s);
   return FB_OK;
 }
 

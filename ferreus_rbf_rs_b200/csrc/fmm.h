@@ -132,6 +132,8 @@ struct fb_tree {
   bool timing = false;
   double last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   cudaEvent_t ev[10] = {};
+  cudaEvent_t ev_mv[2] = {};
+  double last_matvec_ms = 0;
 
   ~fb_tree();
   void build(const double *points, size_t n_, int dim_, ptrdiff_t rs, ptrdiff_t cs, int order_,

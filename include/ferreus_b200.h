@@ -111,6 +111,10 @@ int fb_tree_download_result(fb_tree *t, double *out_vals, ptrdiff_t o_rs, ptrdif
 /* per-pass device time (ms, CUDA events) of the last fb_tree_matvec_resident call when timing is
  * enabled with fb_tree_set_timing(t, 1).  names: p2m m2m m2l p2l l2l l2p p2p_m2p total          */
 int fb_tree_set_timing(fb_tree *t, int enabled);
+/* device time (ms, CUDA events on the handle's stream) of the last fb_tree_matvec_resident call */
+int fb_tree_last_matvec_ms(fb_tree *t, double *ms_out);
+/* FP64 FMA-pipe peak of the current device (TFLOP/s): in-run DFMA micro-benchmark, CUDA-event timed */
+int fb_measure_fp64_tflops(double *tflops_out);
 int fb_tree_last_timing(fb_tree *t, double *ms_out8);
 
 /* FmmTree::source_points (utils.rs:486-492): n x dim copy with the given strides. */
@@ -137,6 +141,20 @@ int fb_tree_dump_list(const fb_tree *t, int which, uint64_t *ptr, uint64_t *idx)
 int fb_tree_m2l_rank(const fb_tree *t, int level, int ref);
 /* dense copy of U (P x rank, column-major) / Vt (rank x P, column-major) */
 int fb_tree_m2l_operator(const fb_tree *t, int level, int ref, double *u_or_null, double *vt_or_null);
+
+
+/* ---- host-only operator precompute (no GPU needed): used by the CPU test-suite to check the
+ * Chebyshev / ACA / SVD restatement (chebyshev.rs:650-814, aca.rs:23-247) against the oracle. ---- */
+typedef struct fb_ops fb_ops;
+int fb_ops_new(int interpolation_order, int dim, double radius, int depth, const fb_kernel_params *kernel,
+               int compression_type, double epsilon, fb_ops **out);
+void fb_ops_free(fb_ops *o);
+int fb_ops_rank(const fb_ops *o, int level, int ref);
+/* u: P x rank column-major, vt: rank x P column-major (vt untouched when uncompressed) */
+int fb_ops_get(const fb_ops *o, int level, int ref, double *u_or_null, double *vt_or_null);
+/* tables: perm / inv_perm are n_perm x P (row-major), lookups have 7^dim entries; any pointer may be NULL */
+int fb_ops_tables(const fb_ops *o, int32_t *n_perm, int32_t *n_ref, int32_t *perm, int32_t *inv_perm,
+                  int32_t *perm_lookup, int32_t *ref_lookup, double *m2m_child_s);
 
 #ifdef __cplusplus
 }

@@ -140,15 +140,15 @@ def aca_partial_pivoting(nrows, ncols, row_fn, col_fn, epsilon):
     for _ in range(max_it):
         row = row_fn(i).copy()
         unused_rows[i] = 0
-        if k > 0:
-            row -= u[i, :k] @ v[:, :k].T
+        for l in range(k):          # sequential rank-1 downdates (summation order of the product's host code)
+            row -= u[i, l] * v[:, l]
         j = _argmax_masked(row, unused_cols)
         with np.errstate(divide="ignore", invalid="ignore"):
             row = row * (1.0 / row[j])
         col = col_fn(j).copy()
         unused_cols[j] = 0
-        if k > 0:
-            col -= u[:, :k] @ v[j, :k]
+        for l in range(k):
+            col -= v[j, l] * u[:, l]
         i = _argmax_masked(col, unused_rows)
         if k > 0:
             sum_k = float((u[:, :k].T @ col) @ (v[:, :k].T @ row))

@@ -140,7 +140,22 @@ def build_tree(points, center, radius, max_points_per_cell, store_empty_leaves, 
 def get_interaction_lists_adaptive(tree, leaves, center, radius, dim):
     """linear_tree.rs:270-394"""
     u_lists, v_lists, w_lists, x_lists = {}, {}, {}, {}
-    adj = lambda a, b: morton.are_adjacent(a, b, center, radius, dim)
+    geom = {}
+
+    def center_length(k):  # memoised morton.get_center_length
+        g = geom.get(k)
+        if g is None:
+            g = geom[k] = morton.get_center_length(k, center, radius, dim)
+        return g
+
+    def adj(a, b):  # morton.rs:308-325
+        ca, la = center_length(a)
+        cb, lb = center_length(b)
+        length = 0.5 * (la + lb)
+        for va, vb in zip(ca, cb):
+            if not (abs(vb - va) <= 1e-6 + length):
+                return False
+        return True
     for key in tree:
         u, v, w = set(), set(), set()
         parent = morton.get_parent(key, dim)

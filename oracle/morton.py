@@ -4,6 +4,7 @@ Keys are ``(bit_interleave(x, y, z; x = LSB) << 15) | level`` with 16 bits per
 coordinate (morton.rs:58-119, morton_constants.rs:12-22).  The reference's byte
 LUTs are replaced by explicit bit loops; results are identical.
 """
+import functools
 import math
 
 import numpy as np
@@ -78,6 +79,7 @@ def get_level(key):
     return key & LEVEL_MASK
 
 
+@functools.lru_cache(maxsize=1 << 20)
 def decode_key(key, dim):
     """morton.rs:127-167 -> (anchor tuple, level)."""
     level = key & LEVEL_MASK
