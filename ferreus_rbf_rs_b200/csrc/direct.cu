@@ -32,7 +32,7 @@ __device__ __forceinline__ void accumulate_tile(const SrcTile<NR> &t, int m, dou
       g[1] += fw * dy;
       g[2] += fw * dz;
     } else {
-      const double v = kernel_value<FAM>(r2, kp);
+      const double v = kernel_value_dev<FAM>(r2, kp);
 #pragma unroll
       for (int r = 0; r < NR; ++r) acc[r] += v * t.w[r][j];
     }

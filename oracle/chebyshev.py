@@ -125,6 +125,12 @@ def _argmax_masked(data, mask):
     return best
 
 
+def _seq_dot(a, b):
+    """strictly sequential dot product (the summation order of the product's host code; faer's own
+    order is unknowable, and the ACA pivot / stopping decisions are sensitive to it at round-off level)"""
+    return float(np.cumsum(a * b)[-1])
+
+
 def aca_partial_pivoting(nrows, ncols, row_fn, col_fn, epsilon):
     """aca.rs:23-136"""
     unused_rows = np.ones(nrows)
@@ -151,8 +157,10 @@ def aca_partial_pivoting(nrows, ncols, row_fn, col_fn, epsilon):
             col -= v[j, l] * u[:, l]
         i = _argmax_masked(col, unused_rows)
         if k > 0:
-            sum_k = float((u[:, :k].T @ col) @ (v[:, :k].T @ row))
-        norm_u_v_2 = float(col @ col) * float(row @ row)
+            sum_k = 0.0
+            for l in range(k):
+                sum_k += _seq_dot(u[:, l], col) * _seq_dot(v[:, l], row)
+        norm_u_v_2 = _seq_dot(col, col) * _seq_dot(row, row)
         residual_norm += norm_u_v_2 + 2.0 * sum_k
         u[:, k] = col
         v[:, k] = row

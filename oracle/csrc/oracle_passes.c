@@ -37,8 +37,8 @@ static inline double kval(const orc_kernel *k, double r2) {
     case 3: case 4: case 5: case 6: {
       double sr2 = k->s2 * r2;
       if (sr2 <= k->ip2) return k->total_sill - k->near_slope * sqrt(r2);
-      double t = 1.0 + sr2, tp = t;
-      for (int i = 1; i < k->pw; ++i) tp *= t;
+      double t = 1.0 + sr2, t2 = t * t;
+      double tp = k->pw == 1 ? t : (k->pw == 2 ? t2 : (k->pw == 3 ? t2 * t : t2 * t2));
       return k->far_coef / (tp * sqrt(t));
     }
     case 7: { double r = sqrt(r2); return fabs(r) < EPS ? 0.0 : 1.0 / r; }

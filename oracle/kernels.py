@@ -55,7 +55,9 @@ class Kernel:
         if kt in SPHEROIDAL_CONSTANTS:                          # :243-256
             sr2 = self.s2 * r2
             t = 1.0 + sr2
-            far = self.far_coef / (t ** self.pow * np.sqrt(t))
+            t2 = t * t                                          # powi: binary exponentiation, as LLVM lowers it
+            tp = {1: t, 2: t2, 3: t2 * t, 4: t2 * t2}[self.pow]
+            far = self.far_coef / (tp * np.sqrt(t))
             near = self.total_sill - self.near_slope * r
             return np.where(sr2 <= self.ip2, near, far)
         with np.errstate(divide="ignore", invalid="ignore"):
