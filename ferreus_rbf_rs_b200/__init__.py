@@ -4,3 +4,5 @@ modules (``ferreus_bbfmm``, ``ferreus_rbf``) over the C ABI in ``include/ferreus
 from . import _lib  # noqa: F401
 from .bbfmm import (FmmKernelType, FmmParams, FmmTree, KernelParams, M2LCompressionType,  # noqa: F401
                     SpheroidalOrder)
+from . import config, interpolant_config, progress  # noqa: F401,E402
+from .rbf import Coefficients, RBFInterpolator  # noqa: F401,E402

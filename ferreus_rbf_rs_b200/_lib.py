@@ -34,6 +34,35 @@ class FbTreeInfo(C.Structure):
                 ("m2p_pairs", C.c_uint64), ("p2l_pairs", C.c_uint64)]
 
 
+class FrSettings(C.Structure):
+    _fields_ = [("kernel_type", C.c_int32), ("drift", C.c_int32), ("spheroidal_order", C.c_int32),
+                ("nugget", C.c_double), ("base_range", C.c_double), ("total_sill", C.c_double),
+                ("tolerance", C.c_double), ("tolerance_type", C.c_int32)]
+
+
+class FrParams(C.Structure):
+    _fields_ = [("solver_type", C.c_int32), ("leaf_threshold", C.c_uint64), ("overlap_quota", C.c_double),
+                ("coarse_ratio", C.c_double), ("coarse_threshold", C.c_uint64), ("interpolation_order", C.c_uint64),
+                ("max_points_per_cell", C.c_uint64), ("compression_type", C.c_int32), ("epsilon", C.c_double),
+                ("eval_chunk_size", C.c_uint64), ("naive_solve_threshold", C.c_uint64), ("test_unique", C.c_int32)]
+
+
+class FrEvent(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("iter", C.c_uint64), ("residual", C.c_double), ("progress", C.c_double),
+                ("message", C.c_char_p)]
+
+
+class FrModelInfo(C.Structure):
+    _fields_ = [("n_points", C.c_uint64), ("n_duplicates", C.c_uint64), ("n_cols", C.c_uint64),
+                ("basis_size", C.c_uint64), ("dim", C.c_uint64), ("iterations", C.c_uint64),
+                ("last_residual", C.c_double), ("ddm_levels", C.c_uint64), ("ddm_domains", C.c_uint64 * 8),
+                ("fit_seconds", C.c_double), ("setup_seconds", C.c_double), ("solve_seconds", C.c_double),
+                ("matvecs", C.c_uint64)]
+
+
+FR_PROGRESS_CB = C.CFUNCTYPE(None, C.POINTER(FrEvent), C.c_void_p)
+
+
 def build(force=False, jobs=8):
     """Compile the library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     if force:
@@ -88,6 +117,23 @@ SIGNATURES = {
 }
 
 
+SOLVER_SIGNATURES = {
+    "fr_settings_default": (None, [C.c_int32, C.POINTER(FrSettings)]),
+    "fr_params_default": (None, [C.c_int32, C.POINTER(FrParams)]),
+    "fr_fit": (C.c_int, [_dp, _sz, C.c_int, _pd, _pd, _dp, _sz, _pd, _pd, C.POINTER(FrSettings), C.POINTER(FrParams),
+                         FR_PROGRESS_CB, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "fr_free": (None, [C.c_void_p]),
+    "fr_get_info": (C.c_int, [C.c_void_p, C.POINTER(FrModelInfo)]),
+    "fr_source_points": (C.c_int, [C.c_void_p, _dp, _dp]),
+    "fr_coefficients": (C.c_int, [C.c_void_p, _dp, _dp]),
+    "fr_evaluate": (C.c_int, [C.c_void_p, _dp, _sz, _pd, _pd, _dp, _dp]),
+    "fr_evaluate_at_source": (C.c_int, [C.c_void_p, C.c_int, _dp]),
+    "fr_build_evaluator": (C.c_int, [C.c_void_p, _dp]),
+    "fr_evaluate_targets": (C.c_int, [C.c_void_p, _dp, _sz, _pd, _pd, _dp, _dp]),
+    "fr_ddm_level": (C.c_int, [C.c_void_p, C.c_int, _u64p, _u64p, _u64p, _u64p, _u64p, _u8p]),
+}
+
+
 def lib():
     """Load the shared library (once).  Raises if it has not been built: there is no fallback."""
     global _lib
@@ -98,7 +144,7 @@ def lib():
             f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
             "(or `make -C ferreus_rbf_rs_b200/csrc`). The CUDA library is the only implementation.")
     l = C.CDLL(LIB_PATH)
-    for name, (res, args) in SIGNATURES.items():
+    for name, (res, args) in list(SIGNATURES.items()) + list(SOLVER_SIGNATURES.items()):
         fn = getattr(l, name)
         fn.restype = res
         fn.argtypes = args

@@ -164,7 +164,6 @@ void fb_tree::build(const double *points, size_t n_, int dim_, ptrdiff_t rs, ptr
   d_child_idx.upload(ht.child_idx, stream);
   std::vector<uint8_t> ones(nc, 1);
   d_flag_all.upload(ones, stream);
-  d_flag.reserve(nc);
 
   // leaves
   std::vector<int> cell_to_leaf(nc, -1);
@@ -543,48 +542,50 @@ TargetSet fb_tree::source_target_set() {
 }
 
 // shared tail of bin_targets / subset_target_set: keys (leaf slot or sorted source position) -> TargetSet
-static TargetSet finish_target_set(fb_tree &t, size_t m, int key_bits, bool keys_are_positions) {
+TargetSet fb_tree::finish_target_set(TargetBuffers &tb, size_t m, int key_bits, bool keys_are_positions) {
+  fb_tree &t = *this;
   const int nl = (int)t.ht.leaves.size();
   size_t cub_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, t.d_t_key.p, t.d_t_key2.p, t.d_t_val.p, t.d_t_val2.p, (int)m, 0,
-                                  key_bits, t.stream);
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, tb.key.p, tb.key2.p, tb.val.p, tb.val2.p, (int)m, 0, key_bits,
+                                  t.stream);
   size_t scan_bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, t.d_tile_cnt.p, t.d_tile_cnt.p, nl, t.stream);
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, tb.tile_cnt.p, tb.tile_cnt.p, nl, t.stream);
   t.d_cub.reserve(std::max(cub_bytes, scan_bytes));
-  FB_CUDA(cub::DeviceRadixSort::SortPairs(t.d_cub.p, cub_bytes, t.d_t_key.p, t.d_t_key2.p, t.d_t_val.p, t.d_t_val2.p,
-                                          (int)m, 0, key_bits, t.stream));
+  FB_CUDA(cub::DeviceRadixSort::SortPairs(t.d_cub.p, cub_bytes, tb.key.p, tb.key2.p, tb.val.p, tb.val2.p, (int)m, 0,
+                                          key_bits, t.stream));
   g_launches.fetch_add(3);
-  t.d_tl_begin.reserve(nl);
-  t.d_tl_end.reserve(nl);
-  t.d_tile_cnt.reserve(2 * (size_t)nl);
-  FB_LAUNCH(k_leaf_ranges, nblocks(nl, 128), 128, 0, t.stream, t.d_t_key2.p, m,
+  tb.tl_begin.reserve(nl);
+  tb.tl_end.reserve(nl);
+  tb.tile_cnt.reserve(2 * (size_t)nl);
+  FB_LAUNCH(k_leaf_ranges, nblocks(nl, 128), 128, 0, t.stream, tb.key2.p, m,
             keys_are_positions ? t.d_src_tl_begin.p : nullptr, keys_are_positions ? t.d_src_tl_end.p : nullptr, nl,
-            t.d_tl_begin.p, t.d_tl_end.p, t.d_tile_cnt.p);
-  int *scan_out = t.d_tile_cnt.p + nl;
-  FB_CUDA(cub::DeviceScan::ExclusiveSum(t.d_cub.p, scan_bytes, t.d_tile_cnt.p, scan_out, nl, t.stream));
+            tb.tl_begin.p, tb.tl_end.p, tb.tile_cnt.p);
+  int *scan_out = tb.tile_cnt.p + nl;
+  FB_CUDA(cub::DeviceScan::ExclusiveSum(t.d_cub.p, scan_bytes, tb.tile_cnt.p, scan_out, nl, t.stream));
   g_launches.fetch_add(1);
   const int max_tiles = (int)std::min<size_t>((m + kTile - 1) / kTile + (size_t)nl, m);
-  t.d_tile_leaf.reserve(max_tiles);
-  t.d_tile_off.reserve(max_tiles);
-  t.d_ntiles.reserve(1);
-  FB_LAUNCH(k_fill_tiles, nblocks(nl, 128), 128, 0, t.stream, scan_out, t.d_tile_cnt.p, nl, t.d_tile_leaf.p,
-            t.d_tile_off.p, t.d_ntiles.p);
-  FB_CUDA(cudaMemsetAsync(t.d_flag.p, 0, t.ht.ncells(), t.stream));
-  FB_LAUNCH(k_flag_cells, nblocks(nl, 128), 128, 0, t.stream, t.d_leaf_cell.p, t.d_tl_begin.p, t.d_tl_end.p, nl,
-            t.d_cell_parent.p, t.d_flag.p);
+  tb.tile_leaf.reserve(max_tiles);
+  tb.tile_off.reserve(max_tiles);
+  tb.ntiles.reserve(1);
+  FB_LAUNCH(k_fill_tiles, nblocks(nl, 128), 128, 0, t.stream, scan_out, tb.tile_cnt.p, nl, tb.tile_leaf.p,
+            tb.tile_off.p, tb.ntiles.p);
+  tb.flag.reserve(t.ht.ncells());
+  FB_CUDA(cudaMemsetAsync(tb.flag.p, 0, t.ht.ncells(), t.stream));
+  FB_LAUNCH(k_flag_cells, nblocks(nl, 128), 128, 0, t.stream, t.d_leaf_cell.p, tb.tl_begin.p, tb.tl_end.p, nl,
+            t.d_cell_parent.p, tb.flag.p);
   TargetSet ts;
   ts.m = m;
-  ts.x = t.d_tx.p;
-  ts.y = t.d_ty.p;
-  ts.z = t.d_tz.p;
-  ts.out_row = t.d_t_val2.p;
-  ts.leaf_begin = t.d_tl_begin.p;
-  ts.leaf_end = t.d_tl_end.p;
-  ts.tile_leaf = t.d_tile_leaf.p;
-  ts.tile_off = t.d_tile_off.p;
-  ts.n_tiles_dev = t.d_ntiles.p;
+  ts.x = tb.tx.p;
+  ts.y = tb.ty.p;
+  ts.z = tb.tz.p;
+  ts.out_row = tb.val2.p;
+  ts.leaf_begin = tb.tl_begin.p;
+  ts.leaf_end = tb.tl_end.p;
+  ts.tile_leaf = tb.tile_leaf.p;
+  ts.tile_off = tb.tile_off.p;
+  ts.n_tiles_dev = tb.ntiles.p;
   ts.max_tiles = max_tiles;
-  ts.cell_flag = t.d_flag.p;
+  ts.cell_flag = tb.flag.p;
   return ts;
 }
 
@@ -607,18 +608,19 @@ TargetSet fb_tree::bin_targets(const double *targets, size_t m, ptrdiff_t rs, pt
       for (int d = 0; d < dim; ++d) h_stage.p[i * dim + d] = targets[(ptrdiff_t)i * rs + (ptrdiff_t)d * cs];
     FB_CUDA(cudaMemcpyAsync(d_t_user.p, h_stage.p, m * dim * sizeof(double), cudaMemcpyHostToDevice, stream));
   }
-  d_t_key.reserve(m);
-  d_t_key2.reserve(m);
-  d_t_val.reserve(m);
-  d_t_val2.reserve(m);
-  d_tx.reserve(m);
-  d_ty.reserve(m);
-  d_tz.reserve(m);
+  TargetBuffers &tb = tb_scratch;
+  tb.key.reserve(m);
+  tb.key2.reserve(m);
+  tb.val.reserve(m);
+  tb.val2.reserve(m);
+  tb.tx.reserve(m);
+  tb.ty.reserve(m);
+  tb.tz.reserve(m);
   d_err.reserve(1);
   FB_CUDA(cudaMemsetAsync(d_err.p, 0xFF, sizeof(unsigned long long), stream));
   const double side_depth = 2.0 * ht.radius / (double)(1ull << ht.depth);  // linear_tree.rs:495
   FB_LAUNCH(k_target_leaf, nblocks(m, 256), 256, 0, stream, d_t_user.p, m, dim, ht.depth, ht.disp[0], ht.disp[1],
-            ht.disp[2], side_depth, d_leaf_lo.p, d_leaf_hi.p, nl, d_t_key.p, d_t_val.p, d_err.p);
+            ht.disp[2], side_depth, d_leaf_lo.p, d_leaf_hi.p, nl, tb.key.p, tb.val.p, d_err.p);
   unsigned long long h_err = 0;
   FB_CUDA(cudaMemcpyAsync(&h_err, d_err.p, sizeof(h_err), cudaMemcpyDeviceToHost, stream));
   FB_CUDA(cudaStreamSynchronize(stream));
@@ -629,9 +631,9 @@ TargetSet fb_tree::bin_targets(const double *targets, size_t m, ptrdiff_t rs, pt
                     " lies outside the tree extents",
                 h_err);
   }
-  TargetSet ts = finish_target_set(*this, m, bits_for((size_t)nl), false);
-  FB_LAUNCH(k_gather_targets, nblocks(m, 256), 256, 0, stream, d_t_user.p, d_t_val2.p, m, dim, d_tx.p, d_ty.p,
-            d_tz.p);
+  TargetSet ts = finish_target_set(tb, m, bits_for((size_t)nl), false);
+  FB_LAUNCH(k_gather_targets, nblocks(m, 256), 256, 0, stream, d_t_user.p, tb.val2.p, m, dim, tb.tx.p, tb.ty.p,
+            tb.tz.p);
   return ts;
 }
 
@@ -639,25 +641,36 @@ TargetSet fb_tree::subset_target_set(const uint64_t *idx, size_t m) {
   FB_REQUIRE(idx != nullptr && m > 0 && m < (1ull << 31), "index list must be non-empty");
   d_idx64.reserve(m);
   FB_CUDA(cudaMemcpyAsync(d_idx64.p, idx, m * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
-  d_t_key.reserve(m);
-  d_t_key2.reserve(m);
-  d_t_val.reserve(m);
-  d_t_val2.reserve(m);
-  d_tx.reserve(m);
-  d_ty.reserve(m);
-  d_tz.reserve(m);
+  return subset_target_set_dev(d_idx64.p, m, tb_scratch);
+}
+
+TargetSet fb_tree::subset_target_set_dev(const unsigned long long *d_idx, size_t m, TargetBuffers &tb) {
+  tb.key.reserve(m);
+  tb.key2.reserve(m);
+  tb.val.reserve(m);
+  tb.val2.reserve(m);
+  tb.tx.reserve(m);
+  tb.ty.reserve(m);
+  tb.tz.reserve(m);
   d_err.reserve(1);
   FB_CUDA(cudaMemsetAsync(d_err.p, 0xFF, sizeof(unsigned long long), stream));
-  FB_LAUNCH(k_subset_positions, nblocks(m, 256), 256, 0, stream, d_idx64.p, d_inv.p, m, n, d_t_key.p, d_t_val.p,
-            d_err.p);
+  FB_LAUNCH(k_subset_positions, nblocks(m, 256), 256, 0, stream, d_idx, d_inv.p, m, n, tb.key.p, tb.val.p, d_err.p);
   unsigned long long h_err = 0;
   FB_CUDA(cudaMemcpyAsync(&h_err, d_err.p, sizeof(h_err), cudaMemcpyDeviceToHost, stream));
   FB_CUDA(cudaStreamSynchronize(stream));
   FB_REQUIRE(h_err == ~0ull, "source index out of range at position " + std::to_string(h_err));
-  TargetSet ts = finish_target_set(*this, m, bits_for(n), true);
-  FB_LAUNCH(k_gather_coords, nblocks(m, 256), 256, 0, stream, d_sx.p, d_sy.p, d_sz.p, d_t_key2.p, m, d_tx.p, d_ty.p,
-            d_tz.p);
+  TargetSet ts = finish_target_set(tb, m, bits_for(n), true);
+  FB_LAUNCH(k_gather_coords, nblocks(m, 256), 256, 0, stream, d_sx.p, d_sy.p, d_sz.p, tb.key2.p, m, tb.tx.p, tb.ty.p,
+            tb.tz.p);
   return ts;
+}
+
+// weights already in d_w_user: upward pass, downward pass restricted to the target set, leaf pass -> d_out
+void fb_tree::matvec_dev(const TargetSet &ts) {
+  sort_weights();
+  upward();
+  downward(ts.cell_flag);
+  leaf_pass(ts, false);
 }
 
 void fb_tree::fetch_output(size_t m, bool grads, double *out_vals, double *out_grads, ptrdiff_t o_rs,

@@ -24,6 +24,14 @@ struct TargetSet {
   const uint8_t *cell_flag = nullptr;                      // per cell: subtree contains targets
 };
 
+// device storage behind a TargetSet that is not the tree's own source set
+struct TargetBuffers {
+  DBuf<double> tx, ty, tz;
+  DBuf<uint32_t> key, key2, val, val2;
+  DBuf<int> tl_begin, tl_end, tile_leaf, tile_off, ntiles, tile_cnt;
+  DBuf<uint8_t> flag;
+};
+
 struct DirectArgs {  // leaf pass: P2P over U ranges + M2P over W cells (bbfmm.rs:1162-1355)
   TargetSet ts;
   const long long *u_ptr;
@@ -94,7 +102,7 @@ struct fb_tree {
   fb::DBuf<double> d_ccx, d_ccy, d_ccz, d_chalf;
   fb::DBuf<int> d_cell_parent, d_cell_slot, d_cell_ptb, d_cell_pte;
   fb::DBuf<int> d_child_ptr, d_child_idx;
-  fb::DBuf<uint8_t> d_flag_all, d_flag;       // per-cell "has targets" flags
+  fb::DBuf<uint8_t> d_flag_all;               // per-cell "has targets" flags (all ones)
   fb::DBuf<int> d_leaf_cell;                  // leaf slot -> cell
   fb::DBuf<unsigned long long> d_leaf_lo, d_leaf_hi;  // level-16 code range of each leaf slot
   fb::DBuf<int> d_src_leaves;                 // cells of leaves that hold sources (P2M grid)
@@ -112,9 +120,8 @@ struct fb_tree {
   fb::DBuf<uint32_t> d_src_out_row;
   int src_tiles = 0;
   // general target set scratch
-  fb::DBuf<double> d_t_user, d_tx, d_ty, d_tz;
-  fb::DBuf<uint32_t> d_t_key, d_t_key2, d_t_val, d_t_val2;
-  fb::DBuf<int> d_tl_begin, d_tl_end, d_tile_leaf, d_tile_off, d_ntiles, d_tile_cnt;
+  fb::DBuf<double> d_t_user;
+  fb::TargetBuffers tb_scratch;
   fb::DBuf<unsigned long long> d_err;
   fb::DBuf<unsigned char> d_cub;
   fb::DBuf<unsigned long long> d_idx64;
@@ -147,5 +154,10 @@ struct fb_tree {
   fb::TargetSet source_target_set();
   fb::TargetSet bin_targets(const double *targets, size_t m, ptrdiff_t rs, ptrdiff_t cs, uint64_t *bad);
   fb::TargetSet subset_target_set(const uint64_t *idx, size_t n_idx);
+  // subset of the sources as targets, index list already on the device; storage owned by `tb`
+  fb::TargetSet subset_target_set_dev(const unsigned long long *d_idx, size_t n_idx, fb::TargetBuffers &tb);
+  fb::TargetSet finish_target_set(fb::TargetBuffers &tb, size_t m, int key_bits, bool keys_are_positions);
+  // device-resident matvec pieces used by the solver (weights already in d_w_user, [n][nrhs])
+  void matvec_dev(const fb::TargetSet &ts);
   void fetch_output(size_t m, bool grads, double *out_vals, double *out_grads, ptrdiff_t o_rs, ptrdiff_t o_cs);
 };

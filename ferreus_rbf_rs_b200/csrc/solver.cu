@@ -1,0 +1,1166 @@
+// fr_model: device-resident RBF solve (FGMRES + multilevel Schwarz DDM) and interpolant evaluation.
+//   fgmres / schwarz_ddm_solver     ferreus_rbf/src/iterative_solvers.rs:38-281
+//   schwarz_preconditioner           ferreus_rbf/src/preconditioning/schwarz.rs:32-155
+//   Domain::factorise / solve        ferreus_rbf/src/domain.rs:153-467 (device part: Q^T A Q assembly, Cholesky,
+//                                    triangular solves; the packed RFP storage of linalg.rs is replaced by a
+//                                    full row-major square per domain, only the lower triangle is streamed)
+//   fast_matrix_vector_product       ferreus_rbf/src/rbf.rs:1338-1379
+//   RBFInterpolator fit / evaluate   ferreus_rbf/src/rbf.rs:317-582, 676-924, 1180-1270
+#include <chrono>
+#include <cstring>
+#include <memory>
+
+#include "fmm.h"
+#include "solver_host.h"
+
+namespace fb {
+
+static inline unsigned nblk(size_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+// ------------------------------------------------------------------------------------ vector kernels
+__global__ void k_dot(const double *a, const double *b, size_t n, double *out) {
+  __shared__ double red[32];
+  double s = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) s += a[i] * b[i];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) atomicAdd(out, s);
+  }
+}
+
+__global__ void k_absmax(const double *a, size_t n, unsigned long long *out) {
+  double s = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) s = fmax(s, fabs(a[i]));
+  for (int o = 16; o > 0; o >>= 1) s = fmax(s, __shfl_down_sync(0xffffffffu, s, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(s));  // non-negative doubles order as integers
+}
+
+__global__ void k_axpy(double a, const double *x, double *y, size_t n) {  // y += a x
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) y[i] += a * x[i];
+}
+
+__global__ void k_scale_to(double a, const double *x, double *y, size_t n) {  // y = a x
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) y[i] = a * x[i];
+}
+
+__global__ void k_sub_to(const double *a, const double *b, double *y, size_t n) {  // y = a - b
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) y[i] = a[i] - b[i];
+}
+
+// y[row] = fmm[i] + nugget * w[row] + P[row, :] . w[n:]   for row = idx[i] (or i); other rows stay zero
+__global__ void k_matvec_finish(const double *fmm, const unsigned long long *idx, size_t cnt, const double *w, size_t n,
+                                int m, const double *P, double nugget, double *y) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= cnt) return;
+  const size_t row = idx ? (size_t)idx[i] : i;
+  double v = fmm[i] + nugget * w[row];
+  for (int k = 0; k < m; ++k) v += P[row * m + k] * w[n + k];
+  y[row] = v;
+}
+
+// s1[:n] -= Q (Q^T s1[:n]):  first the m projections, then the update (schwarz.rs:122-126)
+__global__ void k_project_dots(const double *Q, const double *v, size_t n, int m, double *out) {
+  __shared__ double red[32];
+  for (int k = 0; k < m; ++k) {
+    double s = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) s += Q[i * m + k] * v[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+      if (threadIdx.x == 0) atomicAdd(out + k, s);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void k_project_apply(const double *Q, const double *coef, size_t n, int m, double *v) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0;
+  for (int k = 0; k < m; ++k) s += Q[i * m + k] * coef[k];
+  v[i] -= s;
+}
+
+// ------------------------------------------------------------------------------------ domain kernels
+struct DomainTable {  // one DDM level on the device
+  int n_domains = 0;
+  const long long *pt_ptr;   // n_domains+1 into pt_idx / pt_mask
+  const int *pt_idx;         // global point index, special points first
+  const uint8_t *pt_mask;    // internal flag
+  const int *rank;           // special points per domain
+  const long long *q_off;    // offset of Q_top (rank x mm, row-major) in the q pool
+  const long long *l_off;    // offset of the mm x mm factor in the factor pool
+  const long long *s_off;    // offset of the 2 x rank x mm assembly scratch (A12, C)
+};
+
+__device__ __forceinline__ double kval_rt(double r2, const KParams &kp) {
+  switch (kp.fam) {
+    case KF_LINEAR: return kernel_value<KF_LINEAR>(r2, kp);
+    case KF_TPS: return kernel_value<KF_TPS>(r2, kp);
+    case KF_CUBIC: return kernel_value<KF_CUBIC>(r2, kp);
+    case KF_SPH: return kernel_value<KF_SPH>(r2, kp);
+    case KF_LAPLACE: return kernel_value<KF_LAPLACE>(r2, kp);
+    case KF_R2: return kernel_value<KF_R2>(r2, kp);
+    default: return kernel_value<KF_R4>(r2, kp);
+  }
+}
+
+__device__ __forceinline__ double pair_r2(const double *px, const double *py, const double *pz, int a, int b) {
+  const double dx = px[a] - px[b], dy = py[a] - py[b], dz = pz[a] - pz[b];
+  double r2 = dx * dx;
+  r2 += dy * dy;
+  r2 += dz * dz;
+  return r2;
+}
+
+// scratch rows for the Q^T A Q assembly: A12[a][j] = k(s_a, x_j) and C[a][j] = A12[a][j] + sum_b A11[a][b] Q[b][j]
+__global__ void k_dom_prep(DomainTable t, const double *px, const double *py, const double *pz, KParams kp,
+                           double nugget, const double *qpool, double *scratch) {
+  const int d = blockIdx.x;
+  const int rk = t.rank[d];
+  if (rk == 0) return;
+  const long long p0 = t.pt_ptr[d];
+  const int n = (int)(t.pt_ptr[d + 1] - p0), mm = n - rk;
+  const int *idx = t.pt_idx + p0;
+  const double *Q = qpool + t.q_off[d];
+  double *A12 = scratch + t.s_off[d], *C = A12 + (size_t)rk * mm;
+  __shared__ double A11[16][16];
+  for (int e = threadIdx.x; e < rk * rk; e += blockDim.x) {
+    const int a = e / rk, b = e % rk;
+    A11[a][b] = kval_rt(pair_r2(px, py, pz, idx[a], idx[b]), kp) + (a == b ? nugget : 0.0);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < mm; j += blockDim.x) {
+    double a12[16];
+    for (int a = 0; a < rk; ++a) {
+      a12[a] = kval_rt(pair_r2(px, py, pz, idx[a], idx[rk + j]), kp);
+      A12[(size_t)a * mm + j] = a12[a];
+    }
+    for (int a = 0; a < rk; ++a) {
+      double c = a12[a];
+      for (int b = 0; b < rk; ++b) c += A11[a][b] * Q[(size_t)b * mm + j];
+      C[(size_t)a * mm + j] = c;
+    }
+  }
+}
+
+// lower triangle of  Q^T A Q = A22 + Q^T (A12 + A11 Q) + A21 Q   (domain.rs:322-356), 32 x 32 tiles
+__global__ void __launch_bounds__(256) k_dom_assemble(DomainTable t, const double *px, const double *py,
+                                                      const double *pz, KParams kp, double nugget,
+                                                      const double *qpool, const double *scratch, double *lpool) {
+  const int d = blockIdx.z;
+  const int rk = t.rank[d];
+  const long long p0 = t.pt_ptr[d];
+  const int n = (int)(t.pt_ptr[d + 1] - p0), mm = n - rk;
+  const int ti = blockIdx.y, tj = blockIdx.x;
+  if (tj > ti || ti * 32 >= mm) return;
+  const int *idx = t.pt_idx + p0 + rk;
+  const double *Q = qpool + t.q_off[d];
+  const double *A12 = scratch + t.s_off[d], *C = A12 + (size_t)rk * mm;
+  double *L = lpool + t.l_off[d];
+  __shared__ double xi[3][32], xj[3][32];
+  __shared__ double Qi[16][32], Ai[16][32], Qj[16][32], Cj[16][32];
+  const int tid = threadIdx.x;
+  if (tid < 32) {
+    const int i = ti * 32 + tid;
+    const int g = i < mm ? idx[i] : idx[0];
+    xi[0][tid] = px[g]; xi[1][tid] = py[g]; xi[2][tid] = pz[g];
+  } else if (tid < 64) {
+    const int j = tj * 32 + tid - 32;
+    const int g = j < mm ? idx[j] : idx[0];
+    xj[0][tid - 32] = px[g]; xj[1][tid - 32] = py[g]; xj[2][tid - 32] = pz[g];
+  }
+  for (int e = tid; e < rk * 32; e += 256) {
+    const int a = e / 32, c = e % 32;
+    const int i = ti * 32 + c, j = tj * 32 + c;
+    Qi[a][c] = i < mm ? Q[(size_t)a * mm + i] : 0.0;
+    Ai[a][c] = i < mm ? A12[(size_t)a * mm + i] : 0.0;
+    Qj[a][c] = j < mm ? Q[(size_t)a * mm + j] : 0.0;
+    Cj[a][c] = j < mm ? C[(size_t)a * mm + j] : 0.0;
+  }
+  __syncthreads();
+  const int c = tid & 31;
+  for (int r = tid >> 5; r < 32; r += 8) {
+    const int i = ti * 32 + r, j = tj * 32 + c;
+    if (i >= mm || j >= mm || j > i) continue;
+    const double dx = xi[0][r] - xj[0][c], dy = xi[1][r] - xj[1][c], dz = xi[2][r] - xj[2][c];
+    double r2 = dx * dx;
+    r2 += dy * dy;
+    r2 += dz * dz;
+    double v = kval_rt(r2, kp) + (i == j ? nugget : 0.0);
+    for (int a = 0; a < rk; ++a) v += Qi[a][r] * Cj[a][c] + Ai[a][r] * Qj[a][c];
+    L[(size_t)i * mm + j] = v;
+  }
+}
+
+// blocked right-looking Cholesky, one CTA per domain, lower triangle of a row-major mm x mm matrix in place
+constexpr int kNB = 32;
+__global__ void __launch_bounds__(256) k_cholesky(DomainTable t, double *lpool, int *fail) {
+  const int d = blockIdx.x;
+  const int n = (int)(t.pt_ptr[d + 1] - t.pt_ptr[d]) - t.rank[d];
+  double *A = lpool + t.l_off[d];
+  extern __shared__ double sm[];
+  double(*Dk)[kNB + 1] = reinterpret_cast<double(*)[kNB + 1]>(sm);                          // diagonal block
+  double(*Pj)[kNB + 1] = reinterpret_cast<double(*)[kNB + 1]>(sm + kNB * (kNB + 1));        // panel rows of the j tile
+  double(*Pi)[kNB + 1] = reinterpret_cast<double(*)[kNB + 1]>(sm + 2 * kNB * (kNB + 1));    // 8 warps x panel rows of an i tile
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int kb = 0; kb < n; kb += kNB) {
+    const int bs = min(kNB, n - kb);
+    for (int e = tid; e < kNB * kNB; e += 256) {
+      const int r = e / kNB, c = e % kNB;
+      Dk[r][c] = (r < bs && c <= r) ? A[(size_t)(kb + r) * n + kb + c] : (r == c ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      for (int k = 0; k < bs; ++k) {
+        double dkk = Dk[k][k];
+        if (lane == 0 && !(dkk > 0.0)) atomicExch(fail, d + 1);
+        dkk = sqrt(fmax(dkk, 1e-300));
+        __syncwarp();
+        if (lane == k) Dk[k][k] = dkk;
+        if (lane > k && lane < bs) Dk[lane][k] /= dkk;
+        __syncwarp();
+        if (lane > k && lane < bs) {
+          const double lk = Dk[lane][k];
+          for (int c = k + 1; c <= lane; ++c) Dk[lane][c] -= lk * Dk[c][k];
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    for (int e = tid; e < bs * bs; e += 256) {
+      const int r = e / bs, c = e % bs;
+      if (c <= r) A[(size_t)(kb + r) * n + kb + c] = Dk[r][c];
+    }
+    // panel: rows below the diagonal block, one thread per row:  L[i, kb:kb+bs] = A[i, kb:kb+bs] Dk^-T
+    for (int i = kb + bs + tid; i < n; i += 256) {
+      double x[kNB];
+      double *row = A + (size_t)i * n + kb;
+#pragma unroll
+      for (int c = 0; c < kNB; ++c) x[c] = c < bs ? row[c] : 0.0;
+#pragma unroll
+      for (int c = 0; c < kNB; ++c) {
+        if (c < bs) {
+          double v = x[c];
+#pragma unroll
+          for (int k = 0; k < c; ++k) v -= x[k] * Dk[c][k];
+          x[c] = v / Dk[c][c];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < kNB; ++c)
+        if (c < bs) row[c] = x[c];
+    }
+    __syncthreads();
+    // trailing update: A[ib.., jb..] -= P_i P_j^T for the lower tiles; 8 warps take 8 i-tiles per j-tile
+    const int t0 = kb + bs;
+    for (int jb = t0; jb < n; jb += kNB) {
+      const int bj = min(kNB, n - jb);
+      __syncthreads();
+      for (int e = tid; e < kNB * kNB; e += 256) {
+        const int r = e / kNB, c = e % kNB;
+        Pj[r][c] = (r < bj && c < bs) ? A[(size_t)(jb + r) * n + kb + c] : 0.0;
+      }
+      __syncthreads();
+      for (int ib = jb + warp * kNB; ib < n; ib += 8 * kNB) {
+        const int bi = min(kNB, n - ib);
+        double(*P)[kNB + 1] = Pi + warp * kNB;
+        for (int r = 0; r < kNB; ++r) P[r][lane] = (r < bi && lane < bs) ? A[(size_t)(ib + r) * n + kb + lane] : 0.0;
+        __syncwarp();
+        if (lane < bj) {
+          for (int r = 0; r < bi; ++r) {
+            if (ib + r < jb + lane) continue;  // strictly upper part of the diagonal tile
+            double s = 0.0;
+#pragma unroll 8
+            for (int k = 0; k < kNB; ++k) s += P[r][k] * Pj[lane][k];
+            A[(size_t)(ib + r) * n + jb + lane] -= s;
+          }
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Domain::solve (domain.rs:393-467) + scatter of schwarz.rs:94-155, one CTA per domain.
+//   mode 0: fine level — write internal points only;  mode 1: coarse — write all points (+ polynomial tail)
+__global__ void __launch_bounds__(256) k_dom_solve(DomainTable t, const double *qpool, const double *lpool,
+                                                   const double *res, double *out, int mode, int add_poly,
+                                                   const double *a_special, const double *sp_inv, size_t n_total,
+                                                   int basis) {
+  const int d = blockIdx.x;
+  const int rk = t.rank[d];
+  const long long p0 = t.pt_ptr[d];
+  const int n = (int)(t.pt_ptr[d + 1] - p0), mm = n - rk;
+  const int *idx = t.pt_idx + p0;
+  const uint8_t *mask = t.pt_mask + p0;
+  const double *Q = qpool + t.q_off[d];
+  const double *L = lpool + t.l_off[d];
+  extern __shared__ double sm[];
+  double *dv = sm;        // n gathered residuals
+  double *x = dv + n;     // mm rhs / solution
+  double *red = x + mm;   // 8 x 32 partial sums
+  double *top = red + 256;  // rk
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < n; i += 256) dv[i] = res[idx[i]];
+  __syncthreads();
+  for (int j = tid; j < mm; j += 256) {  // rhs = Q^T d_special + d_rest
+    double v = dv[rk + j];
+    for (int a = 0; a < rk; ++a) v += Q[(size_t)a * mm + j] * dv[a];
+    x[j] = v;
+  }
+  __syncthreads();
+  // forward substitution L y = rhs
+  for (int kb = 0; kb < mm; kb += 32) {
+    const int bs = min(32, mm - kb);
+    for (int r = warp; r < bs; r += 8) {
+      const double *row = L + (size_t)(kb + r) * mm;
+      double s = 0.0;
+      for (int c = lane; c < kb; c += 32) s += row[c] * x[c];
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+      if (lane == 0) red[r] = s;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double v = lane < bs ? x[kb + lane] - red[lane] : 0.0;
+      for (int k = 0; k < bs; ++k) {
+        const double piv = __shfl_sync(0xffffffffu, v, k) / L[(size_t)(kb + k) * mm + kb + k];
+        if (lane == k) v = piv;
+        if (lane > k && lane < bs) v -= L[(size_t)(kb + lane) * mm + kb + k] * piv;
+      }
+      if (lane < bs) x[kb + lane] = v;
+    }
+    __syncthreads();
+  }
+  // backward substitution L^T gamma = y
+  for (int kb = ((mm - 1) / 32) * 32; kb >= 0; kb -= 32) {
+    const int bs = min(32, mm - kb);
+    double s = 0.0;
+    if (lane < bs)
+      for (int j = kb + bs + warp; j < mm; j += 8) s += L[(size_t)j * mm + kb + lane] * x[j];
+    red[warp * 32 + lane] = s;
+    __syncthreads();
+    if (warp == 0) {
+      double acc = 0.0;
+      for (int w = 0; w < 8; ++w) acc += red[w * 32 + lane];
+      double v = lane < bs ? x[kb + lane] - acc : 0.0;
+      for (int k = bs - 1; k >= 0; --k) {
+        const double piv = __shfl_sync(0xffffffffu, v, k) / L[(size_t)(kb + k) * mm + kb + k];
+        if (lane == k) v = piv;
+        if (lane < k) v -= L[(size_t)(kb + k) * mm + kb + lane] * piv;
+      }
+      if (lane < bs) x[kb + lane] = v;
+    }
+    __syncthreads();
+  }
+  // lambda_top = Q gamma
+  for (int a = warp; a < rk; a += 8) {
+    double s = 0.0;
+    for (int j = lane; j < mm; j += 32) s += Q[(size_t)a * mm + j] * x[j];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) top[a] = s;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += 256) {
+    const double lam = i < rk ? top[i] : x[i - rk];
+    if (mode == 1 || mask[i]) out[idx[i]] = lam;
+  }
+  if (mode == 1 && add_poly && rk > 0 && a_special) {
+    // r = d_special - A_special lambda;  poly = sp_mono^-1 r  (domain.rs:446-463)
+    __syncthreads();
+    for (int a = warp; a < rk; a += 8) {
+      const double *row = a_special + (size_t)a * n;
+      double s = 0.0;
+      for (int i = lane; i < n; i += 32) s += row[i] * (i < rk ? top[i] : x[i - rk]);
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+      if (lane == 0) red[a] = dv[a] - s;
+    }
+    __syncthreads();
+    if (tid < rk) {
+      double s = 0.0;
+      for (int b = 0; b < rk; ++b) s += sp_inv[tid * rk + b] * red[b];
+      out[n_total - rk + tid] = s;  // schwarz.rs:147-152: tail rows
+    }
+  }
+}
+
+// A[special, :] rows of the coarse domain (domain.rs:366)
+__global__ void k_special_rows(const int *idx, int n, int rk, const double *px, const double *py, const double *pz,
+                               KParams kp, double nugget, double *out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int a = 0; a < rk; ++a)
+    out[(size_t)a * n + i] = kval_rt(pair_r2(px, py, pz, idx[a], idx[i]), kp) + (a == i ? nugget : 0.0);
+}
+
+// ------------------------------------------------------------------------------------------ level
+struct LevelDev {
+  DomainTable tab{};
+  int n_domains = 0;
+  size_t max_n = 0, max_mm = 0;
+  DBuf<long long> pt_ptr, q_off, l_off, s_off;
+  DBuf<int> pt_idx, rank;
+  DBuf<uint8_t> pt_mask;
+  DBuf<double> qpool, lpool;
+  DBuf<unsigned long long> level_idx;  // point_indices of the level (matvec_partial target set)
+  size_t n_level_pts = 0;
+  TargetBuffers tb;
+  TargetSet ts{};
+  bool all_points = false;
+  // coarse extras
+  DBuf<double> a_special, sp_inv;
+  bool solve_for_poly = false;
+};
+
+}  // namespace fb
+
+using namespace fb;
+
+struct fr_model {
+  int dim = 0;
+  size_t n = 0, n_cols = 0, n_in = 0;
+  Settings st;
+  fr_params params{};
+  KParams kp{};
+  std::vector<double> points, values;  // after duplicate removal, row-major
+  std::vector<double> translation, scale;
+  std::vector<double> point_coeff, poly_coeff;
+  std::vector<LevelHost> ddm;
+  fr_model_info info{};
+  std::unique_ptr<fb_tree, void (*)(fb_tree *)> evaluator{nullptr, fb_tree_free};
+  fr_progress_cb cb = nullptr;
+  void *cb_user = nullptr;
+
+  void fit();
+  fb_tree *make_tree(bool sparse, const double *extents);
+  void eval_tree(fb_tree *t, const double *targets, size_t m, ptrdiff_t rs, ptrdiff_t cs, bool leaves, bool add_nugget,
+                 double *out_vals, double *out_grads);
+  void emit(int kind, uint64_t iter, double residual, double progress, const char *msg) {
+    if (!cb) return;
+    fr_event ev{kind, iter, residual, progress, msg};
+    cb(&ev, cb_user);
+  }
+};
+
+namespace {
+
+double progress_from_rel(double current_res, double start_res, double target_res) {  // progress.rs:124-130
+  if (current_res <= target_res) return 1.0;
+  return (std::log10(start_res) - std::log10(current_res)) / (std::log10(start_res) - std::log10(target_res));
+}
+
+struct DeviceSolver {
+  fr_model &M;
+  fb_tree *tree;
+  cudaStream_t s;
+  size_t n, m, nt;  // points, basis, n + m
+  DBuf<double> px, py, pz, P, Qp, proj, scalar;
+  DBuf<unsigned long long> umax;
+  std::vector<std::unique_ptr<LevelDev>> levels;
+  DBuf<int> fail;
+  DBuf<double> scratch;
+  uint64_t matvecs = 0;
+
+  DeviceSolver(fr_model &model, fb_tree *t) : M(model), tree(t), s(t ? t->stream : nullptr) {}
+
+  void upload_points(cudaStream_t stream) {
+    n = M.n;
+    m = (size_t)M.st.basis_size;
+    nt = n + m;
+    std::vector<double> x(n), y(n, 0.0), z(n, 0.0);
+    for (size_t i = 0; i < n; ++i) {
+      x[i] = M.points[i * M.dim];
+      if (M.dim > 1) y[i] = M.points[i * M.dim + 1];
+      if (M.dim > 2) z[i] = M.points[i * M.dim + 2];
+    }
+    px.upload(x, stream);
+    py.upload(y, stream);
+    pz.upload(z, stream);
+    scalar.reserve(16);
+    umax.reserve(1);
+    fail.reserve(1);
+  }
+
+  // ---- factorise one level on the device (domain.rs:322-382)
+  void build_level(const LevelHost &lh, bool coarse, cudaStream_t stream) {
+    auto lv = std::make_unique<LevelDev>();
+    const size_t nd = lh.domains.size();
+    std::vector<long long> pt_ptr(nd + 1, 0), q_off(nd, 0), l_off(nd, 0), s_off(nd, 0);
+    std::vector<int> rank(nd, 0), pt_idx;
+    std::vector<uint8_t> pt_mask;
+    std::vector<double> qpool;
+    long long lsize = 0, ssize = 0;
+    for (size_t d = 0; d < nd; ++d) {
+      const DomainHost &dh = lh.domains[d];
+      const size_t nn = dh.idx.size(), mm = nn - dh.rank;
+      FB_REQUIRE(dh.rank <= 16, "more than 16 special points per domain");
+      rank[d] = dh.rank;
+      for (size_t i = 0; i < nn; ++i) {
+        pt_idx.push_back((int)dh.idx[i]);
+        pt_mask.push_back(i < dh.mask.size() ? dh.mask[i] : 0);
+      }
+      pt_ptr[d + 1] = (long long)pt_idx.size();
+      q_off[d] = (long long)qpool.size();
+      qpool.insert(qpool.end(), dh.qtop.begin(), dh.qtop.end());
+      l_off[d] = lsize;
+      lsize += (long long)(mm * mm);
+      s_off[d] = ssize;
+      ssize += (long long)(2 * dh.rank * mm);
+      lv->max_n = std::max(lv->max_n, nn);
+      lv->max_mm = std::max(lv->max_mm, mm);
+    }
+    lv->n_domains = (int)nd;
+    lv->pt_ptr.upload(pt_ptr, stream);
+    lv->q_off.upload(q_off, stream);
+    lv->l_off.upload(l_off, stream);
+    lv->s_off.upload(s_off, stream);
+    lv->rank.upload(rank, stream);
+    lv->pt_idx.upload(pt_idx, stream);
+    lv->pt_mask.upload(pt_mask, stream);
+    lv->qpool.upload(qpool, stream);
+    lv->lpool.reserve((size_t)lsize);
+    scratch.reserve((size_t)std::max<long long>(ssize, 1));
+    DomainTable &t = lv->tab;
+    t.n_domains = (int)nd;
+    t.pt_ptr = lv->pt_ptr.p;
+    t.pt_idx = lv->pt_idx.p;
+    t.pt_mask = lv->pt_mask.p;
+    t.rank = lv->rank.p;
+    t.q_off = lv->q_off.p;
+    t.l_off = lv->l_off.p;
+    t.s_off = lv->s_off.p;
+    const KParams kp = M.kp;
+    FB_LAUNCH(k_dom_prep, (unsigned)nd, 128, 0, stream, t, px.p, py.p, pz.p, kp, M.st.nugget, lv->qpool.p, scratch.p);
+    const unsigned tiles = (unsigned)((lv->max_mm + 31) / 32);
+    for (size_t d0 = 0; d0 < nd; d0 += 32768) {  // grid.z limit
+      DomainTable tt = t;
+      const unsigned cnt = (unsigned)std::min<size_t>(32768, nd - d0);
+      tt.pt_ptr += d0;
+      tt.rank += d0;
+      tt.q_off += d0;
+      tt.l_off += d0;
+      tt.s_off += d0;
+      FB_LAUNCH(k_dom_assemble, dim3(tiles, tiles, cnt), 256, 0, stream, tt, px.p, py.p, pz.p, kp, M.st.nugget,
+                lv->qpool.p, scratch.p, lv->lpool.p);
+    }
+    FB_CUDA(cudaMemsetAsync(fail.p, 0, sizeof(int), stream));
+    const size_t smem = sizeof(double) * (size_t)(kNB + 1) * kNB * (2 + 8);
+    FB_CUDA(cudaFuncSetAttribute(k_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FB_LAUNCH(k_cholesky, (unsigned)nd, 256, smem, stream, t, lv->lpool.p, fail.p);
+    int h_fail = 0;
+    FB_CUDA(cudaMemcpyAsync(&h_fail, fail.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    FB_CUDA(cudaStreamSynchronize(stream));
+    if (h_fail)
+      throw Error(FB_ERR_INVALID_ARGUMENT,
+                  "subdomain matrix Q^T A Q is not positive definite (domain " + std::to_string(h_fail - 1) +
+                      "); the reference's Bunch-Kaufman fallback (domain.rs:63-68) is not implemented");
+    if (coarse && !lh.domains.empty() && lh.domains[0].solve_for_poly) {
+      const DomainHost &dh = lh.domains[0];
+      const int nn = (int)dh.idx.size();
+      lv->solve_for_poly = true;
+      lv->a_special.reserve((size_t)dh.rank * nn);
+      lv->sp_inv.upload(dh.sp_inv, stream);
+      FB_LAUNCH(k_special_rows, nblk(nn, 128), 128, 0, stream, lv->pt_idx.p, nn, dh.rank, px.p, py.p, pz.p, kp,
+                M.st.nugget, lv->a_special.p);
+    }
+    // target set of matvec_partial for this level
+    lv->n_level_pts = lh.point_indices.size();
+    lv->all_points = lv->n_level_pts == n;
+    if (tree && !lv->all_points) {
+      std::vector<unsigned long long> li(lh.point_indices.begin(), lh.point_indices.end());
+      lv->level_idx.upload(li, stream);
+      lv->ts = tree->subset_target_set_dev(lv->level_idx.p, li.size(), lv->tb);
+    }
+    levels.push_back(std::move(lv));
+  }
+
+  void solve_level(const LevelDev &lv, const double *res, double *out, int mode, int add_poly, cudaStream_t stream) {
+    const size_t smem = sizeof(double) * (lv.max_n + lv.max_mm + 256 + 32);
+    FB_CUDA(cudaFuncSetAttribute(k_dom_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+    FB_LAUNCH(k_dom_solve, (unsigned)lv.n_domains, 256, smem, stream, lv.tab, lv.qpool.p, lv.lpool.p, res, out, mode,
+              add_poly, lv.solve_for_poly ? lv.a_special.p : nullptr, lv.solve_for_poly ? lv.sp_inv.p : nullptr, nt,
+              (int)m);
+  }
+
+  // ---- vector helpers (device scalars are read back: Givens rotations stay on the host)
+  double dot(const double *a, const double *b, size_t len) {
+    FB_CUDA(cudaMemsetAsync(scalar.p, 0, sizeof(double), s));
+    FB_LAUNCH(k_dot, std::min<unsigned>(nblk(len, 256), 592), 256, 0, s, a, b, len, scalar.p);
+    double h = 0;
+    FB_CUDA(cudaMemcpyAsync(&h, scalar.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+    FB_CUDA(cudaStreamSynchronize(s));
+    return h;
+  }
+  double norm2(const double *a, size_t len) { return std::sqrt(dot(a, a, len)); }
+  double norm_max(const double *a, size_t len) {
+    FB_CUDA(cudaMemsetAsync(umax.p, 0, sizeof(unsigned long long), s));
+    FB_LAUNCH(k_absmax, std::min<unsigned>(nblk(len, 256), 592), 256, 0, s, a, len, umax.p);
+    unsigned long long h = 0;
+    FB_CUDA(cudaMemcpyAsync(&h, umax.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    FB_CUDA(cudaStreamSynchronize(s));
+    double d;
+    std::memcpy(&d, &h, sizeof(d));
+    return d;
+  }
+  void axpy(double a, const double *x, double *y, size_t len) { FB_LAUNCH(k_axpy, nblk(len, 256), 256, 0, s, a, x, y, len); }
+  void scale_to(double a, const double *x, double *y, size_t len) {
+    FB_LAUNCH(k_scale_to, nblk(len, 256), 256, 0, s, a, x, y, len);
+  }
+  void sub_to(const double *a, const double *b, double *y, size_t len) {
+    FB_LAUNCH(k_sub_to, nblk(len, 256), 256, 0, s, a, b, y, len);
+  }
+
+  // ---- fast_matrix_vector_product (rbf.rs:1338-1379); lv == nullptr or all_points => all rows
+  void matvec(const double *w, const LevelDev *lv, double *y) {
+    FB_CUDA(cudaMemsetAsync(y, 0, nt * sizeof(double), s));
+    tree->nrhs = 1;
+    tree->d_w_user.reserve(n);
+    FB_CUDA(cudaMemcpyAsync(tree->d_w_user.p, w, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    const bool all = lv == nullptr || lv->all_points;
+    TargetSet ts = all ? tree->source_target_set() : lv->ts;
+    tree->matvec_dev(ts);
+    ++matvecs;
+    const size_t cnt = all ? n : lv->n_level_pts;
+    FB_LAUNCH(k_matvec_finish, nblk(cnt, 256), 256, 0, s, tree->d_out.p, all ? nullptr : lv->level_idx.p, cnt, w, n,
+              (int)m, m ? P.p : nullptr, M.st.nugget, y);
+  }
+
+  // ---- schwarz_preconditioner (schwarz.rs:32-79)
+  DBuf<double> sl, res, tmp, s1;
+  void precon(const double *rg, double *out) {
+    sl.reserve(nt);
+    res.reserve(nt);
+    tmp.reserve(nt);
+    s1.reserve(nt);
+    FB_CUDA(cudaMemsetAsync(sl.p, 0, nt * sizeof(double), s));
+    const int coarse = (int)levels.size() - 1;
+    auto coarse_step = [&](bool add_poly) {
+      matvec(sl.p, levels[coarse].get(), tmp.p);
+      sub_to(rg, tmp.p, res.p, nt);
+      FB_CUDA(cudaMemsetAsync(s1.p, 0, nt * sizeof(double), s));
+      solve_level(*levels[coarse], res.p, s1.p, 1, add_poly ? 1 : 0, s);
+      axpy(1.0, s1.p, sl.p, nt);
+    };
+    if (coarse > 0) {
+      for (int i = 0; i < coarse; ++i) {
+        matvec(sl.p, levels[i].get(), tmp.p);
+        sub_to(rg, tmp.p, res.p, nt);
+        FB_CUDA(cudaMemsetAsync(s1.p, 0, nt * sizeof(double), s));
+        solve_level(*levels[i], res.p, s1.p, 0, 0, s);
+        if (m) {  // orthogonalise against the global polynomial space (schwarz.rs:111-117)
+          FB_CUDA(cudaMemsetAsync(proj.p, 0, m * sizeof(double), s));
+          FB_LAUNCH(k_project_dots, std::min<unsigned>(nblk(n, 256), 592), 256, 0, s, Qp.p, s1.p, n, (int)m, proj.p);
+          FB_LAUNCH(k_project_apply, nblk(n, 256), 256, 0, s, Qp.p, proj.p, n, (int)m, s1.p);
+        }
+        axpy(1.0, s1.p, sl.p, nt);
+        coarse_step(i == coarse - 1);
+      }
+    } else {
+      coarse_step(true);
+    }
+    FB_CUDA(cudaMemcpyAsync(out, sl.p, nt * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  }
+};
+
+void givens_rotation(double f, double g, double &c, double &s, double &r) {  // iterative_solvers.rs:192-232
+  const double safmin = 2.2250738585072014e-308, safmax = 1.7976931348623157e308;
+  const double rtmin = std::sqrt(safmin), rtmax = std::sqrt(safmax / 2.0);
+  if (g == 0.0) { c = 1.0; s = 0.0; r = f; return; }
+  if (f == 0.0) { c = 0.0; s = g > 0 ? 1.0 : -1.0; r = std::fabs(g); return; }
+  const double f1 = std::fabs(f), g1 = std::fabs(g);
+  if (f1 >= rtmin && f1 < rtmax && g1 >= rtmin && g1 < rtmax) {
+    r = std::copysign(std::sqrt(f * f + g * g), f);
+    c = f1 / std::fabs(r);
+    s = g / r;
+  } else {
+    const double u = std::min(std::max(std::max(f1, g1), safmin), safmax);
+    const double fs = f / u, gs = g / u;
+    const double mag = std::sqrt(fs * fs + gs * gs);
+    r = std::copysign(mag, f) * u;
+    c = std::fabs(fs) / mag;
+    s = gs / mag;
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------- fit
+fb_tree *fr_model::make_tree(bool sparse, const double *extents) {
+  fb_fmm_params fp;
+  fp.max_points_per_cell = params.max_points_per_cell;
+  fp.compression_type = params.compression_type;
+  fp.epsilon = params.epsilon;
+  fp.eval_chunk_size = params.eval_chunk_size;
+  fb_tree *t = new fb_tree();
+  try {
+    t->build(points.data(), n, dim, dim, 1, (int)params.interpolation_order, &st.kparams, 1, sparse ? 1 : 0, extents,
+             &fp);
+  } catch (...) {
+    delete t;
+    throw;
+  }
+  return t;
+}
+
+void fr_model::fit() {
+  using clk = std::chrono::steady_clock;
+  const auto t_start = clk::now();
+  info = fr_model_info{};
+  info.dim = (uint64_t)dim;
+  info.n_cols = n_cols;
+  info.basis_size = (uint64_t)st.basis_size;
+  const size_t m = (size_t)st.basis_size;
+  translation.assign(dim, 0.0);
+  scale.assign(dim, 1.0);
+  if (m) cheb_cube_scaling(points.data(), nullptr, n, dim, translation.data(), scale.data());  // rbf.rs:418-421
+  point_coeff.assign(n * n_cols, 0.0);
+  poly_coeff.assign(m * n_cols, 0.0);
+  const size_t nt = n + m;
+
+  std::unique_ptr<fb_tree, void (*)(fb_tree *)> tree(nullptr, fb_tree_free);
+  const bool naive = n < params.naive_solve_threshold;
+  if (naive) {  // single dense domain (rbf.rs:423-454)
+    LevelHost lh;
+    lh.point_indices.resize(n);
+    for (size_t i = 0; i < n; ++i) lh.point_indices[i] = (int64_t)i;
+    DomainHost d;
+    d.idx = lh.point_indices;
+    d.mask.assign(n, 1);
+    d.prepare(points.data(), dim, st, true);
+    lh.domains.push_back(std::move(d));
+    ddm.clear();
+    ddm.push_back(std::move(lh));
+  } else {
+    tree.reset(make_tree(true, nullptr));  // adaptive, sparse, own extents (rbf.rs:456-467)
+    ddm = build_ddm(points.data(), n, dim, st, params);
+  }
+  cudaStream_t stream = nullptr;
+  std::unique_ptr<DeviceSolver> solver(new DeviceSolver(*this, tree.get()));
+  bool own_stream = false;
+  if (!tree) {
+    FB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    own_stream = true;
+    solver->s = stream;
+  } else {
+    stream = tree->stream;
+  }
+  try {
+    DeviceSolver &S = *solver;
+    S.upload_points(stream);
+    if (m && !naive) {
+      std::vector<double> Pm(n * m), Qm(n * m);
+      evaluate_monomials(points.data(), nullptr, n, dim, st.polynomial_degree, (int)m, translation.data(),
+                         scale.data(), Pm.data());
+      thin_q_rowmajor(Pm.data(), n, (int)m, Qm.data());
+      S.P.upload(Pm, stream);
+      S.Qp.upload(Qm, stream);
+      S.proj.reserve(m);
+    }
+    for (size_t l = 0; l < ddm.size(); ++l) S.build_level(ddm[l], l + 1 == ddm.size(), stream);
+    info.ddm_levels = ddm.size();
+    for (size_t l = 0; l < ddm.size() && l < 8; ++l) info.ddm_domains[l] = ddm[l].domains.size();
+    const auto t_setup = clk::now();
+    info.setup_seconds = std::chrono::duration<double>(t_setup - t_start).count();
+
+    DBuf<double> b, x, r, w, wj, V, Z, tmp;
+    b.reserve(nt);
+    x.reserve(nt);
+    std::vector<double> hb(nt), hx(nt);
+    for (size_t col = 0; col < n_cols; ++col) {
+      for (size_t i = 0; i < n; ++i) hb[i] = values[i * n_cols + col];
+      for (size_t k = 0; k < m; ++k) hb[n + k] = 0.0;
+      FB_CUDA(cudaMemcpyAsync(b.p, hb.data(), nt * sizeof(double), cudaMemcpyHostToDevice, stream));
+      if (naive) {
+        FB_CUDA(cudaMemsetAsync(x.p, 0, nt * sizeof(double), stream));
+        S.solve_level(*S.levels[0], b.p, x.p, 1, 1, stream);
+      } else if (params.solver_type == FR_SOLVER_FGMRES) {
+        // ---- fgmres(matvec, rhs, precon, x0 = None, 20 outer, 5 inner)  (rbf.rs:536-547)
+        const int max_outer = 20, mi = 5;
+        r.reserve(nt);
+        w.reserve(nt);
+        wj.reserve(nt);
+        tmp.reserve(nt);
+        V.reserve(nt * (mi + 1));
+        Z.reserve(nt * mi);
+        FB_CUDA(cudaMemsetAsync(x.p, 0, nt * sizeof(double), stream));
+        // r = b - A x0 with x0 = 0: the reference runs a zero matvec here (iterative_solvers.rs:56); A 0 = 0
+        FB_CUDA(cudaMemcpyAsync(r.p, b.p, nt * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+        const bool absolute = st.tolerance_type == FR_TOL_ABSOLUTE;
+        const double beta = absolute ? S.norm_max(r.p, nt) : S.norm2(r.p, nt);
+        uint64_t iteration = 1;
+        bool done = beta == 0.0;
+        double H[6][5], g[6], cs[5], sn[5];
+        for (int outer = 0; outer < max_outer && !done; ++outer) {
+          std::memset(H, 0, sizeof(H));
+          std::memset(g, 0, sizeof(g));
+          std::memset(cs, 0, sizeof(cs));
+          std::memset(sn, 0, sizeof(sn));
+          const double r_norm = S.norm2(r.p, nt);
+          S.scale_to(1.0 / r_norm, r.p, V.p, nt);
+          g[0] = r_norm;
+          int used = mi;
+          for (int j = 0; j < mi; ++j) {
+            double *zj = Z.p + (size_t)j * nt;
+            S.precon(V.p + (size_t)j * nt, zj);
+            S.matvec(zj, nullptr, wj.p);
+            for (int i = 0; i <= j; ++i) {  // modified Gram-Schmidt
+              const double hij = S.dot(V.p + (size_t)i * nt, wj.p, nt);
+              H[i][j] = hij;
+              S.axpy(-hij, V.p + (size_t)i * nt, wj.p, nt);
+            }
+            const double norm = S.norm2(wj.p, nt);
+            H[j + 1][j] = norm;
+            for (int i = 0; i < j; ++i) {
+              const double temp = cs[i] * H[i][j] + sn[i] * H[i + 1][j];
+              H[i + 1][j] = -sn[i] * H[i][j] + cs[i] * H[i + 1][j];
+              H[i][j] = temp;
+            }
+            double c, sv, rr;
+            givens_rotation(H[j][j], H[j + 1][j], c, sv, rr);
+            H[j][j] = c * H[j][j] + sv * H[j + 1][j];
+            H[j + 1][j] = 0.0;
+            const double temp = c * g[j] + sv * g[j + 1];
+            g[j + 1] = -sv * g[j] + c * g[j + 1];
+            g[j] = temp;
+            cs[j] = c;
+            sn[j] = sv;
+            if (norm != 0.0) S.scale_to(1.0 / norm, wj.p, V.p + (size_t)(j + 1) * nt, nt);
+            const double res_norm = absolute ? std::fabs(g[j + 1]) : std::fabs(g[j + 1]) / beta;
+            info.iterations += 1;
+            info.last_residual = res_norm;
+            emit(FR_EVENT_SOLVER_ITERATION, iteration, res_norm, progress_from_rel(res_norm, beta, st.tolerance),
+                 nullptr);
+            if (res_norm < st.tolerance) {
+              used = j + 1;
+              done = true;
+              break;
+            }
+            ++iteration;
+          }
+          // x += Z[:, :used] (H[:used,:used]^-1 g[:used])   (iterative_solvers.rs:175-183)
+          double y[5];
+          for (int i = used - 1; i >= 0; --i) {
+            double v = g[i];
+            for (int k = i + 1; k < used; ++k) v -= H[i][k] * y[k];
+            y[i] = v / H[i][i];
+          }
+          for (int i = 0; i < used; ++i) S.axpy(y[i], Z.p + (size_t)i * nt, x.p, nt);
+          if (done) break;
+          S.matvec(x.p, nullptr, tmp.p);
+          S.sub_to(b.p, tmp.p, r.p, nt);
+          const double res_norm = absolute ? S.norm_max(r.p, nt) : S.norm2(r.p, nt) / beta;
+          if (res_norm < st.tolerance) break;
+        }
+      } else {
+        // ---- schwarz_ddm_solver, 100 iterations (iterative_solvers.rs:234-281)
+        r.reserve(nt);
+        tmp.reserve(nt);
+        w.reserve(nt);
+        FB_CUDA(cudaMemsetAsync(x.p, 0, nt * sizeof(double), stream));
+        FB_CUDA(cudaMemcpyAsync(r.p, b.p, nt * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+        const bool absolute = st.tolerance_type == FR_TOL_ABSOLUTE;
+        const double beta = absolute ? S.norm_max(r.p, nt) : S.norm2(r.p, nt);
+        double res_norm = beta;
+        uint64_t it = 0;
+        while (res_norm > st.tolerance && it < 100) {
+          S.precon(r.p, w.p);
+          S.axpy(1.0, w.p, x.p, nt);
+          S.matvec(x.p, nullptr, tmp.p);
+          S.sub_to(b.p, tmp.p, r.p, nt);
+          res_norm = absolute ? S.norm_max(r.p, nt) : S.norm2(r.p, nt) / beta;
+          ++it;
+          info.iterations += 1;
+          info.last_residual = res_norm;
+          emit(FR_EVENT_SOLVER_ITERATION, it, res_norm, progress_from_rel(res_norm, beta, st.tolerance), nullptr);
+        }
+      }
+      FB_CUDA(cudaMemcpyAsync(hx.data(), x.p, nt * sizeof(double), cudaMemcpyDeviceToHost, stream));
+      FB_CUDA(cudaStreamSynchronize(stream));
+      for (size_t i = 0; i < n; ++i) point_coeff[i * n_cols + col] = hx[i];
+      // coarse / naive solves write the recovered polynomial into the last `rank` rows (schwarz.rs:147-152)
+      for (size_t k = 0; k < m; ++k) poly_coeff[k * n_cols + col] = hx[n + k];
+    }
+    info.matvecs = S.matvecs;
+    info.solve_seconds = std::chrono::duration<double>(clk::now() - t_setup).count();
+  } catch (...) {
+    solver.reset();
+    if (own_stream) cudaStreamDestroy(stream);
+    throw;
+  }
+  solver.reset();
+  if (own_stream) cudaStreamDestroy(stream);
+  info.n_points = n;
+  info.fit_seconds = std::chrono::duration<double>(clk::now() - t_start).count();
+}
+
+// evaluate the interpolant through a tree whose multipoles hold the point coefficients (rbf.rs:1180-1270)
+void fr_model::eval_tree(fb_tree *t, const double *targets, size_t mt, ptrdiff_t rs, ptrdiff_t cs, bool leaves,
+                         bool add_nugget, double *out_vals, double *out_grads) {
+  uint64_t bad = 0;
+  TargetSet ts = t->bin_targets(targets, mt, rs, cs, &bad);
+  t->upload_weights(point_coeff.data(), n, n_cols, (ptrdiff_t)n_cols, 1);
+  if (!leaves) t->downward(ts.cell_flag);
+  t->leaf_pass(ts, out_grads != nullptr);
+  t->fetch_output(mt, out_grads != nullptr, out_vals, out_grads, (ptrdiff_t)n_cols, 1);
+  if (add_nugget)
+    for (size_t i = 0; i < mt && i < n; ++i)
+      for (size_t c = 0; c < n_cols; ++c) out_vals[i * n_cols + c] += point_coeff[i * n_cols + c] * st.nugget;
+  const int m = st.basis_size;
+  if (m == 0) return;
+  std::vector<double> tp(mt * dim), mono(mt * (size_t)m);
+  for (size_t i = 0; i < mt; ++i)
+    for (int d = 0; d < dim; ++d) tp[i * dim + d] = targets[(ptrdiff_t)i * rs + (ptrdiff_t)d * cs];
+  evaluate_monomials(tp.data(), nullptr, mt, dim, st.polynomial_degree, m, translation.data(), scale.data(),
+                     mono.data());
+  for (size_t i = 0; i < mt; ++i)
+    for (size_t c = 0; c < n_cols; ++c) {
+      double v = 0;
+      for (int k = 0; k < m; ++k) v += mono[i * m + k] * poly_coeff[(size_t)k * n_cols + c];
+      out_vals[i * n_cols + c] += v;
+    }
+  if (out_grads && st.polynomial_degree >= 1) {  // evaluate_monomial_gradients, polynomials.rs:64-116
+    const int deg = st.polynomial_degree;
+    for (size_t i = 0; i < mt; ++i) {
+      double sp[3] = {0, 0, 0};
+      for (int d = 0; d < dim; ++d) sp[d] = (tp[i * dim + d] - translation[d]) / scale[d];
+      for (size_t c = 0; c < n_cols; ++c) {
+        double *g = out_grads + i * (n_cols * dim) + c * dim;
+        for (int d = 0; d < dim; ++d) g[d] += poly_coeff[(size_t)(1 + d) * n_cols + c] / scale[d];
+        if (deg == 2) {
+          int k = 1 + dim;
+          for (int a = 0; a < dim; ++a)
+            for (int b = a; b < dim; ++b) {
+              const double cf = poly_coeff[(size_t)k * n_cols + c];
+              if (a == b) {
+                g[a] += cf * (2.0 * sp[a] / scale[a]);
+              } else {
+                g[a] += cf * (sp[b] / scale[a]);
+                g[b] += cf * (sp[a] / scale[b]);
+              }
+              ++k;
+            }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ C ABI
+template <class F>
+static int fr_guarded(F &&f) {
+  try {
+    f();
+    return FB_OK;
+  } catch (const fb::Error &e) {
+    set_last_error(e.what());
+    return e.code;
+  } catch (const std::exception &e) {
+    set_last_error(e.what());
+    return FB_ERR_CUDA;
+  }
+}
+
+extern "C" {
+
+void fr_settings_default(int32_t kernel_type, fr_settings *out) {
+  if (!out) return;
+  out->kernel_type = kernel_type;
+  out->drift = FR_DRIFT_DEFAULT;
+  out->spheroidal_order = 3;
+  out->nugget = 0.0;
+  out->base_range = 1.0;
+  out->total_sill = 1.0;
+  out->tolerance = 1e-6;
+  out->tolerance_type = FR_TOL_RELATIVE;
+}
+
+void fr_params_default(int32_t kernel_type, fr_params *out) {
+  if (!out) return;
+  out->solver_type = FR_SOLVER_FGMRES;
+  out->leaf_threshold = 1024;
+  out->overlap_quota = 0.5;
+  out->coarse_ratio = 0.125;
+  out->coarse_threshold = 4096;
+  const int order = kernel_type == FR_KERNEL_THIN_PLATE_SPLINE ? 9 : (kernel_type == FR_KERNEL_CUBIC ? 11 : 7);
+  out->interpolation_order = (uint64_t)order;
+  out->max_points_per_cell = 256;
+  out->compression_type = FB_COMPRESSION_ACA;
+  out->epsilon = std::pow(10.0, -order);
+  out->eval_chunk_size = 1024;
+  out->naive_solve_threshold = 4096;
+  out->test_unique = 1;
+}
+
+int fr_fit(const double *points, size_t n, int dim, ptrdiff_t p_rs, ptrdiff_t p_cs, const double *values, size_t n_cols,
+           ptrdiff_t v_rs, ptrdiff_t v_cs, const fr_settings *settings, const fr_params *params_or_null,
+           fr_progress_cb cb_or_null, void *user, fr_model **out) {
+  if (!out) return FB_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  fr_model *M = nullptr;
+  const int rc = fr_guarded([&] {
+    FB_REQUIRE(points && values && settings && n > 0 && n_cols > 0, "points, values and settings are required");
+    FB_REQUIRE(dim >= 1 && dim <= 3, "Unsupported number of dimensions: " + std::to_string(dim));  // rbf.rs:329-333
+    M = new fr_model();
+    M->dim = dim;
+    M->cb = cb_or_null;
+    M->cb_user = user;
+    std::string err;
+    FB_REQUIRE(resolve_settings(*settings, dim, M->st, err), err);
+    FB_REQUIRE(make_kparams(M->st.kparams, M->kp), "unknown kernel");
+    if (params_or_null)
+      M->params = *params_or_null;
+    else
+      fr_params_default(settings->kernel_type, &M->params);
+    std::vector<double> pts(n * dim), vals(n * n_cols);
+    for (size_t i = 0; i < n; ++i) {
+      for (int d = 0; d < dim; ++d) pts[i * dim + d] = points[(ptrdiff_t)i * p_rs + (ptrdiff_t)d * p_cs];
+      for (size_t c = 0; c < n_cols; ++c) vals[i * n_cols + c] = values[(ptrdiff_t)i * v_rs + (ptrdiff_t)c * v_cs];
+    }
+    M->n_in = n;
+    if (M->params.test_unique) {  // rbf.rs:341-359
+      std::vector<int64_t> keep = remove_duplicates(pts.data(), n, dim, M->kp);
+      if (keep.size() != n) {
+        M->emit(FR_EVENT_DUPLICATES_REMOVED, n - keep.size(), 0, 0, nullptr);
+        std::vector<double> p2(keep.size() * dim), v2(keep.size() * n_cols);
+        for (size_t k = 0; k < keep.size(); ++k) {
+          std::copy(&pts[keep[k] * dim], &pts[keep[k] * dim] + dim, &p2[k * dim]);
+          std::copy(&vals[keep[k] * n_cols], &vals[keep[k] * n_cols] + n_cols, &v2[k * n_cols]);
+        }
+        pts.swap(p2);
+        vals.swap(v2);
+      }
+    }
+    M->points.swap(pts);
+    M->values.swap(vals);
+    M->n = M->points.size() / dim;
+    M->n_cols = n_cols;
+    M->fit();
+    M->info.n_duplicates = n - M->n;
+    char msg[256];
+    snprintf(msg, sizeof(msg), "Took %.3fs to solve RBF for %zu points (%llu iterations, %llu FMM matvecs)",
+             M->info.fit_seconds, M->n, (unsigned long long)M->info.iterations, (unsigned long long)M->info.matvecs);
+    M->emit(FR_EVENT_MESSAGE, 0, 0, 0, msg);
+  });
+  if (rc != FB_OK) {
+    delete M;
+    return rc;
+  }
+  *out = M;
+  return FB_OK;
+}
+
+void fr_free(fr_model *m) { delete m; }
+
+int fr_get_info(const fr_model *m, fr_model_info *info) {
+  if (!m || !info) return FB_ERR_INVALID_ARGUMENT;
+  *info = m->info;
+  return FB_OK;
+}
+
+int fr_source_points(const fr_model *m, double *points_out, double *values_out) {
+  if (!m) return FB_ERR_INVALID_ARGUMENT;
+  if (points_out) std::copy(m->points.begin(), m->points.end(), points_out);
+  if (values_out) std::copy(m->values.begin(), m->values.end(), values_out);
+  return FB_OK;
+}
+
+int fr_coefficients(const fr_model *m, double *point_out, double *poly_out) {
+  if (!m) return FB_ERR_INVALID_ARGUMENT;
+  if (point_out) std::copy(m->point_coeff.begin(), m->point_coeff.end(), point_out);
+  if (poly_out) std::copy(m->poly_coeff.begin(), m->poly_coeff.end(), poly_out);
+  return FB_OK;
+}
+
+int fr_evaluate(fr_model *m, const double *targets, size_t n_targets, ptrdiff_t t_rs, ptrdiff_t t_cs, double *out_vals,
+                double *out_grads_or_null) {
+  return fr_guarded([&] {
+    FB_REQUIRE(m && targets && out_vals && n_targets > 0, "model, targets and output are required");
+    // union of source and target extents (rbf.rs:640-668), non-sparse adaptive tree (rbf.rs:677-681)
+    const int dim = m->dim;
+    double ext[6];
+    for (int d = 0; d < dim; ++d) {
+      double lo = m->points[d], hi = lo;
+      for (size_t i = 0; i < m->n; ++i) {
+        lo = std::min(lo, m->points[i * dim + d]);
+        hi = std::max(hi, m->points[i * dim + d]);
+      }
+      for (size_t i = 0; i < n_targets; ++i) {
+        const double v = targets[(ptrdiff_t)i * t_rs + (ptrdiff_t)d * t_cs];
+        lo = std::min(lo, v);
+        hi = std::max(hi, v);
+      }
+      ext[d] = lo;
+      ext[dim + d] = hi;
+    }
+    std::unique_ptr<fb_tree, void (*)(fb_tree *)> tree(m->make_tree(false, ext), fb_tree_free);
+    tree->upload_weights(m->point_coeff.data(), m->n, m->n_cols, (ptrdiff_t)m->n_cols, 1);
+    tree->upward();
+    m->eval_tree(tree.get(), targets, n_targets, t_rs, t_cs, false, false, out_vals, out_grads_or_null);
+  });
+}
+
+int fr_evaluate_at_source(fr_model *m, int add_nugget, double *out_vals) {
+  return fr_guarded([&] {
+    FB_REQUIRE(m && out_vals, "model and output are required");
+    std::unique_ptr<fb_tree, void (*)(fb_tree *)> tree(m->make_tree(true, nullptr), fb_tree_free);  // rbf.rs:777-781
+    tree->upload_weights(m->point_coeff.data(), m->n, m->n_cols, (ptrdiff_t)m->n_cols, 1);
+    tree->upward();
+    m->eval_tree(tree.get(), m->points.data(), m->n, m->dim, 1, false, add_nugget != 0, out_vals, nullptr);
+  });
+}
+
+int fr_build_evaluator(fr_model *m, const double *extents_or_null) {
+  return fr_guarded([&] {
+    FB_REQUIRE(m, "model required");
+    m->evaluator.reset(m->make_tree(false, extents_or_null));  // rbf.rs:830-838
+    fb_tree *t = m->evaluator.get();
+    t->upload_weights(m->point_coeff.data(), m->n, m->n_cols, (ptrdiff_t)m->n_cols, 1);
+    t->upward();
+    t->downward(t->d_flag_all.p);
+    FB_CUDA(cudaStreamSynchronize(t->stream));
+  });
+}
+
+int fr_evaluate_targets(fr_model *m, const double *targets, size_t n_targets, ptrdiff_t t_rs, ptrdiff_t t_cs,
+                        double *out_vals, double *out_grads_or_null) {
+  return fr_guarded([&] {
+    FB_REQUIRE(m && targets && out_vals && n_targets > 0, "model, targets and output are required");
+    FB_REQUIRE(m->evaluator != nullptr, "build_evaluator must be called before evaluate_targets");
+    m->eval_tree(m->evaluator.get(), targets, n_targets, t_rs, t_cs, true, false, out_vals, out_grads_or_null);
+  });
+}
+
+int fr_ddm_level(const fr_model *m, int level, uint64_t *n_domains, uint64_t *n_level_points, uint64_t *level_points,
+                 uint64_t *dom_ptr, uint64_t *dom_idx, uint8_t *dom_internal) {
+  if (!m || level < 0 || level >= (int)m->ddm.size()) return FB_ERR_INVALID_ARGUMENT;
+  const LevelHost &lh = m->ddm[level];
+  if (n_domains) *n_domains = lh.domains.size();
+  if (n_level_points) *n_level_points = lh.point_indices.size();
+  if (level_points)
+    for (size_t i = 0; i < lh.point_indices.size(); ++i) level_points[i] = (uint64_t)lh.point_indices[i];
+  uint64_t off = 0;
+  for (size_t d = 0; d < lh.domains.size(); ++d) {
+    if (dom_ptr) dom_ptr[d] = off;
+    const DomainHost &dh = lh.domains[d];
+    for (size_t i = 0; i < dh.idx.size(); ++i) {
+      if (dom_idx) dom_idx[off + i] = (uint64_t)dh.idx[i];
+      if (dom_internal) dom_internal[off + i] = i < dh.mask.size() ? dh.mask[i] : 0;
+    }
+    off += dh.idx.size();
+  }
+  if (dom_ptr) dom_ptr[lh.domains.size()] = off;
+  return FB_OK;
+}
+
+}  // extern "C"

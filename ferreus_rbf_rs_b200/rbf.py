@@ -1,0 +1,181 @@
+"""Mirror of the reference class ``ferreus_rbf.RBFInterpolator`` over the C ABI of include/ferreus_rbf_b200.h
+(py_ferreus_rbf/src/python_bindings.rs:696-930).  All compute is in libferreus_b200.so."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .config import Params
+from .interpolant_config import InterpolantSettings
+from .progress import DuplicatesRemoved, Message, SolverIteration
+
+
+class Coefficients:
+    def __init__(self, point_coefficients, poly_coefficients):
+        self.point_coefficients = point_coefficients
+        self.poly_coefficients = poly_coefficients
+
+
+def _one_col(a):
+    """mat_to_numpy: a single value column comes back 1-D (python_bindings.rs:81-99)"""
+    return a[:, 0].copy() if a.ndim == 2 and a.shape[1] == 1 else a
+
+
+def _points2d(obj, what):
+    if not isinstance(obj, np.ndarray) or obj.dtype != np.float64 or obj.ndim != 2:
+        raise TypeError(f"Expected a 2D float64 array for {what}")
+    return obj
+
+
+class RBFInterpolator:
+    """RBFInterpolator(points, values, interpolant_settings, *, params=None, global_trend=None,
+    progress_callback=None) -> fr_fit"""
+
+    def __init__(self, points, values, interpolant_settings, *, params=None, global_trend=None,
+                 progress_callback=None):
+        if global_trend is not None:
+            raise NotImplementedError("GlobalTrend is outside the B200 hot path (SURVEY.md §8f)")
+        pts = _points2d(points, "points")
+        if not isinstance(values, np.ndarray) or values.dtype != np.float64 or values.ndim not in (1, 2):
+            raise TypeError("Expected a 1D/2D float64 array for values")
+        vals = values[:, None] if values.ndim == 1 else values
+        if vals.shape[0] != pts.shape[0]:
+            raise ValueError("points and values must have the same number of rows")
+        s: InterpolantSettings = interpolant_settings
+        L = _lib.lib()
+        cs = _lib.FrSettings()
+        L.fr_settings_default(int(s.kernel_type), C.byref(cs))
+        cs.drift = -1 if s.drift is None else int(s.drift)
+        cs.spheroidal_order = int(s.spheroidal_order)
+        cs.nugget, cs.base_range, cs.total_sill = s.nugget, s.base_range, s.total_sill
+        cs.tolerance = s.fitting_accuracy.tolerance
+        cs.tolerance_type = int(s.fitting_accuracy.tolerance_type)
+        p: Params = params if params is not None else Params(s.kernel_type)
+        cp = _lib.FrParams()
+        L.fr_params_default(int(s.kernel_type), C.byref(cp))
+        cp.solver_type = int(p.solver_type)
+        cp.leaf_threshold = p.ddm_params.leaf_threshold
+        cp.overlap_quota = p.ddm_params.overlap_quota
+        cp.coarse_ratio = p.ddm_params.coarse_ratio
+        cp.coarse_threshold = p.ddm_params.coarse_threshold
+        cp.interpolation_order = p.fmm_params.interpolation_order
+        cp.max_points_per_cell = p.fmm_params.max_points_per_cell
+        cp.compression_type = int(p.fmm_params.compression_type)
+        cp.epsilon = p.fmm_params.epsilon
+        cp.eval_chunk_size = p.fmm_params.eval_chunk_size
+        cp.naive_solve_threshold = p.naive_solve_threshold
+        cp.test_unique = int(p.test_unique)
+        self.params = p
+        self.interpolant_settings = s
+        self._progress = progress_callback
+
+        def _cb(ev_ptr, _user):
+            if self._progress is None:
+                return
+            ev = ev_ptr.contents
+            if ev.kind == 1:
+                self._progress._emit(SolverIteration(ev.iter, ev.residual, ev.progress))
+            elif ev.kind == 0:
+                self._progress._emit(DuplicatesRemoved(ev.iter))
+            else:
+                self._progress._emit(Message(ev.message.decode() if ev.message else ""))
+
+        self._cb = _lib.FR_PROGRESS_CB(_cb)
+        self._L = L
+        self._h = C.c_void_p()
+        pr, pc = _lib.strides_of(pts)
+        vr, vc = _lib.strides_of(vals)
+        rc = L.fr_fit(_lib.dptr(pts), pts.shape[0], pts.shape[1], pr, pc, _lib.dptr(vals), vals.shape[1], vr, vc,
+                      C.byref(cs), C.byref(cp), self._cb, None, C.byref(self._h))
+        if rc != _lib.FB_OK:
+            self._h = C.c_void_p()
+            raise (ValueError if rc == _lib.FB_ERR_INVALID_ARGUMENT else RuntimeError)(_lib.last_error())
+        info = self.info()
+        self._n, self._cols, self._m, self._dim = info["n_points"], info["n_cols"], info["basis_size"], info["dim"]
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self._L.fr_free(h)
+            self._h = C.c_void_p()
+
+    def _check(self, rc):
+        if rc != _lib.FB_OK:
+            msg = _lib.last_error()
+            if rc == _lib.FB_ERR_POINT_OUTSIDE_TREE:
+                raise ValueError(msg)
+            raise (ValueError if rc == _lib.FB_ERR_INVALID_ARGUMENT else RuntimeError)(msg)
+
+    # ---- fields ------------------------------------------------------------------------------
+    def info(self):
+        inf = _lib.FrModelInfo()
+        self._check(self._L.fr_get_info(self._h, C.byref(inf)))
+        d = {name: getattr(inf, name) for name, _ in inf._fields_ if name != "ddm_domains"}
+        d["ddm_domains"] = list(inf.ddm_domains)[: inf.ddm_levels]
+        return d
+
+    @property
+    def source_points(self):
+        out = np.zeros((self._n, self._dim))
+        self._check(self._L.fr_source_points(self._h, _lib.dptr(out), None))
+        return out
+
+    @property
+    def source_values(self):
+        out = np.zeros((self._n, self._cols))
+        self._check(self._L.fr_source_points(self._h, None, _lib.dptr(out)))
+        return _one_col(out)
+
+    @property
+    def coefficients(self):
+        pc = np.zeros((self._n, self._cols))
+        poly = np.zeros((max(self._m, 1), self._cols))
+        self._check(self._L.fr_coefficients(self._h, _lib.dptr(pc), _lib.dptr(poly)))
+        return Coefficients(pc, poly[: self._m] if self._m else None)
+
+    # ---- evaluation --------------------------------------------------------------------------
+    def _eval(self, fn, targets, grads):
+        x = _points2d(targets, "target_points")
+        m = x.shape[0]
+        out = np.zeros((m, self._cols))
+        g = np.zeros((m, self._cols * self._dim)) if grads else None
+        xr, xc = _lib.strides_of(x)
+        self._check(fn(self._h, _lib.dptr(x), m, xr, xc, _lib.dptr(out), _lib.dptr(g) if grads else None))
+        return (_one_col(out), g) if grads else _one_col(out)
+
+    def evaluate(self, target_points):
+        return self._eval(self._L.fr_evaluate, target_points, False)
+
+    def evaluate_with_gradients(self, target_points):
+        return self._eval(self._L.fr_evaluate, target_points, True)
+
+    def evaluate_at_source(self, *, add_nugget=False):
+        out = np.zeros((self._n, self._cols))
+        self._check(self._L.fr_evaluate_at_source(self._h, int(bool(add_nugget)), _lib.dptr(out)))
+        return _one_col(out)
+
+    def build_evaluator(self, extents=None):
+        ext = None if extents is None else np.ascontiguousarray(np.asarray(extents, dtype=np.float64).ravel())
+        self._check(self._L.fr_build_evaluator(self._h, _lib.dptr(ext) if ext is not None else None))
+
+    def evaluate_targets(self, target_points):
+        return self._eval(self._L.fr_evaluate_targets, target_points, False)
+
+    def evaluate_targets_with_gradients(self, target_points):
+        # python_bindings.rs:818-826 routes this to the one-shot evaluate_with_gradients (SURVEY.md quirk viii)
+        return self._eval(self._L.fr_evaluate, target_points, True)
+
+    # ---- introspection -----------------------------------------------------------------------
+    def ddm_level(self, level):
+        nd, npts = C.c_uint64(), C.c_uint64()
+        u64 = C.POINTER(C.c_uint64)
+        self._check(self._L.fr_ddm_level(self._h, level, C.byref(nd), C.byref(npts), None, None, None, None))
+        lp = np.zeros(npts.value, dtype=np.uint64)
+        ptr = np.zeros(nd.value + 1, dtype=np.uint64)
+        self._check(self._L.fr_ddm_level(self._h, level, None, None, lp.ctypes.data_as(u64), ptr.ctypes.data_as(u64),
+                                          None, None))
+        idx = np.zeros(int(ptr[-1]), dtype=np.uint64)
+        internal = np.zeros(int(ptr[-1]), dtype=np.uint8)
+        self._check(self._L.fr_ddm_level(self._h, level, None, None, None, None, idx.ctypes.data_as(u64),
+                                          internal.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return lp, ptr, idx, internal
