@@ -44,8 +44,8 @@ void fb_tree::build(const double *points, size_t n_, int dim_, ptrdiff_t rs, ptr
   FB_REQUIRE(order_ >= 1 && order_ <= kMaxOrder, "interpolation_order must be in 1.." + std::to_string(kMaxOrder));
   FB_REQUIRE(n_ < (1ull << 31), "at most 2^31-1 source points per tree");
   FB_REQUIRE(k != nullptr, "kernel params required");
-  FB_REQUIRE(k->base_range > 0.0 && k->total_sill <= k->base_range,
-             "KernelParams: base_range > 0 and total_sill <= base_range required");  // kernel_helpers.rs:72-73
+  // kernel_helpers.rs:72-73 asserts live in KernelParamsBuilder::build (mirrored by the Python KernelParams class);
+  // FmmTree::new itself accepts any KernelParams
   FB_REQUIRE(make_kparams(*k, kp), "unknown kernel_type");
   kparams_c = *k;
   n = n_;

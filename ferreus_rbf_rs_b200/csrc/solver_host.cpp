@@ -54,10 +54,8 @@ bool resolve_settings(const fr_settings &in, int dim, Settings &out, std::string
   out.kparams.kernel_type = kt;
   out.kparams.base_range = in.base_range;
   out.kparams.total_sill = in.total_sill;
-  if (!(in.base_range > 0.0) || !(in.total_sill <= in.base_range)) {
-    err = "KernelParams: base_range > 0 and total_sill <= base_range required";
-    return false;
-  }
+  // (the builder asserts of kernel_helpers.rs:72-73 are not on this path: From<InterpolantSettings> builds the
+  //  struct directly, interpolant_config.rs:267-291)
   return true;
 }
 
