@@ -183,6 +183,201 @@ __global__ void __launch_bounds__(kTile) k_p2l(const P2LArgs a) {
   }
 }
 
+
+// ======================================================================================================
+// Value-only fast path of the leaf pass.  Measured on B200 (profiles/): the one-target-per-lane kernels are
+// FP64-pipe bound per issued warp; what is lost is lane utilisation and operation count, so:
+//  * P2P: every warp streams its own 32-source tiles through a private, double-buffered shared-memory slot
+//    (next tile prefetched into registers while the current one is consumed; only __syncwarp, no block barrier),
+//    and warps without targets skip the loop entirely;
+//  * M2P: the sources are a tensor grid of Chebyshev nodes, so r^2 = (dx2[i0] + dy2[i1]) + dz2[i2] with the
+//    squared axis offsets computed once per (target, W cell): 1 + 7 FP64 operations per pair instead of 13, with
+//    the reference's association (ferreus_rbf_utils/src/utils.rs:230-237).  For p <= 8 the dz2 table lives in
+//    registers (uniformly predicated unroll), otherwise in shared memory.
+// ======================================================================================================
+constexpr int kWarpTile = 32;
+constexpr int kRegOrder = 8;
+
+template <int NR>
+struct WarpTile {  // [buffer][component][lane]
+  double v[2][3 + NR][kWarpTile];
+};
+
+template <int FAM, int NR, bool REGZ>
+__global__ void __launch_bounds__(kTile) k_leaf_direct_v2(const DirectArgs a) {
+  const int tile = blockIdx.x;
+  if (tile >= *a.ts.n_tiles_dev) return;
+  const int li = a.ts.tile_leaf[tile];
+  const int tb = a.ts.leaf_begin[li] + a.ts.tile_off[tile];
+  const int cnt = min(kTile, a.ts.leaf_end[li] - tb);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool active = tid < cnt;
+  double xt = 0, yt = 0, zt = 0;
+  if (active) {
+    xt = a.ts.x[tb + tid];
+    yt = a.ts.y[tb + tid];
+    zt = a.ts.z[tb + tid];
+  }
+  double acc[NR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) acc[r] = 0.0;
+
+  extern __shared__ double dsm[];
+  WarpTile<NR> *wt = reinterpret_cast<WarpTile<NR> *>(dsm) + warp;
+  double *mw = dsm + (sizeof(WarpTile<NR>) / sizeof(double)) * (kTile / 32);  // [NR][P] multipoles of the W cell
+  double *d2 = mw + (size_t)NR * a.P;                                          // [2 or 3][p][kTile] squared offsets
+  const bool warp_has_targets = warp * 32 < cnt;
+
+  // ---- P2P: warp-private tiles over the merged U ranges
+  if (warp_has_targets) {
+    long long e = a.u_ptr[li];
+    const long long e_end = a.u_ptr[li + 1];
+    int rb = 0, rn = 0, c0 = 0;
+    if (e < e_end) {
+      rb = a.u_begin[e];
+      rn = a.u_count[e];
+    }
+    double reg[3 + NR];
+    auto fetch = [&](int &m) {  // this lane's element of the current tile, then advance
+      m = 0;
+      if (e >= e_end) return;
+      m = min(kWarpTile, rn - c0);
+      if (lane < m) {
+        const int s = rb + c0 + lane;
+        reg[0] = a.sx[s];
+        reg[1] = a.sy[s];
+        reg[2] = a.sz[s];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) reg[3 + r] = a.w[(size_t)(a.rhs0 + r) * a.n + s];
+      }
+      c0 += kWarpTile;
+      if (c0 >= rn) {
+        ++e;
+        c0 = 0;
+        if (e < e_end) {
+          rb = a.u_begin[e];
+          rn = a.u_count[e];
+        }
+      }
+    };
+    int m_cur = 0, m_next = 0, buf = 0;
+    fetch(m_cur);
+    if (lane < m_cur) {
+#pragma unroll
+      for (int k = 0; k < 3 + NR; ++k) wt->v[0][k][lane] = reg[k];
+    }
+    __syncwarp();
+    while (m_cur > 0) {
+      fetch(m_next);  // global loads of the next tile overlap the arithmetic below
+      const double(*t)[kWarpTile] = wt->v[buf];
+#pragma unroll 4
+      for (int j = 0; j < m_cur; ++j) {
+        const double dx = xt - t[0][j], dy = yt - t[1][j], dz = zt - t[2][j];
+        double r2 = dx * dx;
+        r2 += dy * dy;
+        r2 += dz * dz;
+        const double v = kernel_value_dev<FAM>(r2, a.kp);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) acc[r] += v * t[3 + r][j];
+      }
+      buf ^= 1;
+      if (lane < m_next) {
+#pragma unroll
+        for (int k = 0; k < 3 + NR; ++k) wt->v[buf][k][lane] = reg[k];
+      }
+      __syncwarp();
+      m_cur = m_next;
+    }
+  }
+  // ---- M2P: tensor grid of the W cell's Chebyshev nodes
+  const int p = a.p, P = a.P;
+  const int p1 = a.dim > 1 ? p : 1, p2 = a.dim > 2 ? p : 1;
+  for (long long e = a.w_ptr[li]; e < a.w_ptr[li + 1]; ++e) {
+    const int c = a.w_cell[e];
+    const double h = a.chalf[c];
+    __syncthreads();
+    for (int i = tid; i < NR * P; i += kTile) mw[i] = a.mult[((size_t)c * a.nrhs + a.rhs0) * P + i];
+    double dzr[kRegOrder];
+#pragma unroll
+    for (int i = 0; i < kRegOrder; ++i) dzr[i] = 0.0;
+    for (int i = 0; i < p; ++i) {
+      const double nd = a.nodes[i];
+      const double ox = xt - (a.ccx[c] + h * nd);
+      d2[(0 * p + i) * kTile + tid] = ox * ox;
+      if (a.dim > 1) {
+        const double oy = yt - (a.ccy[c] + h * nd);
+        d2[(1 * p + i) * kTile + tid] = oy * oy;
+      }
+      if (a.dim > 2 && !REGZ) {
+        const double oz = zt - (a.ccz[c] + h * nd);
+        d2[(2 * p + i) * kTile + tid] = oz * oz;
+      }
+    }
+    if (REGZ && a.dim > 2) {
+#pragma unroll
+      for (int i = 0; i < kRegOrder; ++i)
+        if (i < p) {
+          const double oz = zt - (a.ccz[c] + h * a.nodes[i]);
+          dzr[i] = oz * oz;
+        }
+    }
+    __syncthreads();
+    if (!warp_has_targets) continue;
+    for (int i0 = 0; i0 < p; ++i0) {
+      const double ax = d2[(0 * p + i0) * kTile + tid];
+      for (int i1 = 0; i1 < p1; ++i1) {
+        const double axy = a.dim > 1 ? ax + d2[(1 * p + i1) * kTile + tid] : ax;
+        const double *wrow = mw + (i0 * p1 + i1) * p2;
+        if (REGZ) {
+#pragma unroll
+          for (int i2 = 0; i2 < kRegOrder; ++i2)
+            if (i2 < p2) {
+              const double r2 = axy + dzr[i2];
+              const double v = kernel_value_dev<FAM>(r2, a.kp);
+#pragma unroll
+              for (int r = 0; r < NR; ++r) acc[r] += v * wrow[(size_t)r * P + i2];
+            }
+        } else {
+#pragma unroll 4
+          for (int i2 = 0; i2 < p2; ++i2) {
+            const double r2 = a.dim > 2 ? axy + d2[(2 * p + i2) * kTile + tid] : axy;
+            const double v = kernel_value_dev<FAM>(r2, a.kp);
+#pragma unroll
+            for (int r = 0; r < NR; ++r) acc[r] += v * wrow[(size_t)r * P + i2];
+          }
+        }
+      }
+    }
+  }
+  if (active) {
+    const size_t row = a.ts.out_row[tb + tid];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) a.out[row * a.nrhs + a.rhs0 + r] += acc[r];
+  }
+}
+
+template <int FAM, int NR>
+static void launch_leaf_v2(const DirectArgs &a, cudaStream_t s) {
+  const bool regz = a.dim == 3 && a.p <= kRegOrder;
+  const size_t smem = sizeof(WarpTile<NR>) * (kTile / 32) +
+                      sizeof(double) * ((size_t)NR * a.P + (regz ? 2 : 3) * (size_t)a.p * kTile);
+  if (regz) {
+    if (smem > 48 * 1024)
+      FB_CUDA(cudaFuncSetAttribute(k_leaf_direct_v2<FAM, NR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FB_LAUNCH((k_leaf_direct_v2<FAM, NR, true>), a.ts.max_tiles, kTile, smem, s, a);
+  } else {
+    if (smem > 48 * 1024)
+      FB_CUDA(cudaFuncSetAttribute(k_leaf_direct_v2<FAM, NR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FB_LAUNCH((k_leaf_direct_v2<FAM, NR, false>), a.ts.max_tiles, kTile, smem, s, a);
+  }
+}
+
+template <int FAM, int NR>
+static void launch_p2l_v2(const P2LArgs &a, cudaStream_t s) {
+  dim3 grid(a.n_cells, (a.P + kTile - 1) / kTile);
+  FB_LAUNCH((k_p2l<FAM, NR>), grid, kTile, 0, s, a);
+}
+
 // ---------------------------------------------------------------------------------- dispatch
 template <int FAM>
 static void leaf_direct_fam(DirectArgs a, cudaStream_t s) {
@@ -200,16 +395,16 @@ static void leaf_direct_fam(DirectArgs a, cudaStream_t s) {
     a.rhs0 = r;
     const int left = a.nrhs - r;
     if (left >= 8) {
-      FB_LAUNCH((k_leaf_direct<FAM, 8, false>), grid, kTile, 0, s, a);
+      launch_leaf_v2<FAM, 8>(a, s);
       r += 8;
     } else if (left >= 4) {
-      FB_LAUNCH((k_leaf_direct<FAM, 4, false>), grid, kTile, 0, s, a);
+      launch_leaf_v2<FAM, 4>(a, s);
       r += 4;
     } else if (left >= 2) {
-      FB_LAUNCH((k_leaf_direct<FAM, 2, false>), grid, kTile, 0, s, a);
+      launch_leaf_v2<FAM, 2>(a, s);
       r += 2;
     } else {
-      FB_LAUNCH((k_leaf_direct<FAM, 1, false>), grid, kTile, 0, s, a);
+      launch_leaf_v2<FAM, 1>(a, s);
       r += 1;
     }
   }
@@ -218,22 +413,21 @@ static void leaf_direct_fam(DirectArgs a, cudaStream_t s) {
 template <int FAM>
 static void p2l_fam(P2LArgs a, cudaStream_t s) {
   if (a.n_cells <= 0) return;
-  dim3 grid(a.n_cells, (a.P + kTile - 1) / kTile);
   int r = 0;
   while (r < a.nrhs) {
     a.rhs0 = r;
     const int left = a.nrhs - r;
     if (left >= 8) {
-      FB_LAUNCH((k_p2l<FAM, 8>), grid, kTile, 0, s, a);
+      launch_p2l_v2<FAM, 8>(a, s);
       r += 8;
     } else if (left >= 4) {
-      FB_LAUNCH((k_p2l<FAM, 4>), grid, kTile, 0, s, a);
+      launch_p2l_v2<FAM, 4>(a, s);
       r += 4;
     } else if (left >= 2) {
-      FB_LAUNCH((k_p2l<FAM, 2>), grid, kTile, 0, s, a);
+      launch_p2l_v2<FAM, 2>(a, s);
       r += 2;
     } else {
-      FB_LAUNCH((k_p2l<FAM, 1>), grid, kTile, 0, s, a);
+      launch_p2l_v2<FAM, 1>(a, s);
       r += 1;
     }
   }

@@ -300,6 +300,7 @@ void fb_tree::build(const double *points, size_t n_, int dim_, ptrdiff_t rs, ptr
     std::vector<double> pool;
     std::vector<int> e_tgt, e_src, e_perm;
     const bool compressed = fparams.compression_type != FB_COMPRESSION_NONE;
+    const int P4 = ((P + 3) / 4) * 4, P8 = ((P + 7) / 8) * 8;
     for (int lvl = 2; lvl <= ht.depth; ++lvl) {
       std::vector<std::vector<std::array<int, 3>>> per_ref(ops.n_ref);
       for (int c = ht.level_ptr[lvl]; c < ht.level_ptr[lvl + 1]; ++c) {
@@ -321,7 +322,7 @@ void fb_tree::build(const double *points, size_t n_, int dim_, ptrdiff_t rs, ptr
         g.level = lvl;
         g.ref = r;
         g.rank = op.rank;
-        g.rank_pad = compressed ? ((op.rank + 3) / 4) * 4 : P;
+        g.rank_pad = compressed ? std::max(8, ((op.rank + 7) / 8) * 8) : P4;
         g.n_entries = per_ref[r].size();
         g.entry_off = e_tgt.size();
         for (auto &t : per_ref[r]) {
@@ -329,23 +330,26 @@ void fb_tree::build(const double *points, size_t n_, int dim_, ptrdiff_t rs, ptr
           e_src.push_back(t[1]);
           e_perm.push_back(t[2]);
         }
-        if (compressed) {  // VtT [P][rank_pad], UT [rank_pad][P]
-          g.v_off = pool.size();
-          pool.resize(pool.size() + (size_t)P * g.rank_pad, 0.0);
-          for (int j = 0; j < P; ++j)
-            for (int k2 = 0; k2 < op.rank; ++k2) pool[g.v_off + (size_t)j * g.rank_pad + k2] = op.Vt(k2, j);
-          g.u_off = pool.size();
-          pool.resize(pool.size() + (size_t)g.rank_pad * P, 0.0);
-          for (int k2 = 0; k2 < op.rank; ++k2)
-            for (int m2 = 0; m2 < P; ++m2) pool[g.u_off + (size_t)k2 * P + m2] = op.U(m2, k2);
-        } else {  // UT[k][m] = K[m][k]
+        // operators in DMMA fragment order: frag(mt, ks)[lane] = Op[mt*8 + lane/4][ks*4 + lane%4], zero padded
+        auto pack = [&](int rows, int cols, int rows_pad, int cols_pad, auto get) {
+          const size_t off = pool.size();
+          const int mtn = rows_pad / 8, ksn = cols_pad / 4;
+          pool.resize(off + (size_t)mtn * ksn * 32, 0.0);
+          for (int mt = 0; mt < mtn; ++mt)
+            for (int ks = 0; ks < ksn; ++ks)
+              for (int l = 0; l < 32; ++l) {
+                const int rr = mt * 8 + l / 4, cc = ks * 4 + l % 4;
+                if (rr < rows && cc < cols) pool[off + ((size_t)mt * ksn + ks) * 32 + l] = get(rr, cc);
+              }
+          return off;
+        };
+        if (compressed) {
+          g.v_off = pack(op.rank, P, g.rank_pad, P4, [&](int rr, int cc) { return op.Vt(rr, cc); });
+          g.u_off = pack(P, op.rank, P8, g.rank_pad, [&](int rr, int cc) { return op.U(rr, cc); });
+        } else {
           g.v_off = 0;
-          g.u_off = pool.size();
-          pool.resize(pool.size() + (size_t)P * P, 0.0);
-          for (int k2 = 0; k2 < P; ++k2)
-            for (int m2 = 0; m2 < P; ++m2) pool[g.u_off + (size_t)k2 * P + m2] = op.U(m2, k2);
+          g.u_off = pack(P, P, P8, P4, [&](int rr, int cc) { return op.U(rr, cc); });
         }
-        if (pool.size() & 1) pool.push_back(0.0);
         m2l_groups.push_back(g);
       }
     }
@@ -353,14 +357,13 @@ void fb_tree::build(const double *points, size_t n_, int dim_, ptrdiff_t rs, ptr
     d_m2l_tgt.upload(e_tgt, stream);
     d_m2l_src.upload(e_src, stream);
     d_m2l_perm.upload(e_perm, stream);
-    // columns per CTA: as many as fit next to the Y tile in shared memory, multiple of 4, at most 64
-    int max_rp = 4;
+    int max_rp = 8;
     for (auto &g : m2l_groups) max_rp = std::max(max_rp, compressed ? g.rank_pad : 0);
-    const size_t budget = 200 * 1024;
-    int ncol = (int)(budget / (sizeof(double) * (size_t)(P + (compressed ? max_rp : 0))));
-    ncol = std::min(64, (ncol / 4) * 4);
-    FB_REQUIRE(ncol >= 4, "interpolation order too large for the M2L shared-memory tile");
-    m2l_nc = ncol;
+    m2l_P4 = P4;
+    m2l_Pp = P4;
+    while (m2l_Pp % 16 != 4 && m2l_Pp % 16 != 12) m2l_Pp += 4;  // bank-conflict-free B fragments
+    m2l_smem = sizeof(double) * ((size_t)kM2LCols * m2l_Pp + 2 * (size_t)max_rp * kM2LColsPad);
+    FB_REQUIRE(m2l_smem <= 220 * 1024, "interpolation order too large for the M2L shared-memory tile");
   }
   FB_CUDA(cudaStreamSynchronize(stream));
   have_weights = have_locals = false;
@@ -424,14 +427,41 @@ void fb_tree::downward(const uint8_t *flags) {
   if (timing) FB_CUDA(cudaEventRecord(ev[3], stream));
   // M2L (loop A of bbfmm.rs:781-832)
   const bool compressed = fparams.compression_type != FB_COMPRESSION_NONE;
-  for (const M2LGroup &g : m2l_groups) {
-    const size_t ncols = g.n_entries * (size_t)nrhs;
-    const unsigned grid = (unsigned)((ncols + m2l_nc - 1) / m2l_nc);
-    const size_t smem = sizeof(double) * (size_t)m2l_nc * (size_t)(P + (compressed ? g.rank_pad : 0));
-    set_smem(k_m2l, 200 * 1024);
-    FB_LAUNCH(k_m2l, grid, 256, smem, stream, d_m2l_tgt.p + g.entry_off, d_m2l_src.p + g.entry_off,
-              d_m2l_perm.p + g.entry_off, g.n_entries, compressed ? d_oppool.p + g.v_off : nullptr,
-              d_oppool.p + g.u_off, g.rank, g.rank_pad, d_perm_tab.p, P, nrhs, m2l_nc, flags, d_mult.p, d_loc.p);
+  if (compressed)
+    set_smem(k_m2l<true>, m2l_smem);
+  else
+    set_smem(k_m2l<false>, m2l_smem);
+  if (!m2l_groups.empty()) {
+    if (m2l_table_nrhs != nrhs) {  // CTA ranges depend on the number of right-hand sides
+      std::vector<M2LGroupDev> tab;
+      long long cta = 0;
+      for (const M2LGroup &g : m2l_groups) {
+        M2LGroupDev t;
+        t.cta_begin = (int)cta;
+        t.rank_pad = g.rank_pad;
+        t.entry_off = (long long)g.entry_off;
+        t.n_entries = (long long)g.n_entries;
+        t.v_off = (long long)g.v_off;
+        t.u_off = (long long)g.u_off;
+        tab.push_back(t);
+        cta += (long long)((g.n_entries * (size_t)nrhs + kM2LCols - 1) / kM2LCols);
+      }
+      FB_REQUIRE(cta < (1ll << 31), "too many M2L tiles");
+      m2l_ctas = (unsigned)cta;
+      d_m2l_table.reserve(tab.size() * sizeof(M2LGroupDev));
+      FB_CUDA(cudaMemcpyAsync(d_m2l_table.p, tab.data(), tab.size() * sizeof(M2LGroupDev), cudaMemcpyHostToDevice,
+                              stream));
+      FB_CUDA(cudaStreamSynchronize(stream));
+      m2l_table_nrhs = nrhs;
+    }
+    const M2LGroupDev *tab = reinterpret_cast<const M2LGroupDev *>(d_m2l_table.p);
+    if (compressed) {
+      FB_LAUNCH(k_m2l<true>, m2l_ctas, 256, m2l_smem, stream, tab, (int)m2l_groups.size(), d_m2l_tgt.p, d_m2l_src.p,
+                d_m2l_perm.p, d_oppool.p, d_perm_tab.p, P, m2l_P4, m2l_Pp, nrhs, flags, d_mult.p, d_loc.p);
+    } else {
+      FB_LAUNCH(k_m2l<false>, m2l_ctas, 256, m2l_smem, stream, tab, (int)m2l_groups.size(), d_m2l_tgt.p, d_m2l_src.p,
+                d_m2l_perm.p, d_oppool.p, d_perm_tab.p, P, m2l_P4, m2l_Pp, nrhs, flags, d_mult.p, d_loc.p);
+    }
   }
   if (timing) FB_CUDA(cudaEventRecord(ev[4], stream));
   // P2L (adaptive only)

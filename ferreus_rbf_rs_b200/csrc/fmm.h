@@ -134,7 +134,11 @@ struct fb_tree {
   // M2L
   std::vector<fb::M2LGroup> m2l_groups;
   fb::DBuf<int> d_m2l_tgt, d_m2l_src, d_m2l_perm;
-  int m2l_nc = 16;  // columns per CTA
+  int m2l_P4 = 0, m2l_Pp = 0;  // padded node counts of the M2L tiles
+  size_t m2l_smem = 0;
+  fb::DBuf<unsigned char> d_m2l_table;  // M2LGroupDev[] of the fused launch
+  int m2l_table_nrhs = -1;
+  unsigned m2l_ctas = 0;
   // timing
   bool timing = false;
   double last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};

@@ -337,28 +337,66 @@ __global__ void __launch_bounds__(128) k_l2l(int cell0, const int *cell_parent, 
   }
 }
 
-// M2L for one (level, reference vector) group (bbfmm.rs:864-986).  A CTA owns NC (entry, rhs) columns:
-//   Xs[j][c] = M_src[perm[j]]  (symmetry permutation applied while staging into shared memory)
-//   Ys = Vt * Xs   (rank x NC)      Zs = U * Ys   (P x NC)      L_tgt[perm[m]] += Zs[m]   (atomic)
-// Operators are stored transposed for coalesced register-tile loads: VtT[j][k] (P x rank_pad), UT[k][m]
-// (rank_pad x P).  Uncompressed operators skip the first product (Ys aliases Xs, rank = P).
-__global__ void __launch_bounds__(256) k_m2l(const int *e_tgt, const int *e_src, const int *e_perm, size_t n_entries,
-                                             const double *VtT, const double *UT, int rank, int rank_pad,
-                                             const int *perm_tab, int P, int nrhs, int NC, const uint8_t *flag,
-                                             const double *mult, double *loc) {
+// ---- FP64 tensor-core helpers: mma.sync.aligned.m8n8k4 (SASS: DMMA.8x8x4) -------------------------------
+// fragments: A[lane>>2][lane&3], B[lane&3][lane>>2], C/D[lane>>2][(lane&3)*2 + {0,1}]
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+constexpr int kM2LCols = 32;                 // (entry, rhs) columns per CTA
+constexpr int kM2LColsPad = kM2LCols + 4;    // row stride of Ys: == 4 (mod 16) -> conflict-free B fragments
+constexpr int kM2LChunk = 4;                 // rank tiles (8 rows each) accumulated per pass over the reduction
+
+// M2L for one (level, reference vector) group (bbfmm.rs:864-986) as two dense contractions on the FP64 tensor
+// cores.  A CTA owns 32 (entry, rhs) columns:
+//   Xs[c][j] = M_src[perm[j]]   permuted multipoles, staged once in shared memory (column stride Pp, Pp == 4 or
+//                               12 mod 16 so the B fragments are bank-conflict free)
+//   Ys = Vt Xs  (rank x 32)     8 warps = 4 column tiles x 2 halves of the P-long reduction, summed in smem
+//   Zs = U  Ys  (P x 32)        warps stride over the 8-row tiles of U; accumulators are scattered straight from
+//                               the fragments through the inverse permutation:  L_tgt[perm[m]] += Zs[m]
+// Operators are stored in DMMA fragment order, zero padded: frag(mt, ks)[lane] = Op[mt*8 + lane/4][ks*4 + lane%4],
+// so every A fragment is one coalesced 256-byte load shared by all warps through L1.
+struct M2LGroupDev {  // one (level, reference vector) group of the fused M2L launch
+  int cta_begin;        // first CTA of the group
+  int rank_pad;
+  long long entry_off;  // into the entry arrays
+  long long n_entries;
+  long long v_off, u_off;  // operator pool offsets (fragment order)
+};
+
+template <bool COMPRESSED>
+__global__ void __launch_bounds__(256, 2) k_m2l(const M2LGroupDev *groups, int n_groups, const int *e_tgt_all,
+                                                const int *e_src_all, const int *e_perm_all, const double *pool,
+                                                const int *perm_tab, int P, int P4, int Pp, int nrhs,
+                                                const uint8_t *flag, const double *mult, double *loc) {
+  // all levels and reference vectors run in ONE launch: M2L at different levels is independent
+  int glo = 0, ghi = n_groups;
+  while (ghi - glo > 1) {
+    const int mid = (glo + ghi) >> 1;
+    if (groups[mid].cta_begin <= (int)blockIdx.x) glo = mid; else ghi = mid;
+  }
+  const M2LGroupDev g = groups[glo];
+  const int *e_tgt = e_tgt_all + g.entry_off, *e_src = e_src_all + g.entry_off, *e_perm = e_perm_all + g.entry_off;
+  const size_t n_entries = (size_t)g.n_entries;
+  const int rank_pad = g.rank_pad;
+  const double *VtF = pool + g.v_off, *UF = pool + g.u_off;
+  const unsigned cta = blockIdx.x - g.cta_begin;
   extern __shared__ double sm[];
-  const int tid = threadIdx.x, nt = blockDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t ncols = n_entries * (size_t)nrhs;
-  const size_t col0 = (size_t)blockIdx.x * NC;
-  const int nc = (int)min((size_t)NC, ncols - col0);
-  double *Xs = sm;                                   // P x NC  (row j, column c)
-  double *Ys = VtT ? Xs + (size_t)P * NC : Xs;       // rank_pad x NC
-  __shared__ int s_tgt[64], s_rhs[64], s_perm[64], s_src[64];
+  const size_t col0 = (size_t)cta * kM2LCols;
+  const int nc = (int)min((size_t)kM2LCols, ncols - col0);
+  double *Xs = sm;                                        // [32][Pp]
+  double *Ys = Xs + (size_t)kM2LCols * Pp;                // [rank_pad][36]
+  double *Yh = Ys + (size_t)rank_pad * kM2LColsPad;       // second half of the split reduction
+  __shared__ int s_tgt[kM2LCols], s_rhs[kM2LCols], s_perm[kM2LCols], s_src[kM2LCols];
   __shared__ int s_any;
   if (tid == 0) s_any = 0;
   __syncthreads();
-  if (tid < NC) {
-    int tg = -1, sr = -1, pm = 0, rh = 0;
+  if (tid < kM2LCols) {
+    int tg = -1, sr = 0, pm = 0, rh = 0;
     if (tid < nc) {
       const size_t col = col0 + tid;
       const size_t e = col / nrhs;
@@ -375,81 +413,94 @@ __global__ void __launch_bounds__(256) k_m2l(const int *e_tgt, const int *e_src,
   }
   __syncthreads();
   if (!s_any) return;
-  // stage permuted multipoles
-  for (int c = 0; c < NC; ++c) {
+  // stage permuted multipoles (zero padding up to P4 and for idle columns); 4 gathers in flight per lane
+  for (int c = warp; c < kM2LCols; c += 8) {
+    double *dst = Xs + (size_t)c * Pp;
     if (s_tgt[c] >= 0) {
       const double *src = mult + ((size_t)s_src[c] * nrhs + s_rhs[c]) * P;
       const int *pm = perm_tab + (size_t)s_perm[c] * P;
-      for (int j = tid; j < P; j += nt) Xs[(size_t)j * NC + c] = src[pm[j]];
+      for (int j0 = lane; j0 < P4; j0 += 128) {
+        int idx[4];
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) idx[u] = (j0 + 32 * u < P) ? __ldg(pm + j0 + 32 * u) : -1;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = idx[u] >= 0 ? __ldg(src + idx[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (j0 + 32 * u < P4) dst[j0 + 32 * u] = v[u];
+      }
     } else {
-      for (int j = tid; j < P; j += nt) Xs[(size_t)j * NC + c] = 0.0;
+      for (int j = lane; j < P4; j += 32) dst[j] = 0.0;
     }
   }
   __syncthreads();
-  const int ctiles = NC / 4;
-  if (VtT) {  // Ys = Vt * Xs with 2 x 4 register tiles
-    const int ktiles = rank_pad / 2;
-    for (int tile = tid; tile < ktiles * ctiles; tile += nt) {
-      const int kt = tile % ktiles, ct = tile / ktiles;
-      double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-      const double *vp = VtT + kt * 2;
-      const double *xp = Xs + ct * 4;
-      for (int j = 0; j < P; ++j) {
-        const double2 v = *reinterpret_cast<const double2 *>(vp + (size_t)j * rank_pad);
-        const double2 x0 = *reinterpret_cast<const double2 *>(xp + (size_t)j * NC);
-        const double2 x1 = *reinterpret_cast<const double2 *>(xp + (size_t)j * NC + 2);
-        acc[0][0] += v.x * x0.x; acc[0][1] += v.x * x0.y; acc[0][2] += v.x * x1.x; acc[0][3] += v.x * x1.y;
-        acc[1][0] += v.y * x0.x; acc[1][1] += v.y * x0.y; acc[1][2] += v.y * x1.x; acc[1][3] += v.y * x1.y;
+  const int ar = lane >> 2, ak = lane & 3;  // fragment coordinates
+  if (COMPRESSED) {
+    // ---- Ys = Vt * Xs: warp -> column tile nt, reduction half kh; rank tiles in chunks of 4
+    const int nt = warp & 3, kh = warp >> 2;
+    const int mtiles = rank_pad >> 3;
+    const int ksteps = P4 >> 2;
+    const int k_begin = kh ? (ksteps >> 1) : 0, k_end = kh ? ksteps : (ksteps >> 1);
+    const double *bx = Xs + (size_t)(nt * 8 + ar) * Pp + ak;
+    double *yo = kh ? Yh : Ys;
+    for (int m0 = 0; m0 < mtiles; m0 += kM2LChunk) {
+      double acc[kM2LChunk][2];
+#pragma unroll
+      for (int i = 0; i < kM2LChunk; ++i) acc[i][0] = acc[i][1] = 0.0;
+      const double *af = VtF + ((size_t)m0 * ksteps) * 32 + lane;
+#pragma unroll 4
+      for (int ks = k_begin; ks < k_end; ++ks) {
+        const double b = bx[ks * 4];
+#pragma unroll
+        for (int i = 0; i < kM2LChunk; ++i)
+          if (m0 + i < mtiles) dmma884(acc[i][0], acc[i][1], __ldg(af + ((size_t)i * ksteps + ks) * 32), b);
       }
-      for (int a = 0; a < 2; ++a)
-        for (int b = 0; b < 4; ++b) Ys[(size_t)(kt * 2 + a) * NC + ct * 4 + b] = acc[a][b];
+#pragma unroll
+      for (int i = 0; i < kM2LChunk; ++i)
+        if (m0 + i < mtiles) {
+          double *y = yo + (size_t)((m0 + i) * 8 + ar) * kM2LColsPad + nt * 8 + ak * 2;
+          y[0] = acc[i][0];
+          y[1] = acc[i][1];
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < rank_pad * kM2LCols; e += 256) {
+      const int k = e / kM2LCols, c = e % kM2LCols;
+      Ys[(size_t)k * kM2LColsPad + c] += Yh[(size_t)k * kM2LColsPad + c];
     }
     __syncthreads();
   }
-  // Zs = U * Ys with 4 x 4 register tiles, scattered through the inverse permutation
-  const int rk = VtT ? rank_pad : P;
-  const int mtiles = (P + 3) / 4;
-  for (int tile = tid; tile < mtiles * ctiles; tile += nt) {
-    const int mt = tile % mtiles, ct = tile / mtiles;
-    const int m0 = mt * 4;
-    double acc[4][4];
+  // ---- Zs = U * Ys (or K * Xs), scattered from the accumulator fragments
+  const int mt_total = (P + 7) >> 3;
+  const int ksteps2 = (COMPRESSED ? rank_pad : P4) >> 2;
+  for (int mt = warp; mt < mt_total; mt += 8) {
+    double z[4][2];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int i = 0; i < 4; ++i) z[i][0] = z[i][1] = 0.0;
+    const double *af = UF + ((size_t)mt * ksteps2) * 32 + lane;
+#pragma unroll 2
+    for (int ks = 0; ks < ksteps2; ++ks) {
+      const double a = __ldg(af + (size_t)ks * 32);
 #pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-    const double *yp = Ys + ct * 4;
-    if (m0 + 3 < P) {
-      for (int k = 0; k < rk; ++k) {
-        const double *up = UT + (size_t)k * P + m0;
-        const double u0 = up[0], u1 = up[1], u2 = up[2], u3 = up[3];
-        const double2 y0 = *reinterpret_cast<const double2 *>(yp + (size_t)k * NC);
-        const double2 y1 = *reinterpret_cast<const double2 *>(yp + (size_t)k * NC + 2);
-        acc[0][0] += u0 * y0.x; acc[0][1] += u0 * y0.y; acc[0][2] += u0 * y1.x; acc[0][3] += u0 * y1.y;
-        acc[1][0] += u1 * y0.x; acc[1][1] += u1 * y0.y; acc[1][2] += u1 * y1.x; acc[1][3] += u1 * y1.y;
-        acc[2][0] += u2 * y0.x; acc[2][1] += u2 * y0.y; acc[2][2] += u2 * y1.x; acc[2][3] += u2 * y1.y;
-        acc[3][0] += u3 * y0.x; acc[3][1] += u3 * y0.y; acc[3][2] += u3 * y1.x; acc[3][3] += u3 * y1.y;
-      }
-    } else {
-      for (int k = 0; k < rk; ++k) {
-        const double *up = UT + (size_t)k * P;
-        const double2 y0 = *reinterpret_cast<const double2 *>(yp + (size_t)k * NC);
-        const double2 y1 = *reinterpret_cast<const double2 *>(yp + (size_t)k * NC + 2);
-        for (int a = 0; a < 4; ++a) {
-          const double u = (m0 + a < P) ? up[m0 + a] : 0.0;
-          acc[a][0] += u * y0.x; acc[a][1] += u * y0.y; acc[a][2] += u * y1.x; acc[a][3] += u * y1.y;
-        }
+      for (int nt = 0; nt < 4; ++nt) {
+        const double b = COMPRESSED ? Ys[(size_t)(ks * 4 + ak) * kM2LColsPad + nt * 8 + ar]
+                                    : Xs[(size_t)(nt * 8 + ar) * Pp + ks * 4 + ak];
+        dmma884(z[nt][0], z[nt][1], a, b);
       }
     }
+    const int m = mt * 8 + ar;
+    if (m < P) {
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int c = ct * 4 + b;
-      const int tg = s_tgt[c];
-      if (tg < 0) continue;
-      double *dst = loc + ((size_t)tg * nrhs + s_rhs[c]) * P;
-      const int *pm = perm_tab + (size_t)s_perm[c] * P;
+      for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
-        if (m0 + a < P) atomicAdd(dst + pm[m0 + a], acc[a][b]);  // L[i] += y[inv[i]]  <=>  L[perm[m]] += y[m]
+        for (int h = 0; h < 2; ++h) {
+          const int c = nt * 8 + ak * 2 + h;
+          const int tg = s_tgt[c];
+          if (tg < 0) continue;
+          const int *pm = perm_tab + (size_t)s_perm[c] * P;
+          atomicAdd(loc + ((size_t)tg * nrhs + s_rhs[c]) * P + __ldg(pm + m), z[nt][h]);  // L[perm[m]] += y[m]
+        }
     }
   }
 }

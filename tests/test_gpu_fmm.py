@@ -204,7 +204,7 @@ def test_strided_inputs_and_single_column_shapes():
     va = a.evaluate(w, pts)
     vb = b.evaluate(np.ascontiguousarray(w), np.ascontiguousarray(pts))
     assert va.shape == (n, 2)
-    assert np.array_equal(va, vb)
+    assert H.rel_l2(va, vb) <= 1e-13      # M2L accumulates with atomics: summation order varies at round-off
     w1 = np.random.default_rng(43).random(n)  # 1-D weights -> 1-D result (python_bindings.rs:39-51)
     a.set_weights(w1)
     assert a.evaluate(w1, pts).shape == (n,)
