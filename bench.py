@@ -101,6 +101,27 @@ def cpu_baseline(pts, w, leaf_fraction):
     return ff, build_s, fast.lib().orc_num_threads()
 
 
+def full_fit(n):
+    """second half of BASELINE.json's metric: full RBF fit wall time (config C3: clustered 3-D points, linear
+    kernel, tol 1e-6 relative, default Params), through RBFInterpolator with host buffers."""
+    import ferreus_rbf_rs_b200 as fb
+    rng = np.random.default_rng(0)
+    centres = rng.random((64, 3))
+    pts = centres[rng.integers(0, 64, n)] + 0.02 * rng.standard_normal((n, 3))
+    x, y, z = pts[:, 0], pts[:, 1], pts[:, 2]
+    vals = 0.75 * np.exp(-((9 * x - 2) ** 2 + (9 * y - 2) ** 2 + (9 * z - 2) ** 2) / 4) + \
+        0.5 * np.exp(-((9 * x - 7) ** 2 + (9 * y - 3) ** 2 + (9 * z - 5) ** 2) / 4)
+    ic = fb.interpolant_config
+    t0 = time.perf_counter()
+    model = fb.RBFInterpolator(pts, vals, ic.InterpolantSettings(ic.RBFKernelType.Linear))
+    wall = time.perf_counter() - t0
+    info = model.info()
+    return {"workload": f"ferreus_rbf 3D global fit, linear kernel, tol 1e-6, N={n} clustered (64 Gaussian blobs)",
+            "wall_s": wall, "setup_s": info["setup_seconds"], "solve_s": info["solve_seconds"],
+            "iterations": info["iterations"], "fmm_matvecs": info["matvecs"], "ddm_domains": info["ddm_domains"],
+            "final_relative_residual": info["last_residual"]}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port, all host threads) on the same workload."""
     rank = int(os.environ.get("RANK", "0"))
@@ -146,6 +167,7 @@ def main():
     ap.add_argument("--n", type=int, default=1_000_000)
     ap.add_argument("--cpu-leaf-fraction", type=float, default=0.02)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fit", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -219,10 +241,52 @@ def main():
     e2e_s = time.perf_counter() - e0
     clocks = sampler.finish()
 
-    tms = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    # ---- strong scaling (extra, N > 1): ONE shared cloud, Morton-contiguous leaf ranges per rank, result
+    #      slices all-gathered over NCCL (ferreus_rbf_rs_b200/sharding.py)
+    strong = None
+    if world > 1:
+        from ferreus_rbf_rs_b200.sharding import ShardedMatvec
+        spts, sw = make_workload(n, 1000)
+        stree = fb.FmmTree(spts, ORDER, fb.KernelParams(fb.FmmKernelType.LinearRbf), True, True)
+        sm = ShardedMatvec(stree, rank, world)
+        stree.set_target_subset(sm.my_rows)
+        stree.upload_weights(sw)
+        sizes = [r.size for r in sm.rows]
+        pad = max(sizes)
+        send = torch.zeros(pad, dtype=torch.float64, device="cuda")
+        recv = torch.zeros(pad * world, dtype=torch.float64, device="cuda")
+
+        class _Dev:
+            def __init__(self, ptr, cnt):
+                self.__cuda_array_interface__ = {"shape": (cnt,), "typestr": "<f8", "data": (ptr, False),
+                                                 "version": 3, "strides": None}
+
+        def strong_step():
+            stree.matvec_resident()
+            ptr, rows, cols = stree.result_device()
+            send[: rows * cols].copy_(torch.as_tensor(_Dev(ptr, rows * cols), device="cuda"))
+            dist.all_gather_into_tensor(recv, send)
+
+        for _ in range(args.warmup):
+            strong_step()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0 = time.perf_counter()
+        for _ in range(args.steps):
+            strong_step()
+        barrier()
+        strong_s = time.perf_counter() - s0
+        full = torch.zeros(n, dtype=torch.float64, device="cuda")
+        for r in range(world):
+            full[torch.from_numpy(sm.rows[r]).cuda()] = recv[r * pad: r * pad + sizes[r]]
+        strong = {"wall_ms_per_step": strong_s / args.steps * 1e3, "rows_per_rank": sizes,
+                  "checksum": float(full.sum().item())}
+
+    tms = torch.tensor([total_ms, e2e_s * 1e3, (strong or {}).get("wall_ms_per_step", 0.0)], dtype=torch.float64,
+                       device="cuda")
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    total_ms_max, e2e_ms_max = [float(v) for v in tms.tolist()]
+    total_ms_max, e2e_ms_max, strong_ms_max = [float(v) for v in tms.tolist()]
 
     if rank == 0:
         ms_per_step = total_ms_max / args.steps
@@ -266,6 +330,14 @@ def main():
                 "tree": {"build_s": build_s, "cells": info["n_cells"], "leaves": info["n_leaves"],
                          "depth": info["depth"]},
                 "wall_s_timed_region": wall_s}
+        if strong is not None:
+            line["strong_scaling"] = {
+                "what": "one shared N-point cloud, tree replicated, targets split by Morton-contiguous leaf ranges "
+                        "balanced by work, result slices all-gathered over NCCL (wall clock incl. the collective)",
+                "ms_per_matvec": strong_ms_max, "value": n / (strong_ms_max * 1e-3) / 1e6, "unit": "Mpts/s",
+                "rows_per_rank": strong["rows_per_rank"]}
+        if world == 1 and not args.no_fit:
+            line["fit"] = full_fit(n)
         if world == 1 and not args.no_cpu_baseline:
             ff, cpu_build_s, cores = cpu_baseline(pts, w, args.cpu_leaf_fraction)
             sec, detail = ff.timed_matvec_estimate(w, args.cpu_leaf_fraction)

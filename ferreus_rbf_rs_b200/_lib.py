@@ -108,6 +108,10 @@ SIGNATURES = {
     "fb_tree_dump_list": (C.c_int, [C.c_void_p, C.c_int, _u64p, _u64p]),
     "fb_tree_m2l_rank": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "fb_tree_m2l_operator": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp]),
+    "fb_tree_leaf_work": (C.c_int, [C.c_void_p, _u64p, _dp]),
+    "fb_tree_morton_order": (C.c_int, [C.c_void_p, _u64p]),
+    "fb_tree_set_target_subset": (C.c_int, [C.c_void_p, _u64p, _sz]),
+    "fb_tree_result_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), _u64p, _u64p]),
     "fb_ops_new": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(FbKernelParams), C.c_int, C.c_double,
                              C.POINTER(C.c_void_p)]),
     "fb_ops_free": (None, [C.c_void_p]),

@@ -211,9 +211,37 @@ class FmmTree:
         self._check(self._lib.fb_tree_matvec_resident(self._h))
 
     def download_result(self):
-        out = np.zeros((self._n, self._nrhs))
+        out = np.zeros((getattr(self, "_subset_n", None) or self._n, self._nrhs))
         self._check(self._lib.fb_tree_download_result(self._h, _lib.dptr(out), self._nrhs, 1))
         return _to_numpy(out)
+
+    # -- sharding by Morton-contiguous leaf ranges (include/ferreus_b200.h, multi-GPU section) ---------
+    def leaf_work(self):
+        nl = self.info()["n_leaves"]
+        ptr = np.zeros(nl + 1, dtype=np.uint64)
+        work = np.zeros(nl)
+        self._check(self._lib.fb_tree_leaf_work(self._h, ptr.ctypes.data_as(C.POINTER(C.c_uint64)), _lib.dptr(work)))
+        return ptr.astype(np.int64), work
+
+    def morton_order(self):
+        order = np.zeros(self._n, dtype=np.uint64)
+        self._check(self._lib.fb_tree_morton_order(self._h, order.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return order.astype(np.int64)
+
+    def set_target_subset(self, indices):
+        if indices is None or len(indices) == 0:
+            self._check(self._lib.fb_tree_set_target_subset(self._h, None, 0))
+            self._subset_n = None
+            return
+        idx = np.ascontiguousarray(indices, dtype=np.uint64)
+        self._check(self._lib.fb_tree_set_target_subset(self._h, idx.ctypes.data_as(C.POINTER(C.c_uint64)), idx.size))
+        self._subset_n = idx.size
+
+    def result_device(self):
+        """(device pointer, rows, cols) of the last resident matvec result"""
+        ptr, rows, cols = C.c_void_p(), C.c_uint64(), C.c_uint64()
+        self._check(self._lib.fb_tree_result_device(self._h, C.byref(ptr), C.byref(rows), C.byref(cols)))
+        return ptr.value, rows.value, cols.value
 
     def last_matvec_ms(self):
         ms = C.c_double(0.0)

@@ -3,7 +3,9 @@
 
 #include <algorithm>
 #include <array>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <cub/cub.cuh>
 
@@ -63,6 +65,14 @@ void fb_tree::build(const double *points, size_t n_, int dim_, ptrdiff_t rs, ptr
   }
   FB_REQUIRE(fparams.compression_type >= 0 && fparams.compression_type <= 2, "unknown compression type");
 
+  const bool verbose = std::getenv("FB_TIMING") != nullptr;
+  auto t_lap = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (verbose)
+      fprintf(stderr, "[fb_tree] %-28s %8.3f s\n", what,
+              std::chrono::duration<double>(std::chrono::steady_clock::now() - t_lap).count());
+    t_lap = std::chrono::steady_clock::now();
+  };
   FB_CUDA(cudaGetDevice(&device));
   FB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   for (auto &e : ev) FB_CUDA(cudaEventCreate(&e));
@@ -131,14 +141,17 @@ void fb_tree::build(const double *points, size_t n_, int dim_, ptrdiff_t rs, ptr
     throw Error(FB_ERR_INVALID_ARGUMENT,
                 "source point at row " + std::to_string(h_err) + " lies outside the given tree extents", h_err);
 
+  lap("copy + device sort");
   // ---- host: adaptive/uniform subdivision over the sorted codes + interaction lists
   ht.build((const uint64_t *)h_codes.data(), n, dim, center, radius, (size_t)fparams.max_points_per_cell, !sparse,
            adaptive != 0);
   const size_t nc = ht.ncells();
   const int nl = (int)ht.leaves.size();
 
+  lap("tree + lists (host)");
   // ---- host: operators
   ops.build(order, dim, radius, ht.depth, kp, fparams.compression_type, fparams.epsilon);
+  lap("operators (host)");
 
   // ---- upload cells
   std::vector<double> ccx(nc), ccy(nc), ccz(nc), chalf(nc);
@@ -366,6 +379,7 @@ void fb_tree::build(const double *points, size_t n_, int dim_, ptrdiff_t rs, ptr
     FB_REQUIRE(m2l_smem <= 220 * 1024, "interpolation order too large for the M2L shared-memory tile");
   }
   FB_CUDA(cudaStreamSynchronize(stream));
+  lap("list packing + upload");
   have_weights = have_locals = false;
 }
 
@@ -892,9 +906,10 @@ int fb_tree_matvec_resident(fb_tree *t) {
     FB_CUDA(cudaEventRecord(t->ev_mv[0], t->stream));
     t->sort_weights();
     t->upward();
-    TargetSet ts = t->source_target_set();
+    TargetSet ts = t->have_subset ? t->ts_subset : t->source_target_set();
     t->downward(ts.cell_flag);
     t->leaf_pass(ts, false);
+    t->last_out_rows = ts.m;
     FB_CUDA(cudaEventRecord(t->ev_mv[1], t->stream));
     FB_CUDA(cudaStreamSynchronize(t->stream));
     float mv_ms = 0;
@@ -908,8 +923,72 @@ int fb_tree_download_result(fb_tree *t, double *out_vals, ptrdiff_t o_rs, ptrdif
   return guarded([&] {
     FB_REQUIRE(t && out_vals, "null argument");
     FB_CUDA(cudaSetDevice(t->device));
-    t->fetch_output(t->n, false, out_vals, nullptr, o_rs, o_cs);
+    t->fetch_output(t->have_subset ? t->ts_subset.m : t->n, false, out_vals, nullptr, o_rs, o_cs);
   });
+}
+
+int fb_tree_leaf_work(const fb_tree *t, uint64_t *leaf_ptr, double *work) {
+  if (!t) return FB_ERR_INVALID_ARGUMENT;
+  const fb::HostTree &ht = t->ht;
+  const size_t nl = ht.leaves.size();
+  // M2L entries of every cell, accumulated down the tree so a leaf carries its ancestors' share
+  std::vector<double> v_share(ht.ncells(), 0.0);
+  for (size_t c = 1; c < ht.ncells(); ++c) {
+    const double own = (double)(ht.v_ptr[c + 1] - ht.v_ptr[c]) * 4.0 * 24.0 * t->P;  // ~4 r P flops per entry
+    const int nch = std::max(1, ht.child_ptr[c + 1] - ht.child_ptr[c]);
+    v_share[c] += own;
+    for (int k = ht.child_ptr[c]; k < ht.child_ptr[c + 1]; ++k) v_share[ht.child_idx[k]] += v_share[c] / nch;
+  }
+  for (size_t l = 0; l < nl; ++l) {
+    const int c = ht.leaves[l];
+    if (leaf_ptr) leaf_ptr[l] = (uint64_t)ht.pt_begin[c];
+    if (work) {
+      const double nt = ht.pt_end[c] - ht.pt_begin[c];
+      double nsrc = 0;
+      for (long long e = ht.u_ptr[c]; e < ht.u_ptr[c + 1]; ++e) nsrc += ht.pt_end[ht.u_idx[e]] - ht.pt_begin[ht.u_idx[e]];
+      const double nw = (double)(ht.w_ptr[c + 1] - ht.w_ptr[c]);
+      double nx = 0;
+      for (long long e = ht.x_ptr[c]; e < ht.x_ptr[c + 1]; ++e) nx += ht.pt_end[ht.x_idx[e]] - ht.pt_begin[ht.x_idx[e]];
+      work[l] = 12.0 * (nt * (nsrc + nw * t->P) + nx * t->P) + v_share[c] + 1.0;
+    }
+  }
+  if (leaf_ptr) leaf_ptr[nl] = (uint64_t)t->n;
+  return FB_OK;
+}
+
+int fb_tree_morton_order(const fb_tree *t, uint64_t *order) {
+  if (!t || !order) return FB_ERR_INVALID_ARGUMENT;
+  return guarded([&] {
+    std::vector<uint32_t> perm(t->n);
+    FB_CUDA(cudaSetDevice(t->device));
+    FB_CUDA(cudaMemcpy(perm.data(), t->d_perm.p, t->n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < t->n; ++i) order[i] = perm[i];
+  });
+}
+
+int fb_tree_set_target_subset(fb_tree *t, const uint64_t *idx, size_t n_idx) {
+  return guarded([&] {
+    FB_REQUIRE(t, "null tree");
+    FB_CUDA(cudaSetDevice(t->device));
+    if (n_idx == 0 || idx == nullptr) {
+      t->have_subset = false;
+      return;
+    }
+    FB_REQUIRE(n_idx < (1ull << 31), "subset too large");
+    t->d_subset_idx.reserve(n_idx);
+    FB_CUDA(cudaMemcpyAsync(t->d_subset_idx.p, idx, n_idx * sizeof(uint64_t), cudaMemcpyHostToDevice, t->stream));
+    t->ts_subset = t->subset_target_set_dev(t->d_subset_idx.p, n_idx, t->tb_subset);
+    FB_CUDA(cudaStreamSynchronize(t->stream));
+    t->have_subset = true;
+  });
+}
+
+int fb_tree_result_device(fb_tree *t, const double **dev_ptr, uint64_t *n_rows, uint64_t *n_cols) {
+  if (!t || !dev_ptr) return FB_ERR_INVALID_ARGUMENT;
+  *dev_ptr = t->d_out.p;
+  if (n_rows) *n_rows = t->last_out_rows;
+  if (n_cols) *n_cols = (uint64_t)t->nrhs;
+  return FB_OK;
 }
 
 int fb_tree_last_matvec_ms(fb_tree *t, double *ms_out) {

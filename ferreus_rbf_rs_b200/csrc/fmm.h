@@ -122,6 +122,11 @@ struct fb_tree {
   // general target set scratch
   fb::DBuf<double> d_t_user;
   fb::TargetBuffers tb_scratch;
+  fb::TargetBuffers tb_subset;          // persistent subset for sharded matvecs
+  fb::TargetSet ts_subset{};
+  fb::DBuf<unsigned long long> d_subset_idx;
+  bool have_subset = false;
+  size_t last_out_rows = 0;
   fb::DBuf<unsigned long long> d_err;
   fb::DBuf<unsigned char> d_cub;
   fb::DBuf<unsigned long long> d_idx64;

@@ -136,14 +136,29 @@ FB_HD void kernel_value_grad(double r2, const KParams &kp, double &val, double &
 
 #ifdef __CUDACC__
 // ---- device fast path ---------------------------------------------------------------------------
-// 1/sqrt(a) for a > 0 (normal): MUFU.RSQ64H seed (2^-22 relative) + one third-order refinement,
-// y <- y (1 + e/2 + 3e^2/8), e = 1 - a y^2.  ~1 ulp, branch-free (no IEEE slow path), 5 FP64 ops.
+// sqrt(a) and 1/sqrt(a) for a > 0 (normal): MUFU.RSQ64H seed y0 (~2^-21 relative: it reads the high word only)
+// refined with one third-order Goldschmidt step — full double precision (~1 ulp), branch-free (no IEEE slow
+// path), 5 FP64 operations + one integer add (the halving of y0 is an exponent decrement on the ALU pipe):
+//   r = a y0, h = y0 / 2, e = 1/2 - r h (= (1 - a y0^2) / 2), c = 1 + 3e/2, sqrt ~= r + (r e) c, rsqrt ~= y0 + (y0 e) c
+struct SqrtPair {
+  double r, y;  // sqrt(a), 1/sqrt(a)
+};
+__device__ __forceinline__ double fast_sqrt(double a) {
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(a));
+  const double h = __hiloint2double(__double2hiint(y0) - 0x00100000, __double2loint(y0));
+  const double r = a * y0;
+  const double e = fma(-r, h, 0.5);
+  const double c = fma(1.5, e, 1.0);
+  return fma(r * e, c, r);
+}
 __device__ __forceinline__ double fast_rsqrt(double a) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-  const double e = fma(a, -(y * y), 1.0);
-  const double p = fma(e, 0.375, 0.5);
-  return fma(p, y * e, y);
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(a));
+  const double h = __hiloint2double(__double2hiint(y0) - 0x00100000, __double2loint(y0));
+  const double e = fma(-(a * y0), h, 0.5);
+  const double c = fma(1.5, e, 1.0);
+  return fma(y0 * e, c, y0);
 }
 // true when a (a sum of squares, sign bit clear) is a normal positive number: integer test on the high word
 __device__ __forceinline__ bool pos_normal(double a) { return __double2hiint(a) >= 0x00100000; }
@@ -153,13 +168,13 @@ template <int FAM>
 __device__ __forceinline__ double kernel_value_dev(double r2, const KParams &kp) {
   const bool ok = pos_normal(r2);
   if (FAM == KF_LINEAR) {
-    const double r = r2 * fast_rsqrt(r2);
+    const double r = fast_sqrt(r2);
     return ok ? -r : 0.0;
   } else if (FAM == KF_TPS) {  // r^2 ln r = r2 * ln(r2) / 2
     const double v = (0.5 * r2) * log(r2);
     return (r2 >= kEps * kEps) ? v : 0.0;
   } else if (FAM == KF_CUBIC) {
-    const double r = r2 * fast_rsqrt(r2);
+    const double r = fast_sqrt(r2);
     return ok ? r2 * r : 0.0;
   } else if (FAM == KF_SPH) {
     const double sr2 = kp.s2 * r2;

@@ -7,6 +7,7 @@
 //   fast_matrix_vector_product       ferreus_rbf/src/rbf.rs:1338-1379
 //   RBFInterpolator fit / evaluate   ferreus_rbf/src/rbf.rs:317-582, 676-924, 1180-1270
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -730,6 +731,12 @@ void fr_model::fit() {
 
   std::unique_ptr<fb_tree, void (*)(fb_tree *)> tree(nullptr, fb_tree_free);
   const bool naive = n < params.naive_solve_threshold;
+  const bool verbose = std::getenv("FB_TIMING") != nullptr;
+  auto lap = [&](const char *what, clk::time_point &t0) {
+    if (verbose) fprintf(stderr, "[fr_fit] %-28s %8.3f s\n", what, std::chrono::duration<double>(clk::now() - t0).count());
+    t0 = clk::now();
+  };
+  auto t_lap = clk::now();
   if (naive) {  // single dense domain (rbf.rs:423-454)
     LevelHost lh;
     lh.point_indices.resize(n);
@@ -743,7 +750,9 @@ void fr_model::fit() {
     ddm.push_back(std::move(lh));
   } else {
     tree.reset(make_tree(true, nullptr));  // adaptive, sparse, own extents (rbf.rs:456-467)
+    lap("fmm tree + operators", t_lap);
     ddm = build_ddm(points.data(), n, dim, st, params);
+    lap("ddm hierarchy (host)", t_lap);
   }
   cudaStream_t stream = nullptr;
   std::unique_ptr<DeviceSolver> solver(new DeviceSolver(*this, tree.get()));
@@ -767,7 +776,11 @@ void fr_model::fit() {
       S.Qp.upload(Qm, stream);
       S.proj.reserve(m);
     }
-    for (size_t l = 0; l < ddm.size(); ++l) S.build_level(ddm[l], l + 1 == ddm.size(), stream);
+    lap("monomials / thin Q / upload", t_lap);
+    for (size_t l = 0; l < ddm.size(); ++l) {
+      S.build_level(ddm[l], l + 1 == ddm.size(), stream);
+      lap("factorise level", t_lap);
+    }
     info.ddm_levels = ddm.size();
     for (size_t l = 0; l < ddm.size() && l < 8; ++l) info.ddm_domains[l] = ddm[l].domains.size();
     const auto t_setup = clk::now();

@@ -363,47 +363,63 @@ std::vector<LevelHost> build_ddm(const double *pts, size_t n, int dim, const Set
       root.extents[d] = lo;
       root.extents[dim + d] = hi;
     }
-    std::deque<DomainHost> queue;
-    queue.push_back(std::move(root));
-    while (!queue.empty()) {
-      DomainHost cur = std::move(queue.front());
-      queue.pop_front();
-      const size_t nd = cur.idx.size();
-      double len[3] = {0, 0, 0};
-      for (int d = 0; d < dim; ++d) {
-        double lo = pts[cur.idx[0] * dim + d], hi = lo;
-        for (int64_t i : cur.idx) {
-          lo = std::min(lo, pts[i * dim + d]);
-          hi = std::max(hi, pts[i * dim + d]);
+    // Bisection, generation by generation: the reference pops a FIFO deque (domain_decomposition.rs:93-162), so a
+    // generation is processed completely, in order, before the next one; children and leaves are appended in
+    // that same order here, while the domains of one generation are split in parallel.
+    std::vector<DomainHost> gen;
+    gen.push_back(std::move(root));
+    while (!gen.empty()) {
+      const size_t ng = gen.size();
+      std::vector<DomainHost> lefts(ng), rights(ng);
+      std::vector<uint8_t> split_more(ng, 0);
+#pragma omp parallel for schedule(dynamic, 1)
+      for (long gi = 0; gi < (long)ng; ++gi) {
+        DomainHost &cur = gen[gi];
+        const size_t nd = cur.idx.size();
+        double len[3] = {0, 0, 0};
+        for (int d = 0; d < dim; ++d) {
+          double lo = pts[cur.idx[0] * dim + d], hi = lo;
+          for (int64_t i : cur.idx) {
+            lo = std::min(lo, pts[i * dim + d]);
+            hi = std::max(hi, pts[i * dim + d]);
+          }
+          len[d] = hi - lo;
         }
-        len[d] = hi - lo;
+        const int axis = argmax_first_positive(len, dim);
+        // stable argsort by the axis coordinate == sort of (coordinate, position) pairs
+        std::vector<std::pair<double, int>> ord(nd);
+        for (size_t k = 0; k < nd; ++k) ord[k] = {pts[cur.idx[k] * dim + axis], (int)k};
+        std::sort(ord.begin(), ord.end());
+        const size_t mid = nd / 2;
+        DomainHost &left = lefts[gi], &right = rights[gi];
+        left.idx.resize(mid);
+        right.idx.resize(nd - mid);
+        for (size_t k = 0; k < mid; ++k) left.idx[k] = cur.idx[ord[k].second];
+        for (size_t k = mid; k < nd; ++k) right.idx[k - mid] = cur.idx[ord[k].second];
+        const double mid_coord = ord[mid].first;
+        std::sort(left.idx.begin(), left.idx.end());
+        std::sort(right.idx.begin(), right.idx.end());
+        left.extents = cur.extents;
+        left.extents[axis + dim] = mid_coord;
+        right.extents = cur.extents;
+        right.extents[axis] = mid_coord;
+        split_more[gi] = ((double)nd + (double)nd * p.overlap_quota >= 2.0 * (double)p.leaf_threshold) ? 1 : 0;
+        if (!split_more[gi]) {
+          left.mask.assign(left.idx.size(), 1);
+          right.mask.assign(right.idx.size(), 1);
+        }
       }
-      const int axis = argmax_first_positive(len, dim);
-      std::vector<int> ord(nd);
-      std::iota(ord.begin(), ord.end(), 0);
-      std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) {
-        return pts[cur.idx[a] * dim + axis] < pts[cur.idx[b] * dim + axis];
-      });
-      const size_t mid = nd / 2;
-      DomainHost left, right;
-      for (size_t k = 0; k < mid; ++k) left.idx.push_back(cur.idx[ord[k]]);
-      for (size_t k = mid; k < nd; ++k) right.idx.push_back(cur.idx[ord[k]]);
-      const double mid_coord = pts[cur.idx[ord[mid]] * dim + axis];
-      std::sort(left.idx.begin(), left.idx.end());
-      std::sort(right.idx.begin(), right.idx.end());
-      left.extents = cur.extents;
-      left.extents[axis + dim] = mid_coord;
-      right.extents = cur.extents;
-      right.extents[axis] = mid_coord;
-      if ((double)nd + (double)nd * p.overlap_quota >= 2.0 * (double)p.leaf_threshold) {
-        queue.push_back(std::move(left));
-        queue.push_back(std::move(right));
-      } else {
-        left.mask.assign(left.idx.size(), 1);
-        right.mask.assign(right.idx.size(), 1);
-        level.domains.push_back(std::move(left));
-        level.domains.push_back(std::move(right));
+      std::vector<DomainHost> next_gen;
+      for (size_t gi = 0; gi < ng; ++gi) {
+        if (split_more[gi]) {
+          next_gen.push_back(std::move(lefts[gi]));
+          next_gen.push_back(std::move(rights[gi]));
+        } else {
+          level.domains.push_back(std::move(lefts[gi]));
+          level.domains.push_back(std::move(rights[gi]));
+        }
       }
+      gen.swap(next_gen);
     }
     const size_t nl = level.domains.size();
     const size_t num_coarse =

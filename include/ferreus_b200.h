@@ -143,6 +143,18 @@ int fb_tree_m2l_rank(const fb_tree *t, int level, int ref);
 int fb_tree_m2l_operator(const fb_tree *t, int level, int ref, double *u_or_null, double *vt_or_null);
 
 
+/* ---- multi-GPU sharding by Morton-contiguous leaf ranges ---------------------------------
+ * The tree is replicated on every rank; a rank evaluates only the targets of its own contiguous range of
+ * leaves.  fb_tree_leaf_work returns the leaves in Morton order with an estimate of their evaluation work
+ * (direct pairs + M2L entries of the leaf and its ancestors), fb_tree_morton_order the source rows in that
+ * order; fb_tree_set_target_subset makes fb_tree_matvec_resident evaluate at that subset only (n_idx = 0
+ * restores all sources) and fb_tree_result_device exposes the device result buffer (rows in subset order) so it
+ * can be handed to NCCL without a host round trip.                                                          */
+int fb_tree_leaf_work(const fb_tree *t, uint64_t *leaf_ptr /* n_leaves+1 */, double *work /* n_leaves */);
+int fb_tree_morton_order(const fb_tree *t, uint64_t *order /* n_points */);
+int fb_tree_set_target_subset(fb_tree *t, const uint64_t *idx, size_t n_idx);
+int fb_tree_result_device(fb_tree *t, const double **dev_ptr, uint64_t *n_rows, uint64_t *n_cols);
+
 /* ---- host-only operator precompute (no GPU needed): used by the CPU test-suite to check the
  * Chebyshev / ACA / SVD restatement (chebyshev.rs:650-814, aca.rs:23-247) against the oracle. ---- */
 typedef struct fb_ops fb_ops;

@@ -210,3 +210,61 @@ def test_strided_inputs_and_single_column_shapes():
     assert a.evaluate(w1, pts).shape == (n,)
     assert a.source_points().shape == (n, 3)
     assert np.array_equal(a.source_points(), pts)
+
+
+def test_morton_sharding_matches_full_matvec():
+    """multi-GPU path on one device: work-balanced Morton-contiguous ranges, each evaluated as a target subset
+    (resident path), reassemble and compare with the unsharded matvec."""
+    from ferreus_rbf_rs_b200.sharding import ShardedMatvec
+    n = 20000
+    pts = H.make_points(n, 3, "clustered", seed=51)
+    w = np.random.default_rng(52).random((n, 1))
+    pt = H.product_tree(pts, 5, 0, True, True, 64, 2, 1e-5)
+    pt.upload_weights(w)
+    pt.matvec_resident()
+    full = np.asarray(pt.download_result()).reshape(n)
+    out = np.zeros(n)
+    world = 3
+    sizes = []
+    for rank in range(world):
+        sm = ShardedMatvec(pt, rank, world)
+        pt.set_target_subset(sm.my_rows)
+        pt.matvec_resident()
+        ptr, rows, cols = pt.result_device()
+        assert rows == sm.my_rows.size and cols == 1 and ptr
+        out[sm.my_rows] = np.asarray(pt.download_result()).reshape(-1)
+        sizes.append(rows)
+    pt.set_target_subset(None)
+    assert sum(sizes) == n and min(sizes) > 0
+    assert H.rel_l2(out, full) <= 1e-13
+    _, work = pt.leaf_work()
+    assert work.min() > 0
+
+
+def test_full_size_properties_1m():
+    """BASELINE.json headline size (3-D uniform N = 1M, linear, order 7): size-independent properties —
+    linearity in the weights, agreement with exact dense summation on sampled targets, subset consistency."""
+    from oracle import kernels as okern
+    n = 1_000_000
+    rng = np.random.default_rng(1000)
+    pts = rng.random((n, 3))
+    w1, w2 = rng.random((n, 1)), rng.random((n, 1)) - 0.5
+    import ferreus_rbf_rs_b200 as fb
+    tree = fb.FmmTree(pts, 7, fb.KernelParams(fb.FmmKernelType.LinearRbf), True, True)
+    info = tree.info()
+    assert info["depth"] >= 4 and info["n_w"] == info["n_x"]
+    tree.set_weights(w1)
+    y1 = tree.evaluate_at_sources(w1)
+    tree.set_weights(w2)
+    y2 = tree.evaluate_at_sources(w2)
+    w3 = 2.0 * w1 - 3.0 * w2
+    tree.set_weights(w3)
+    y3 = tree.evaluate_at_sources(w3)
+    assert H.rel_l2(y3, 2.0 * y1 - 3.0 * y2) <= 1e-12                      # linearity
+    sample = rng.integers(0, n, 300)
+    dense = okern.dense_matvec(okern.Kernel(okern.LINEAR), pts[sample], pts, w3)[:, 0]
+    assert H.rel_l2(y3[sample], dense) <= 1e-6                              # Chebyshev p=7 + ACA 1e-7 accuracy
+    sub = tree.evaluate_at_sources(w3, sample)
+    assert H.rel_l2(sub, y3[sample]) <= 1e-12                               # subset == rows of the full result
+    gen = tree.evaluate(w3, pts[sample])
+    assert H.rel_l2(gen, y3[sample]) <= 1e-12                               # re-binned targets == source fast path
