@@ -375,8 +375,16 @@ void fb_tree::build(const double *points, size_t n_, int dim_, ptrdiff_t rs, ptr
     m2l_P4 = P4;
     m2l_Pp = P4;
     while (m2l_Pp % 16 != 4 && m2l_Pp % 16 != 12) m2l_Pp += 4;  // bank-conflict-free B fragments
-    m2l_smem = sizeof(double) * ((size_t)kM2LCols * m2l_Pp + 2 * (size_t)max_rp * kM2LColsPad);
-    FB_REQUIRE(m2l_smem <= 220 * 1024, "interpolation order too large for the M2L shared-memory tile");
+    m2l_nc = 0;
+    for (int nc : {32, 16, 8}) {  // columns per CTA: the largest tile that fits in shared memory
+      const size_t need = sizeof(double) * ((size_t)nc * m2l_Pp + (size_t)(64 / nc) * max_rp * (nc + 4));
+      if (need <= 220 * 1024) {
+        m2l_nc = nc;
+        m2l_smem = need;
+        break;
+      }
+    }
+    FB_REQUIRE(m2l_nc != 0, "interpolation order too large for the M2L shared-memory tile (p^d <= ~3300)");
   }
   FB_CUDA(cudaStreamSynchronize(stream));
   lap("list packing + upload");
@@ -441,10 +449,6 @@ void fb_tree::downward(const uint8_t *flags) {
   if (timing) FB_CUDA(cudaEventRecord(ev[3], stream));
   // M2L (loop A of bbfmm.rs:781-832)
   const bool compressed = fparams.compression_type != FB_COMPRESSION_NONE;
-  if (compressed)
-    set_smem(k_m2l<true>, m2l_smem);
-  else
-    set_smem(k_m2l<false>, m2l_smem);
   if (!m2l_groups.empty()) {
     if (m2l_table_nrhs != nrhs) {  // CTA ranges depend on the number of right-hand sides
       std::vector<M2LGroupDev> tab;
@@ -458,7 +462,7 @@ void fb_tree::downward(const uint8_t *flags) {
         t.v_off = (long long)g.v_off;
         t.u_off = (long long)g.u_off;
         tab.push_back(t);
-        cta += (long long)((g.n_entries * (size_t)nrhs + kM2LCols - 1) / kM2LCols);
+        cta += (long long)((g.n_entries * (size_t)nrhs + m2l_nc - 1) / m2l_nc);
       }
       FB_REQUIRE(cta < (1ll << 31), "too many M2L tiles");
       m2l_ctas = (unsigned)cta;
@@ -469,13 +473,23 @@ void fb_tree::downward(const uint8_t *flags) {
       m2l_table_nrhs = nrhs;
     }
     const M2LGroupDev *tab = reinterpret_cast<const M2LGroupDev *>(d_m2l_table.p);
+#define FB_M2L_LAUNCH(COMP, NCV)                                                                                   \
+  do {                                                                                                             \
+    set_smem(k_m2l<COMP, NCV>, m2l_smem);                                                                          \
+    FB_LAUNCH((k_m2l<COMP, NCV>), m2l_ctas, 256, m2l_smem, stream, tab, (int)m2l_groups.size(), d_m2l_tgt.p,       \
+              d_m2l_src.p, d_m2l_perm.p, d_oppool.p, d_perm_tab.p, P, m2l_P4, m2l_Pp, nrhs, flags, d_mult.p,      \
+              d_loc.p);                                                                                            \
+  } while (0)
     if (compressed) {
-      FB_LAUNCH(k_m2l<true>, m2l_ctas, 256, m2l_smem, stream, tab, (int)m2l_groups.size(), d_m2l_tgt.p, d_m2l_src.p,
-                d_m2l_perm.p, d_oppool.p, d_perm_tab.p, P, m2l_P4, m2l_Pp, nrhs, flags, d_mult.p, d_loc.p);
+      if (m2l_nc == 32) FB_M2L_LAUNCH(true, 32);
+      else if (m2l_nc == 16) FB_M2L_LAUNCH(true, 16);
+      else FB_M2L_LAUNCH(true, 8);
     } else {
-      FB_LAUNCH(k_m2l<false>, m2l_ctas, 256, m2l_smem, stream, tab, (int)m2l_groups.size(), d_m2l_tgt.p, d_m2l_src.p,
-                d_m2l_perm.p, d_oppool.p, d_perm_tab.p, P, m2l_P4, m2l_Pp, nrhs, flags, d_mult.p, d_loc.p);
+      if (m2l_nc == 32) FB_M2L_LAUNCH(false, 32);
+      else if (m2l_nc == 16) FB_M2L_LAUNCH(false, 16);
+      else FB_M2L_LAUNCH(false, 8);
     }
+#undef FB_M2L_LAUNCH
   }
   if (timing) FB_CUDA(cudaEventRecord(ev[4], stream));
   // P2L (adaptive only)

@@ -141,6 +141,7 @@ struct fb_tree {
   fb::DBuf<int> d_m2l_tgt, d_m2l_src, d_m2l_perm;
   int m2l_P4 = 0, m2l_Pp = 0;  // padded node counts of the M2L tiles
   size_t m2l_smem = 0;
+  int m2l_nc = 32;  // (entry, rhs) columns per M2L CTA
   fb::DBuf<unsigned char> d_m2l_table;  // M2LGroupDev[] of the fused launch
   int m2l_table_nrhs = -1;
   unsigned m2l_ctas = 0;

@@ -345,8 +345,8 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
                : "d"(a), "d"(b));
 }
 
-constexpr int kM2LCols = 32;                 // (entry, rhs) columns per CTA
-constexpr int kM2LColsPad = kM2LCols + 4;    // row stride of Ys: == 4 (mod 16) -> conflict-free B fragments
+// (entry, rhs) columns per CTA: NC = 32, 16 or 8 (chosen so the staged multipoles fit in shared memory);
+// the row stride of Ys is NC + 4 == 4 or 12 (mod 16) -> conflict-free B fragments
 constexpr int kM2LChunk = 4;                 // rank tiles (8 rows each) accumulated per pass over the reduction
 
 // M2L for one (level, reference vector) group (bbfmm.rs:864-986) as two dense contractions on the FP64 tensor
@@ -366,8 +366,8 @@ struct M2LGroupDev {  // one (level, reference vector) group of the fused M2L la
   long long v_off, u_off;  // operator pool offsets (fragment order)
 };
 
-template <bool COMPRESSED>
-__global__ void __launch_bounds__(256, 2) k_m2l(const M2LGroupDev *groups, int n_groups, const int *e_tgt_all,
+template <bool COMPRESSED, int NC>
+__global__ void __launch_bounds__(256, NC == 32 ? 2 : 1) k_m2l(const M2LGroupDev *groups, int n_groups, const int *e_tgt_all,
                                                 const int *e_src_all, const int *e_perm_all, const double *pool,
                                                 const int *perm_tab, int P, int P4, int Pp, int nrhs,
                                                 const uint8_t *flag, const double *mult, double *loc) {
@@ -386,11 +386,13 @@ __global__ void __launch_bounds__(256, 2) k_m2l(const M2LGroupDev *groups, int n
   extern __shared__ double sm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t ncols = n_entries * (size_t)nrhs;
+  constexpr int kM2LCols = NC, kM2LColsPad = NC + 4;
+  constexpr int kNT = NC / 8;        // 8-column tiles
+  constexpr int kKSplit = 8 / kNT;   // warps sharing one column tile split the P-long reduction
   const size_t col0 = (size_t)cta * kM2LCols;
   const int nc = (int)min((size_t)kM2LCols, ncols - col0);
-  double *Xs = sm;                                        // [32][Pp]
-  double *Ys = Xs + (size_t)kM2LCols * Pp;                // [rank_pad][36]
-  double *Yh = Ys + (size_t)rank_pad * kM2LColsPad;       // second half of the split reduction
+  double *Xs = sm;                                        // [NC][Pp]
+  double *Ys = Xs + (size_t)kM2LCols * Pp;                // [kKSplit][rank_pad][NC + 4] partial products
   __shared__ int s_tgt[kM2LCols], s_rhs[kM2LCols], s_perm[kM2LCols], s_src[kM2LCols];
   __shared__ int s_any;
   if (tid == 0) s_any = 0;
@@ -437,13 +439,13 @@ __global__ void __launch_bounds__(256, 2) k_m2l(const M2LGroupDev *groups, int n
   __syncthreads();
   const int ar = lane >> 2, ak = lane & 3;  // fragment coordinates
   if (COMPRESSED) {
-    // ---- Ys = Vt * Xs: warp -> column tile nt, reduction half kh; rank tiles in chunks of 4
-    const int nt = warp & 3, kh = warp >> 2;
+    // ---- Ys = Vt * Xs: warp -> column tile nt, reduction slice kh; rank tiles in chunks of 4
+    const int nt = warp % kNT, kh = warp / kNT;
     const int mtiles = rank_pad >> 3;
     const int ksteps = P4 >> 2;
-    const int k_begin = kh ? (ksteps >> 1) : 0, k_end = kh ? ksteps : (ksteps >> 1);
+    const int k_begin = (int)((long long)ksteps * kh / kKSplit), k_end = (int)((long long)ksteps * (kh + 1) / kKSplit);
     const double *bx = Xs + (size_t)(nt * 8 + ar) * Pp + ak;
-    double *yo = kh ? Yh : Ys;
+    double *yo = Ys + (size_t)kh * rank_pad * kM2LColsPad;
     for (int m0 = 0; m0 < mtiles; m0 += kM2LChunk) {
       double acc[kM2LChunk][2];
 #pragma unroll
@@ -467,7 +469,10 @@ __global__ void __launch_bounds__(256, 2) k_m2l(const M2LGroupDev *groups, int n
     __syncthreads();
     for (int e = tid; e < rank_pad * kM2LCols; e += 256) {
       const int k = e / kM2LCols, c = e % kM2LCols;
-      Ys[(size_t)k * kM2LColsPad + c] += Yh[(size_t)k * kM2LColsPad + c];
+      double v = Ys[(size_t)k * kM2LColsPad + c];
+#pragma unroll
+      for (int q = 1; q < kKSplit; ++q) v += Ys[((size_t)q * rank_pad + k) * kM2LColsPad + c];
+      Ys[(size_t)k * kM2LColsPad + c] = v;
     }
     __syncthreads();
   }
@@ -475,15 +480,15 @@ __global__ void __launch_bounds__(256, 2) k_m2l(const M2LGroupDev *groups, int n
   const int mt_total = (P + 7) >> 3;
   const int ksteps2 = (COMPRESSED ? rank_pad : P4) >> 2;
   for (int mt = warp; mt < mt_total; mt += 8) {
-    double z[4][2];
+    double z[kNT][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) z[i][0] = z[i][1] = 0.0;
+    for (int i = 0; i < kNT; ++i) z[i][0] = z[i][1] = 0.0;
     const double *af = UF + ((size_t)mt * ksteps2) * 32 + lane;
 #pragma unroll 2
     for (int ks = 0; ks < ksteps2; ++ks) {
       const double a = __ldg(af + (size_t)ks * 32);
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
+      for (int nt = 0; nt < kNT; ++nt) {
         const double b = COMPRESSED ? Ys[(size_t)(ks * 4 + ak) * kM2LColsPad + nt * 8 + ar]
                                     : Xs[(size_t)(nt * 8 + ar) * Pp + ks * 4 + ak];
         dmma884(z[nt][0], z[nt][1], a, b);
@@ -492,7 +497,7 @@ __global__ void __launch_bounds__(256, 2) k_m2l(const M2LGroupDev *groups, int n
     const int m = mt * 8 + ar;
     if (m < P) {
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
+      for (int nt = 0; nt < kNT; ++nt)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int c = nt * 8 + ak * 2 + h;

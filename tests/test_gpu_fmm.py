@@ -65,6 +65,8 @@ MATVEC_CASES = [
     (3000, 3, "clustered", 5, 5, 2, 8, True, True, 30),
     (3000, 3, "clustered", 8, 5, 0, 1, True, True, 30),
     (3000, 3, "clustered", 9, 5, 2, 5, True, True, 30),
+    (1500, 3, "uniform", 2, 10, 2, 1, True, True, 60),     # P = 1000: M2L tile of 16 columns
+    (1200, 3, "uniform", 2, 12, 0, 1, True, True, 80),     # P = 1728 uncompressed: M2L tile of 8 columns
 ]
 
 
