@@ -377,7 +377,7 @@ void fb_tree::build(const double *points, size_t n_, int dim_, ptrdiff_t rs, ptr
     while (m2l_Pp % 16 != 4 && m2l_Pp % 16 != 12) m2l_Pp += 4;  // bank-conflict-free B fragments
     m2l_nc = 0;
     for (int nc : {32, 16, 8}) {  // columns per CTA: the largest tile that fits in shared memory
-      const size_t need = sizeof(double) * ((size_t)nc * m2l_Pp + (size_t)(64 / nc) * max_rp * (nc + 4));
+      const size_t need = sizeof(double) * ((size_t)nc * m2l_Pp + (size_t)max_rp * (nc + 4));
       if (need <= 220 * 1024) {
         m2l_nc = nc;
         m2l_smem = need;

@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(256, NC == 32 ? 2 : 1) k_m2l(const M2LGroupDev
   const size_t col0 = (size_t)cta * kM2LCols;
   const int nc = (int)min((size_t)kM2LCols, ncols - col0);
   double *Xs = sm;                                        // [NC][Pp]
-  double *Ys = Xs + (size_t)kM2LCols * Pp;                // [kKSplit][rank_pad][NC + 4] partial products
+  double *Ys = Xs + (size_t)kM2LCols * Pp;                // [rank_pad][NC + 4]
   __shared__ int s_tgt[kM2LCols], s_rhs[kM2LCols], s_perm[kM2LCols], s_src[kM2LCols];
   __shared__ int s_any;
   if (tid == 0) s_any = 0;
@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(256, NC == 32 ? 2 : 1) k_m2l(const M2LGroupDev
     const int ksteps = P4 >> 2;
     const int k_begin = (int)((long long)ksteps * kh / kKSplit), k_end = (int)((long long)ksteps * (kh + 1) / kKSplit);
     const double *bx = Xs + (size_t)(nt * 8 + ar) * Pp + ak;
-    double *yo = Ys + (size_t)kh * rank_pad * kM2LColsPad;
+    (void)kKSplit;
     for (int m0 = 0; m0 < mtiles; m0 += kM2LChunk) {
       double acc[kM2LChunk][2];
 #pragma unroll
@@ -458,23 +458,25 @@ __global__ void __launch_bounds__(256, NC == 32 ? 2 : 1) k_m2l(const M2LGroupDev
         for (int i = 0; i < kM2LChunk; ++i)
           if (m0 + i < mtiles) dmma884(acc[i][0], acc[i][1], __ldg(af + ((size_t)i * ksteps + ks) * 32), b);
       }
+      // the reduction slices take turns adding their partial products into the single Ys buffer
+      for (int turn = 0; turn < kKSplit; ++turn) {
+        if (turn == kh) {
 #pragma unroll
-      for (int i = 0; i < kM2LChunk; ++i)
-        if (m0 + i < mtiles) {
-          double *y = yo + (size_t)((m0 + i) * 8 + ar) * kM2LColsPad + nt * 8 + ak * 2;
-          y[0] = acc[i][0];
-          y[1] = acc[i][1];
+          for (int i = 0; i < kM2LChunk; ++i)
+            if (m0 + i < mtiles) {
+              double *y = Ys + (size_t)((m0 + i) * 8 + ar) * kM2LColsPad + nt * 8 + ak * 2;
+              if (turn == 0) {
+                y[0] = acc[i][0];
+                y[1] = acc[i][1];
+              } else {
+                y[0] += acc[i][0];
+                y[1] += acc[i][1];
+              }
+            }
         }
+        __syncthreads();
+      }
     }
-    __syncthreads();
-    for (int e = tid; e < rank_pad * kM2LCols; e += 256) {
-      const int k = e / kM2LCols, c = e % kM2LCols;
-      double v = Ys[(size_t)k * kM2LColsPad + c];
-#pragma unroll
-      for (int q = 1; q < kKSplit; ++q) v += Ys[((size_t)q * rank_pad + k) * kM2LColsPad + c];
-      Ys[(size_t)k * kM2LColsPad + c] = v;
-    }
-    __syncthreads();
   }
   // ---- Zs = U * Ys (or K * Xs), scattered from the accumulator fragments
   const int mt_total = (P + 7) >> 3;
