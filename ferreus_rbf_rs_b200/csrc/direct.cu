@@ -5,6 +5,9 @@
 // warp-wide broadcasts; the kernel function is evaluated once per pair for all right-hand sides.
 #include "fmm.h"
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace fb {
 
 template <int NR>
@@ -356,6 +359,413 @@ __global__ void __launch_bounds__(kTile) k_leaf_direct_v2(const DirectArgs a) {
   }
 }
 
+
+// ======================================================================================================
+// Leaf pass, warp-granular (value only).  ncu on the CTA-granular kernel above (profiles/r1_s2_ncu_full.txt):
+// FP64 pipe 58 % busy, 41 % warps active — a 128-thread CTA serving a 30-point leaf parks three idle warps on
+// the M2P barriers.  Here the work item is one warp = 32 targets of one leaf: no block barrier anywhere, warps
+// without targets retire at once, CTAs are two warps so the block scheduler balances uneven leaves.
+//   P2P  warp-private double-buffered 32-source tiles (as above);
+//   M2P  squared axis offsets per (target, W cell) in a warp-private table, multipoles staged in warp-private
+//        chunks of whole i0-slabs, r^2 = (dx2[i0] + dy2[i1]) + dz2[i2] (utils.rs:230-237 association); W cells
+//        are never adjacent to the leaf, so r^2 > 0 and the zero-distance select is dropped.
+// ======================================================================================================
+constexpr int kLeafWPC = 2;         // warps per CTA
+constexpr int kLeafMwDoubles = 512;  // multipole staging budget per warp (doubles)
+constexpr int kM2PQB = 4;            // (i0, i1) node columns in flight per lane
+
+struct LeafWarpCfg {  // per-warp shared-memory layout (doubles) and M2P chunking
+  int slabs_per_chunk, plane, d2, total;
+};
+static inline LeafWarpCfg leaf_warp_cfg(int nr, int p, int dim, bool regz) {
+  const int p1 = dim > 1 ? p : 1, p2 = dim > 2 ? p : 1;
+  auto plane_of = [&](int slabs) { return ((slabs * p1 + kM2PQB - 1) / kM2PQB) * kM2PQB * p2; };
+  LeafWarpCfg c;
+  c.slabs_per_chunk = p;
+  while (c.slabs_per_chunk > 1 && nr * plane_of(c.slabs_per_chunk) > kLeafMwDoubles) --c.slabs_per_chunk;
+  c.plane = plane_of(c.slabs_per_chunk);  // node columns padded to whole groups of kM2PQB (zero multipoles)
+  c.d2 = (regz ? 2 : 3) * p * 32;
+  const int p2p = 2 * (4 + nr) * kWarpTile;  // double-buffered {x,y},{z,w0},{w1,w2}... pairs
+  c.total = std::max(p2p, nr * c.plane + c.d2);
+  c.total = (c.total + 1) & ~1;  // keep every warp's slice 16-byte aligned
+  return c;
+}
+
+template <int FAM, int NR, bool REGZ>
+__global__ void __launch_bounds__(kLeafWPC * 32, NR >= 4 ? 7 : 10) k_leaf_warp(const DirectArgs a, const int slabs_per_chunk,
+                                                                 const int plane, const int warp_doubles) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long gw = (long long)blockIdx.x * kLeafWPC + warp;
+  const int tile = (int)(gw >> 2), sub = (int)(gw & 3);
+  if (tile >= *a.ts.n_tiles_dev) return;
+  const int li = a.ts.tile_leaf[tile];
+  const int tb = a.ts.leaf_begin[li] + a.ts.tile_off[tile] + sub * 32;
+  const int cnt = min(32, a.ts.leaf_end[li] - tb);
+  if (cnt <= 0) return;
+  const bool active = lane < cnt;
+  double xt = 0, yt = 0, zt = 0;
+  if (active) {
+    xt = a.ts.x[tb + lane];
+    yt = a.ts.y[tb + lane];
+    zt = a.ts.z[tb + lane];
+  }
+  double acc[NR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) acc[r] = 0.0;
+
+  extern __shared__ __align__(16) double dsm[];
+  double *wsm = dsm + (size_t)warp * warp_doubles;
+
+  // ---- P2P: warp-private tiles over the merged U ranges; a tile row is {x,y},{z,w0},{w1,w2},... so a source costs
+  //      two 128-bit broadcast loads (one more per further pair of right-hand sides)
+  {
+    constexpr int NC2 = (4 + NR) / 2;  // double2 components per source
+    double2(*wt)[NC2][kWarpTile] = reinterpret_cast<double2(*)[NC2][kWarpTile]>(wsm);
+    long long e = a.u_ptr[li];
+    const long long e_end = a.u_ptr[li + 1];
+    int rb = 0, rn = 0, c0 = 0;
+    if (e < e_end) {
+      rb = a.u_begin[e];
+      rn = a.u_count[e];
+    }
+    double reg[2 * NC2];
+#pragma unroll
+    for (int k = 0; k < 2 * NC2; ++k) reg[k] = 0.0;
+    auto fetch = [&](int &m) {  // this lane's element of the current tile, then advance
+      m = 0;
+      if (e >= e_end) return;
+      m = min(kWarpTile, rn - c0);
+      if (lane < m) {
+        const int s = rb + c0 + lane;
+        reg[0] = a.sx[s];
+        reg[1] = a.sy[s];
+        reg[2] = a.sz[s];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) reg[3 + r] = a.w[(size_t)(a.rhs0 + r) * a.n + s];
+      }
+      c0 += kWarpTile;
+      if (c0 >= rn) {
+        ++e;
+        c0 = 0;
+        if (e < e_end) {
+          rb = a.u_begin[e];
+          rn = a.u_count[e];
+        }
+      }
+    };
+    auto stash = [&](int buf, int m) {
+      if (lane < m) {
+#pragma unroll
+        for (int k = 0; k < NC2; ++k) wt[buf][k][lane] = make_double2(reg[2 * k], reg[2 * k + 1]);
+      }
+    };
+    int m_cur = 0, m_next = 0, buf = 0;
+    fetch(m_cur);
+    stash(0, m_cur);
+    __syncwarp();
+    while (m_cur > 0) {
+      fetch(m_next);  // global loads of the next tile overlap the arithmetic below
+      const double2(*t)[kWarpTile] = wt[buf];
+#pragma unroll 4
+      for (int j = 0; j < m_cur; ++j) {
+        double sv[2 * NC2];
+#pragma unroll
+        for (int k = 0; k < NC2; ++k) {
+          const double2 v2 = t[k][j];
+          sv[2 * k] = v2.x;
+          sv[2 * k + 1] = v2.y;
+        }
+        const double dx = xt - sv[0], dy = yt - sv[1], dz = zt - sv[2];
+        double r2 = dx * dx;
+        r2 += dy * dy;
+        r2 += dz * dz;
+        const double v = kernel_mag_dev<FAM>(r2, a.kp);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) kernel_acc<FAM>(acc[r], v, sv[3 + r]);
+      }
+      buf ^= 1;
+      stash(buf, m_next);
+      __syncwarp();
+      m_cur = m_next;
+    }
+  }
+  // ---- M2P: tensor grid of the W cell's Chebyshev nodes
+  const int p = a.p, P = a.P;
+  const int p1 = a.dim > 1 ? p : 1, p2 = a.dim > 2 ? p : 1;
+  const int slab = p1 * p2;  // nodes sharing one i0
+  double *mw = wsm;          // [NR][plane]: multipoles of the staged i0 slabs, zero padded to whole column groups
+  double *d2 = wsm + NR * plane;  // [2 or 3][p][32]
+  for (long long e = a.w_ptr[li]; e < a.w_ptr[li + 1]; ++e) {
+    const int c = a.w_cell[e];
+    const double h = a.chalf[c];
+    const double ccx = a.ccx[c], ccy = a.ccy[c], ccz = a.ccz[c];
+    double dzr[kRegOrder];
+#pragma unroll
+    for (int i = 0; i < kRegOrder; ++i) dzr[i] = 1.0;
+    __syncwarp();
+    for (int i = 0; i < p; ++i) {
+      const double nd = a.nodes[i];
+      const double ox = xt - (ccx + h * nd);
+      d2[(0 * p + i) * 32 + lane] = ox * ox;
+      if (a.dim > 1) {
+        const double oy = yt - (ccy + h * nd);
+        d2[(1 * p + i) * 32 + lane] = oy * oy;
+      }
+      if (a.dim > 2 && !REGZ) {
+        const double oz = zt - (ccz + h * nd);
+        d2[(2 * p + i) * 32 + lane] = oz * oz;
+      }
+    }
+    if (REGZ && a.dim > 2) {
+#pragma unroll
+      for (int i = 0; i < kRegOrder; ++i)
+        if (i < p) {
+          const double oz = zt - (ccz + h * a.nodes[i]);
+          dzr[i] = oz * oz;
+        }
+    }
+    const double *msrc = a.mult + ((size_t)c * a.nrhs + a.rhs0) * P;
+    for (int s0 = 0; s0 < p; s0 += slabs_per_chunk) {
+      const int ns = min(slabs_per_chunk, p - s0);
+      const int cn = ns * slab;  // nodes in this chunk
+      const int nq = ns * p1;    // (i0, i1) columns in this chunk
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < NR; ++r)
+        for (int k = lane; k < plane; k += 32) mw[r * plane + k] = k < cn ? msrc[(size_t)r * P + s0 * slab + k] : 0.0;
+      __syncwarp();
+      // kM2PQB columns at a time: independent kernel evaluations in flight inside every (uniformly predicated) i2
+      // step; columns past nq re-read the last column's offsets against zero multipoles
+      int csi = s0, ci1 = 0;
+      for (int q0 = 0; q0 < nq; q0 += kM2PQB) {
+        double axy[kM2PQB];
+        const double *wrow[kM2PQB];
+#pragma unroll
+        for (int u = 0; u < kM2PQB; ++u) {
+          const double ax = d2[(0 * p + csi) * 32 + lane];
+          axy[u] = a.dim > 1 ? ax + d2[(1 * p + ci1) * 32 + lane] : ax;
+          wrow[u] = mw + (q0 + u) * p2;
+          if (q0 + u + 1 < nq && ++ci1 == p1) {
+            ci1 = 0;
+            ++csi;
+          }
+        }
+        if (REGZ) {
+#pragma unroll
+          for (int i2 = 0; i2 < kRegOrder; ++i2)
+            if (i2 < p2) {
+              double v[kM2PQB];
+#pragma unroll
+              for (int u = 0; u < kM2PQB; ++u) v[u] = kernel_mag_far<FAM>(axy[u] + dzr[i2], a.kp);
+#pragma unroll
+              for (int u = 0; u < kM2PQB; ++u)
+#pragma unroll
+                for (int r = 0; r < NR; ++r) kernel_acc<FAM>(acc[r], v[u], wrow[u][r * plane + i2]);
+            }
+        } else {
+          for (int i2 = 0; i2 < p2; ++i2) {
+            const double dz2 = a.dim > 2 ? d2[(2 * p + i2) * 32 + lane] : 0.0;
+            double v[kM2PQB];
+#pragma unroll
+            for (int u = 0; u < kM2PQB; ++u) v[u] = kernel_mag_far<FAM>(a.dim > 2 ? axy[u] + dz2 : axy[u], a.kp);
+#pragma unroll
+            for (int u = 0; u < kM2PQB; ++u)
+#pragma unroll
+              for (int r = 0; r < NR; ++r) kernel_acc<FAM>(acc[r], v[u], wrow[u][r * plane + i2]);
+          }
+        }
+      }
+    }
+  }
+  if (active) {
+    const size_t row = a.ts.out_row[tb + lane];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) a.out[row * a.nrhs + a.rhs0 + r] += acc[r];
+  }
+}
+
+template <int FAM, int NR>
+static void launch_leaf_v3(const DirectArgs &a, cudaStream_t s) {
+  const bool regz = a.dim == 3 && a.p <= kRegOrder;
+  const LeafWarpCfg cfg = leaf_warp_cfg(NR, a.p, a.dim, regz);
+  const size_t smem = sizeof(double) * (size_t)cfg.total * kLeafWPC;
+  const unsigned grid = (unsigned)(((long long)a.ts.max_tiles * 4 + kLeafWPC - 1) / kLeafWPC);
+  if (regz) {
+    if (smem > 48 * 1024)
+      FB_CUDA(cudaFuncSetAttribute(k_leaf_warp<FAM, NR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FB_LAUNCH((k_leaf_warp<FAM, NR, true>), grid, kLeafWPC * 32, smem, s, a, cfg.slabs_per_chunk, cfg.plane, cfg.total);
+  } else {
+    if (smem > 48 * 1024)
+      FB_CUDA(cudaFuncSetAttribute(k_leaf_warp<FAM, NR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FB_LAUNCH((k_leaf_warp<FAM, NR, false>), grid, kLeafWPC * 32, smem, s, a, cfg.slabs_per_chunk, cfg.plane, cfg.total);
+  }
+}
+
+// ======================================================================================================
+// P2L on the tensor grid of the target cell's Chebyshev nodes (bbfmm.rs:1001-1048).  The targets are the p^d
+// nodes of the cell, so r^2 = (dx2[i0] + dy2[i1]) + dz2[i2] with the squared axis offsets tabulated once per
+// source: a thread owns one (i0, i1) column of nodes (p accumulators per right-hand side in registers) and a
+// slice of the source tile; per pair that is 1 add + kernel + 1 FMA instead of 6 + kernel + 1.  X-list leaves are
+// never adjacent to the cell, so r^2 > 0.  Slices are summed through shared memory in a fixed order, one CTA per
+// cell: deterministic, no atomics.
+// ======================================================================================================
+constexpr int kP2LTileMax = 128;  // sources per staged tile (upper bound)
+constexpr int kP2LJB = 4;          // sources in flight per thread (independent kernel evaluations)
+constexpr int kP2LPF = 3;          // coordinates a thread prefetches per tile (tile * dim <= kP2LPF * blockDim)
+
+template <int FAM, int NR, int PREG>
+__global__ void __launch_bounds__(256, (NR * PREG <= 16) ? 2 : 1) k_p2l_grid(const P2LArgs a, const int nslices, const int cols, const int T) {
+  const int ci = blockIdx.x;
+  const int c = a.cells[ci];
+  if (!a.cell_flag[c]) return;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int p = a.p, P = a.P, dim = a.dim;
+  extern __shared__ double sm[];
+  double *tab = sm;                                 // [dim][T][PREG]
+  double *wts = sm + (size_t)dim * T * PREG;        // [NR][T]
+  const int q = tid % cols, slice = tid / cols;
+  const bool active = slice < nslices;
+  const int i0 = dim == 3 ? q / p : q, i1 = dim == 3 ? q % p : 0;
+  const double ccx = a.ccx[c], ccy = a.ccy[c], ccz = a.ccz[c];
+  const double h = a.chalf[c];
+  const double *tabA = tab, *tabB = tab + (size_t)T * PREG, *tabL = tab + (size_t)(dim - 1) * T * PREG;
+  double acc[NR][PREG];
+#pragma unroll
+  for (int r = 0; r < NR; ++r)
+#pragma unroll
+    for (int i = 0; i < PREG; ++i) acc[r][i] = 0.0;
+
+  // cursor over the tiles of the merged X ranges; the next tile's coordinates and weights are fetched into
+  // registers while the current one is consumed
+  long long e = a.x_ptr[ci];
+  const long long e_end = a.x_ptr[ci + 1];
+  int rb = 0, rn = 0, c0 = 0;
+  if (e < e_end) {
+    rb = a.x_begin[e];
+    rn = a.x_count[e];
+  }
+  double pc[kP2LPF], pw[NR];
+  auto prefetch = [&](int &m) {
+    m = 0;
+    if (e >= e_end) return;
+    m = min(T, rn - c0);
+    const int base = rb + c0;
+#pragma unroll
+    for (int k = 0; k < kP2LPF; ++k) {
+      const int t = tid + k * nt;
+      const int j = t / dim, d = t - j * dim;
+      if (j < m) pc[k] = d == 0 ? a.sx[base + j] : (d == 1 ? a.sy[base + j] : a.sz[base + j]);
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) pw[r] = tid < m ? a.w[(size_t)(a.rhs0 + r) * a.n + base + tid] : 0.0;
+    c0 += T;
+    if (c0 >= rn) {
+      ++e;
+      c0 = 0;
+      if (e < e_end) {
+        rb = a.x_begin[e];
+        rn = a.x_count[e];
+      }
+    }
+  };
+  int m_cur = 0, m_next = 0;
+  prefetch(m_cur);
+  while (m_cur > 0) {
+    const int m = m_cur;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kP2LPF; ++k) {  // squared offsets node - source per axis (chebyshev.rs:951-968)
+      const int t = tid + k * nt;
+      const int j = t / dim, d = t - j * dim;
+      if (j < T) {
+        double *row = tab + ((size_t)d * T + j) * PREG;
+        if (j < m) {
+          const double cd = d == 0 ? ccx : (d == 1 ? ccy : ccz);
+          for (int i = 0; i < p; ++i) {
+            const double o = (cd + h * a.nodes[i]) - pc[k];
+            row[i] = o * o;
+          }
+        } else if (m < T) {  // neutral padding rows (r^2 = 1, weight 0) so every thread runs whole groups of kP2LJB
+          const double fill = d == dim - 1 ? 1.0 : 0.0;
+          for (int i = 0; i < p; ++i) row[i] = fill;
+        }
+      }
+    }
+    if (tid < T) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) wts[r * T + tid] = pw[r];
+    }
+    __syncthreads();
+    prefetch(m_next);
+    if (active) {
+      const int kmax = (m + nslices - 1) / nslices;
+      for (int k = 0; k < kmax; k += kP2LJB) {
+        double axy[kP2LJB], wj[kP2LJB][NR], nx[kP2LJB];
+        const double *dl[kP2LJB];
+#pragma unroll
+        for (int u = 0; u < kP2LJB; ++u) {
+          const int j = slice + nslices * (k + u);  // < T: T / nslices is a multiple of kP2LJB
+          axy[u] = 0.0;
+          if (dim == 3) axy[u] = tabA[j * PREG + i0] + tabB[j * PREG + i1];
+          else if (dim == 2) axy[u] = tabA[j * PREG + i0];
+          dl[u] = tabL + j * PREG;
+          nx[u] = dl[u][0];
+#pragma unroll
+          for (int r = 0; r < NR; ++r) wj[u][r] = wts[r * T + j];
+        }
+#pragma unroll
+        for (int il = 0; il < PREG; ++il)
+          if (il < p) {
+            double v[kP2LJB];
+#pragma unroll
+            for (int u = 0; u < kP2LJB; ++u) {
+              const double r2 = axy[u] + nx[u];
+              if (il + 1 < PREG) nx[u] = dl[u][il + 1];  // next step's offsets are in flight during this one
+              v[u] = kernel_mag_far<FAM>(r2, a.kp);
+            }
+#pragma unroll
+            for (int u = 0; u < kP2LJB; ++u)
+#pragma unroll
+              for (int r = 0; r < NR; ++r) kernel_acc<FAM>(acc[r][il], v[u], wj[u][r]);
+          }
+      }
+    }
+    m_cur = m_next;
+  }
+  // ---- sum the slices in a fixed order and add to the cell's local expansion
+  double *red = sm;  // [nslices][P]
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    __syncthreads();
+    if (active) {
+#pragma unroll
+      for (int il = 0; il < PREG; ++il)
+        if (il < p) red[(size_t)slice * P + q * p + il] = acc[r][il];
+    }
+    __syncthreads();
+    for (int nd = tid; nd < P; nd += nt) {
+      double s = 0.0;
+      for (int sl = 0; sl < nslices; ++sl) s += red[(size_t)sl * P + nd];
+      a.loc[((size_t)c * a.nrhs + a.rhs0 + r) * P + nd] += s;
+    }
+  }
+}
+
+template <int FAM, int NR, int PREG>
+static void launch_p2l_grid(const P2LArgs &a, cudaStream_t s) {
+  const int cols = a.dim == 3 ? a.p * a.p : (a.dim == 2 ? a.p : 1);
+  const int nslices = std::min(32, std::max(1, 256 / cols));
+  const int nthreads = std::max(128, std::min(256, ((nslices * cols + 31) / 32) * 32));
+  const int group = kP2LJB * nslices;
+  const int T = group * std::max(1, kP2LTileMax / group);  // <= 128 <= nthreads, T * dim <= kP2LPF * nthreads
+  const size_t tab_d = (size_t)a.dim * T * PREG + (size_t)NR * T;
+  const size_t red_d = (size_t)nslices * a.P;
+  const size_t smem = sizeof(double) * std::max(tab_d, red_d);
+  if (smem > 48 * 1024)
+    FB_CUDA(cudaFuncSetAttribute(k_p2l_grid<FAM, NR, PREG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  FB_LAUNCH((k_p2l_grid<FAM, NR, PREG>), a.n_cells, nthreads, smem, s, a, nslices, cols, T);
+}
+
 template <int FAM, int NR>
 static void launch_leaf_v2(const DirectArgs &a, cudaStream_t s) {
   const bool regz = a.dim == 3 && a.p <= kRegOrder;
@@ -379,6 +789,18 @@ static void launch_p2l_v2(const P2LArgs &a, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------- dispatch
+static int env_int(const char *name, int dflt) {
+  const char *v = std::getenv(name);
+  return v ? std::atoi(v) : dflt;
+}
+
+template <int FAM, int NR>
+static void launch_leaf(const DirectArgs &a, cudaStream_t s) {
+  static const int impl = env_int("FB_LEAF_IMPL", 3);  // 2 = CTA-granular kernel (kept for A/B profiling)
+  if (impl == 2) launch_leaf_v2<FAM, NR>(a, s);
+  else launch_leaf_v3<FAM, NR>(a, s);
+}
+
 template <int FAM>
 static void leaf_direct_fam(DirectArgs a, cudaStream_t s) {
   const int grid = a.ts.max_tiles;
@@ -395,16 +817,16 @@ static void leaf_direct_fam(DirectArgs a, cudaStream_t s) {
     a.rhs0 = r;
     const int left = a.nrhs - r;
     if (left >= 8) {
-      launch_leaf_v2<FAM, 8>(a, s);
+      launch_leaf<FAM, 8>(a, s);
       r += 8;
     } else if (left >= 4) {
-      launch_leaf_v2<FAM, 4>(a, s);
+      launch_leaf<FAM, 4>(a, s);
       r += 4;
     } else if (left >= 2) {
-      launch_leaf_v2<FAM, 2>(a, s);
+      launch_leaf<FAM, 2>(a, s);
       r += 2;
     } else {
-      launch_leaf_v2<FAM, 1>(a, s);
+      launch_leaf<FAM, 1>(a, s);
       r += 1;
     }
   }
@@ -413,22 +835,41 @@ static void leaf_direct_fam(DirectArgs a, cudaStream_t s) {
 template <int FAM>
 static void p2l_fam(P2LArgs a, cudaStream_t s) {
   if (a.n_cells <= 0) return;
+  static const int impl = env_int("FB_P2L_IMPL", 2);  // 1 = one-thread-per-node kernel (kept for A/B profiling)
   int r = 0;
   while (r < a.nrhs) {
     a.rhs0 = r;
     const int left = a.nrhs - r;
-    if (left >= 8) {
-      launch_p2l_v2<FAM, 8>(a, s);
-      r += 8;
-    } else if (left >= 4) {
-      launch_p2l_v2<FAM, 4>(a, s);
-      r += 4;
-    } else if (left >= 2) {
-      launch_p2l_v2<FAM, 2>(a, s);
-      r += 2;
+    if (impl == 1) {
+      if (left >= 4) {
+        launch_p2l_v2<FAM, 4>(a, s);
+        r += 4;
+      } else if (left >= 2) {
+        launch_p2l_v2<FAM, 2>(a, s);
+        r += 2;
+      } else {
+        launch_p2l_v2<FAM, 1>(a, s);
+        r += 1;
+      }
+    } else if (a.p <= 8) {
+      if (left >= 4) {
+        launch_p2l_grid<FAM, 4, 8>(a, s);
+        r += 4;
+      } else if (left >= 2) {
+        launch_p2l_grid<FAM, 2, 8>(a, s);
+        r += 2;
+      } else {
+        launch_p2l_grid<FAM, 1, 8>(a, s);
+        r += 1;
+      }
     } else {
-      launch_p2l_v2<FAM, 1>(a, s);
-      r += 1;
+      if (left >= 2) {
+        launch_p2l_grid<FAM, 2, 16>(a, s);
+        r += 2;
+      } else {
+        launch_p2l_grid<FAM, 1, 16>(a, s);
+        r += 1;
+      }
     }
   }
 }

@@ -137,27 +137,45 @@ FB_HD void kernel_value_grad(double r2, const KParams &kp, double &val, double &
 #ifdef __CUDACC__
 // ---- device fast path ---------------------------------------------------------------------------
 // sqrt(a) and 1/sqrt(a) for a > 0 (normal): MUFU.RSQ64H seed y0 (~2^-21 relative: it reads the high word only)
-// refined with one third-order Goldschmidt step — full double precision (~1 ulp), branch-free (no IEEE slow
-// path), 5 FP64 operations + one integer add (the halving of y0 is an exponent decrement on the ALU pipe):
-//   r = a y0, h = y0 / 2, e = 1/2 - r h (= (1 - a y0^2) / 2), c = 1 + 3e/2, sqrt ~= r + (r e) c, rsqrt ~= y0 + (y0 e) c
-struct SqrtPair {
-  double r, y;  // sqrt(a), 1/sqrt(a)
-};
-__device__ __forceinline__ double fast_sqrt(double a) {
+// refined with one third-order step — full double precision (~1 ulp).  tools/fp64_ubench.cu measures the rates this
+// is designed around: DFMA 1.90 warp-instr/clk/SM, MUFU.RSQ64H 0.50, IEEE sqrt() 2.6x slower than this sequence.
+__device__ __forceinline__ double rsq64h(double a) {
   double y0;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(a));
-  const double h = __hiloint2double(__double2hiint(y0) - 0x00100000, __double2loint(y0));
+  return y0;
+}
+// With y0 = (1 + d) / sqrt(a):  r = a y0,  e = 1 - r y0 = 1 - (1 + d)^2,  and  (1 - e)^(-1/2) = 1 + e/2 + 3e^2/8 + O(e^3):
+//   sqrt(a)   = r  + (r  e)(1/2 + 3e/8),      1/sqrt(a) = y0 + (y0 e)(1/2 + 3e/8)        (remainder 5e^3/16 < 2^-61)
+// 5 FP64 operations, branch-free, no IEEE slow path, no exponent fix-up of the seed.
+__device__ __forceinline__ double fast_sqrt(double a) {
+  const double y0 = rsq64h(a);
   const double r = a * y0;
-  const double e = fma(-r, h, 0.5);
-  const double c = fma(1.5, e, 1.0);
+  const double e = fma(-r, y0, 1.0);
+  const double c = fma(e, 0.375, 0.5);
   return fma(r * e, c, r);
 }
 __device__ __forceinline__ double fast_rsqrt(double a) {
-  double y0;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(a));
-  const double h = __hiloint2double(__double2hiint(y0) - 0x00100000, __double2loint(y0));
-  const double e = fma(-(a * y0), h, 0.5);
-  const double c = fma(1.5, e, 1.0);
+  const double y0 = rsq64h(a);
+  const double e = fma(-(a * y0), y0, 1.0);
+  const double c = fma(e, 0.375, 0.5);
+  return fma(y0 * e, c, y0);
+}
+// seed taken from max(a, 2^-1022) (one integer max on the high word): a == 0 then gives r = 0 * finite = 0, e = 1 and
+// the results sqrt -> exactly 0, a * rsqrt -> exactly 0, without a select on the FP64 result
+__device__ __forceinline__ double seed_operand(double a) {
+  return __hiloint2double(max(__double2hiint(a), 0x00100000), __double2loint(a));
+}
+__device__ __forceinline__ double fast_sqrt_z(double a) {  // sqrt(a) for a >= 0 (0 -> 0)
+  const double y0 = rsq64h(seed_operand(a));
+  const double r = a * y0;
+  const double e = fma(-r, y0, 1.0);
+  const double c = fma(e, 0.375, 0.5);
+  return fma(r * e, c, r);
+}
+__device__ __forceinline__ double fast_rsqrt_z(double a) {  // finite for a == 0 (a * result == 0)
+  const double y0 = rsq64h(seed_operand(a));
+  const double e = fma(-(a * y0), y0, 1.0);
+  const double c = fma(e, 0.375, 0.5);
   return fma(y0 * e, c, y0);
 }
 // true when a (a sum of squares, sign bit clear) is a normal positive number: integer test on the high word
@@ -198,6 +216,61 @@ __device__ __forceinline__ double kernel_value_dev(double r2, const KParams &kp)
     const double y2 = y * y;
     return (r2 >= kEps * kEps) ? y2 * y2 : 0.0;
   }
+}
+
+// sign-stripped value + signed accumulate: for the linear kernel (-r) the negation rides on the DFMA operand
+// modifier instead of costing an FP64 instruction per pair (the compiler hoists a plain negation above the select)
+template <int FAM>
+__device__ __forceinline__ double kernel_mag_dev(double r2, const KParams &kp) {
+  if (FAM == KF_LINEAR) return fast_sqrt_z(r2);
+  if (FAM == KF_CUBIC) return r2 * fast_sqrt_z(r2);
+  if (FAM == KF_SPH) {
+    const double sr2 = kp.s2 * r2;
+    const bool near = sr2 <= kp.ip2;
+    const double t = 1.0 + sr2;
+    const double y = fast_rsqrt_z(near ? r2 : t);
+    const double vn = kp.total_sill - kp.near_slope * (r2 * y);
+    const double y2 = y * y;
+    double tp = y2;
+    for (int i = 1; i < kp.pw; ++i) tp *= y2;  // t^-pw
+    const double vf = kp.far_coef * (y * tp);
+    return near ? vn : vf;
+  }
+  return kernel_value_dev<FAM>(r2, kp);
+}
+template <int FAM>
+__device__ __forceinline__ void kernel_acc(double &acc, double mag, double w) {
+  if (FAM == KF_LINEAR) acc -= mag * w;
+  else acc += mag * w;
+}
+
+// kernel value for well-separated pairs (M2P, P2L: the cells are not adjacent, so r2 is a positive normal
+// number and the zero-distance guards of kernel_value_dev are dead code)
+template <int FAM>
+__device__ __forceinline__ double kernel_value_far(double r2, const KParams &kp) {
+  if (FAM == KF_LINEAR) {
+    return -fast_sqrt(r2);
+  } else if (FAM == KF_TPS) {
+    return (0.5 * r2) * log(r2);
+  } else if (FAM == KF_CUBIC) {
+    return r2 * fast_sqrt(r2);
+  } else if (FAM == KF_SPH) {
+    return kernel_value_dev<KF_SPH>(r2, kp);
+  } else if (FAM == KF_LAPLACE) {
+    return fast_rsqrt(r2);
+  } else if (FAM == KF_R2) {
+    const double y = fast_rsqrt(r2);
+    return y * y;
+  } else {
+    const double y = fast_rsqrt(r2);
+    const double y2 = y * y;
+    return y2 * y2;
+  }
+}
+template <int FAM>
+__device__ __forceinline__ double kernel_mag_far(double r2, const KParams &kp) {
+  if (FAM == KF_LINEAR) return fast_sqrt(r2);
+  return kernel_value_far<FAM>(r2, kp);
 }
 #endif
 
