@@ -85,6 +85,8 @@ SIGNATURES = {
     "fb_last_error": (C.c_char_p, []),
     "fb_kernel_launch_count": (C.c_uint64, []),
     "fb_set_device": (C.c_int, [C.c_int]),
+    "fb_set_sqrt_mode": (C.c_int, [C.c_int]),
+    "fb_get_sqrt_mode": (C.c_int, []),
     "fb_tree_new": (C.c_int, [_dp, _sz, C.c_int, _pd, _pd, C.c_int, C.POINTER(FbKernelParams), C.c_int, C.c_int,
                               _dp, C.POINTER(FbFmmParams), C.POINTER(C.c_void_p)]),
     "fb_tree_free": (None, [C.c_void_p]),

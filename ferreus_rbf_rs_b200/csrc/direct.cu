@@ -35,9 +35,9 @@ __device__ __forceinline__ void accumulate_tile(const SrcTile<NR> &t, int m, dou
       g[1] += fw * dy;
       g[2] += fw * dz;
     } else {
-      const double v = kernel_value_dev<FAM>(r2, kp);
+      const double v = kernel_mag<FAM, false, true>(r2, kp);
 #pragma unroll
-      for (int r = 0; r < NR; ++r) acc[r] += v * t.w[r][j];
+      for (int r = 0; r < NR; ++r) kernel_acc<FAM>(acc[r], v, t.w[r][j]);
     }
   }
 }
@@ -128,244 +128,16 @@ __global__ void __launch_bounds__(kTile) k_leaf_direct(const DirectArgs a) {
   }
 }
 
-// P2L: targets are the Chebyshev nodes of a cell, sources the points of its X-list leaves.
-template <int FAM, int NR>
-__global__ void __launch_bounds__(kTile) k_p2l(const P2LArgs a) {
-  const int ci = blockIdx.x;
-  const int c = a.cells[ci];
-  if (!a.cell_flag[c]) return;
-  const int tid = threadIdx.x;
-  const int p = a.p, P = a.P;
-  const int nd = blockIdx.y * kTile + tid;
-  const bool active = nd < P;
-  double xt = 0, yt = 0, zt = 0;
-  if (active) {
-    int i0, i1, i2;
-    if (a.dim == 3) {
-      i2 = nd % p;
-      i1 = (nd / p) % p;
-      i0 = nd / (p * p);
-    } else if (a.dim == 2) {
-      i1 = nd % p;
-      i0 = nd / p;
-      i2 = 0;
-    } else {
-      i0 = nd;
-      i1 = i2 = 0;
-    }
-    const double h = a.chalf[c];
-    xt = a.ccx[c] + h * a.nodes[i0];
-    yt = a.dim > 1 ? a.ccy[c] + h * a.nodes[i1] : 0.0;
-    zt = a.dim > 2 ? a.ccz[c] + h * a.nodes[i2] : 0.0;
-  }
-  double acc[NR];
-  double g[1] = {0.0};
-#pragma unroll
-  for (int r = 0; r < NR; ++r) acc[r] = 0.0;
-  __shared__ SrcTile<NR> st;
-  for (long long e = a.x_ptr[ci]; e < a.x_ptr[ci + 1]; ++e) {
-    const int b = a.x_begin[e], n = a.x_count[e];
-    for (int c0 = 0; c0 < n; c0 += kTile) {
-      const int m = min(kTile, n - c0);
-      __syncthreads();
-      if (tid < m) {
-        const int s = b + c0 + tid;
-        st.x[tid] = a.sx[s];
-        st.y[tid] = a.sy[s];
-        st.z[tid] = a.sz[s];
-#pragma unroll
-        for (int r = 0; r < NR; ++r) st.w[r][tid] = a.w[(size_t)(a.rhs0 + r) * a.n + s];
-      }
-      __syncthreads();
-      accumulate_tile<FAM, NR, false>(st, m, xt, yt, zt, a.kp, acc, g);
-    }
-  }
-  if (active) {
-#pragma unroll
-    for (int r = 0; r < NR; ++r) a.loc[((size_t)c * a.nrhs + a.rhs0 + r) * P + nd] += acc[r];
-  }
-}
-
-
-// ======================================================================================================
-// Value-only fast path of the leaf pass.  Measured on B200 (profiles/): the one-target-per-lane kernels are
-// FP64-pipe bound per issued warp; what is lost is lane utilisation and operation count, so:
-//  * P2P: every warp streams its own 32-source tiles through a private, double-buffered shared-memory slot
-//    (next tile prefetched into registers while the current one is consumed; only __syncwarp, no block barrier),
-//    and warps without targets skip the loop entirely;
-//  * M2P: the sources are a tensor grid of Chebyshev nodes, so r^2 = (dx2[i0] + dy2[i1]) + dz2[i2] with the
-//    squared axis offsets computed once per (target, W cell): 1 + 7 FP64 operations per pair instead of 13, with
-//    the reference's association (ferreus_rbf_utils/src/utils.rs:230-237).  For p <= 8 the dz2 table lives in
-//    registers (uniformly predicated unroll), otherwise in shared memory.
-// ======================================================================================================
 constexpr int kWarpTile = 32;
 constexpr int kRegOrder = 8;
 
-template <int NR>
-struct WarpTile {  // [buffer][component][lane]
-  double v[2][3 + NR][kWarpTile];
-};
-
-template <int FAM, int NR, bool REGZ>
-__global__ void __launch_bounds__(kTile) k_leaf_direct_v2(const DirectArgs a) {
-  const int tile = blockIdx.x;
-  if (tile >= *a.ts.n_tiles_dev) return;
-  const int li = a.ts.tile_leaf[tile];
-  const int tb = a.ts.leaf_begin[li] + a.ts.tile_off[tile];
-  const int cnt = min(kTile, a.ts.leaf_end[li] - tb);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool active = tid < cnt;
-  double xt = 0, yt = 0, zt = 0;
-  if (active) {
-    xt = a.ts.x[tb + tid];
-    yt = a.ts.y[tb + tid];
-    zt = a.ts.z[tb + tid];
-  }
-  double acc[NR];
-#pragma unroll
-  for (int r = 0; r < NR; ++r) acc[r] = 0.0;
-
-  extern __shared__ double dsm[];
-  WarpTile<NR> *wt = reinterpret_cast<WarpTile<NR> *>(dsm) + warp;
-  double *mw = dsm + (sizeof(WarpTile<NR>) / sizeof(double)) * (kTile / 32);  // [NR][P] multipoles of the W cell
-  double *d2 = mw + (size_t)NR * a.P;                                          // [2 or 3][p][kTile] squared offsets
-  const bool warp_has_targets = warp * 32 < cnt;
-
-  // ---- P2P: warp-private tiles over the merged U ranges
-  if (warp_has_targets) {
-    long long e = a.u_ptr[li];
-    const long long e_end = a.u_ptr[li + 1];
-    int rb = 0, rn = 0, c0 = 0;
-    if (e < e_end) {
-      rb = a.u_begin[e];
-      rn = a.u_count[e];
-    }
-    double reg[3 + NR];
-    auto fetch = [&](int &m) {  // this lane's element of the current tile, then advance
-      m = 0;
-      if (e >= e_end) return;
-      m = min(kWarpTile, rn - c0);
-      if (lane < m) {
-        const int s = rb + c0 + lane;
-        reg[0] = a.sx[s];
-        reg[1] = a.sy[s];
-        reg[2] = a.sz[s];
-#pragma unroll
-        for (int r = 0; r < NR; ++r) reg[3 + r] = a.w[(size_t)(a.rhs0 + r) * a.n + s];
-      }
-      c0 += kWarpTile;
-      if (c0 >= rn) {
-        ++e;
-        c0 = 0;
-        if (e < e_end) {
-          rb = a.u_begin[e];
-          rn = a.u_count[e];
-        }
-      }
-    };
-    int m_cur = 0, m_next = 0, buf = 0;
-    fetch(m_cur);
-    if (lane < m_cur) {
-#pragma unroll
-      for (int k = 0; k < 3 + NR; ++k) wt->v[0][k][lane] = reg[k];
-    }
-    __syncwarp();
-    while (m_cur > 0) {
-      fetch(m_next);  // global loads of the next tile overlap the arithmetic below
-      const double(*t)[kWarpTile] = wt->v[buf];
-#pragma unroll 4
-      for (int j = 0; j < m_cur; ++j) {
-        const double dx = xt - t[0][j], dy = yt - t[1][j], dz = zt - t[2][j];
-        double r2 = dx * dx;
-        r2 += dy * dy;
-        r2 += dz * dz;
-        const double v = kernel_value_dev<FAM>(r2, a.kp);
-#pragma unroll
-        for (int r = 0; r < NR; ++r) acc[r] += v * t[3 + r][j];
-      }
-      buf ^= 1;
-      if (lane < m_next) {
-#pragma unroll
-        for (int k = 0; k < 3 + NR; ++k) wt->v[buf][k][lane] = reg[k];
-      }
-      __syncwarp();
-      m_cur = m_next;
-    }
-  }
-  // ---- M2P: tensor grid of the W cell's Chebyshev nodes
-  const int p = a.p, P = a.P;
-  const int p1 = a.dim > 1 ? p : 1, p2 = a.dim > 2 ? p : 1;
-  for (long long e = a.w_ptr[li]; e < a.w_ptr[li + 1]; ++e) {
-    const int c = a.w_cell[e];
-    const double h = a.chalf[c];
-    __syncthreads();
-    for (int i = tid; i < NR * P; i += kTile) mw[i] = a.mult[((size_t)c * a.nrhs + a.rhs0) * P + i];
-    double dzr[kRegOrder];
-#pragma unroll
-    for (int i = 0; i < kRegOrder; ++i) dzr[i] = 0.0;
-    for (int i = 0; i < p; ++i) {
-      const double nd = a.nodes[i];
-      const double ox = xt - (a.ccx[c] + h * nd);
-      d2[(0 * p + i) * kTile + tid] = ox * ox;
-      if (a.dim > 1) {
-        const double oy = yt - (a.ccy[c] + h * nd);
-        d2[(1 * p + i) * kTile + tid] = oy * oy;
-      }
-      if (a.dim > 2 && !REGZ) {
-        const double oz = zt - (a.ccz[c] + h * nd);
-        d2[(2 * p + i) * kTile + tid] = oz * oz;
-      }
-    }
-    if (REGZ && a.dim > 2) {
-#pragma unroll
-      for (int i = 0; i < kRegOrder; ++i)
-        if (i < p) {
-          const double oz = zt - (a.ccz[c] + h * a.nodes[i]);
-          dzr[i] = oz * oz;
-        }
-    }
-    __syncthreads();
-    if (!warp_has_targets) continue;
-    for (int i0 = 0; i0 < p; ++i0) {
-      const double ax = d2[(0 * p + i0) * kTile + tid];
-      for (int i1 = 0; i1 < p1; ++i1) {
-        const double axy = a.dim > 1 ? ax + d2[(1 * p + i1) * kTile + tid] : ax;
-        const double *wrow = mw + (i0 * p1 + i1) * p2;
-        if (REGZ) {
-#pragma unroll
-          for (int i2 = 0; i2 < kRegOrder; ++i2)
-            if (i2 < p2) {
-              const double r2 = axy + dzr[i2];
-              const double v = kernel_value_dev<FAM>(r2, a.kp);
-#pragma unroll
-              for (int r = 0; r < NR; ++r) acc[r] += v * wrow[(size_t)r * P + i2];
-            }
-        } else {
-#pragma unroll 4
-          for (int i2 = 0; i2 < p2; ++i2) {
-            const double r2 = a.dim > 2 ? axy + d2[(2 * p + i2) * kTile + tid] : axy;
-            const double v = kernel_value_dev<FAM>(r2, a.kp);
-#pragma unroll
-            for (int r = 0; r < NR; ++r) acc[r] += v * wrow[(size_t)r * P + i2];
-          }
-        }
-      }
-    }
-  }
-  if (active) {
-    const size_t row = a.ts.out_row[tb + tid];
-#pragma unroll
-    for (int r = 0; r < NR; ++r) a.out[row * a.nrhs + a.rhs0 + r] += acc[r];
-  }
-}
-
-
 // ======================================================================================================
-// Leaf pass, warp-granular (value only).  ncu on the CTA-granular kernel above (profiles/r1_s2_ncu_full.txt):
+// Leaf pass, warp-granular (value only).  ncu on the earlier CTA-granular kernel (profiles/r1_s2_ncu_full.txt):
 // FP64 pipe 58 % busy, 41 % warps active — a 128-thread CTA serving a 30-point leaf parks three idle warps on
 // the M2P barriers.  Here the work item is one warp = 32 targets of one leaf: no block barrier anywhere, warps
 // without targets retire at once, CTAs are two warps so the block scheduler balances uneven leaves.
-//   P2P  warp-private double-buffered 32-source tiles (as above);
+//   P2P  warp-private double-buffered 32-source tiles: the next tile is prefetched into registers while the
+//        current one is consumed, only __syncwarp;
 //   M2P  squared axis offsets per (target, W cell) in a warp-private table, multipoles staged in warp-private
 //        chunks of whole i0-slabs, r^2 = (dx2[i0] + dy2[i1]) + dz2[i2] (utils.rs:230-237 association); W cells
 //        are never adjacent to the leaf, so r^2 > 0 and the zero-distance select is dropped.
@@ -391,7 +163,7 @@ static inline LeafWarpCfg leaf_warp_cfg(int nr, int p, int dim, bool regz) {
   return c;
 }
 
-template <int FAM, int NR, bool REGZ>
+template <int FAM, int NR, bool REGZ, bool FAST>
 __global__ void __launch_bounds__(kLeafWPC * 32, NR >= 4 ? 7 : 10) k_leaf_warp(const DirectArgs a, const int slabs_per_chunk,
                                                                  const int plane, const int warp_doubles) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -479,7 +251,7 @@ __global__ void __launch_bounds__(kLeafWPC * 32, NR >= 4 ? 7 : 10) k_leaf_warp(c
         double r2 = dx * dx;
         r2 += dy * dy;
         r2 += dz * dz;
-        const double v = kernel_mag_dev<FAM>(r2, a.kp);
+        const double v = kernel_mag<FAM, FAST, true>(r2, a.kp);
 #pragma unroll
         for (int r = 0; r < NR; ++r) kernel_acc<FAM>(acc[r], v, sv[3 + r]);
       }
@@ -556,7 +328,7 @@ __global__ void __launch_bounds__(kLeafWPC * 32, NR >= 4 ? 7 : 10) k_leaf_warp(c
             if (i2 < p2) {
               double v[kM2PQB];
 #pragma unroll
-              for (int u = 0; u < kM2PQB; ++u) v[u] = kernel_mag_far<FAM>(axy[u] + dzr[i2], a.kp);
+              for (int u = 0; u < kM2PQB; ++u) v[u] = kernel_mag<FAM, FAST, false>(axy[u] + dzr[i2], a.kp);
 #pragma unroll
               for (int u = 0; u < kM2PQB; ++u)
 #pragma unroll
@@ -567,7 +339,7 @@ __global__ void __launch_bounds__(kLeafWPC * 32, NR >= 4 ? 7 : 10) k_leaf_warp(c
             const double dz2 = a.dim > 2 ? d2[(2 * p + i2) * 32 + lane] : 0.0;
             double v[kM2PQB];
 #pragma unroll
-            for (int u = 0; u < kM2PQB; ++u) v[u] = kernel_mag_far<FAM>(a.dim > 2 ? axy[u] + dz2 : axy[u], a.kp);
+            for (int u = 0; u < kM2PQB; ++u) v[u] = kernel_mag<FAM, FAST, false>(a.dim > 2 ? axy[u] + dz2 : axy[u], a.kp);
 #pragma unroll
             for (int u = 0; u < kM2PQB; ++u)
 #pragma unroll
@@ -584,20 +356,25 @@ __global__ void __launch_bounds__(kLeafWPC * 32, NR >= 4 ? 7 : 10) k_leaf_warp(c
   }
 }
 
+template <int FAM, int NR, bool REGZ, bool FAST>
+static void launch_leaf_warp(const DirectArgs &a, const LeafWarpCfg &cfg, cudaStream_t s) {
+  const size_t smem = sizeof(double) * (size_t)cfg.total * kLeafWPC;
+  const unsigned grid = (unsigned)(((long long)a.ts.max_tiles * 4 + kLeafWPC - 1) / kLeafWPC);
+  if (smem > 48 * 1024)
+    FB_CUDA(cudaFuncSetAttribute(k_leaf_warp<FAM, NR, REGZ, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  FB_LAUNCH((k_leaf_warp<FAM, NR, REGZ, FAST>), grid, kLeafWPC * 32, smem, s, a, cfg.slabs_per_chunk, cfg.plane, cfg.total);
+}
+
 template <int FAM, int NR>
 static void launch_leaf_v3(const DirectArgs &a, cudaStream_t s) {
   const bool regz = a.dim == 3 && a.p <= kRegOrder;
   const LeafWarpCfg cfg = leaf_warp_cfg(NR, a.p, a.dim, regz);
-  const size_t smem = sizeof(double) * (size_t)cfg.total * kLeafWPC;
-  const unsigned grid = (unsigned)(((long long)a.ts.max_tiles * 4 + kLeafWPC - 1) / kLeafWPC);
-  if (regz) {
-    if (smem > 48 * 1024)
-      FB_CUDA(cudaFuncSetAttribute(k_leaf_warp<FAM, NR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FB_LAUNCH((k_leaf_warp<FAM, NR, true>), grid, kLeafWPC * 32, smem, s, a, cfg.slabs_per_chunk, cfg.plane, cfg.total);
+  if (kernel_has_fast<FAM>() && a.kp.fast) {
+    if (regz) launch_leaf_warp<FAM, NR, true, kernel_has_fast<FAM>()>(a, cfg, s);
+    else launch_leaf_warp<FAM, NR, false, kernel_has_fast<FAM>()>(a, cfg, s);
   } else {
-    if (smem > 48 * 1024)
-      FB_CUDA(cudaFuncSetAttribute(k_leaf_warp<FAM, NR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FB_LAUNCH((k_leaf_warp<FAM, NR, false>), grid, kLeafWPC * 32, smem, s, a, cfg.slabs_per_chunk, cfg.plane, cfg.total);
+    if (regz) launch_leaf_warp<FAM, NR, true, false>(a, cfg, s);
+    else launch_leaf_warp<FAM, NR, false, false>(a, cfg, s);
   }
 }
 
@@ -613,7 +390,7 @@ constexpr int kP2LTileMax = 128;  // sources per staged tile (upper bound)
 constexpr int kP2LJB = 4;          // sources in flight per thread (independent kernel evaluations)
 constexpr int kP2LPF = 3;          // coordinates a thread prefetches per tile (tile * dim <= kP2LPF * blockDim)
 
-template <int FAM, int NR, int PREG>
+template <int FAM, int NR, int PREG, bool FAST>
 __global__ void __launch_bounds__(256, (NR * PREG <= 16) ? 2 : 1) k_p2l_grid(const P2LArgs a, const int nslices, const int cols, const int T) {
   const int ci = blockIdx.x;
   const int c = a.cells[ci];
@@ -721,7 +498,7 @@ __global__ void __launch_bounds__(256, (NR * PREG <= 16) ? 2 : 1) k_p2l_grid(con
             for (int u = 0; u < kP2LJB; ++u) {
               const double r2 = axy[u] + nx[u];
               if (il + 1 < PREG) nx[u] = dl[u][il + 1];  // next step's offsets are in flight during this one
-              v[u] = kernel_mag_far<FAM>(r2, a.kp);
+              v[u] = kernel_mag<FAM, FAST, false>(r2, a.kp);
             }
 #pragma unroll
             for (int u = 0; u < kP2LJB; ++u)
@@ -751,8 +528,8 @@ __global__ void __launch_bounds__(256, (NR * PREG <= 16) ? 2 : 1) k_p2l_grid(con
   }
 }
 
-template <int FAM, int NR, int PREG>
-static void launch_p2l_grid(const P2LArgs &a, cudaStream_t s) {
+template <int FAM, int NR, int PREG, bool FAST>
+static void launch_p2l_grid_impl(const P2LArgs &a, cudaStream_t s) {
   const int cols = a.dim == 3 ? a.p * a.p : (a.dim == 2 ? a.p : 1);
   const int nslices = std::min(32, std::max(1, 256 / cols));
   const int nthreads = std::max(128, std::min(256, ((nslices * cols + 31) / 32) * 32));
@@ -762,45 +539,16 @@ static void launch_p2l_grid(const P2LArgs &a, cudaStream_t s) {
   const size_t red_d = (size_t)nslices * a.P;
   const size_t smem = sizeof(double) * std::max(tab_d, red_d);
   if (smem > 48 * 1024)
-    FB_CUDA(cudaFuncSetAttribute(k_p2l_grid<FAM, NR, PREG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  FB_LAUNCH((k_p2l_grid<FAM, NR, PREG>), a.n_cells, nthreads, smem, s, a, nslices, cols, T);
+    FB_CUDA(cudaFuncSetAttribute(k_p2l_grid<FAM, NR, PREG, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  FB_LAUNCH((k_p2l_grid<FAM, NR, PREG, FAST>), a.n_cells, nthreads, smem, s, a, nslices, cols, T);
 }
-
-template <int FAM, int NR>
-static void launch_leaf_v2(const DirectArgs &a, cudaStream_t s) {
-  const bool regz = a.dim == 3 && a.p <= kRegOrder;
-  const size_t smem = sizeof(WarpTile<NR>) * (kTile / 32) +
-                      sizeof(double) * ((size_t)NR * a.P + (regz ? 2 : 3) * (size_t)a.p * kTile);
-  if (regz) {
-    if (smem > 48 * 1024)
-      FB_CUDA(cudaFuncSetAttribute(k_leaf_direct_v2<FAM, NR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FB_LAUNCH((k_leaf_direct_v2<FAM, NR, true>), a.ts.max_tiles, kTile, smem, s, a);
-  } else {
-    if (smem > 48 * 1024)
-      FB_CUDA(cudaFuncSetAttribute(k_leaf_direct_v2<FAM, NR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FB_LAUNCH((k_leaf_direct_v2<FAM, NR, false>), a.ts.max_tiles, kTile, smem, s, a);
-  }
-}
-
-template <int FAM, int NR>
-static void launch_p2l_v2(const P2LArgs &a, cudaStream_t s) {
-  dim3 grid(a.n_cells, (a.P + kTile - 1) / kTile);
-  FB_LAUNCH((k_p2l<FAM, NR>), grid, kTile, 0, s, a);
+template <int FAM, int NR, int PREG>
+static void launch_p2l_grid(const P2LArgs &a, cudaStream_t s) {
+  if (kernel_has_fast<FAM>() && a.kp.fast) launch_p2l_grid_impl<FAM, NR, PREG, kernel_has_fast<FAM>()>(a, s);
+  else launch_p2l_grid_impl<FAM, NR, PREG, false>(a, s);
 }
 
 // ---------------------------------------------------------------------------------- dispatch
-static int env_int(const char *name, int dflt) {
-  const char *v = std::getenv(name);
-  return v ? std::atoi(v) : dflt;
-}
-
-template <int FAM, int NR>
-static void launch_leaf(const DirectArgs &a, cudaStream_t s) {
-  static const int impl = env_int("FB_LEAF_IMPL", 3);  // 2 = CTA-granular kernel (kept for A/B profiling)
-  if (impl == 2) launch_leaf_v2<FAM, NR>(a, s);
-  else launch_leaf_v3<FAM, NR>(a, s);
-}
-
 template <int FAM>
 static void leaf_direct_fam(DirectArgs a, cudaStream_t s) {
   const int grid = a.ts.max_tiles;
@@ -817,16 +565,16 @@ static void leaf_direct_fam(DirectArgs a, cudaStream_t s) {
     a.rhs0 = r;
     const int left = a.nrhs - r;
     if (left >= 8) {
-      launch_leaf<FAM, 8>(a, s);
+      launch_leaf_v3<FAM, 8>(a, s);
       r += 8;
     } else if (left >= 4) {
-      launch_leaf<FAM, 4>(a, s);
+      launch_leaf_v3<FAM, 4>(a, s);
       r += 4;
     } else if (left >= 2) {
-      launch_leaf<FAM, 2>(a, s);
+      launch_leaf_v3<FAM, 2>(a, s);
       r += 2;
     } else {
-      launch_leaf<FAM, 1>(a, s);
+      launch_leaf_v3<FAM, 1>(a, s);
       r += 1;
     }
   }
@@ -835,23 +583,11 @@ static void leaf_direct_fam(DirectArgs a, cudaStream_t s) {
 template <int FAM>
 static void p2l_fam(P2LArgs a, cudaStream_t s) {
   if (a.n_cells <= 0) return;
-  static const int impl = env_int("FB_P2L_IMPL", 2);  // 1 = one-thread-per-node kernel (kept for A/B profiling)
   int r = 0;
   while (r < a.nrhs) {
     a.rhs0 = r;
     const int left = a.nrhs - r;
-    if (impl == 1) {
-      if (left >= 4) {
-        launch_p2l_v2<FAM, 4>(a, s);
-        r += 4;
-      } else if (left >= 2) {
-        launch_p2l_v2<FAM, 2>(a, s);
-        r += 2;
-      } else {
-        launch_p2l_v2<FAM, 1>(a, s);
-        r += 1;
-      }
-    } else if (a.p <= 8) {
+    if (a.p <= 8) {  // p accumulators per right-hand side live in registers: 8 or 16 slots
       if (left >= 4) {
         launch_p2l_grid<FAM, 4, 8>(a, s);
         r += 4;

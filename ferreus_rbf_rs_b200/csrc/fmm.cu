@@ -14,6 +14,11 @@
 namespace fb {
 
 std::atomic<uint64_t> g_launches{0};
+static int initial_sqrt_mode() {
+  const char *v = std::getenv("FB_SQRT");
+  return (v && std::string(v) == "fast") ? 1 : 0;
+}
+std::atomic<int> g_sqrt_mode{initial_sqrt_mode()};
 static thread_local std::string t_last_error;
 void set_last_error(const std::string &msg) { t_last_error = msg; }
 
@@ -49,6 +54,7 @@ void fb_tree::build(const double *points, size_t n_, int dim_, ptrdiff_t rs, ptr
   // kernel_helpers.rs:72-73 asserts live in KernelParamsBuilder::build (mirrored by the Python KernelParams class);
   // FmmTree::new itself accepts any KernelParams
   FB_REQUIRE(make_kparams(*k, kp), "unknown kernel_type");
+  kp.fast = g_sqrt_mode.load();
   kparams_c = *k;
   n = n_;
   dim = dim_;
@@ -798,6 +804,11 @@ extern "C" {
 
 const char *fb_last_error(void) { return t_last_error.c_str(); }
 uint64_t fb_kernel_launch_count(void) { return g_launches.load(); }
+int fb_set_sqrt_mode(int fast) {
+  g_sqrt_mode.store(fast ? 1 : 0);
+  return FB_OK;
+}
+int fb_get_sqrt_mode(void) { return g_sqrt_mode.load(); }
 int fb_set_device(int device) {
   return guarded([&] { FB_CUDA(cudaSetDevice(device)); });
 }

@@ -19,6 +19,7 @@ enum KFam { KF_LINEAR = 0, KF_TPS, KF_CUBIC, KF_SPH, KF_LAPLACE, KF_R2, KF_R4, K
 
 struct KParams {
   int fam;
+  int fast;           // 1: second-order square roots in the direct-sum hot loops (see kernel_mag)
   int pw;             // spheroidal POW (1..4), rbf_kernels.rs:176-203
   double s2;          // s^2, s = range_scaling / base_range
   double ip2;         // inflexion_point^2
@@ -146,131 +147,83 @@ __device__ __forceinline__ double rsq64h(double a) {
 }
 // With y0 = (1 + d) / sqrt(a):  r = a y0,  e = 1 - r y0 = 1 - (1 + d)^2,  and  (1 - e)^(-1/2) = 1 + e/2 + 3e^2/8 + O(e^3):
 //   sqrt(a)   = r  + (r  e)(1/2 + 3e/8),      1/sqrt(a) = y0 + (y0 e)(1/2 + 3e/8)        (remainder 5e^3/16 < 2^-61)
-// 5 FP64 operations, branch-free, no IEEE slow path, no exponent fix-up of the seed.
-__device__ __forceinline__ double fast_sqrt(double a) {
-  const double y0 = rsq64h(a);
-  const double r = a * y0;
-  const double e = fma(-r, y0, 1.0);
-  const double c = fma(e, 0.375, 0.5);
-  return fma(r * e, c, r);
-}
-__device__ __forceinline__ double fast_rsqrt(double a) {
-  const double y0 = rsq64h(a);
-  const double e = fma(-(a * y0), y0, 1.0);
-  const double c = fma(e, 0.375, 0.5);
-  return fma(y0 * e, c, y0);
-}
+// 5 FP64 operations, branch-free, no IEEE slow path, no exponent fix-up of the seed (hot_sqrt / hot_rsqrt below).
 // seed taken from max(a, 2^-1022) (one integer max on the high word): a == 0 then gives r = 0 * finite = 0, e = 1 and
 // the results sqrt -> exactly 0, a * rsqrt -> exactly 0, without a select on the FP64 result
 __device__ __forceinline__ double seed_operand(double a) {
   return __hiloint2double(max(__double2hiint(a), 0x00100000), __double2loint(a));
 }
-__device__ __forceinline__ double fast_sqrt_z(double a) {  // sqrt(a) for a >= 0 (0 -> 0)
-  const double y0 = rsq64h(seed_operand(a));
+// ---- hot-loop variants -------------------------------------------------------------------------------
+// FAST = false: third-order step, ~1 ulp (measured 1.7e-16 max relative error, tools/fp64_ubench.cu).
+// FAST = true : second-order step r + r (1/2 - r y0 / 2): 3 FP64 operations instead of 5, relative error
+//               -1.5 d^2 with |d| <= 2^-20.1 the seed error: measured <= 1.24e-12.  Opt-in (fb_set_sqrt_mode /
+//               FB_SQRT=fast); the parity gates (1e-10 matvec, 1e-8 interpolant) hold in both modes.
+__device__ __forceinline__ double half_of(double y) {  // y / 2 as an exponent decrement on the integer pipe
+  return __hiloint2double(__double2hiint(y) - 0x00100000, __double2loint(y));
+}
+template <bool FAST, bool ZERO_OK>
+__device__ __forceinline__ double hot_sqrt(double a) {  // ZERO_OK: a == 0 -> exactly 0 (seed from max(a, 2^-1022))
+  const double y0 = rsq64h(ZERO_OK ? seed_operand(a) : a);
   const double r = a * y0;
+  if (FAST) {
+    const double e = fma(-r, half_of(y0), 0.5);
+    return fma(r, e, r);
+  }
   const double e = fma(-r, y0, 1.0);
   const double c = fma(e, 0.375, 0.5);
   return fma(r * e, c, r);
 }
-__device__ __forceinline__ double fast_rsqrt_z(double a) {  // finite for a == 0 (a * result == 0)
-  const double y0 = rsq64h(seed_operand(a));
+template <bool FAST, bool ZERO_OK>
+__device__ __forceinline__ double hot_rsqrt(double a) {  // ZERO_OK: finite for a == 0, a * result == 0
+  const double y0 = rsq64h(ZERO_OK ? seed_operand(a) : a);
+  if (FAST) {
+    const double e = fma(-(a * y0), half_of(y0), 0.5);
+    return fma(y0, e, y0);
+  }
   const double e = fma(-(a * y0), y0, 1.0);
   const double c = fma(e, 0.375, 0.5);
   return fma(y0 * e, c, y0);
 }
-// true when a (a sum of squares, sign bit clear) is a normal positive number: integer test on the high word
-__device__ __forceinline__ bool pos_normal(double a) { return __double2hiint(a) >= 0x00100000; }
 
-// device kernel value: same math as kernel_value<FAM> to ~2 ulp, no divisions, no branches in the hot loop
-template <int FAM>
-__device__ __forceinline__ double kernel_value_dev(double r2, const KParams &kp) {
-  const bool ok = pos_normal(r2);
+// Sign-stripped kernel value + signed accumulate: for the linear kernel (-r) the negation rides on the DFMA
+// operand modifier instead of costing an FP64 instruction per pair (the compiler hoists a plain negation above a
+// select).  NEAR = true: r2 may be 0 (P2P, self term included); false: well-separated cells (M2P, P2L), r2 > 0.
+template <int FAM, bool FAST, bool NEAR>
+__device__ __forceinline__ double kernel_mag(double r2, const KParams &kp) {
   if (FAM == KF_LINEAR) {
-    const double r = fast_sqrt(r2);
-    return ok ? -r : 0.0;
-  } else if (FAM == KF_TPS) {  // r^2 ln r = r2 * ln(r2) / 2
-    const double v = (0.5 * r2) * log(r2);
-    return (r2 >= kEps * kEps) ? v : 0.0;
+    return hot_sqrt<FAST, NEAR>(r2);
   } else if (FAM == KF_CUBIC) {
-    const double r = fast_sqrt(r2);
-    return ok ? r2 * r : 0.0;
+    return r2 * hot_sqrt<FAST, NEAR>(r2);
   } else if (FAM == KF_SPH) {
     const double sr2 = kp.s2 * r2;
     const bool near = sr2 <= kp.ip2;
     const double t = 1.0 + sr2;
-    const double y = fast_rsqrt(near ? r2 : t);
-    const double vn = kp.total_sill - kp.near_slope * (ok ? r2 * y : 0.0);
-    const double y2 = y * y;
-    double tp = y2;
-    for (int i = 1; i < kp.pw; ++i) tp *= y2;  // t^-pw
-    const double vf = kp.far_coef * (y * tp);
-    return near ? vn : vf;
-  } else if (FAM == KF_LAPLACE) {
-    const double y = fast_rsqrt(r2);
-    return (r2 >= kEps * kEps) ? y : 0.0;
-  } else if (FAM == KF_R2) {
-    const double y = fast_rsqrt(r2);
-    return (r2 >= kEps * kEps) ? y * y : 0.0;
-  } else {
-    const double y = fast_rsqrt(r2);
-    const double y2 = y * y;
-    return (r2 >= kEps * kEps) ? y2 * y2 : 0.0;
-  }
-}
-
-// sign-stripped value + signed accumulate: for the linear kernel (-r) the negation rides on the DFMA operand
-// modifier instead of costing an FP64 instruction per pair (the compiler hoists a plain negation above the select)
-template <int FAM>
-__device__ __forceinline__ double kernel_mag_dev(double r2, const KParams &kp) {
-  if (FAM == KF_LINEAR) return fast_sqrt_z(r2);
-  if (FAM == KF_CUBIC) return r2 * fast_sqrt_z(r2);
-  if (FAM == KF_SPH) {
-    const double sr2 = kp.s2 * r2;
-    const bool near = sr2 <= kp.ip2;
-    const double t = 1.0 + sr2;
-    const double y = fast_rsqrt_z(near ? r2 : t);
+    const double y = hot_rsqrt<FAST, NEAR>(near ? r2 : t);
     const double vn = kp.total_sill - kp.near_slope * (r2 * y);
     const double y2 = y * y;
     double tp = y2;
     for (int i = 1; i < kp.pw; ++i) tp *= y2;  // t^-pw
     const double vf = kp.far_coef * (y * tp);
     return near ? vn : vf;
+  } else if (FAM == KF_TPS) {  // r^2 ln r = r2 * ln(r2) / 2
+    const double v = (0.5 * r2) * log(r2);
+    return (!NEAR || r2 >= kEps * kEps) ? v : 0.0;
+  } else {
+    const double y = hot_rsqrt<false, false>(r2);
+    const double y2 = y * y;
+    const double v = FAM == KF_LAPLACE ? y : (FAM == KF_R2 ? y2 : y2 * y2);
+    return (!NEAR || r2 >= kEps * kEps) ? v : 0.0;
   }
-  return kernel_value_dev<FAM>(r2, kp);
 }
 template <int FAM>
 __device__ __forceinline__ void kernel_acc(double &acc, double mag, double w) {
   if (FAM == KF_LINEAR) acc -= mag * w;
   else acc += mag * w;
 }
-
-// kernel value for well-separated pairs (M2P, P2L: the cells are not adjacent, so r2 is a positive normal
-// number and the zero-distance guards of kernel_value_dev are dead code)
+// families whose hot loop has a FAST variant (the others ignore the switch)
 template <int FAM>
-__device__ __forceinline__ double kernel_value_far(double r2, const KParams &kp) {
-  if (FAM == KF_LINEAR) {
-    return -fast_sqrt(r2);
-  } else if (FAM == KF_TPS) {
-    return (0.5 * r2) * log(r2);
-  } else if (FAM == KF_CUBIC) {
-    return r2 * fast_sqrt(r2);
-  } else if (FAM == KF_SPH) {
-    return kernel_value_dev<KF_SPH>(r2, kp);
-  } else if (FAM == KF_LAPLACE) {
-    return fast_rsqrt(r2);
-  } else if (FAM == KF_R2) {
-    const double y = fast_rsqrt(r2);
-    return y * y;
-  } else {
-    const double y = fast_rsqrt(r2);
-    const double y2 = y * y;
-    return y2 * y2;
-  }
-}
-template <int FAM>
-__device__ __forceinline__ double kernel_mag_far(double r2, const KParams &kp) {
-  if (FAM == KF_LINEAR) return fast_sqrt(r2);
-  return kernel_value_far<FAM>(r2, kp);
+constexpr bool kernel_has_fast() {
+  return FAM == KF_LINEAR || FAM == KF_CUBIC || FAM == KF_SPH;
 }
 #endif
 

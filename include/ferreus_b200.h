@@ -69,6 +69,11 @@ const char *fb_last_error(void);
 uint64_t fb_kernel_launch_count(void);
 /* CUDA device used by handles created afterwards on this thread (default: current device) */
 int fb_set_device(int device);
+/* Square-root mode of the direct-sum hot loops (P2P, M2P, P2L) for trees and models built AFTER the call:
+ * 0 = third-order refinement, ~1 ulp (default); 1 = second-order refinement, relative error <= 1.3e-12 per kernel
+ * value, ~25 % fewer FP64 operations.  The environment variable FB_SQRT=fast|exact sets the initial value.     */
+int fb_set_sqrt_mode(int fast);
+int fb_get_sqrt_mode(void);
 
 /* FmmTree::new  (ferreus_rbf_utils/src/utils.rs:392-421 -> ferreus_bbfmm/src/bbfmm.rs:272-353).
  * points: n x dim (dim 1..3).  extents: NULL or [mins..., maxs...] (2*dim doubles).            */

@@ -1,5 +1,6 @@
 // Micro-benchmarks behind the direct-sum kernel design: FP64 pipe, MUFU.RSQ64H and mixed-loop
 // throughput on the current GPU.  Build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o fp64_ubench fp64_ubench.cu
+#include <cmath>
 #include <cstdio>
 #include <cuda_runtime.h>
 
@@ -31,11 +32,30 @@ __device__ __forceinline__ double sqrt_var(double a) {
     return fma(r, 0.999, 1e-3);
   } else if (VAR == 4) {
     return sqrt(a);
-  } else {
+  } else if (VAR == 5) {
     const float yf = rsqrtf((float)a);
     const double y0 = (double)yf, h = (double)(0.5f * yf), r = a * y0, d = fma(-r, r, a);
     return fma(d, h, r);
+  } else if (VAR == 6) {  // cost probe: integer "magic" seed instead of MUFU (accuracy is not the point)
+    const double y0 = __hiloint2double(0x5fe6eb50 - (__double2hiint(a) >> 1), 0);
+    const double r = a * y0, e = fma(-r, y0, 1.0), c = fma(e, 0.375, 0.5);
+    return fma(r * e, c, r);
+  } else if (VAR == 7) {  // cubic step without the halved seed (the sequence the library uses)
+    const double y0 = rsq64h(a), r = a * y0, e = fma(-r, y0, 1.0), c = fma(e, 0.375, 0.5);
+    return fma(r * e, c, r);
+  } else {  // VAR 8: quadratic step, 3 FP64 ops:  r + r (1/2 - r y0/2)
+    const double y0 = rsq64h(a), h = halve(y0), r = a * y0, e = fma(-r, h, 0.5);
+    return fma(r, e, r);
   }
+}
+
+// accuracy probe: seed, quadratic and cubic results for log-uniform inputs
+__global__ void k_acc(const double *x, double *seed, double *quad, double *cub, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  seed[i] = rsq64h(x[i]);
+  quad[i] = sqrt_var<8>(x[i]);
+  cub[i] = sqrt_var<7>(x[i]);
 }
 
 // the M2P / P2L inner loop: r2 = axy + dz2[i2]; v = sqrt(r2); acc -= v * w  (7 FP64 ops per pair with VAR 0)
@@ -208,8 +228,38 @@ int main() {
     printf("p2p  var %d unr %d  %2d warps/SM: %7.2f Gpair/s  (%.3f pair-warps/clk/SM)\n", VAR, UNR, BPS * TH / 32, \
            pairs / (ms * 1e-3) / 1e9, rate(pairs / 32, ms));                                                       \
   }
+  FAR(6, 4, 8, 256) FAR(6, 4, 2, 256) FAR(7, 4, 8, 256) FAR(7, 4, 2, 256) FAR(8, 4, 8, 256) FAR(8, 4, 2, 256)
+  FAR(7, 4, 1, 256) FAR(7, 4, 3, 256) FAR(7, 2, 3, 256) FAR(7, 2, 4, 256) FAR(7, 8, 2, 256) FAR(8, 4, 3, 256)
+  {
+    const int n = 1 << 20;
+    double *hx = new double[n], *hs = new double[n], *hq = new double[n], *hc = new double[n];
+    unsigned long long st = 88172645463325252ull;
+    for (int i = 0; i < n; ++i) {
+      st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+      const double u = (st >> 11) * (1.0 / 9007199254740992.0);
+      hx[i] = exp2(-40.0 + 80.0 * u);
+    }
+    double *dx, *ds, *dq, *dc;
+    cudaMalloc(&dx, n * 8); cudaMalloc(&ds, n * 8); cudaMalloc(&dq, n * 8); cudaMalloc(&dc, n * 8);
+    cudaMemcpy(dx, hx, n * 8, cudaMemcpyHostToDevice);
+    k_acc<<<n / 256, 256>>>(dx, ds, dq, dc, n);
+    cudaMemcpy(hs, ds, n * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(hq, dq, n * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(hc, dc, n * 8, cudaMemcpyDeviceToHost);
+    long double es = 0, eq = 0, ec = 0;
+    for (int i = 0; i < n; ++i) {
+      const long double t = sqrtl((long double)hx[i]);
+      const long double a = fabsl((long double)hs[i] * t - 1.0L), b = fabsl((long double)hq[i] / t - 1.0L),
+                        c = fabsl((long double)hc[i] / t - 1.0L);
+      if (a > es) es = a;
+      if (b > eq) eq = b;
+      if (c > ec) ec = c;
+    }
+    printf("max relative error over 2^20 log-uniform inputs: MUFU.RSQ64H seed %.3Le (2^%.1Lf), 3-op sqrt %.3Le, 5-op sqrt %.3Le\n",
+           es, log2l(es), eq, ec);
+  }
   P2P(0, 1, 8, 256) P2P(0, 2, 8, 256) P2P(0, 4, 8, 256) P2P(0, 8, 8, 256) P2P(0, 4, 4, 256) P2P(0, 4, 2, 256)
-  P2P(1, 4, 8, 256) P2P(2, 4, 8, 256) P2P(3, 4, 8, 256) P2P(4, 4, 8, 256) P2P(5, 4, 8, 256)
+  P2P(1, 4, 8, 256) P2P(2, 4, 8, 256) P2P(3, 4, 8, 256) P2P(4, 4, 8, 256) P2P(5, 4, 8, 256) P2P(6, 4, 8, 256) P2P(7, 4, 8, 256) P2P(7, 4, 2, 256) P2P(8, 4, 8, 256) P2P(8, 4, 2, 256)
   printf("status: %s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
 }
