@@ -312,6 +312,8 @@ void fb_tree::build(const double *points, size_t n_, int dim_, ptrdiff_t rs, ptr
   {
     std::vector<int> pt(ops.perm.begin(), ops.perm.end());
     d_perm_tab.upload(pt, stream);
+    std::vector<int> it(ops.inv_perm.begin(), ops.inv_perm.end());
+    d_inv_tab.upload(it, stream);
   }
   // M2L groups: entries (target, source, permutation) per (level, reference vector), sorted by target
   {
@@ -483,8 +485,8 @@ void fb_tree::downward(const uint8_t *flags) {
   do {                                                                                                             \
     set_smem(k_m2l<COMP, NCV>, m2l_smem);                                                                          \
     FB_LAUNCH((k_m2l<COMP, NCV>), m2l_ctas, 256, m2l_smem, stream, tab, (int)m2l_groups.size(), d_m2l_tgt.p,       \
-              d_m2l_src.p, d_m2l_perm.p, d_oppool.p, d_perm_tab.p, P, m2l_P4, m2l_Pp, nrhs, flags, d_mult.p,      \
-              d_loc.p);                                                                                            \
+              d_m2l_src.p, d_m2l_perm.p, d_oppool.p, d_perm_tab.p, d_inv_tab.p, P, m2l_P4, m2l_Pp, nrhs, flags,    \
+              d_mult.p, d_loc.p);                                                                                  \
   } while (0)
     if (compressed) {
       if (m2l_nc == 32) FB_M2L_LAUNCH(true, 32);

@@ -347,17 +347,22 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
 
 // (entry, rhs) columns per CTA: NC = 32, 16 or 8 (chosen so the staged multipoles fit in shared memory);
 // the row stride of Ys is NC + 4 == 4 or 12 (mod 16) -> conflict-free B fragments
-constexpr int kM2LChunk = 4;                 // rank tiles (8 rows each) accumulated per pass over the reduction
+
+constexpr int kM2LChunk = 4;  // rank tiles (8 rows each) accumulated per pass over the reduction
+constexpr int kM2LPre = 8;    // k-steps of operator fragments prefetched per block in the second contraction
 
 // M2L for one (level, reference vector) group (bbfmm.rs:864-986) as two dense contractions on the FP64 tensor
-// cores.  A CTA owns 32 (entry, rhs) columns:
+// cores.  A CTA owns NC (entry, rhs) columns:
 //   Xs[c][j] = M_src[perm[j]]   permuted multipoles, staged once in shared memory (column stride Pp, Pp == 4 or
 //                               12 mod 16 so the B fragments are bank-conflict free)
-//   Ys = Vt Xs  (rank x 32)     8 warps = 4 column tiles x 2 halves of the P-long reduction, summed in smem
-//   Zs = U  Ys  (P x 32)        warps stride over the 8-row tiles of U; accumulators are scattered straight from
-//                               the fragments through the inverse permutation:  L_tgt[perm[m]] += Zs[m]
+//   Ys = Vt Xs  (rank x NC)     8 warps = NC/8 column tiles x slices of the P-long reduction, summed in shared memory
+//   Zs = U  Ys  (P x NC)        warps stride over the 8-row tiles of U; the accumulator fragments are parked in
+//                               shared memory (over Xs, which is dead by then)
+//   flush                       L_tgt[i] += sum over the columns of the same (target, rhs) of Zs[c][inv_perm_c[i]]:
+//                               one coalesced RED per (target, node) instead of one scattered RED per (entry, node)
 // Operators are stored in DMMA fragment order, zero padded: frag(mt, ks)[lane] = Op[mt*8 + lane/4][ks*4 + lane%4],
-// so every A fragment is one coalesced 256-byte load shared by all warps through L1.
+// so every A fragment is one coalesced 256-byte load.  ncu before this layout (profiles/r1_s2_ncu_full.txt): 47 % of
+// the stalls were long-scoreboard waits on the per-element permutation loads of the scatter and on the fragment loads.
 struct M2LGroupDev {  // one (level, reference vector) group of the fused M2L launch
   int cta_begin;        // first CTA of the group
   int rank_pad;
@@ -369,7 +374,7 @@ struct M2LGroupDev {  // one (level, reference vector) group of the fused M2L la
 template <bool COMPRESSED, int NC>
 __global__ void __launch_bounds__(256, NC == 32 ? 2 : 1) k_m2l(const M2LGroupDev *groups, int n_groups, const int *e_tgt_all,
                                                 const int *e_src_all, const int *e_perm_all, const double *pool,
-                                                const int *perm_tab, int P, int P4, int Pp, int nrhs,
+                                                const int *perm_tab, const int *inv_tab, int P, int P4, int Pp, int nrhs,
                                                 const uint8_t *flag, const double *mult, double *loc) {
   // all levels and reference vectors run in ONE launch: M2L at different levels is independent
   int glo = 0, ghi = n_groups;
@@ -388,12 +393,13 @@ __global__ void __launch_bounds__(256, NC == 32 ? 2 : 1) k_m2l(const M2LGroupDev
   const size_t ncols = n_entries * (size_t)nrhs;
   constexpr int kM2LCols = NC, kM2LColsPad = NC + 4;
   constexpr int kNT = NC / 8;        // 8-column tiles
-  constexpr int kKSplit = 8 / kNT;   // warps sharing one column tile split the P-long reduction
   const size_t col0 = (size_t)cta * kM2LCols;
   const int nc = (int)min((size_t)kM2LCols, ncols - col0);
-  double *Xs = sm;                                        // [NC][Pp]
+  double *Xs = sm;                                        // [NC][Pp]; reused as Zs after the first contraction
   double *Ys = Xs + (size_t)kM2LCols * Pp;                // [rank_pad][NC + 4]
   __shared__ int s_tgt[kM2LCols], s_rhs[kM2LCols], s_perm[kM2LCols], s_src[kM2LCols];
+  __shared__ int s_list[kM2LCols], s_off[kM2LCols], s_len[kM2LCols];  // columns grouped by (target, rhs) run
+  __shared__ int s_runs[kM2LCols], s_nruns;                          // first column of every run
   __shared__ int s_any;
   if (tid == 0) s_any = 0;
   __syncthreads();
@@ -415,6 +421,30 @@ __global__ void __launch_bounds__(256, NC == 32 ? 2 : 1) k_m2l(const M2LGroupDev
   }
   __syncthreads();
   if (!s_any) return;
+  if (warp == 0) {
+    // runs of columns that add into the same (target, rhs): s_list holds the columns run by run; the first column
+    // of a run carries the run's offset and length, every other column length 0
+    const bool valid = lane < kM2LCols && s_tgt[lane] >= 0;
+    const int key = valid ? s_tgt[lane] * nrhs + s_rhs[lane] : -(lane + 1);
+    const unsigned same = __match_any_sync(0xffffffffu, key);
+    const int first = __ffs(same) - 1;
+    const int rank_in_run = __popc(same & ((1u << lane) - 1u));
+    int before = 0;  // columns of runs that start earlier
+    for (int k = 0; k < 32; ++k) {
+      const int fk = __shfl_sync(0xffffffffu, first, k);
+      const int vk = __shfl_sync(0xffffffffu, (int)valid, k);
+      before += (vk && fk < first) ? 1 : 0;
+    }
+    const bool is_first = valid && first == lane;
+    const unsigned firsts = __ballot_sync(0xffffffffu, is_first);
+    if (lane < kM2LCols) {
+      if (valid) s_list[before + rank_in_run] = lane;
+      s_off[lane] = before;
+      s_len[lane] = is_first ? __popc(same) : 0;
+      if (is_first) s_runs[__popc(firsts & ((1u << lane) - 1u))] = lane;
+    }
+    if (lane == 0) s_nruns = __popc(firsts);
+  }
   // stage permuted multipoles (zero padding up to P4 and for idle columns); 4 gathers in flight per lane
   for (int c = warp; c < kM2LCols; c += 8) {
     double *dst = Xs + (size_t)c * Pp;
@@ -439,13 +469,13 @@ __global__ void __launch_bounds__(256, NC == 32 ? 2 : 1) k_m2l(const M2LGroupDev
   __syncthreads();
   const int ar = lane >> 2, ak = lane & 3;  // fragment coordinates
   if (COMPRESSED) {
-    // ---- Ys = Vt * Xs: warp -> column tile nt, reduction slice kh; rank tiles in chunks of 4
+    // ---- Ys = Vt * Xs: warp -> column tile nt, reduction slice kh; rank tiles in chunks of kM2LChunk
+    constexpr int kKSplit = 8 / kNT;   // warps sharing one column tile split the P-long reduction
     const int nt = warp % kNT, kh = warp / kNT;
     const int mtiles = rank_pad >> 3;
     const int ksteps = P4 >> 2;
     const int k_begin = (int)((long long)ksteps * kh / kKSplit), k_end = (int)((long long)ksteps * (kh + 1) / kKSplit);
     const double *bx = Xs + (size_t)(nt * 8 + ar) * Pp + ak;
-    (void)kKSplit;
     for (int m0 = 0; m0 < mtiles; m0 += kM2LChunk) {
       double acc[kM2LChunk][2];
 #pragma unroll
@@ -478,24 +508,43 @@ __global__ void __launch_bounds__(256, NC == 32 ? 2 : 1) k_m2l(const M2LGroupDev
       }
     }
   }
-  // ---- Zs = U * Ys (or K * Xs), scattered from the accumulator fragments
+  // ---- Zs = U * Ys (or K * Xs)
   const int mt_total = (P + 7) >> 3;
   const int ksteps2 = (COMPRESSED ? rank_pad : P4) >> 2;
-  for (int mt = warp; mt < mt_total; mt += 8) {
-    double z[kNT][2];
+  // operator fragments are read once per CTA (no reuse to hide their L2 latency behind): blocks of kM2LPre k-steps
+  // are double buffered in registers, the next block's loads issued before the current block's DMMAs
+  const int kblocks = (ksteps2 + kM2LPre - 1) / kM2LPre;
+  const int my_tiles = mt_total > warp ? (mt_total - warp + 7) / 8 : 0;
+  const int nblocks = my_tiles * kblocks;
+  double a_cur[kM2LPre], a_nxt[kM2LPre];
+  auto load_block = [&](int blk, double (&dst)[kM2LPre]) {
+    const int mt = warp + 8 * (blk / kblocks), ks0 = (blk % kblocks) * kM2LPre;
+    const double *af = UF + ((size_t)mt * ksteps2 + ks0) * 32 + lane;
 #pragma unroll
-    for (int i = 0; i < kNT; ++i) z[i][0] = z[i][1] = 0.0;
-    const double *af = UF + ((size_t)mt * ksteps2) * 32 + lane;
-#pragma unroll 2
-    for (int ks = 0; ks < ksteps2; ++ks) {
-      const double a = __ldg(af + (size_t)ks * 32);
+    for (int u = 0; u < kM2LPre; ++u) dst[u] = ks0 + u < ksteps2 ? __ldg(af + (size_t)u * 32) : 0.0;
+  };
+  if (nblocks > 0) load_block(0, a_cur);
+  double z[kNT][2];
 #pragma unroll
-      for (int nt = 0; nt < kNT; ++nt) {
-        const double b = COMPRESSED ? Ys[(size_t)(ks * 4 + ak) * kM2LColsPad + nt * 8 + ar]
-                                    : Xs[(size_t)(nt * 8 + ar) * Pp + ks * 4 + ak];
-        dmma884(z[nt][0], z[nt][1], a, b);
+  for (int i = 0; i < kNT; ++i) z[i][0] = z[i][1] = 0.0;
+  for (int blk = 0; blk < nblocks; ++blk) {
+    if (blk + 1 < nblocks) load_block(blk + 1, a_nxt);
+    const int mt = warp + 8 * (blk / kblocks), kb = blk % kblocks, ks0 = kb * kM2LPre;
+#pragma unroll
+    for (int u = 0; u < kM2LPre; ++u) {
+      const int ks = ks0 + u;
+      if (ks < ksteps2) {
+#pragma unroll
+        for (int nt = 0; nt < kNT; ++nt) {
+          const double b = COMPRESSED ? Ys[(size_t)(ks * 4 + ak) * kM2LColsPad + nt * 8 + ar]
+                                      : Xs[(size_t)(nt * 8 + ar) * Pp + ks * 4 + ak];
+          dmma884(z[nt][0], z[nt][1], a_cur[u], b);
+        }
       }
     }
+#pragma unroll
+    for (int u = 0; u < kM2LPre; ++u) a_cur[u] = a_nxt[u];
+    if (kb + 1 < kblocks) continue;
     const int m = mt * 8 + ar;
     if (m < P) {
 #pragma unroll
@@ -503,11 +552,45 @@ __global__ void __launch_bounds__(256, NC == 32 ? 2 : 1) k_m2l(const M2LGroupDev
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int c = nt * 8 + ak * 2 + h;
-          const int tg = s_tgt[c];
-          if (tg < 0) continue;
-          const int *pm = perm_tab + (size_t)s_perm[c] * P;
-          atomicAdd(loc + ((size_t)tg * nrhs + s_rhs[c]) * P + __ldg(pm + m), z[nt][h]);  // L[perm[m]] += y[m]
+          if (COMPRESSED) {
+            Xs[(size_t)c * Pp + m] = z[nt][h];  // Zs: Xs is no longer read once Ys is complete
+          } else {  // the dense operator still reads Xs: scatter straight from the fragments
+            const int tg = s_tgt[c];
+            if (tg < 0) continue;
+            const int *pm = perm_tab + (size_t)s_perm[c] * P;
+            atomicAdd(loc + ((size_t)tg * nrhs + s_rhs[c]) * P + __ldg(pm + m), z[nt][h]);  // L[perm[m]] += y[m]
+          }
         }
+    }
+#pragma unroll
+    for (int i = 0; i < kNT; ++i) z[i][0] = z[i][1] = 0.0;
+  }
+  if (!COMPRESSED) return;
+  __syncthreads();
+  // ---- flush: L_tgt[i] += sum_{c in run} Zs[c][inv_perm_c[i]]; four gathers in flight per lane
+  const int nchunks = (P + 31) >> 5;
+  const int nitems = s_nruns * nchunks;  // (run, 32-node chunk) pairs, dealt round-robin to the warps
+  for (int item = warp; item < nitems; item += 8) {
+    const int run = item / nchunks, i = (item - run * nchunks) * 32 + lane;
+    const int c0 = s_runs[run];
+    const int len = s_len[c0];
+    const int *lst = s_list + s_off[c0];
+    if (i < P) {
+      double v = 0.0;
+      for (int k = 0; k < len; k += 4) {
+        int cc[4], id[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          cc[u] = lst[min(k + u, len - 1)];
+          id[u] = __ldg(inv_tab + (size_t)s_perm[cc[u]] * P + i);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double x = Xs[(size_t)cc[u] * Pp + id[u]];
+          if (k + u < len) v += x;
+        }
+      }
+      atomicAdd(loc + ((size_t)s_tgt[c0] * nrhs + s_rhs[c0]) * P + i, v);
     }
   }
 }
