@@ -386,12 +386,11 @@ static void launch_leaf_v3(const DirectArgs &a, cudaStream_t s) {
 // never adjacent to the cell, so r^2 > 0.  Slices are summed through shared memory in a fixed order, one CTA per
 // cell: deterministic, no atomics.
 // ======================================================================================================
-constexpr int kP2LTileMax = 128;  // sources per staged tile (upper bound)
+constexpr int kP2LTileMax = 256;  // sources per staged tile (upper bound; one tile point per thread)
 constexpr int kP2LJB = 4;          // sources in flight per thread (independent kernel evaluations)
-constexpr int kP2LPF = 3;          // coordinates a thread prefetches per tile (tile * dim <= kP2LPF * blockDim)
 
-template <int FAM, int NR, int PREG, bool FAST>
-__global__ void __launch_bounds__(256, (NR * PREG <= 16) ? 2 : 1) k_p2l_grid(const P2LArgs a, const int nslices, const int cols, const int T) {
+template <int FAM, int NR, int PREG, bool FAST, bool FUSE>
+__global__ void __launch_bounds__(256, (NR * PREG <= (FUSE ? 8 : 16)) ? 2 : 1) k_p2l_grid(const P2LArgs a, const int nslices, const int cols, const int T) {
   const int ci = blockIdx.x;
   const int c = a.cells[ci];
   if (!a.cell_flag[c]) return;
@@ -400,8 +399,35 @@ __global__ void __launch_bounds__(256, (NR * PREG <= 16) ? 2 : 1) k_p2l_grid(con
   extern __shared__ double sm[];
   double *tab = sm;                                 // [dim][T][PREG]
   double *wts = sm + (size_t)dim * T * PREG;        // [NR][T]
+  double *part = wts + (size_t)NR * T;              // FUSE: [3][NR][T] per-warp-part M2P partial sums of a slice
   const int q = tid % cols, slice = tid / cols;
   const bool active = slice < nslices;
+  // FUSE: the kernel matrix of (cell nodes) x (X-leaf points) is the transpose of the M2P matrix of (W-list targets) x
+  // (cell nodes) — X is the transpose of W (linear_tree.rs:330-395) and the kernels are symmetric — so every value
+  // computed here also feeds out[point] += K * M_cell[node].  A thread sums its column's nodes, the columns of a slice
+  // are summed by a segmented warp shuffle (a slice's cols threads span at most 3 warps), the warp parts through
+  // shared memory, and one RED per (tile point, rhs) goes to the output.
+  const int lane = tid & 31;
+  const int seg_first = slice * cols;                 // first thread of my slice
+  const int my_part = (tid >> 5) - (seg_first >> 5);  // which warp part of the slice this warp holds (0..2)
+  unsigned addmask = 0;                               // bit k: lane + (16 >> k) is in my warp and my slice
+  if (FUSE) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int off = 16 >> k;
+      if (lane + off < 32 && tid + off < nslices * cols && (tid + off) / cols == slice) addmask |= 1u << k;
+    }
+  }
+  const bool seg_head = FUSE && active && (lane == 0 || tid == seg_first);
+  double mreg[FUSE ? NR : 1][FUSE ? PREG : 1];
+  if (FUSE) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+#pragma unroll
+      for (int il = 0; il < PREG; ++il)
+        mreg[r][il] = (active && il < p) ? a.mult[((size_t)c * a.nrhs + a.rhs0 + r) * P + q * p + il] : 0.0;
+  }
+  const unsigned warp_active = __ballot_sync(0xffffffffu, active);
   const int i0 = dim == 3 ? q / p : q, i1 = dim == 3 ? q % p : 0;
   const double ccx = a.ccx[c], ccy = a.ccy[c], ccz = a.ccz[c];
   const double h = a.chalf[c];
@@ -421,17 +447,16 @@ __global__ void __launch_bounds__(256, (NR * PREG <= 16) ? 2 : 1) k_p2l_grid(con
     rb = a.x_begin[e];
     rn = a.x_count[e];
   }
-  double pc[kP2LPF], pw[NR];
-  auto prefetch = [&](int &m) {
+  double pc[3] = {0.0, 0.0, 0.0}, pw[NR];
+  auto prefetch = [&](int &m, int &base) {  // thread j < m takes tile point j
     m = 0;
     if (e >= e_end) return;
     m = min(T, rn - c0);
-    const int base = rb + c0;
-#pragma unroll
-    for (int k = 0; k < kP2LPF; ++k) {
-      const int t = tid + k * nt;
-      const int j = t / dim, d = t - j * dim;
-      if (j < m) pc[k] = d == 0 ? a.sx[base + j] : (d == 1 ? a.sy[base + j] : a.sz[base + j]);
+    base = rb + c0;
+    if (tid < m) {
+      pc[0] = a.sx[base + tid];
+      if (dim > 1) pc[1] = a.sy[base + tid];
+      if (dim > 2) pc[2] = a.sz[base + tid];
     }
 #pragma unroll
     for (int r = 0; r < NR; ++r) pw[r] = tid < m ? a.w[(size_t)(a.rhs0 + r) * a.n + base + tid] : 0.0;
@@ -445,21 +470,19 @@ __global__ void __launch_bounds__(256, (NR * PREG <= 16) ? 2 : 1) k_p2l_grid(con
       }
     }
   };
-  int m_cur = 0, m_next = 0;
-  prefetch(m_cur);
+  int m_cur = 0, m_next = 0, tile_base = 0, next_base = 0;
+  prefetch(m_cur, tile_base);
   while (m_cur > 0) {
     const int m = m_cur;
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < kP2LPF; ++k) {  // squared offsets node - source per axis (chebyshev.rs:951-968)
-      const int t = tid + k * nt;
-      const int j = t / dim, d = t - j * dim;
-      if (j < T) {
-        double *row = tab + ((size_t)d * T + j) * PREG;
-        if (j < m) {
+    if (tid < T) {  // squared offsets node - source per axis (chebyshev.rs:951-968)
+      for (int d = 0; d < dim; ++d) {
+        double *row = tab + ((size_t)d * T + tid) * PREG;
+        if (tid < m) {
           const double cd = d == 0 ? ccx : (d == 1 ? ccy : ccz);
+          const double xs = d == 0 ? pc[0] : (d == 1 ? pc[1] : pc[2]);
           for (int i = 0; i < p; ++i) {
-            const double o = (cd + h * a.nodes[i]) - pc[k];
+            const double o = (cd + h * a.nodes[i]) - xs;
             row[i] = o * o;
           }
         } else if (m < T) {  // neutral padding rows (r^2 = 1, weight 0) so every thread runs whole groups of kP2LJB
@@ -467,13 +490,12 @@ __global__ void __launch_bounds__(256, (NR * PREG <= 16) ? 2 : 1) k_p2l_grid(con
           for (int i = 0; i < p; ++i) row[i] = fill;
         }
       }
-    }
-    if (tid < T) {
 #pragma unroll
       for (int r = 0; r < NR; ++r) wts[r * T + tid] = pw[r];
     }
     __syncthreads();
-    prefetch(m_next);
+    const int cur_base = tile_base;
+    prefetch(m_next, next_base);
     if (active) {
       const int kmax = (m + nslices - 1) / nslices;
       for (int k = 0; k < kmax; k += kP2LJB) {
@@ -490,6 +512,13 @@ __global__ void __launch_bounds__(256, (NR * PREG <= 16) ? 2 : 1) k_p2l_grid(con
 #pragma unroll
           for (int r = 0; r < NR; ++r) wj[u][r] = wts[r * T + j];
         }
+        double tp[FUSE ? kP2LJB : 1][FUSE ? NR : 1];
+        if (FUSE) {
+#pragma unroll
+          for (int u = 0; u < kP2LJB; ++u)
+#pragma unroll
+            for (int r = 0; r < NR; ++r) tp[u][r] = 0.0;
+        }
 #pragma unroll
         for (int il = 0; il < PREG; ++il)
           if (il < p) {
@@ -503,11 +532,44 @@ __global__ void __launch_bounds__(256, (NR * PREG <= 16) ? 2 : 1) k_p2l_grid(con
 #pragma unroll
             for (int u = 0; u < kP2LJB; ++u)
 #pragma unroll
-              for (int r = 0; r < NR; ++r) kernel_acc<FAM>(acc[r][il], v[u], wj[u][r]);
+              for (int r = 0; r < NR; ++r) {
+                kernel_acc<FAM>(acc[r][il], v[u], wj[u][r]);
+                if (FUSE) kernel_acc<FAM>(tp[u][r], v[u], mreg[r][il]);
+              }
           }
+        if (FUSE) {
+#pragma unroll
+          for (int u = 0; u < kP2LJB; ++u)
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+              double x = tp[u][r];
+#pragma unroll
+              for (int k2 = 0; k2 < 5; ++k2) {
+                const double y = __shfl_down_sync(warp_active, x, 16 >> k2);
+                if (addmask & (1u << k2)) x += y;
+              }
+              if (seg_head) part[((size_t)my_part * NR + r) * T + slice + nslices * (k + u)] = x;
+            }
+        }
+      }
+    }
+    if (FUSE) {
+      __syncthreads();
+      if (tid < m) {  // tile point tid belongs to slice tid % nslices, whose threads span nparts warps
+        const int sl = tid % nslices;
+        const int nparts = ((sl * cols + cols - 1) >> 5) - ((sl * cols) >> 5) + 1;
+        const size_t row = a.out_row[cur_base + tid];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          double v = part[(size_t)r * T + tid];
+          if (nparts > 1) v += part[((size_t)NR + r) * T + tid];
+          if (nparts > 2) v += part[((size_t)2 * NR + r) * T + tid];
+          atomicAdd(a.out + row * a.nrhs + a.rhs0 + r, v);
+        }
       }
     }
     m_cur = m_next;
+    tile_base = next_base;
   }
   // ---- sum the slices in a fixed order and add to the cell's local expansion
   double *red = sm;  // [nslices][P]
@@ -528,24 +590,32 @@ __global__ void __launch_bounds__(256, (NR * PREG <= 16) ? 2 : 1) k_p2l_grid(con
   }
 }
 
-template <int FAM, int NR, int PREG, bool FAST>
+template <int FAM, int NR, int PREG, bool FAST, bool FUSE>
 static void launch_p2l_grid_impl(const P2LArgs &a, cudaStream_t s) {
   const int cols = a.dim == 3 ? a.p * a.p : (a.dim == 2 ? a.p : 1);
   const int nslices = std::min(32, std::max(1, 256 / cols));
   const int nthreads = std::max(128, std::min(256, ((nslices * cols + 31) / 32) * 32));
   const int group = kP2LJB * nslices;
-  const int T = group * std::max(1, kP2LTileMax / group);  // <= 128 <= nthreads, T * dim <= kP2LPF * nthreads
-  const size_t tab_d = (size_t)a.dim * T * PREG + (size_t)NR * T;
+  const int T = group * std::max(1, std::min(kP2LTileMax, nthreads) / group);  // <= nthreads: one tile point per thread
+  const size_t tab_d = (size_t)a.dim * T * PREG + (size_t)NR * T + (FUSE ? (size_t)3 * NR * T : 0);
   const size_t red_d = (size_t)nslices * a.P;
   const size_t smem = sizeof(double) * std::max(tab_d, red_d);
   if (smem > 48 * 1024)
-    FB_CUDA(cudaFuncSetAttribute(k_p2l_grid<FAM, NR, PREG, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  FB_LAUNCH((k_p2l_grid<FAM, NR, PREG, FAST>), a.n_cells, nthreads, smem, s, a, nslices, cols, T);
+    FB_CUDA(cudaFuncSetAttribute(k_p2l_grid<FAM, NR, PREG, FAST, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+  FB_LAUNCH((k_p2l_grid<FAM, NR, PREG, FAST, FUSE>), a.n_cells, nthreads, smem, s, a, nslices, cols, T);
 }
 template <int FAM, int NR, int PREG>
 static void launch_p2l_grid(const P2LArgs &a, cudaStream_t s) {
-  if (kernel_has_fast<FAM>() && a.kp.fast) launch_p2l_grid_impl<FAM, NR, PREG, kernel_has_fast<FAM>()>(a, s);
-  else launch_p2l_grid_impl<FAM, NR, PREG, false>(a, s);
+  constexpr bool kFast = kernel_has_fast<FAM>();
+  const bool fast = kFast && a.kp.fast;
+  if (a.out) {  // fused M2P (targets = all sources)
+    if (fast) launch_p2l_grid_impl<FAM, NR, PREG, kFast, true>(a, s);
+    else launch_p2l_grid_impl<FAM, NR, PREG, false, true>(a, s);
+  } else {
+    if (fast) launch_p2l_grid_impl<FAM, NR, PREG, kFast, false>(a, s);
+    else launch_p2l_grid_impl<FAM, NR, PREG, false, false>(a, s);
+  }
 }
 
 // ---------------------------------------------------------------------------------- dispatch

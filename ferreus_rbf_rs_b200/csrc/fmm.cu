@@ -271,6 +271,7 @@ void fb_tree::build(const double *points, size_t n_, int dim_, ptrdiff_t rs, ptr
     d_u_begin.upload(u_b, stream);
     d_u_count.upload(u_c, stream);
     d_w_ptr.upload(w_ptr, stream);
+    d_w_ptr_none.upload(std::vector<long long>(nl + 1, 0), stream);
     d_w_cell.upload(w_c, stream);
     std::vector<int> x_cells, x_b, x_c;
     std::vector<long long> x_ptr{0};
@@ -450,10 +451,11 @@ void fb_tree::upward() {
 }
 
 // -------------------------------------------------------------------------------------- downward
-void fb_tree::downward(const uint8_t *flags) {
+void fb_tree::downward(const uint8_t *flags, bool fuse_m2p) {
   const size_t nc = ht.ncells();
   const int p = order;
   d_loc.zero(nc * (size_t)nrhs * P, stream);
+  if (fuse_m2p) d_out.zero(n * (size_t)nrhs, stream);
   if (timing) FB_CUDA(cudaEventRecord(ev[3], stream));
   // M2L (loop A of bbfmm.rs:781-832)
   const bool compressed = fparams.compression_type != FB_COMPRESSION_NONE;
@@ -526,6 +528,11 @@ void fb_tree::downward(const uint8_t *flags) {
     a.nrhs = nrhs;
     a.rhs0 = 0;
     a.kp = kp;
+    if (fuse_m2p) {
+      a.mult = d_mult.p;
+      a.out = d_out.p;
+      a.out_row = source_target_set().out_row;
+    }
     launch_p2l(a, stream);
   }
   if (timing) FB_CUDA(cudaEventRecord(ev[5], stream));
@@ -543,9 +550,9 @@ void fb_tree::downward(const uint8_t *flags) {
 }
 
 // ------------------------------------------------------------------------------------- leaf pass
-void fb_tree::leaf_pass(const TargetSet &ts, bool grads) {
+void fb_tree::leaf_pass(const TargetSet &ts, bool grads, bool m2p_done) {
   const int p = order;
-  d_out.zero(ts.m * (size_t)nrhs, stream);
+  if (!m2p_done) d_out.zero(ts.m * (size_t)nrhs, stream);
   if (grads) d_gout.zero(ts.m * (size_t)nrhs * dim, stream);
   if (timing) FB_CUDA(cudaEventRecord(ev[7], stream));
   if (ts.max_tiles > 0) {
@@ -560,7 +567,7 @@ void fb_tree::leaf_pass(const TargetSet &ts, bool grads) {
   a.u_ptr = d_u_ptr.p;
   a.u_begin = d_u_begin.p;
   a.u_count = d_u_count.p;
-  a.w_ptr = d_w_ptr.p;
+  a.w_ptr = m2p_done ? d_w_ptr_none.p : d_w_ptr.p;  // fused: the W lists were applied by the P2L kernel
   a.w_cell = d_w_cell.p;
   a.sx = d_sx.p;
   a.sy = d_sy.p;
@@ -604,7 +611,16 @@ TargetSet fb_tree::source_target_set() {
   ts.n_tiles_dev = d_src_ntiles.p;
   ts.max_tiles = src_tiles;
   ts.cell_flag = d_flag_all.p;
+  ts.all_sources = true;
   return ts;
+}
+
+// targets = all sources: X is the transpose of W, so the P2L kernel applies the M2P half as well
+void fb_tree::evaluate_sources_fused() {
+  TargetSet ts = source_target_set();
+  const bool fuse = ht.adaptive && n_x_cells > 0;
+  downward(ts.cell_flag, fuse);
+  leaf_pass(ts, false, fuse);
 }
 
 // shared tail of bin_targets / subset_target_set: keys (leaf slot or sorted source position) -> TargetSet
@@ -735,8 +751,12 @@ TargetSet fb_tree::subset_target_set_dev(const unsigned long long *d_idx, size_t
 void fb_tree::matvec_dev(const TargetSet &ts) {
   sort_weights();
   upward();
-  downward(ts.cell_flag);
-  leaf_pass(ts, false);
+  if (ts.all_sources) {
+    evaluate_sources_fused();
+  } else {
+    downward(ts.cell_flag);
+    leaf_pass(ts, false);
+  }
 }
 
 void fb_tree::fetch_output(size_t m, bool grads, double *out_vals, double *out_grads, ptrdiff_t o_rs,
@@ -910,8 +930,12 @@ int fb_tree_evaluate_at_sources(fb_tree *t, const double *w, size_t n_rows, size
     FB_REQUIRE((int)nrhs == t->nrhs, "weights must have the column count given to set_weights");
     TargetSet ts = idx_or_null ? t->subset_target_set(idx_or_null, n_idx) : t->source_target_set();
     t->upload_weights(w, n_rows, nrhs, w_rs, w_cs);
-    t->downward(ts.cell_flag);
-    t->leaf_pass(ts, false);
+    if (ts.all_sources) {
+      t->evaluate_sources_fused();
+    } else {
+      t->downward(ts.cell_flag);
+      t->leaf_pass(ts, false);
+    }
     t->fetch_output(ts.m, false, out_vals, nullptr, o_rs, o_cs);
   });
 }
@@ -934,8 +958,12 @@ int fb_tree_matvec_resident(fb_tree *t) {
     t->sort_weights();
     t->upward();
     TargetSet ts = t->have_subset ? t->ts_subset : t->source_target_set();
-    t->downward(ts.cell_flag);
-    t->leaf_pass(ts, false);
+    if (ts.all_sources) {
+      t->evaluate_sources_fused();
+    } else {
+      t->downward(ts.cell_flag);
+      t->leaf_pass(ts, false);
+    }
     t->last_out_rows = ts.m;
     FB_CUDA(cudaEventRecord(t->ev_mv[1], t->stream));
     FB_CUDA(cudaStreamSynchronize(t->stream));

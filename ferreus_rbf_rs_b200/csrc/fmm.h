@@ -21,6 +21,7 @@ struct TargetSet {
   const int *tile_leaf = nullptr, *tile_off = nullptr;     // CTA tiles of <= kTile targets
   const int *n_tiles_dev = nullptr;                        // device scalar: number of valid tiles
   int max_tiles = 0;                                       // launch bound for the tile grid
+  bool all_sources = false;                                // the tree's own source set (enables the fused W/X pass)
   const uint8_t *cell_flag = nullptr;                      // per cell: subtree contains targets
 };
 
@@ -62,6 +63,10 @@ struct P2LArgs {  // bbfmm.rs:1001-1048
   const double *nodes;
   int p, dim, P, nrhs, rhs0;
   KParams kp;
+  // fused M2P (non-null only when the targets are all sources): out[out_row[s]] += K(point s, nodes) . M_cell
+  const double *mult;       // multipoles [cell][rhs][P]
+  double *out;              // [n][nrhs]
+  const uint32_t *out_row;  // output row of each sorted source
 };
 
 void launch_leaf_direct(const DirectArgs &a, cudaStream_t s);
@@ -111,7 +116,7 @@ struct fb_tree {
   std::vector<int> parents_off;
   fb::DBuf<int> d_level_cells;                // cells level-major == identity, kept for clarity
   // lists
-  fb::DBuf<long long> d_u_ptr, d_w_ptr, d_x_ptr;
+  fb::DBuf<long long> d_u_ptr, d_w_ptr, d_x_ptr, d_w_ptr_none;
   fb::DBuf<int> d_u_begin, d_u_count, d_w_cell, d_x_begin, d_x_count, d_x_cells;
   int n_x_cells = 0;
   int n_src_leaves = 0;
@@ -159,8 +164,11 @@ struct fb_tree {
   void upload_weights(const double *w, size_t n_rows, size_t nrhs_, ptrdiff_t rs, ptrdiff_t cs);
   void sort_weights();
   void upward();
-  void downward(const uint8_t *flags);
-  void leaf_pass(const fb::TargetSet &ts, bool grads);
+  // fuse_m2p: the P2L kernel also applies the M2P transpose into d_out (zeroed here); leaf_pass(.., m2p_done = true)
+  // must follow with the all-sources target set
+  void downward(const uint8_t *flags, bool fuse_m2p = false);
+  void leaf_pass(const fb::TargetSet &ts, bool grads, bool m2p_done = false);
+  void evaluate_sources_fused();  // downward + leaf pass for targets = all sources
   fb::TargetSet source_target_set();
   fb::TargetSet bin_targets(const double *targets, size_t m, ptrdiff_t rs, ptrdiff_t cs, uint64_t *bad);
   fb::TargetSet subset_target_set(const uint64_t *idx, size_t n_idx);
