@@ -388,6 +388,7 @@ static void launch_leaf_v3(const DirectArgs &a, cudaStream_t s) {
 // ======================================================================================================
 constexpr int kP2LTileMax = 256;  // sources per staged tile (upper bound; one tile point per thread)
 constexpr int kP2LJB = 4;          // sources in flight per thread (independent kernel evaluations)
+constexpr size_t kP2LFuseBytes = 48 * 1024;  // shared-memory budget of the fused M2P partial sums
 
 template <int FAM, int NR, int PREG, bool FAST, bool FUSE>
 __global__ void __launch_bounds__(256, (NR * PREG <= (FUSE ? 8 : 16)) ? 2 : 1) k_p2l_grid(const P2LArgs a, const int nslices, const int cols, const int T) {
@@ -399,26 +400,15 @@ __global__ void __launch_bounds__(256, (NR * PREG <= (FUSE ? 8 : 16)) ? 2 : 1) k
   extern __shared__ double sm[];
   double *tab = sm;                                 // [dim][T][PREG]
   double *wts = sm + (size_t)dim * T * PREG;        // [NR][T]
-  double *part = wts + (size_t)NR * T;              // FUSE: [3][NR][T] per-warp-part M2P partial sums of a slice
+  double *part = wts + (size_t)NR * T;              // FUSE: [NR][cols][T + 1] per-column M2P partial sums of the tile points
   const int q = tid % cols, slice = tid / cols;
   const bool active = slice < nslices;
   // FUSE: the kernel matrix of (cell nodes) x (X-leaf points) is the transpose of the M2P matrix of (W-list targets) x
   // (cell nodes) — X is the transpose of W (linear_tree.rs:330-395) and the kernels are symmetric — so every value
-  // computed here also feeds out[point] += K * M_cell[node].  A thread sums its column's nodes, the columns of a slice
-  // are summed by a segmented warp shuffle (a slice's cols threads span at most 3 warps), the warp parts through
-  // shared memory, and one RED per (tile point, rhs) goes to the output.
-  const int lane = tid & 31;
-  const int seg_first = slice * cols;                 // first thread of my slice
-  const int my_part = (tid >> 5) - (seg_first >> 5);  // which warp part of the slice this warp holds (0..2)
-  unsigned addmask = 0;                               // bit k: lane + (16 >> k) is in my warp and my slice
-  if (FUSE) {
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      const int off = 16 >> k;
-      if (lane + off < 32 && tid + off < nslices * cols && (tid + off) / cols == slice) addmask |= 1u << k;
-    }
-  }
-  const bool seg_head = FUSE && active && (lane == 0 || tid == seg_first);
+  // computed here also feeds out[point] += K * M_cell[node].  A thread sums its column's nodes into a per-(column,
+  // point) slot of shared memory (row stride T + 1: conflict-free for both the column-wise writes and the point-wise
+  // reads); at the end of the tile thread j adds up the columns of point j and issues one RED per (point, rhs).
+  const int Ts = T + 1;
   double mreg[FUSE ? NR : 1][FUSE ? PREG : 1];
   if (FUSE) {
 #pragma unroll
@@ -427,7 +417,6 @@ __global__ void __launch_bounds__(256, (NR * PREG <= (FUSE ? 8 : 16)) ? 2 : 1) k
       for (int il = 0; il < PREG; ++il)
         mreg[r][il] = (active && il < p) ? a.mult[((size_t)c * a.nrhs + a.rhs0 + r) * P + q * p + il] : 0.0;
   }
-  const unsigned warp_active = __ballot_sync(0xffffffffu, active);
   const int i0 = dim == 3 ? q / p : q, i1 = dim == 3 ? q % p : 0;
   const double ccx = a.ccx[c], ccy = a.ccy[c], ccz = a.ccz[c];
   const double h = a.chalf[c];
@@ -541,30 +530,25 @@ __global__ void __launch_bounds__(256, (NR * PREG <= (FUSE ? 8 : 16)) ? 2 : 1) k
 #pragma unroll
           for (int u = 0; u < kP2LJB; ++u)
 #pragma unroll
-            for (int r = 0; r < NR; ++r) {
-              double x = tp[u][r];
-#pragma unroll
-              for (int k2 = 0; k2 < 5; ++k2) {
-                const double y = __shfl_down_sync(warp_active, x, 16 >> k2);
-                if (addmask & (1u << k2)) x += y;
-              }
-              if (seg_head) part[((size_t)my_part * NR + r) * T + slice + nslices * (k + u)] = x;
-            }
+            for (int r = 0; r < NR; ++r) part[((size_t)r * cols + q) * Ts + slice + nslices * (k + u)] = tp[u][r];
         }
       }
     }
     if (FUSE) {
       __syncthreads();
-      if (tid < m) {  // tile point tid belongs to slice tid % nslices, whose threads span nparts warps
-        const int sl = tid % nslices;
-        const int nparts = ((sl * cols + cols - 1) >> 5) - ((sl * cols) >> 5) + 1;
+      if (tid < m) {
         const size_t row = a.out_row[cur_base + tid];
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
-          double v = part[(size_t)r * T + tid];
-          if (nparts > 1) v += part[((size_t)NR + r) * T + tid];
-          if (nparts > 2) v += part[((size_t)2 * NR + r) * T + tid];
-          atomicAdd(a.out + row * a.nrhs + a.rhs0 + r, v);
+          const double *pp = part + (size_t)r * cols * Ts + tid;
+          double v0 = 0.0, v1 = 0.0;
+          int qq = 0;
+          for (; qq + 1 < cols; qq += 2) {
+            v0 += pp[(size_t)qq * Ts];
+            v1 += pp[(size_t)(qq + 1) * Ts];
+          }
+          if (qq < cols) v0 += pp[(size_t)qq * Ts];
+          atomicAdd(a.out + row * a.nrhs + a.rhs0 + r, v0 + v1);
         }
       }
     }
@@ -596,8 +580,12 @@ static void launch_p2l_grid_impl(const P2LArgs &a, cudaStream_t s) {
   const int nslices = std::min(32, std::max(1, 256 / cols));
   const int nthreads = std::max(128, std::min(256, ((nslices * cols + 31) / 32) * 32));
   const int group = kP2LJB * nslices;
-  const int T = group * std::max(1, std::min(kP2LTileMax, nthreads) / group);  // <= nthreads: one tile point per thread
-  const size_t tab_d = (size_t)a.dim * T * PREG + (size_t)NR * T + (FUSE ? (size_t)3 * NR * T : 0);
+  int T = group * std::max(1, std::min(kP2LTileMax, nthreads) / group);  // <= nthreads: one tile point per thread
+  if (FUSE) {  // per-(column, point) partial sums: keep them within ~48 KB
+    const int cap = (int)(kP2LFuseBytes / (sizeof(double) * (size_t)NR * cols)) - 1;
+    T = group * std::max(1, std::min(T, cap) / group);
+  }
+  const size_t tab_d = (size_t)a.dim * T * PREG + (size_t)NR * T + (FUSE ? (size_t)NR * cols * (T + 1) : 0);
   const size_t red_d = (size_t)nslices * a.P;
   const size_t smem = sizeof(double) * std::max(tab_d, red_d);
   if (smem > 48 * 1024)
