@@ -9,11 +9,15 @@ One "step" = one matvec = set_weights(w) + evaluate(w, targets = sources) on a p
 * `value`  : whole-job Mpts/s with inputs resident in HBM (fb_tree_matvec_resident), device time from CUDA
              events on the library's launch stream, max over ranks.
 * `e2e`    : same metric through the reference-facing API with HOST buffers: FmmTree.set_weights(w) +
-             FmmTree.evaluate(w, points) (H2D of weights and targets, target binning, D2H of the result inside
-             the timed region).
-* `roofline`: dominant kernel (k_leaf_direct = P2P + M2P), algorithmic FLOPs / CUDA-event time against the
-             FP64 FMA peak measured in the same run (MEASURED_PEAKS.json has no FP64 entry).
+             FmmTree.evaluate(w, points) (H2D of weights and targets, target check / binning, D2H of the result
+             inside the timed region).
+* `roofline`: dominant kernel = k_p2l_grid<FUSE> (the fused W/X pass: P2L and the M2P transpose from one kernel
+             evaluation per point-node pair), algorithmic FLOPs of both passes / CUDA-event time against the FP64
+             FMA peak measured in the same run (MEASURED_PEAKS.json has no FP64 entry); the other stages are in
+             `stages`.
 * `cpu_baseline`: the oracle port (oracle/fast.py + oracle/csrc/oracle_passes.c, OpenMP) on this host.
+* `sqrt_exact`: the same resident matvec with the third-order (~1 ulp) square root (fb_set_sqrt_mode(0)); the
+             default is the second-order one (<= 1.3e-12 per kernel value, see include/ferreus_b200.h).
 N > 1: one process per GPU (torchrun), each rank owns an independent 1M-point tree (weak scaling, no
 data-path collective; see DESIGN.md "multi-GPU").
 """
@@ -154,6 +158,7 @@ def workload_config(n, n_gpus):
                         f"Chebyshev order {ORDER}, 1 RHS, adaptive sparse tree, 256 pts/leaf, ACA eps=1e-{ORDER} "
                         "(BASELINE.md headline H)",
             "points_per_gpu": n, "order": ORDER, "nrhs": 1, "kernel": "LinearRbf", "compression": "ACA",
+            "sqrt_mode": "second-order (default; <= 1.3e-12 per kernel value; sqrt_exact holds the ~1 ulp variant)",
             "l2_policy": "256 MiB buffer written between timed iterations (L2 flush)",
             "parallelism": f"{n_gpus} independent trees (one per GPU), no data-path collective"}
 
@@ -227,6 +232,26 @@ def main():
     barrier()
     wall_s = time.perf_counter() - wall0
     total_ms = float(np.sum(dev_ms))
+
+    # ---- the same resident matvec with the third-order square root (tree rebuilt in that mode)
+    exact = None
+    if world == 1:
+        fb.set_sqrt_mode(False)
+        tree_x = fb.FmmTree(pts, ORDER, fb.KernelParams(fb.FmmKernelType.LinearRbf), True, True)
+        fb.set_sqrt_mode(True)
+        tree_x.set_timing(True)
+        tree_x.upload_weights(w)
+        for _ in range(args.warmup):
+            tree_x.matvec_resident()
+        xs = []
+        for _ in range(args.steps):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            tree_x.matvec_resident()
+            xs.append(tree_x.last_matvec_ms())
+        exact = {"ms_per_step": float(np.mean(xs)), "value": n / (float(np.mean(xs)) * 1e-3) / 1e6, "unit": "Mpts/s",
+                 "what": "fb_set_sqrt_mode(0): ~1 ulp square roots in the direct sums"}
+        del tree_x
 
     # ---- e2e: reference-facing calls with host buffers (H2D + binning + D2H inside the timed region)
     for _ in range(2):
@@ -303,21 +328,29 @@ def main():
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         P = ORDER ** 3
         f_pair = (3 * 3 - 1) + KERNEL_FLOPS["linear"] + 2 * 1          # (3d-1) + c_k + 2K
-        pairs_leaf = info["p2p_pairs"] + info["m2p_pairs"] * P
+        pairs_p2p = info["p2p_pairs"]
+        pairs_m2p = info["m2p_pairs"] * P
         pairs_p2l = info["p2l_pairs"] * P
         med = {k: float(np.median([s[k] for s in stage_ms])) for k in stage_ms[0]}
-        leaf_tf = pairs_leaf * f_pair / (med["p2p_m2p"] * 1e-3) / 1e12
-        p2l_tf = pairs_p2l * f_pair / max(med["p2l"] * 1e-3, 1e-9) / 1e12
-        roofline = {"kernel": "k_leaf_direct (P2P + M2P)", "bound": "fp64", "achieved": leaf_tf,
-                    "peak": float(fp64_peak[0]), "unit": "TFLOP/s", "frac": leaf_tf / float(fp64_peak[0]),
+        wx_flops = (pairs_m2p + pairs_p2l) * f_pair
+        wx_tf = wx_flops / max(med["wx"] * 1e-3, 1e-9) / 1e12
+        p2p_tf = pairs_p2p * f_pair / max(med["leaf"] * 1e-3, 1e-9) / 1e12
+        direct_tf = (wx_flops + pairs_p2p * f_pair) / max((med["wx"] + med["leaf"]) * 1e-3, 1e-9) / 1e12
+        peak = float(fp64_peak[0])
+        roofline = {"kernel": "k_p2l_grid<FUSE> (W/X pass: P2L + M2P transpose, one kernel evaluation per pair)",
+                    "bound": "fp64", "achieved": wx_tf, "peak": peak, "unit": "TFLOP/s", "frac": wx_tf / peak,
                     "traffic": None,
                     "peak_source": "in-run DFMA micro-benchmark (fb_measure_fp64_tflops); MEASURED_PEAKS.json has no "
                                    "FP64 entry",
-                    "algorithmic_flops_per_launch": pairs_leaf * f_pair,
-                    "flops_per_pair": f_pair, "launch_ms": med["p2p_m2p"]}
-        stages = {"ms": med, "p2l_tflops": p2l_tf, "hbm_peak_gbs": hbm_peak,
+                    "algorithmic_flops_per_launch": wx_flops, "flops_per_pair": f_pair, "launch_ms": med["wx"],
+                    "note": "algorithmic count = SURVEY.md §8(d): M2P and P2L pairs x 11 FLOP; the kernel evaluates the "
+                            "symmetric kernel once per (point, node) and uses it for both passes",
+                    "p2p": {"kernel": "k_leaf_warp (P2P)", "achieved": p2p_tf, "frac": p2p_tf / peak,
+                            "launch_ms": med["leaf"], "algorithmic_flops_per_launch": pairs_p2p * f_pair},
+                    "direct_sums_total": {"achieved": direct_tf, "frac": direct_tf / peak}}
+        stages = {"ms": med, "hbm_peak_gbs": hbm_peak,
                   "hbm_peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                  "pairs": {"p2p": info["p2p_pairs"], "m2p_nodes": info["m2p_pairs"] * P, "p2l_nodes": pairs_p2l,
+                  "pairs": {"p2p": pairs_p2p, "m2p_nodes": pairs_m2p, "p2l_nodes": pairs_p2l,
                             "m2l_entries": info["n_v"]}}
         line = {"metric": "bbfmm_matvec_throughput", "value": value, "unit": "Mpts/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -326,7 +359,7 @@ def main():
                 "e2e": {"value": e2e_val, "unit": "Mpts/s", "h2d_bytes_per_step": int(2 * w.nbytes + pts.nbytes),
                         "d2h_bytes_per_step": int(out.nbytes), "api": "FmmTree.set_weights + FmmTree.evaluate"},
                 "gpu_launches": int(launches_per_step * args.steps),
-                "clocks": clocks, "roofline": roofline, "stages": stages,
+                "clocks": clocks, "roofline": roofline, "stages": stages, "sqrt_exact": exact,
                 "tree": {"build_s": build_s, "cells": info["n_cells"], "leaves": info["n_leaves"],
                          "depth": info["depth"]},
                 "wall_s_timed_region": wall_s}

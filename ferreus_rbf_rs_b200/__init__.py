@@ -6,3 +6,14 @@ from .bbfmm import (FmmKernelType, FmmParams, FmmTree, KernelParams, M2LCompress
                     SpheroidalOrder)
 from . import config, interpolant_config, progress  # noqa: F401,E402
 from .rbf import Coefficients, RBFInterpolator  # noqa: F401,E402
+
+
+def set_sqrt_mode(fast: bool) -> None:
+    """Square-root refinement of the direct-sum hot loops for trees / models built afterwards
+    (fb_set_sqrt_mode, include/ferreus_b200.h): True = second order (default, <= 1.3e-12 per kernel value),
+    False = third order (~1 ulp)."""
+    _lib.lib().fb_set_sqrt_mode(1 if fast else 0)
+
+
+def get_sqrt_mode() -> bool:
+    return bool(_lib.lib().fb_get_sqrt_mode())

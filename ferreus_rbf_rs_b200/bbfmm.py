@@ -254,7 +254,8 @@ class FmmTree:
     def last_timing(self):
         ms = np.zeros(8)
         self._check(self._lib.fb_tree_last_timing(self._h, _lib.dptr(ms)))
-        return dict(zip(["p2m", "m2m", "m2l", "p2l", "l2l", "l2p", "p2p_m2p", "total"], ms.tolist()))
+        # "wx": P2L (fused with the M2P transpose when the targets are all sources); "leaf": P2P (+ M2P otherwise)
+        return dict(zip(["p2m", "m2m", "m2l", "wx", "l2l", "l2p", "leaf", "total"], ms.tolist()))
 
     def info(self):
         inf = _lib.FbTreeInfo()

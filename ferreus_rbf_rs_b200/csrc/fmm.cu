@@ -16,7 +16,7 @@ namespace fb {
 std::atomic<uint64_t> g_launches{0};
 static int initial_sqrt_mode() {
   const char *v = std::getenv("FB_SQRT");
-  return (v && std::string(v) == "fast") ? 1 : 0;
+  return (v && std::string(v) == "exact") ? 0 : 1;
 }
 std::atomic<int> g_sqrt_mode{initial_sqrt_mode()};
 static thread_local std::string t_last_error;
@@ -111,7 +111,7 @@ void fb_tree::build(const double *points, size_t n_, int dim_, ptrdiff_t rs, ptr
   FB_REQUIRE(std::isfinite(radius) && radius > 0, "invalid extents");
 
   // ---- device radix sort of the level-16 Morton codes
-  DBuf<double> d_pts;
+  DBuf<double> &d_pts = d_pts_user;  // kept: evaluate() recognises targets that are exactly the source points
   d_pts.reserve(n * dim);
   FB_CUDA(cudaMemcpyAsync(d_pts.p, host_points.data(), n * dim * sizeof(double), cudaMemcpyHostToDevice, stream));
   DBuf<unsigned long long> d_codes, d_codes2;
@@ -698,14 +698,23 @@ TargetSet fb_tree::bin_targets(const double *targets, size_t m, ptrdiff_t rs, pt
   tb.tx.reserve(m);
   tb.ty.reserve(m);
   tb.tz.reserve(m);
-  d_err.reserve(1);
+  d_err.reserve(2);  // [0] first target outside the tree, [1] != 0 when the targets differ from the source points
   FB_CUDA(cudaMemsetAsync(d_err.p, 0xFF, sizeof(unsigned long long), stream));
+  FB_CUDA(cudaMemsetAsync(d_err.p + 1, 0, sizeof(unsigned long long), stream));
+  const bool maybe_sources = m == n && d_pts_user.cap >= n * (size_t)dim;
+  if (maybe_sources)
+    FB_LAUNCH(k_points_differ, nblocks(n * dim, 256), 256, 0, stream, d_t_user.p, d_pts_user.p, n * (size_t)dim,
+              d_err.p + 1);
   const double side_depth = 2.0 * ht.radius / (double)(1ull << ht.depth);  // linear_tree.rs:495
   FB_LAUNCH(k_target_leaf, nblocks(m, 256), 256, 0, stream, d_t_user.p, m, dim, ht.depth, ht.disp[0], ht.disp[1],
             ht.disp[2], side_depth, d_leaf_lo.p, d_leaf_hi.p, nl, tb.key.p, tb.val.p, d_err.p);
-  unsigned long long h_err = 0;
-  FB_CUDA(cudaMemcpyAsync(&h_err, d_err.p, sizeof(h_err), cudaMemcpyDeviceToHost, stream));
+  unsigned long long h_flags[2] = {0, 0};
+  FB_CUDA(cudaMemcpyAsync(h_flags, d_err.p, sizeof(h_flags), cudaMemcpyDeviceToHost, stream));
   FB_CUDA(cudaStreamSynchronize(stream));
+  const unsigned long long h_err = h_flags[0];
+  // targets bit-identical to the source points, in the same order (what ferreus_rbf's solver passes on every
+  // matvec, rbf.rs:1357-1364): reuse the source binning; evaluate() can then run the fused W/X pass
+  if (maybe_sources && h_flags[1] == 0 && h_err == ~0ull) return source_target_set();
   if (h_err != ~0ull) {
     if (bad) *bad = h_err;
     throw Error(FB_ERR_POINT_OUTSIDE_TREE,
@@ -898,8 +907,12 @@ static int eval_common(fb_tree *t, const double *w, size_t n_rows, size_t nrhs, 
         if (leaves_only) FB_REQUIRE(t->have_locals, "set_local_coefficients must be called before evaluate_leaves");
         TargetSet ts = t->bin_targets(targets, m, t_rs, t_cs, bad);  // before touching weights: errors leave state intact
         t->upload_weights(w, n_rows, nrhs, w_rs, w_cs);
-        if (!leaves_only) t->downward(ts.cell_flag);
-        t->leaf_pass(ts, out_grads != nullptr);
+        if (ts.all_sources && !leaves_only && out_grads == nullptr) {
+          t->evaluate_sources_fused();
+        } else {
+          if (!leaves_only) t->downward(ts.cell_flag);
+          t->leaf_pass(ts, out_grads != nullptr);
+        }
         t->fetch_output(m, out_grads != nullptr, out_vals, out_grads, o_rs, o_cs);
       },
       bad);

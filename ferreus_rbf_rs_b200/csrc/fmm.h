@@ -69,6 +69,18 @@ struct P2LArgs {  // bbfmm.rs:1001-1048
   const uint32_t *out_row;  // output row of each sorted source
 };
 
+// kernel family -> template argument
+#define FB_FAM_SWITCH(fam, CALL)                         \
+  switch (fam) {                                         \
+    case KF_LINEAR: CALL(KF_LINEAR); break;              \
+    case KF_TPS: CALL(KF_TPS); break;                    \
+    case KF_CUBIC: CALL(KF_CUBIC); break;                \
+    case KF_SPH: CALL(KF_SPH); break;                    \
+    case KF_LAPLACE: CALL(KF_LAPLACE); break;            \
+    case KF_R2: CALL(KF_R2); break;                      \
+    default: CALL(KF_R4); break;                         \
+  }
+
 void launch_leaf_direct(const DirectArgs &a, cudaStream_t s);
 void launch_p2l(const P2LArgs &a, cudaStream_t s);
 
@@ -100,6 +112,7 @@ struct fb_tree {
 
   // --- device state
   fb::DBuf<double> d_sx, d_sy, d_sz;          // sorted source coordinates
+  fb::DBuf<double> d_pts_user;                // source points as given (n x dim, row-major)
   fb::DBuf<uint32_t> d_perm, d_inv;           // sorted position -> source row, and inverse
   fb::DBuf<double> d_w;                       // weights, sorted, [rhs][n]
   fb::DBuf<double> d_w_user;                  // weights as uploaded [n][nrhs] row-major

@@ -97,6 +97,13 @@ __global__ void k_target_leaf(const double *tg, size_t m, int dim, int depth, do
   slot[i] = s;
 }
 
+// flag != 0 when the two coordinate arrays differ in any bit
+__global__ void k_points_differ(const double *a, const double *b, size_t count, unsigned long long *flag) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  if (__double_as_longlong(a[i]) != __double_as_longlong(b[i])) *flag = 1ull;
+}
+
 __global__ void k_subset_positions(const unsigned long long *idx, const uint32_t *inv, size_t m, size_t n,
                                    uint32_t *pos, uint32_t *val, unsigned long long *err) {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;

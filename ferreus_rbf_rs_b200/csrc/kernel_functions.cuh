@@ -156,8 +156,9 @@ __device__ __forceinline__ double seed_operand(double a) {
 // ---- hot-loop variants -------------------------------------------------------------------------------
 // FAST = false: third-order step, ~1 ulp (measured 1.7e-16 max relative error, tools/fp64_ubench.cu).
 // FAST = true : second-order step r + r (1/2 - r y0 / 2): 3 FP64 operations instead of 5, relative error
-//               -1.5 d^2 with |d| <= 2^-20.1 the seed error: measured <= 1.24e-12.  Opt-in (fb_set_sqrt_mode /
-//               FB_SQRT=fast); the parity gates (1e-10 matvec, 1e-8 interpolant) hold in both modes.
+//               -1.5 d^2 with |d| <= 2^-20.1 the seed error: measured <= 1.24e-12.  Default; fb_set_sqrt_mode(0) or
+//               FB_SQRT=exact selects the third-order step.  The parity gates (1e-10 matvec, 1e-8 interpolant) hold
+//               in both modes (tests/test_gpu_fmm.py::test_sqrt_modes).
 __device__ __forceinline__ double half_of(double y) {  // y / 2 as an exponent decrement on the integer pipe
   return __hiloint2double(__double2hiint(y) - 0x00100000, __double2loint(y));
 }

@@ -70,8 +70,10 @@ uint64_t fb_kernel_launch_count(void);
 /* CUDA device used by handles created afterwards on this thread (default: current device) */
 int fb_set_device(int device);
 /* Square-root mode of the direct-sum hot loops (P2P, M2P, P2L) for trees and models built AFTER the call:
- * 0 = third-order refinement, ~1 ulp (default); 1 = second-order refinement, relative error <= 1.3e-12 per kernel
- * value, ~25 % fewer FP64 operations.  The environment variable FB_SQRT=fast|exact sets the initial value.     */
+ * 1 = second-order refinement of the hardware seed (default): relative error <= 1.3e-12 per kernel value (measured,
+ *     tools/fp64_ubench.cu), two FP64 operations fewer per pair; 0 = third-order refinement, ~1 ulp.  Both keep the
+ *     parity gates (matvec <= 1e-10, interpolant <= 1e-8).  The environment variable FB_SQRT=exact|fast sets the
+ *     initial value.                                                                                             */
 int fb_set_sqrt_mode(int fast);
 int fb_get_sqrt_mode(void);
 

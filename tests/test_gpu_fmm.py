@@ -99,6 +99,40 @@ def test_matvec_matches_oracle(n, dim, kind, kernel, order, comp, nrhs, adaptive
     pt.matvec_resident()
     got3 = np.asarray(pt.download_result()).reshape(n, nrhs)
     assert H.rel_l2(got3, ref) <= MATVEC_TOL
+    # the calls above recognise targets == sources and run the fused W/X pass (one kernel evaluation serves P2L and
+    # M2P); the same points in another order take the general path (binning + separate M2P and P2L kernels)
+    got4 = np.asarray(pt.evaluate(w, np.ascontiguousarray(pts[::-1]))).reshape(n, nrhs)
+    assert H.rel_l2(got4[::-1], ref) <= MATVEC_TOL
+
+
+@pytest.mark.parametrize("kernel,order", [(0, 7), (2, 6), (6, 6)])
+def test_sqrt_modes(kernel, order):
+    """fb_set_sqrt_mode: the default second-order square root (<= 1.3e-12 per kernel value) and the third-order one
+    (~1 ulp) both meet the 1e-10 bar; the third-order result agrees with the oracle to round-off."""
+    import ferreus_rbf_rs_b200 as fb
+    n = 5000
+    pts = H.make_points(n, 3, "clustered", seed=21)
+    w = np.random.default_rng(22).random((n, 2)) - 0.5
+    eps = 10.0 ** (-order)
+    ot = H.oracle_tree(pts, order, kernel, True, True, 30, 2, eps)
+    ot.set_weights(w)
+    ref = ot.evaluate(w, pts)
+    res = {}
+    was = fb.get_sqrt_mode()
+    try:
+        for fast in (True, False):
+            fb.set_sqrt_mode(fast)
+            pt = H.product_tree(pts, order, kernel, True, True, 30, 2, eps)
+            pt.set_weights(w)
+            res[fast] = (np.asarray(pt.evaluate(w, pts)).reshape(n, 2),
+                         np.asarray(pt.evaluate(w, np.ascontiguousarray(pts[::-1]))).reshape(n, 2)[::-1])
+    finally:
+        fb.set_sqrt_mode(was)
+    for fast in (True, False):
+        for got in res[fast]:
+            assert H.rel_l2(got, ref) <= MATVEC_TOL
+    assert H.rel_l2(res[False][0], ref) <= 2e-13
+    assert H.rel_l2(res[True][0], res[False][0]) <= 2e-11
 
 
 def test_accuracy_vs_dense_improves_with_order():
