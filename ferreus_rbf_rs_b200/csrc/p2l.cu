@@ -17,7 +17,8 @@ namespace fb {
 // ======================================================================================================
 constexpr int kP2LTileMax = 256;  // sources per staged tile (upper bound; one tile point per thread)
 constexpr int kP2LJB = 4;          // sources in flight per thread (independent kernel evaluations)
-constexpr size_t kP2LFuseBytes = 48 * 1024;  // shared-memory budget of the fused M2P partial sums
+constexpr size_t kP2LFuseBytes = 48 * 1024;  // shared-memory budget of the fused M2P partial sums (x2 when NR > 1:
+                                             // those instantiations run one CTA per SM anyway)
 
 template <int FAM, int NR, int PREG, bool FAST, bool FUSE>
 __global__ void __launch_bounds__(256, (NR * PREG <= (FUSE ? 8 : 16)) ? 2 : 1) k_p2l_grid(const P2LArgs a, const int nslices, const int cols, const int T) {
@@ -47,8 +48,12 @@ __global__ void __launch_bounds__(256, (NR * PREG <= (FUSE ? 8 : 16)) ? 2 : 1) k
         mreg[r][il] = (active && il < p) ? a.mult[((size_t)c * a.nrhs + a.rhs0 + r) * P + q * p + il] : 0.0;
   }
   const int i0 = dim == 3 ? q / p : q, i1 = dim == 3 ? q % p : 0;
-  const double ccx = a.ccx[c], ccy = a.ccy[c], ccz = a.ccz[c];
-  const double h = a.chalf[c];
+  __shared__ double ncoord[3 * PREG];  // node coordinates of the cell per axis
+  if (tid < dim * p) {
+    const int d = tid / p, i = tid - d * p;
+    const double cd = d == 0 ? a.ccx[c] : (d == 1 ? a.ccy[c] : a.ccz[c]);
+    ncoord[d * PREG + i] = cd + a.chalf[c] * a.nodes[i];
+  }
   const double *tabA = tab, *tabB = tab + (size_t)T * PREG, *tabL = tab + (size_t)(dim - 1) * T * PREG;
   double acc[NR][PREG];
 #pragma unroll
@@ -65,17 +70,25 @@ __global__ void __launch_bounds__(256, (NR * PREG <= (FUSE ? 8 : 16)) ? 2 : 1) k
     rb = a.x_begin[e];
     rn = a.x_count[e];
   }
-  double pc[3] = {0.0, 0.0, 0.0}, pw[NR];
-  auto prefetch = [&](int &m, int &base) {  // thread j < m takes tile point j
+  // tile item t = tid + k * nt (k = 0, 1) is the table row of axis d = t / T, point j = t % T; items past dim * T
+  // do not exist (T <= nt, so two items per thread cover dim * T <= 3 nt... see the launch: dim * T <= 2 nt)
+  double pc[2] = {0.0, 0.0}, pw[NR];
+  int it_d[2], it_j[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int t = tid + k * nt;
+    it_d[k] = (t >= T) + (t >= 2 * T) + (t >= 3 * T);
+    it_j[k] = t - it_d[k] * T;
+  }
+  auto prefetch = [&](int &m, int &base) {
     m = 0;
     if (e >= e_end) return;
     m = min(T, rn - c0);
     base = rb + c0;
-    if (tid < m) {
-      pc[0] = a.sx[base + tid];
-      if (dim > 1) pc[1] = a.sy[base + tid];
-      if (dim > 2) pc[2] = a.sz[base + tid];
-    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+      if (it_d[k] < dim && it_j[k] < m)
+        pc[k] = it_d[k] == 0 ? a.sx[base + it_j[k]] : (it_d[k] == 1 ? a.sy[base + it_j[k]] : a.sz[base + it_j[k]]);
 #pragma unroll
     for (int r = 0; r < NR; ++r) pw[r] = tid < m ? a.w[(size_t)(a.rhs0 + r) * a.n + base + tid] : 0.0;
     c0 += T;
@@ -88,19 +101,41 @@ __global__ void __launch_bounds__(256, (NR * PREG <= (FUSE ? 8 : 16)) ? 2 : 1) k
       }
     }
   };
+  // FUSE: the M2P sums of a finished tile are flushed by the threads that do not build the next tile's tables
+  // more than one row, concurrently with that build, so the flush costs no barrier of its own
+  const int n_flush = nt - max(0, dim * T - nt);  // threads with at most one table row to build
+  auto flush_m2p = [&](int first, int step, int m_done, int base_done) {
+    for (int j = first; j < m_done; j += step) {
+      const size_t row = a.out_row[base_done + j];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const double *pp = part + (size_t)r * cols * Ts + j;
+        double v0 = 0.0, v1 = 0.0;
+        int qq = 0;
+        for (; qq + 1 < cols; qq += 2) {
+          v0 += pp[(size_t)qq * Ts];
+          v1 += pp[(size_t)(qq + 1) * Ts];
+        }
+        if (qq < cols) v0 += pp[(size_t)qq * Ts];
+        atomicAdd(a.out + row * a.nrhs + a.rhs0 + r, v0 + v1);
+      }
+    }
+  };
+  int m_done = 0, base_done = 0;  // tile whose partial sums are waiting in `part`
   int m_cur = 0, m_next = 0, tile_base = 0, next_base = 0;
   prefetch(m_cur, tile_base);
   while (m_cur > 0) {
     const int m = m_cur;
     __syncthreads();
-    if (tid < T) {  // squared offsets node - source per axis (chebyshev.rs:951-968)
-      for (int d = 0; d < dim; ++d) {
-        double *row = tab + ((size_t)d * T + tid) * PREG;
-        if (tid < m) {
-          const double cd = d == 0 ? ccx : (d == 1 ? ccy : ccz);
-          const double xs = d == 0 ? pc[0] : (d == 1 ? pc[1] : pc[2]);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {  // squared offsets node - source per axis (chebyshev.rs:951-968)
+      const int d = it_d[k], j = it_j[k];
+      if (d < dim) {
+        double *row = tab + ((size_t)d * T + j) * PREG;
+        if (j < m) {
+          const double *nc = ncoord + d * PREG;
           for (int i = 0; i < p; ++i) {
-            const double o = (cd + h * a.nodes[i]) - xs;
+            const double o = nc[i] - pc[k];
             row[i] = o * o;
           }
         } else if (m < T) {  // neutral padding rows (r^2 = 1, weight 0) so every thread runs whole groups of kP2LJB
@@ -108,8 +143,17 @@ __global__ void __launch_bounds__(256, (NR * PREG <= (FUSE ? 8 : 16)) ? 2 : 1) k
           for (int i = 0; i < p; ++i) row[i] = fill;
         }
       }
+    }
+    if (tid < T) {
 #pragma unroll
       for (int r = 0; r < NR; ++r) wts[r * T + tid] = pw[r];
+    }
+    if (FUSE && m_done > 0) {  // the threads that built one row (or none) flush the previous tile's M2P sums
+      if (n_flush >= 32) {
+        if (tid >= nt - n_flush) flush_m2p(tid - (nt - n_flush), n_flush, m_done, base_done);
+      } else {
+        flush_m2p(tid, nt, m_done, base_done);
+      }
     }
     __syncthreads();
     const int cur_base = tile_base;
@@ -163,26 +207,14 @@ __global__ void __launch_bounds__(256, (NR * PREG <= (FUSE ? 8 : 16)) ? 2 : 1) k
         }
       }
     }
-    if (FUSE) {
-      __syncthreads();
-      if (tid < m) {
-        const size_t row = a.out_row[cur_base + tid];
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-          const double *pp = part + (size_t)r * cols * Ts + tid;
-          double v0 = 0.0, v1 = 0.0;
-          int qq = 0;
-          for (; qq + 1 < cols; qq += 2) {
-            v0 += pp[(size_t)qq * Ts];
-            v1 += pp[(size_t)(qq + 1) * Ts];
-          }
-          if (qq < cols) v0 += pp[(size_t)qq * Ts];
-          atomicAdd(a.out + row * a.nrhs + a.rhs0 + r, v0 + v1);
-        }
-      }
-    }
+    m_done = m;
+    base_done = cur_base;
     m_cur = m_next;
     tile_base = next_base;
+  }
+  if (FUSE) {
+    __syncthreads();
+    flush_m2p(tid, nt, m_done, base_done);
   }
   // ---- sum the slices in a fixed order and add to the cell's local expansion
   double *red = sm;  // [nslices][P]
@@ -209,9 +241,10 @@ static void launch_p2l_grid_impl(const P2LArgs &a, cudaStream_t s) {
   const int nslices = std::min(32, std::max(1, 256 / cols));
   const int nthreads = std::max(128, std::min(256, ((nslices * cols + 31) / 32) * 32));
   const int group = kP2LJB * nslices;
-  int T = group * std::max(1, std::min(kP2LTileMax, nthreads) / group);  // <= nthreads: one tile point per thread
+  // T <= nthreads (one weight per thread) and dim * T <= 2 * nthreads (two table rows per thread)
+  int T = group * std::max(1, std::min(kP2LTileMax, (2 * nthreads) / std::max(2, a.dim)) / group);
   if (FUSE) {  // per-(column, point) partial sums: keep them within ~48 KB
-    const int cap = (int)(kP2LFuseBytes / (sizeof(double) * (size_t)NR * cols)) - 1;
+    const int cap = (int)((NR > 1 ? 2 : 1) * kP2LFuseBytes / (sizeof(double) * (size_t)NR * cols)) - 1;
     T = group * std::max(1, std::min(T, cap) / group);
   }
   const size_t tab_d = (size_t)a.dim * T * PREG + (size_t)NR * T + (FUSE ? (size_t)NR * cols * (T + 1) : 0);
