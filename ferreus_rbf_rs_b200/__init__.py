@@ -5,7 +5,7 @@ from . import _lib  # noqa: F401
 from .bbfmm import (FmmKernelType, FmmParams, FmmTree, KernelParams, M2LCompressionType,  # noqa: F401
                     SpheroidalOrder)
 from . import config, interpolant_config, progress  # noqa: F401,E402
-from .rbf import Coefficients, RBFInterpolator  # noqa: F401,E402
+from .rbf import Coefficients, GlobalTrend, RBFInterpolator  # noqa: F401,E402
 
 
 def set_sqrt_mode(fast: bool) -> None:

@@ -47,6 +47,10 @@ class FrParams(C.Structure):
                 ("eval_chunk_size", C.c_uint64), ("naive_solve_threshold", C.c_uint64), ("test_unique", C.c_int32)]
 
 
+class FrGlobalTrend(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("angles", C.c_double * 3), ("ratios", C.c_double * 3)]
+
+
 class FrEvent(C.Structure):
     _fields_ = [("kind", C.c_int32), ("iter", C.c_uint64), ("residual", C.c_double), ("progress", C.c_double),
                 ("message", C.c_char_p)]
@@ -128,6 +132,8 @@ SOLVER_SIGNATURES = {
     "fr_params_default": (None, [C.c_int32, C.POINTER(FrParams)]),
     "fr_fit": (C.c_int, [_dp, _sz, C.c_int, _pd, _pd, _dp, _sz, _pd, _pd, C.POINTER(FrSettings), C.POINTER(FrParams),
                          FR_PROGRESS_CB, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "fr_fit_trend": (C.c_int, [_dp, _sz, C.c_int, _pd, _pd, _dp, _sz, _pd, _pd, C.POINTER(FrSettings), C.POINTER(FrParams),
+                               C.POINTER(FrGlobalTrend), FR_PROGRESS_CB, C.c_void_p, C.POINTER(C.c_void_p)]),
     "fr_free": (None, [C.c_void_p]),
     "fr_get_info": (C.c_int, [C.c_void_p, C.POINTER(FrModelInfo)]),
     "fr_source_points": (C.c_int, [C.c_void_p, _dp, _dp]),

@@ -434,7 +434,17 @@ struct fr_model {
   Settings st;
   fr_params params{};
   KParams kp{};
-  std::vector<double> points, values;  // after duplicate removal, row-major
+  std::vector<double> points, values;  // after duplicate removal, row-major (original coordinates)
+  // global trend (global_trend.rs:128-287): kernel-space coordinates x' = [x 1] * aff; `kpts` holds the kernel-space
+  // copy of `points` the trees / DDM / domain matrices are built from (empty without a trend: `points` is used)
+  bool has_trend = false;
+  fr_global_trend trend{};
+  double aff[16] = {0}, aff_inv[16] = {0};  // (dim+1) x (dim+1), row-major, applied to homogeneous ROW vectors
+  std::vector<double> kpts;
+  const double *kernel_points() const { return has_trend ? kpts.data() : points.data(); }
+  void build_trend_transform();
+  void apply_affine(const double *a, const double *in, size_t cnt, ptrdiff_t rs, ptrdiff_t cs, double *out) const;
+  void transform_extents(double *ext) const;  // [mins..., maxs...] -> extents of the transformed box corners
   std::vector<double> translation, scale;
   std::vector<double> point_coeff, poly_coeff;
   std::vector<LevelHost> ddm;
@@ -481,9 +491,10 @@ struct DeviceSolver {
     nt = n + m;
     std::vector<double> x(n), y(n, 0.0), z(n, 0.0);
     for (size_t i = 0; i < n; ++i) {
-      x[i] = M.points[i * M.dim];
-      if (M.dim > 1) y[i] = M.points[i * M.dim + 1];
-      if (M.dim > 2) z[i] = M.points[i * M.dim + 2];
+      const double *kp = M.kernel_points();
+      x[i] = kp[i * M.dim];
+      if (M.dim > 1) y[i] = kp[i * M.dim + 1];
+      if (M.dim > 2) z[i] = kp[i * M.dim + 2];
     }
     px.upload(x, stream);
     py.upload(y, stream);
@@ -705,7 +716,7 @@ fb_tree *fr_model::make_tree(bool sparse, const double *extents) {
   fp.eval_chunk_size = params.eval_chunk_size;
   fb_tree *t = new fb_tree();
   try {
-    t->build(points.data(), n, dim, dim, 1, (int)params.interpolation_order, &st.kparams, 1, sparse ? 1 : 0, extents,
+    t->build(kernel_points(), n, dim, dim, 1, (int)params.interpolation_order, &st.kparams, 1, sparse ? 1 : 0, extents,
              &fp);
   } catch (...) {
     delete t;
@@ -724,7 +735,19 @@ void fr_model::fit() {
   const size_t m = (size_t)st.basis_size;
   translation.assign(dim, 0.0);
   scale.assign(dim, 1.0);
-  if (m) cheb_cube_scaling(points.data(), nullptr, n, dim, translation.data(), scale.data());  // rbf.rs:418-421
+  // global trend (rbf.rs:361-371): kernel space = transformed points; monomials are evaluated at the inverse
+  // transform of those (rbf.rs:477-484, domain.rs:169-175), which also become the public points (rbf.rs:579-581)
+  std::vector<double> mono_pts;
+  if (has_trend) {
+    build_trend_transform();
+    kpts.resize(n * dim);
+    apply_affine(aff, points.data(), n, dim, 1, kpts.data());
+    mono_pts.resize(n * dim);
+    apply_affine(aff_inv, kpts.data(), n, dim, 1, mono_pts.data());
+  }
+  const double *kp_ptr = kernel_points();
+  const double *mono_ptr = has_trend ? mono_pts.data() : nullptr;
+  if (m) cheb_cube_scaling(kp_ptr, nullptr, n, dim, translation.data(), scale.data());  // rbf.rs:418-421
   point_coeff.assign(n * n_cols, 0.0);
   poly_coeff.assign(m * n_cols, 0.0);
   const size_t nt = n + m;
@@ -744,14 +767,14 @@ void fr_model::fit() {
     DomainHost d;
     d.idx = lh.point_indices;
     d.mask.assign(n, 1);
-    d.prepare(points.data(), dim, st, true);
+    d.prepare(kp_ptr, dim, st, true, mono_ptr);
     lh.domains.push_back(std::move(d));
     ddm.clear();
     ddm.push_back(std::move(lh));
   } else {
     tree.reset(make_tree(true, nullptr));  // adaptive, sparse, own extents (rbf.rs:456-467)
     lap("fmm tree + operators", t_lap);
-    ddm = build_ddm(points.data(), n, dim, st, params);
+    ddm = build_ddm(kp_ptr, n, dim, st, params, mono_ptr);
     lap("ddm hierarchy (host)", t_lap);
   }
   cudaStream_t stream = nullptr;
@@ -769,7 +792,7 @@ void fr_model::fit() {
     S.upload_points(stream);
     if (m && !naive) {
       std::vector<double> Pm(n * m), Qm(n * m);
-      evaluate_monomials(points.data(), nullptr, n, dim, st.polynomial_degree, (int)m, translation.data(),
+      evaluate_monomials(mono_ptr ? mono_ptr : points.data(), nullptr, n, dim, st.polynomial_degree, (int)m, translation.data(),
                          scale.data(), Pm.data());
       thin_q_rowmajor(Pm.data(), n, (int)m, Qm.data());
       S.P.upload(Pm, stream);
@@ -913,19 +936,167 @@ void fr_model::fit() {
   }
   solver.reset();
   if (own_stream) cudaStreamDestroy(stream);
+  if (has_trend) {  // rbf.rs:579-581 and 599-601: public points = inverse transform; evaluators transform them again
+    points.swap(mono_pts);
+    apply_affine(aff, points.data(), n, dim, 1, kpts.data());
+  }
   info.n_points = n;
   info.fit_seconds = std::chrono::duration<double>(clk::now() - t_start).count();
+}
+
+void fr_model::build_trend_transform() {
+  const int d = dim, h = d + 1;
+  auto eye = [&](double *mtx) {
+    for (int i = 0; i < h * h; ++i) mtx[i] = 0.0;
+    for (int i = 0; i < h; ++i) mtx[i * h + i] = 1.0;
+  };
+  auto mul = [&](const double *a, const double *b, double *c) {
+    double t[16] = {0};
+    for (int i = 0; i < h; ++i)
+      for (int j = 0; j < h; ++j) {
+        double v = 0.0;
+        for (int k = 0; k < h; ++k) v += a[i * h + k] * b[k * h + j];
+        t[i * h + j] = v;
+      }
+    std::copy(t, t + h * h, c);
+  };
+  double center[3] = {0, 0, 0};  // get_center: column means (rbf.rs:1300-1305)
+  for (int k = 0; k < d; ++k) {
+    double sum = 0.0;
+    for (size_t i = 0; i < n; ++i) sum += points[i * d + k];
+    center[k] = sum / (double)n;
+  }
+  double T[16], TB[16], S[16], R[16];
+  eye(T);
+  eye(TB);
+  eye(S);
+  eye(R);
+  for (int k = 0; k < d; ++k) {
+    T[k * h + d] = -center[k];
+    TB[k * h + d] = center[k];
+    S[k * h + k] = 1.0 / trend.ratios[k];
+  }
+  const double rad = 3.14159265358979323846 / 180.0;
+  auto rot_z = [&](double a, double *mtx) {
+    eye(mtx);
+    mtx[0] = std::cos(a);
+    mtx[1] = std::sin(a);
+    mtx[h] = -std::sin(a);
+    mtx[h + 1] = std::cos(a);
+  };
+  if (d == 2) {
+    rot_z(-trend.angles[0] * rad, R);
+  } else if (d == 3) {
+    const double dipr = -trend.angles[0] * rad, dipdirr = -trend.angles[1] * rad, pitchr = -trend.angles[2] * rad;
+    double RZ[16], RX[16], RZ2[16];
+    rot_z(dipdirr, RZ);
+    eye(RX);
+    RX[1 * h + 1] = std::cos(dipr);
+    RX[1 * h + 2] = std::sin(dipr);
+    RX[2 * h + 1] = -std::sin(dipr);
+    RX[2 * h + 2] = std::cos(dipr);
+    rot_z(pitchr, RZ2);
+    mul(RZ2, RX, R);
+    mul(R, RZ, R);
+  }
+  double A[16];
+  mul(TB, S, A);
+  mul(A, R, A);
+  mul(A, T, A);
+  for (int i = 0; i < h; ++i)  // stored transposed: homogeneous row vectors multiply from the left
+    for (int j = 0; j < h; ++j) aff[i * h + j] = A[j * h + i];
+  // inverse by Gauss-Jordan with partial pivoting
+  double w[16];
+  std::copy(aff, aff + h * h, w);
+  eye(aff_inv);
+  for (int c = 0; c < h; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < h; ++r)
+      if (std::fabs(w[r * h + c]) > std::fabs(w[piv * h + c])) piv = r;
+    FB_REQUIRE(w[piv * h + c] != 0.0, "singular global trend transform");
+    if (piv != c)
+      for (int k = 0; k < h; ++k) {
+        std::swap(w[c * h + k], w[piv * h + k]);
+        std::swap(aff_inv[c * h + k], aff_inv[piv * h + k]);
+      }
+    const double dgn = w[c * h + c];
+    for (int k = 0; k < h; ++k) {
+      w[c * h + k] /= dgn;
+      aff_inv[c * h + k] /= dgn;
+    }
+    for (int r = 0; r < h; ++r) {
+      if (r == c) continue;
+      const double f = w[r * h + c];
+      if (f == 0.0) continue;
+      for (int k = 0; k < h; ++k) {
+        w[r * h + k] -= f * w[c * h + k];
+        aff_inv[r * h + k] -= f * aff_inv[c * h + k];
+      }
+    }
+  }
+}
+
+void fr_model::apply_affine(const double *a, const double *in, size_t cnt, ptrdiff_t rs, ptrdiff_t cs, double *out) const {
+  const int d = dim, h = d + 1;
+  for (size_t i = 0; i < cnt; ++i) {
+    double x[4] = {0, 0, 0, 1.0};
+    for (int k = 0; k < d; ++k) x[k] = in[(ptrdiff_t)i * rs + (ptrdiff_t)k * cs];
+    x[d] = 1.0;
+    for (int j = 0; j < d; ++j) {
+      double v = 0.0;
+      for (int k = 0; k < h; ++k) v += x[k] * a[k * h + j];
+      out[i * d + j] = v;
+    }
+  }
+}
+
+void fr_model::transform_extents(double *ext) const {  // rbf.rs:603-615 (bounding_box_corners :1307-1317)
+  if (!has_trend) return;
+  const int d = dim;
+  double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+  for (int i = 0; i < (1 << d); ++i) {
+    double c[3] = {0, 0, 0}, tc[3] = {0, 0, 0};
+    for (int j = 0; j < d; ++j) c[j] = ((i >> j) & 1) == 0 ? ext[j] : ext[d + j];
+    apply_affine(aff, c, 1, d, 1, tc);
+    for (int j = 0; j < d; ++j) {
+      lo[j] = i == 0 ? tc[j] : std::min(lo[j], tc[j]);
+      hi[j] = i == 0 ? tc[j] : std::max(hi[j], tc[j]);
+    }
+  }
+  for (int j = 0; j < d; ++j) {
+    ext[j] = lo[j];
+    ext[d + j] = hi[j];
+  }
 }
 
 // evaluate the interpolant through a tree whose multipoles hold the point coefficients (rbf.rs:1180-1270)
 void fr_model::eval_tree(fb_tree *t, const double *targets, size_t mt, ptrdiff_t rs, ptrdiff_t cs, bool leaves,
                          bool add_nugget, double *out_vals, double *out_grads) {
   uint64_t bad = 0;
-  TargetSet ts = t->bin_targets(targets, mt, rs, cs, &bad);
+  std::vector<double> ttg;
+  if (has_trend) {  // the kernel part is evaluated in the transformed space (rbf.rs:1181-1185)
+    ttg.resize(mt * dim);
+    apply_affine(aff, targets, mt, rs, cs, ttg.data());
+  }
+  TargetSet ts = has_trend ? t->bin_targets(ttg.data(), mt, dim, 1, &bad) : t->bin_targets(targets, mt, rs, cs, &bad);
   t->upload_weights(point_coeff.data(), n, n_cols, (ptrdiff_t)n_cols, 1);
   if (!leaves) t->downward(ts.cell_flag);
   t->leaf_pass(ts, out_grads != nullptr);
   t->fetch_output(mt, out_grads != nullptr, out_vals, out_grads, (ptrdiff_t)n_cols, 1);
+  if (has_trend && out_grads) {  // grad_x f = grad_x' f * B^T, B = linear part of the transform (rbf.rs:1272-1298)
+    const int h = dim + 1;
+    for (size_t i = 0; i < mt; ++i)
+      for (size_t c = 0; c < n_cols; ++c) {
+        double *g = out_grads + i * (n_cols * dim) + c * dim;
+        double tmp[3] = {0, 0, 0};
+        for (int d = 0; d < dim; ++d) tmp[d] = g[d];
+        for (int k = 0; k < dim; ++k) {
+          double acc = 0.0;
+          for (int j = 0; j < dim; ++j) acc += tmp[j] * aff[k * h + j];  // B^T[j][k] = B[k][j]
+          g[k] = acc;
+        }
+      }
+  }
   if (add_nugget)
     for (size_t i = 0; i < mt && i < n; ++i)
       for (size_t c = 0; c < n_cols; ++c) out_vals[i * n_cols + c] += point_coeff[i * n_cols + c] * st.nugget;
@@ -1018,6 +1189,14 @@ void fr_params_default(int32_t kernel_type, fr_params *out) {
 int fr_fit(const double *points, size_t n, int dim, ptrdiff_t p_rs, ptrdiff_t p_cs, const double *values, size_t n_cols,
            ptrdiff_t v_rs, ptrdiff_t v_cs, const fr_settings *settings, const fr_params *params_or_null,
            fr_progress_cb cb_or_null, void *user, fr_model **out) {
+  return fr_fit_trend(points, n, dim, p_rs, p_cs, values, n_cols, v_rs, v_cs, settings, params_or_null, nullptr,
+                      cb_or_null, user, out);
+}
+
+int fr_fit_trend(const double *points, size_t n, int dim, ptrdiff_t p_rs, ptrdiff_t p_cs, const double *values,
+                 size_t n_cols, ptrdiff_t v_rs, ptrdiff_t v_cs, const fr_settings *settings,
+                 const fr_params *params_or_null, const fr_global_trend *trend_or_null, fr_progress_cb cb_or_null,
+                 void *user, fr_model **out) {
   if (!out) return FB_ERR_INVALID_ARGUMENT;
   *out = nullptr;
   fr_model *M = nullptr;
@@ -1026,6 +1205,13 @@ int fr_fit(const double *points, size_t n, int dim, ptrdiff_t p_rs, ptrdiff_t p_
     FB_REQUIRE(dim >= 1 && dim <= 3, "Unsupported number of dimensions: " + std::to_string(dim));  // rbf.rs:329-333
     M = new fr_model();
     M->dim = dim;
+    if (trend_or_null) {
+      FB_REQUIRE(trend_or_null->dim == dim, "GlobalTrend variant does not match the dimensionality of the points");
+      for (int d = 0; d < dim; ++d)
+        FB_REQUIRE(trend_or_null->ratios[d] > 0.0, "GlobalTrend ratios must be positive");
+      M->has_trend = true;
+      M->trend = *trend_or_null;
+    }
     M->cb = cb_or_null;
     M->cb_user = user;
     std::string err;
@@ -1116,6 +1302,7 @@ int fr_evaluate(fr_model *m, const double *targets, size_t n_targets, ptrdiff_t 
       ext[d] = lo;
       ext[dim + d] = hi;
     }
+    m->transform_extents(ext);
     std::unique_ptr<fb_tree, void (*)(fb_tree *)> tree(m->make_tree(false, ext), fb_tree_free);
     tree->upload_weights(m->point_coeff.data(), m->n, m->n_cols, (ptrdiff_t)m->n_cols, 1);
     tree->upward();
@@ -1136,7 +1323,12 @@ int fr_evaluate_at_source(fr_model *m, int add_nugget, double *out_vals) {
 int fr_build_evaluator(fr_model *m, const double *extents_or_null) {
   return fr_guarded([&] {
     FB_REQUIRE(m, "model required");
-    m->evaluator.reset(m->make_tree(false, extents_or_null));  // rbf.rs:830-838
+    double ext[6];
+    if (extents_or_null) {
+      std::copy(extents_or_null, extents_or_null + 2 * m->dim, ext);
+      m->transform_extents(ext);
+    }
+    m->evaluator.reset(m->make_tree(false, extents_or_null ? ext : nullptr));  // rbf.rs:830-838
     fb_tree *t = m->evaluator.get();
     t->upload_weights(m->point_coeff.data(), m->n, m->n_cols, (ptrdiff_t)m->n_cols, 1);
     t->upward();

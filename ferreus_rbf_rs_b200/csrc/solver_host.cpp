@@ -262,7 +262,7 @@ static bool invert_small(std::vector<double> &a, int n, std::vector<double> &inv
   return true;
 }
 
-void DomainHost::prepare(const double *pts, int dim, const Settings &s, bool solve_for_poly_) {
+void DomainHost::prepare(const double *pts, int dim, const Settings &s, bool solve_for_poly_, const double *mono_pts) {
   const int n = (int)idx.size();
   if (mask.size() > (size_t)n) mask.resize(n);  // overlap padding beyond the point list (domain_decomposition.rs:303-308)
   rank = 0;
@@ -274,7 +274,7 @@ void DomainHost::prepare(const double *pts, int dim, const Settings &s, bool sol
   double tr[3], sc[3];
   cheb_cube_scaling(pts, idx.data(), n, dim, tr, sc);  // domain.rs:168-169
   std::vector<double> mono((size_t)n * m);
-  evaluate_monomials(pts, idx.data(), n, dim, s.polynomial_degree, m, tr, sc, mono.data());
+  evaluate_monomials(mono_pts ? mono_pts : pts, idx.data(), n, dim, s.polynomial_degree, m, tr, sc, mono.data());
   // column-pivoted QR of the monomials: unisolvent columns (domain.rs:187-204)
   std::vector<double> a((size_t)n * m);
   for (int i = 0; i < n; ++i)
@@ -344,7 +344,8 @@ static int argmax_first_positive(const double *v, int n) {  // ferreus_rbf_utils
   return best;
 }
 
-std::vector<LevelHost> build_ddm(const double *pts, size_t n, int dim, const Settings &s, const fr_params &p) {
+std::vector<LevelHost> build_ddm(const double *pts, size_t n, int dim, const Settings &s, const fr_params &p,
+                                 const double *mono_pts) {
   std::vector<LevelHost> levels;
   std::vector<int64_t> active(n);
   std::iota(active.begin(), active.end(), 0);
@@ -508,7 +509,7 @@ std::vector<LevelHost> build_ddm(const double *pts, size_t n, int dim, const Set
     const bool is_coarse = l + 1 == levels.size();
     std::vector<DomainHost> &doms = levels[l].domains;
 #pragma omp parallel for schedule(dynamic, 4)
-    for (long i = 0; i < (long)doms.size(); ++i) doms[i].prepare(pts, dim, s, is_coarse && s.basis_size != 0);
+    for (long i = 0; i < (long)doms.size(); ++i) doms[i].prepare(pts, dim, s, is_coarse && s.basis_size != 0, mono_pts);
   }
   return levels;
 }

@@ -40,7 +40,8 @@ struct DomainHost {
   std::vector<double> sp_inv;    // rank x rank inverse of the special-point monomials (poly recovery)
   bool solve_for_poly = false;
   // host part of Domain::factorise (domain.rs:163-330): unisolvent columns, special points, reorder, Q_top
-  void prepare(const double *pts, int dim, const Settings &s, bool solve_for_poly_);
+  // mono_pts: coordinates the monomials are evaluated at (global trend: the inverse-transformed points, domain.rs:169-175)
+  void prepare(const double *pts, int dim, const Settings &s, bool solve_for_poly_, const double *mono_pts = nullptr);
 };
 
 struct LevelHost {
@@ -49,7 +50,8 @@ struct LevelHost {
 };
 
 // DDMTree::new without the factorisations (domain_decomposition.rs:67-346)
-std::vector<LevelHost> build_ddm(const double *pts, size_t n, int dim, const Settings &s, const fr_params &p);
+std::vector<LevelHost> build_ddm(const double *pts, size_t n, int dim, const Settings &s, const fr_params &p,
+                                 const double *mono_pts = nullptr);
 
 // thin Q of an n x m matrix (row-major in, row-major out), rbf.rs:493-495
 void thin_q_rowmajor(const double *a, size_t n, int m, double *q);

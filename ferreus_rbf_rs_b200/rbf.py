@@ -10,6 +10,35 @@ from .interpolant_config import InterpolantSettings
 from .progress import DuplicatesRemoved, Message, SolverIteration
 
 
+class GlobalTrend:
+    """Mirror of ``ferreus_rbf.GlobalTrend`` (py_ferreus_rbf/ferreus_rbf/__init__.pyi:21-159; global_trend.rs:36-126):
+    anisotropy by rotation and axis ratios about the centroid of the points; angles in degrees."""
+
+    def __init__(self, dim, angles, ratios):
+        self.dim, self.angles, self.ratios = int(dim), [float(a) for a in angles], [float(r) for r in ratios]
+
+    @classmethod
+    def one(cls, major_ratio):
+        return cls(1, [], [major_ratio])
+
+    @classmethod
+    def two(cls, rotation_angle, major_ratio, minor_ratio):
+        return cls(2, [rotation_angle], [major_ratio, minor_ratio])
+
+    @classmethod
+    def three(cls, dip, dip_direction, pitch, major_ratio, semi_major_ratio, minor_ratio):
+        return cls(3, [dip, dip_direction, pitch], [major_ratio, semi_major_ratio, minor_ratio])
+
+    def _c(self):
+        t = _lib.FrGlobalTrend()
+        t.dim = self.dim
+        for i, a in enumerate(self.angles):
+            t.angles[i] = a
+        for i, r in enumerate(self.ratios):
+            t.ratios[i] = r
+        return t
+
+
 class Coefficients:
     def __init__(self, point_coefficients, poly_coefficients):
         self.point_coefficients = point_coefficients
@@ -33,8 +62,6 @@ class RBFInterpolator:
 
     def __init__(self, points, values, interpolant_settings, *, params=None, global_trend=None,
                  progress_callback=None):
-        if global_trend is not None:
-            raise NotImplementedError("GlobalTrend is outside the B200 hot path (SURVEY.md §8f)")
         pts = _points2d(points, "points")
         if not isinstance(values, np.ndarray) or values.dtype != np.float64 or values.ndim not in (1, 2):
             raise TypeError("Expected a 1D/2D float64 array for values")
@@ -85,8 +112,10 @@ class RBFInterpolator:
         self._h = C.c_void_p()
         pr, pc = _lib.strides_of(pts)
         vr, vc = _lib.strides_of(vals)
-        rc = L.fr_fit(_lib.dptr(pts), pts.shape[0], pts.shape[1], pr, pc, _lib.dptr(vals), vals.shape[1], vr, vc,
-                      C.byref(cs), C.byref(cp), self._cb, None, C.byref(self._h))
+        ct = global_trend._c() if global_trend is not None else None
+        rc = L.fr_fit_trend(_lib.dptr(pts), pts.shape[0], pts.shape[1], pr, pc, _lib.dptr(vals), vals.shape[1], vr, vc,
+                            C.byref(cs), C.byref(cp), C.byref(ct) if ct is not None else None, self._cb, None,
+                            C.byref(self._h))
         if rc != _lib.FB_OK:
             self._h = C.c_void_p()
             raise (ValueError if rc == _lib.FB_ERR_INVALID_ARGUMENT else RuntimeError)(_lib.last_error())

@@ -68,11 +68,25 @@ typedef void (*fr_progress_cb)(const fr_event *ev, void *user);
 
 typedef struct fr_model fr_model; /* opaque: replaces ferreus_rbf::RBFInterpolator */
 
+/* GlobalTrend (ferreus_rbf/src/global_trend.rs:36-126): anisotropy by rotation + axis ratios about the centroid of the
+ * (unique) points; angles in degrees.  dim 1: ratios[0] = major.  dim 2: angles[0] = rotation_angle, ratios = {major,
+ * minor}.  dim 3: angles = {dip, dip_direction, pitch}, ratios = {major, semi_major, minor}.                        */
+typedef struct fr_global_trend {
+  int32_t dim;
+  double angles[3];
+  double ratios[3];
+} fr_global_trend;
+
 /* RBFInterpolator::builder(points, values, settings).params(..).progress_callback(..).build()  (rbf.rs:304-412).
  * points: n x dim, values: n x n_cols.  params NULL => defaults.                                      */
 int fr_fit(const double *points, size_t n, int dim, ptrdiff_t p_rs, ptrdiff_t p_cs, const double *values,
            size_t n_cols, ptrdiff_t v_rs, ptrdiff_t v_cs, const fr_settings *settings,
            const fr_params *params_or_null, fr_progress_cb cb_or_null, void *user, fr_model **out);
+/* ...builder(..).global_trend(trend).build() (rbf.rs:239-242, 361-371); trend NULL == fr_fit */
+int fr_fit_trend(const double *points, size_t n, int dim, ptrdiff_t p_rs, ptrdiff_t p_cs, const double *values,
+                 size_t n_cols, ptrdiff_t v_rs, ptrdiff_t v_cs, const fr_settings *settings,
+                 const fr_params *params_or_null, const fr_global_trend *trend_or_null, fr_progress_cb cb_or_null,
+                 void *user, fr_model **out);
 void fr_free(fr_model *m);
 
 typedef struct fr_model_info {

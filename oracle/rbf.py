@@ -194,6 +194,72 @@ def remove_duplicates(points, kernel):
 
 
 # ------------------------------------------------------------------------------------------ domain
+class GlobalTrend:
+    """global_trend.rs:36-126: One{major_ratio} | Two{rotation_angle, major_ratio, minor_ratio} |
+    Three{dip, dip_direction, pitch, major_ratio, semi_major_ratio, minor_ratio}; angles in degrees."""
+
+    def __init__(self, dim, angles, ratios):
+        self.dim, self.angles, self.ratios = dim, list(angles), list(ratios)
+
+    @staticmethod
+    def one(major_ratio):
+        return GlobalTrend(1, [], [major_ratio])
+
+    @staticmethod
+    def two(rotation_angle, major_ratio, minor_ratio):
+        return GlobalTrend(2, [rotation_angle], [major_ratio, minor_ratio])
+
+    @staticmethod
+    def three(dip, dip_direction, pitch, major_ratio, semi_major_ratio, minor_ratio):
+        return GlobalTrend(3, [dip, dip_direction, pitch], [major_ratio, semi_major_ratio, minor_ratio])
+
+
+def _rot_z(a, d):
+    m = np.eye(d + 1)
+    m[0, 0], m[0, 1], m[1, 0], m[1, 1] = np.cos(a), np.sin(a), -np.sin(a), np.cos(a)
+    return m
+
+
+class GlobalTrendTransform:
+    """global_trend.rs:128-287: affine = (translate_back * scale * rotation * translate)^T applied to homogeneous
+    ROW vectors; inverse by LU."""
+
+    def __init__(self, center, trend):
+        d = trend.dim
+        t = np.eye(d + 1)
+        tb = np.eye(d + 1)
+        t[:d, d] = -np.asarray(center)
+        tb[:d, d] = np.asarray(center)
+        scale = np.eye(d + 1)
+        for i in range(d):
+            scale[i, i] = 1.0 / trend.ratios[i]
+        if d == 1:
+            rot = np.eye(2)
+        elif d == 2:
+            rot = _rot_z(-np.radians(trend.angles[0]), 2)
+        else:
+            dipr, dipdirr, pitchr = (-np.radians(a) for a in trend.angles)
+            rot_z = _rot_z(dipdirr, 3)
+            rot_x = np.eye(4)
+            rot_x[1, 1], rot_x[1, 2], rot_x[2, 1], rot_x[2, 2] = np.cos(dipr), np.sin(dipr), -np.sin(dipr), np.cos(dipr)
+            rot_z2 = _rot_z(pitchr, 3)
+            rot = rot_z2 @ rot_x @ rot_z
+        self.affine = (tb @ scale @ rot @ t).T.copy()
+        self.inverse = np.linalg.inv(self.affine)
+        self.dim = d
+
+    def transform_points(self, pts):
+        h = np.hstack([pts, np.ones((pts.shape[0], 1))])
+        return np.ascontiguousarray((h @ self.affine)[:, :self.dim])
+
+    def inverse_transform_points(self, pts):
+        h = np.hstack([pts, np.ones((pts.shape[0], 1))])
+        return np.ascontiguousarray((h @ self.inverse)[:, :self.dim])
+
+    def linear_part(self):
+        return self.affine[:self.dim, :self.dim].copy()
+
+
 class Domain:
     def __init__(self, indices):
         self.idx = np.array(indices, dtype=np.int64)
@@ -203,13 +269,14 @@ class Domain:
         self.q_top = None
         self.rank = 0
 
-    def factorise(self, points, settings, solve_for_poly):
+    def factorise(self, points, settings, solve_for_poly, gt=None):
         kern = settings.kernel()
         dp = points[self.idx]
         n = len(self.idx)
         if settings.basis_size != 0:
             tr, sc = get_cheb_cube_scaling_factors(dp)
-            mono = evaluate_monomials(dp, settings.polynomial_degree, settings.basis_size, tr, sc)
+            mp = gt.inverse_transform_points(dp) if gt is not None else dp       # domain.rs:169-175
+            mono = evaluate_monomials(mp, settings.polynomial_degree, settings.basis_size, tr, sc)
             _, r, piv = sla.qr(mono, mode="economic", pivoting=True)          # domain.rs:187
             diag = np.abs(np.diag(r))
             rank = int(np.sum(diag > 1e-10 * diag[0]))
@@ -277,7 +344,8 @@ def _argmax_first_positive(v):
 
 
 class DDMTree:
-    def __init__(self, points, settings, leaf_threshold, overlap_quota, coarse_ratio, coarse_threshold, factorise=True):
+    def __init__(self, points, settings, leaf_threshold, overlap_quota, coarse_ratio, coarse_threshold, factorise=True,
+                 gt=None):
         n, dim = points.shape
         self.levels = []
         active = np.arange(n, dtype=np.int64)
@@ -342,14 +410,14 @@ class DDMTree:
                 dmn.mask = np.concatenate([dmn.mask, np.zeros(len(order), dtype=bool)])
             if factorise:
                 for dmn in leaves:
-                    dmn.factorise(points, settings, False)
+                    dmn.factorise(points, settings, False, gt)
             self.levels.append(level)
             active = np.array(sorted(coarse_pts), dtype=np.int64)
         coarse = Level(active)
         cd = Domain(active)
         cd.mask = np.ones(len(active), dtype=bool)
         if factorise:
-            cd.factorise(points, settings, settings.basis_size != 0)
+            cd.factorise(points, settings, settings.basis_size != 0, gt)
         coarse.leaf_domains.append(cd)
         self.levels.append(coarse)
 
@@ -438,9 +506,10 @@ def schwarz_ddm_solver(matvec, rhs, precon, max_iterations, tolerance, tolerance
 
 
 class RBFInterpolator:
-    """rbf.rs:317-582 (fit) and 676-703 / 1180-1270 (evaluate); global trend not restated."""
+    """rbf.rs:317-582 (fit) and 676-703 / 1180-1270 (evaluate), global trend included (rbf.rs:361-371, 477-484,
+    579-581, 599-615, 1183-1229)."""
 
-    def __init__(self, points, values, settings, params=None, callback=None, dense_matvec=False):
+    def __init__(self, points, values, settings, params=None, callback=None, dense_matvec=False, global_trend=None):
         points = np.array(points, dtype=np.float64)
         values = np.array(values, dtype=np.float64)
         if values.ndim == 1:
@@ -456,6 +525,11 @@ class RBFInterpolator:
             self.num_duplicates = points.shape[0] - len(keep)
             if len(keep) != points.shape[0]:
                 points, values = points[keep], values[keep]
+        self.gt = None
+        if global_trend is not None:                         # rbf.rs:361-371: centre = mean of the unique points
+            self.gt = GlobalTrendTransform(points.mean(axis=0), global_trend)
+            points = self.gt.transform_points(points)
+        gt = self.gt
         self.points, self.values = points, values
         n, m = points.shape[0], settings.basis_size
         self.translation, self.scale = (get_cheb_cube_scaling_factors(points) if m else (None, None))
@@ -463,11 +537,13 @@ class RBFInterpolator:
         if n < self.params.naive_solve_threshold:
             dom = Domain(np.arange(n))
             dom.mask = np.ones(n, dtype=bool)
-            dom.factorise(points, settings, True)
+            dom.factorise(points, settings, True, gt)
             coeff, poly = dom.solve(values)
             pc = np.zeros_like(coeff)
             pc[dom.idx] = coeff
             self.point_coefficients, self.poly_coefficients = pc, poly
+            if gt is not None:
+                self.points = gt.inverse_transform_points(self.points)   # rbf.rs:579-581
             return
         p = self.params
         fmm_params = obb.FmmParams(p.max_points_per_cell, p.compression_type, p.epsilon, 1024)
@@ -476,9 +552,11 @@ class RBFInterpolator:
         if dense_matvec is False:
             from . import fast
             self.fast = fast.FastFmm(self.tree)
-        P = evaluate_monomials(points, settings.polynomial_degree, m, self.translation, self.scale) if m else None
+        mono_points = gt.inverse_transform_points(points) if gt is not None else points   # rbf.rs:477-484
+        P = evaluate_monomials(mono_points, settings.polynomial_degree, m, self.translation, self.scale) if m else None
         Qp = np.linalg.qr(P)[0] if m else None
-        self.ddm = DDMTree(points, settings, p.leaf_threshold, p.overlap_quota, p.coarse_ratio, p.coarse_threshold)
+        self.ddm = DDMTree(points, settings, p.leaf_threshold, p.overlap_quota, p.coarse_ratio, p.coarse_threshold,
+                           gt=gt)
         nugget = settings.nugget
 
         def matvec_partial(w, idx=None):                     # rbf.rs:1338-1379
@@ -547,6 +625,8 @@ class RBFInterpolator:
             if m:
                 poly[:, col] = sol[n:]
         self.point_coefficients, self.poly_coefficients = pc, poly
+        if gt is not None:
+            self.points = gt.inverse_transform_points(self.points)       # rbf.rs:579-581
 
     def evaluate(self, targets, with_gradients=False):
         """rbf.rs:676-703 + 1180-1270: non-sparse adaptive tree on the union extents."""
@@ -554,11 +634,23 @@ class RBFInterpolator:
         p = self.params
         lo = np.minimum(self.points.min(axis=0), targets.min(axis=0))
         hi = np.maximum(self.points.max(axis=0), targets.max(axis=0))
-        tree = obb.FmmTree(self.points, p.interpolation_order, self.kernel, True, False, list(lo) + list(hi),
+        src, tgt = self.points, targets
+        if self.gt is not None:                               # rbf.rs:599-615: transform points and the box corners
+            d = src.shape[1]
+            corners = np.array([[lo[j] if ((i >> j) & 1) == 0 else hi[j] for j in range(d)] for i in range(1 << d)])
+            tc = self.gt.transform_points(corners)
+            lo, hi = tc.min(axis=0), tc.max(axis=0)
+            src, tgt = self.gt.transform_points(src), self.gt.transform_points(targets)
+        tree = obb.FmmTree(src, p.interpolation_order, self.kernel, True, False, list(lo) + list(hi),
                            obb.FmmParams(p.max_points_per_cell, p.compression_type, p.epsilon, 1024))
         tree.set_weights(self.point_coefficients)
-        res = tree.evaluate(self.point_coefficients, targets, with_gradients)
+        res = tree.evaluate(self.point_coefficients, tgt, with_gradients)
         vals, grads = res if with_gradients else (res, None)
+        if self.gt is not None and with_gradients:            # rbf.rs:1272-1298: grad_x = grad_x' B^T per rhs
+            d = src.shape[1]
+            bt = self.gt.linear_part().T
+            g = grads.reshape(grads.shape[0], -1, d)
+            grads = np.einsum('irj,jk->irk', g, bt).reshape(grads.shape)
         s = self.settings
         if s.basis_size:
             mono = evaluate_monomials(targets, s.polynomial_degree, s.basis_size, self.translation, self.scale)
@@ -571,7 +663,11 @@ class RBFInterpolator:
     def evaluate_dense(self, targets):
         """exact evaluation of the fitted interpolant (ground truth for accuracy checks)"""
         targets = np.array(targets, dtype=np.float64)
-        vals = self.kernel.matrix(targets, self.points) @ self.point_coefficients
+        if self.gt is not None:
+            vals = self.kernel.matrix(self.gt.transform_points(targets),
+                                      self.gt.transform_points(self.points)) @ self.point_coefficients
+        else:
+            vals = self.kernel.matrix(targets, self.points) @ self.point_coefficients
         s = self.settings
         if s.basis_size:
             vals = vals + evaluate_monomials(targets, s.polynomial_degree, s.basis_size, self.translation,

@@ -40,6 +40,8 @@ def _oracle(kernel, pts, vals, tol, leaf=128, coarse=300, naive=100, order=8, ma
 
 
 def _values(pts):
+    if pts.shape[1] == 1:
+        return np.sin(3 * pts[:, 0]) + pts[:, 0] ** 2
     v = np.sin(3 * pts[:, 0]) + pts[:, 1] ** 2
     return v - pts[:, 2] if pts.shape[1] == 3 else v
 
@@ -183,3 +185,50 @@ def test_stationary_ddm_solver_and_duplicates():
     om = _oracle(kernel, pts, vals, 1e-8, solver=0)
     t = np.random.default_rng(3).random((200, dim))
     assert H.rel_l2(np.asarray(model.evaluate(t)).reshape(-1, 1), om.evaluate(t)) <= 1e-7
+
+
+@pytest.mark.parametrize("kernel,dim,n,naive", [(0, 3, 2400, 100), (2, 3, 600, 4096), (1, 2, 2400, 100), (0, 1, 300, 4096)])
+def test_global_trend_matches_oracle(kernel, dim, n, naive):
+    """GlobalTrend (global_trend.rs:128-287; rbf.rs:361-371, 477-484, 579-615, 1181-1229, 1272-1298): the kernel
+    works in the rotated / scaled space, the polynomial in the original one, gradients are transformed back."""
+    import ferreus_rbf_rs_b200 as fb
+    from oracle import rbf as orbf
+    pts = H.make_points(n, dim, "uniform", seed=61)
+    vals = _values(pts)
+    tol = 1e-10
+    if dim == 3:
+        gt, ogt = fb.GlobalTrend.three(25.0, 70.0, 15.0, 3.0, 2.0, 1.0), orbf.GlobalTrend.three(25.0, 70.0, 15.0, 3.0, 2.0, 1.0)
+    elif dim == 2:
+        gt, ogt = fb.GlobalTrend.two(35.0, 2.5, 1.0), orbf.GlobalTrend.two(35.0, 2.5, 1.0)
+    else:
+        gt, ogt = fb.GlobalTrend.one(2.0), orbf.GlobalTrend.one(2.0)
+    model = fb.RBFInterpolator(pts, vals, _settings(kernel, tol=tol), params=_params(kernel, naive=naive), global_trend=gt)
+    s = orbf.InterpolantSettings(kernel, tolerance=tol)
+    p = orbf.Params(kernel, solver_type=1, leaf_threshold=128, coarse_threshold=300, naive_solve_threshold=naive,
+                    interpolation_order=8, max_points_per_cell=40, epsilon=1e-10)
+    om = orbf.RBFInterpolator(pts, vals, s, p, global_trend=ogt)
+    # public points are the inverse transform of the transformed points (rbf.rs:579-581): equal up to round-off
+    assert np.allclose(model.source_points, om.points, rtol=0, atol=1e-12)
+    co = model.coefficients
+    assert H.rel_l2(co.point_coefficients, om.point_coefficients) <= 1e-6
+    targets = np.random.default_rng(2).random((300, dim)) * (pts.max(0) - pts.min(0)) + pts.min(0)
+    got, gg = model.evaluate_with_gradients(targets)
+    ref, rg = om.evaluate(targets, True)
+    assert H.rel_l2(np.asarray(got).reshape(-1, 1), ref) <= INTERP_TOL
+    assert H.rel_l2(gg, rg) <= 1e-6
+    # exact (dense) evaluation of the oracle's interpolant: same function
+    assert H.rel_l2(np.asarray(got).reshape(-1, 1), om.evaluate_dense(targets)) <= 1e-5
+    # persistent evaluator with user extents given in the ORIGINAL space (corner-transformed, rbf.rs:603-615)
+    ext = list(np.minimum(pts.min(0), targets.min(0)) - 0.1) + list(np.maximum(pts.max(0), targets.max(0)) + 0.1)
+    model.build_evaluator(ext)
+    got2 = np.asarray(model.evaluate_targets(targets)).reshape(-1, 1)
+    assert H.rel_l2(got2, ref) <= 1e-7
+    # the interpolant reproduces the data
+    at_src = np.asarray(model.evaluate_at_source()).reshape(-1)
+    assert H.rel_l2(at_src, vals) <= 1e-6
+    # a trivial trend changes nothing
+    if dim == 3 and n <= 1000:
+        m0 = fb.RBFInterpolator(pts, vals, _settings(kernel, tol=tol), params=_params(kernel, naive=naive))
+        m1 = fb.RBFInterpolator(pts, vals, _settings(kernel, tol=tol), params=_params(kernel, naive=naive),
+                                global_trend=fb.GlobalTrend.three(0.0, 0.0, 0.0, 1.0, 1.0, 1.0))
+        assert H.rel_l2(np.asarray(m1.evaluate(targets)), np.asarray(m0.evaluate(targets))) <= 1e-10
