@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cub/cub.cuh>
+#include <thrust/iterator/transform_iterator.h>
 
 #include "fmm_kernels.cuh"
 
@@ -451,11 +452,11 @@ void fb_tree::upward() {
 }
 
 // -------------------------------------------------------------------------------------- downward
-void fb_tree::downward(const uint8_t *flags, bool fuse_m2p) {
+void fb_tree::downward(const uint8_t *flags, const TargetSet *fuse_m2p) {
   const size_t nc = ht.ncells();
   const int p = order;
   d_loc.zero(nc * (size_t)nrhs * P, stream);
-  if (fuse_m2p) d_out.zero(n * (size_t)nrhs, stream);
+  if (fuse_m2p) d_out.zero(fuse_m2p->m * (size_t)nrhs, stream);
   if (timing) FB_CUDA(cudaEventRecord(ev[3], stream));
   // M2L (loop A of bbfmm.rs:781-832)
   const bool compressed = fparams.compression_type != FB_COMPRESSION_NONE;
@@ -531,7 +532,8 @@ void fb_tree::downward(const uint8_t *flags, bool fuse_m2p) {
     if (fuse_m2p) {
       a.mult = d_mult.p;
       a.out = d_out.p;
-      a.out_row = source_target_set().out_row;
+      a.out_row = fuse_m2p->row_of_pos;
+      a.tgt_prefix = fuse_m2p->tgt_prefix;
     }
     launch_p2l(a, stream);
   }
@@ -612,14 +614,14 @@ TargetSet fb_tree::source_target_set() {
   ts.max_tiles = src_tiles;
   ts.cell_flag = d_flag_all.p;
   ts.all_sources = true;
+  ts.row_of_pos = d_src_out_row.p;
   return ts;
 }
 
 // targets = all sources: X is the transpose of W, so the P2L kernel applies the M2P half as well
-void fb_tree::evaluate_sources_fused() {
-  TargetSet ts = source_target_set();
-  const bool fuse = ht.adaptive && n_x_cells > 0;
-  downward(ts.cell_flag, fuse);
+void fb_tree::evaluate_sources_fused(const TargetSet &ts) {
+  const bool fuse = ht.adaptive && n_x_cells > 0 && ts.row_of_pos != nullptr;
+  downward(ts.cell_flag, fuse ? &ts : nullptr);
   leaf_pass(ts, false, fuse);
 }
 
@@ -753,6 +755,30 @@ TargetSet fb_tree::subset_target_set_dev(const unsigned long long *d_idx, size_t
   TargetSet ts = finish_target_set(tb, m, bits_for(n), true);
   FB_LAUNCH(k_gather_coords, nblocks(m, 256), 256, 0, stream, d_sx.p, d_sy.p, d_sz.p, tb.key2.p, m, tb.tx.p, tb.ty.p,
             tb.tz.p);
+  // sorted position -> output row map and target counts (fused W/X pass); a subset that names a source twice keeps
+  // the separate M2P / P2L kernels
+  tb.row_of_pos.reserve(n);
+  tb.tgt_prefix.reserve(n + 1);
+  tb.dup.reserve(1);
+  FB_CUDA(cudaMemsetAsync(tb.row_of_pos.p, 0xFF, n * sizeof(uint32_t), stream));
+  FB_CUDA(cudaMemsetAsync(tb.dup.p, 0, sizeof(unsigned long long), stream));
+  FB_LAUNCH(k_subset_row_map, nblocks(m, 256), 256, 0, stream, tb.key2.p, tb.val2.p, m, tb.row_of_pos.p, tb.dup.p);
+  size_t scan_bytes = 0;
+  RowIsTarget is_target;
+  auto flags_in = thrust::make_transform_iterator(tb.row_of_pos.p, is_target);
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, flags_in, tb.tgt_prefix.p, (int)n, stream);
+  d_cub.reserve(scan_bytes);
+  // n + 1 outputs: scan the n flags and append the total
+  FB_CUDA(cub::DeviceScan::ExclusiveSum(d_cub.p, scan_bytes, flags_in, tb.tgt_prefix.p, (int)n, stream));
+  FB_LAUNCH(k_prefix_total, 1, 1, 0, stream, tb.tgt_prefix.p, tb.row_of_pos.p, n);
+  g_launches.fetch_add(1);
+  unsigned long long h_dup = 0;
+  FB_CUDA(cudaMemcpyAsync(&h_dup, tb.dup.p, sizeof(h_dup), cudaMemcpyDeviceToHost, stream));
+  FB_CUDA(cudaStreamSynchronize(stream));
+  if (h_dup == 0) {
+    ts.row_of_pos = tb.row_of_pos.p;
+    ts.tgt_prefix = tb.tgt_prefix.p;
+  }
   return ts;
 }
 
@@ -760,12 +786,7 @@ TargetSet fb_tree::subset_target_set_dev(const unsigned long long *d_idx, size_t
 void fb_tree::matvec_dev(const TargetSet &ts) {
   sort_weights();
   upward();
-  if (ts.all_sources) {
-    evaluate_sources_fused();
-  } else {
-    downward(ts.cell_flag);
-    leaf_pass(ts, false);
-  }
+  evaluate_sources_fused(ts);
 }
 
 void fb_tree::fetch_output(size_t m, bool grads, double *out_vals, double *out_grads, ptrdiff_t o_rs,
@@ -908,7 +929,7 @@ static int eval_common(fb_tree *t, const double *w, size_t n_rows, size_t nrhs, 
         TargetSet ts = t->bin_targets(targets, m, t_rs, t_cs, bad);  // before touching weights: errors leave state intact
         t->upload_weights(w, n_rows, nrhs, w_rs, w_cs);
         if (ts.all_sources && !leaves_only && out_grads == nullptr) {
-          t->evaluate_sources_fused();
+          t->evaluate_sources_fused(ts);
         } else {
           if (!leaves_only) t->downward(ts.cell_flag);
           t->leaf_pass(ts, out_grads != nullptr);
@@ -943,12 +964,7 @@ int fb_tree_evaluate_at_sources(fb_tree *t, const double *w, size_t n_rows, size
     FB_REQUIRE((int)nrhs == t->nrhs, "weights must have the column count given to set_weights");
     TargetSet ts = idx_or_null ? t->subset_target_set(idx_or_null, n_idx) : t->source_target_set();
     t->upload_weights(w, n_rows, nrhs, w_rs, w_cs);
-    if (ts.all_sources) {
-      t->evaluate_sources_fused();
-    } else {
-      t->downward(ts.cell_flag);
-      t->leaf_pass(ts, false);
-    }
+    t->evaluate_sources_fused(ts);
     t->fetch_output(ts.m, false, out_vals, nullptr, o_rs, o_cs);
   });
 }
@@ -971,12 +987,7 @@ int fb_tree_matvec_resident(fb_tree *t) {
     t->sort_weights();
     t->upward();
     TargetSet ts = t->have_subset ? t->ts_subset : t->source_target_set();
-    if (ts.all_sources) {
-      t->evaluate_sources_fused();
-    } else {
-      t->downward(ts.cell_flag);
-      t->leaf_pass(ts, false);
-    }
+    t->evaluate_sources_fused(ts);
     t->last_out_rows = ts.m;
     FB_CUDA(cudaEventRecord(t->ev_mv[1], t->stream));
     FB_CUDA(cudaStreamSynchronize(t->stream));

@@ -21,7 +21,10 @@ struct TargetSet {
   const int *tile_leaf = nullptr, *tile_off = nullptr;     // CTA tiles of <= kTile targets
   const int *n_tiles_dev = nullptr;                        // device scalar: number of valid tiles
   int max_tiles = 0;                                       // launch bound for the tile grid
-  bool all_sources = false;                                // the tree's own source set (enables the fused W/X pass)
+  bool all_sources = false;                                // the tree's own source set
+  // targets that are source points (all of them, or a duplicate-free subset): enables the fused W/X pass
+  const uint32_t *row_of_pos = nullptr;  // per sorted source position: output row, 0xFFFFFFFF when not a target
+  const uint32_t *tgt_prefix = nullptr;  // n + 1 exclusive counts of targets over the sorted positions; null = all
   const uint8_t *cell_flag = nullptr;                      // per cell: subtree contains targets
 };
 
@@ -31,6 +34,8 @@ struct TargetBuffers {
   DBuf<uint32_t> key, key2, val, val2;
   DBuf<int> tl_begin, tl_end, tile_leaf, tile_off, ntiles, tile_cnt;
   DBuf<uint8_t> flag;
+  DBuf<uint32_t> row_of_pos, tgt_prefix;  // subset-of-sources sets only
+  DBuf<unsigned long long> dup;
 };
 
 struct DirectArgs {  // leaf pass: P2P over U ranges + M2P over W cells (bbfmm.rs:1162-1355)
@@ -66,7 +71,8 @@ struct P2LArgs {  // bbfmm.rs:1001-1048
   // fused M2P (non-null only when the targets are all sources): out[out_row[s]] += K(point s, nodes) . M_cell
   const double *mult;       // multipoles [cell][rhs][P]
   double *out;              // [n][nrhs]
-  const uint32_t *out_row;  // output row of each sorted source
+  const uint32_t *out_row;  // output row of each sorted source position (0xFFFFFFFF: not a target)
+  const uint32_t *tgt_prefix;  // n + 1 exclusive target counts over the sorted positions, or null (every source)
 };
 
 // kernel family -> template argument
@@ -177,11 +183,11 @@ struct fb_tree {
   void upload_weights(const double *w, size_t n_rows, size_t nrhs_, ptrdiff_t rs, ptrdiff_t cs);
   void sort_weights();
   void upward();
-  // fuse_m2p: the P2L kernel also applies the M2P transpose into d_out (zeroed here); leaf_pass(.., m2p_done = true)
-  // must follow with the all-sources target set
-  void downward(const uint8_t *flags, bool fuse_m2p = false);
+  // fuse_m2p: the P2L kernel also applies the M2P transpose for that target set (ts.row_of_pos != null) into d_out
+  // (zeroed here); leaf_pass(ts, false, m2p_done = true) must follow
+  void downward(const uint8_t *flags, const fb::TargetSet *fuse_m2p = nullptr);
   void leaf_pass(const fb::TargetSet &ts, bool grads, bool m2p_done = false);
-  void evaluate_sources_fused();  // downward + leaf pass for targets = all sources
+  void evaluate_sources_fused(const fb::TargetSet &ts);  // downward + leaf pass for targets that are source points
   fb::TargetSet source_target_set();
   fb::TargetSet bin_targets(const double *targets, size_t m, ptrdiff_t rs, ptrdiff_t cs, uint64_t *bad);
   fb::TargetSet subset_target_set(const uint64_t *idx, size_t n_idx);

@@ -118,6 +118,21 @@ __global__ void k_subset_positions(const unsigned long long *idx, const uint32_t
   val[i] = (uint32_t)i;
 }
 
+// sorted source position -> output row of a subset-of-sources target set; dup != 0 when a position occurs twice
+__global__ void k_subset_row_map(const uint32_t *pos_sorted, const uint32_t *rows, size_t m, uint32_t *row_of_pos,
+                                 unsigned long long *dup) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  if (i + 1 < m && pos_sorted[i + 1] == pos_sorted[i]) *dup = 1ull;
+  row_of_pos[pos_sorted[i]] = rows[i];
+}
+struct RowIsTarget {
+  __host__ __device__ uint32_t operator()(uint32_t row) const { return row != 0xFFFFFFFFu ? 1u : 0u; }
+};
+__global__ void k_prefix_total(uint32_t *prefix, const uint32_t *row_of_pos, size_t n) {
+  prefix[n] = n ? prefix[n - 1] + (row_of_pos[n - 1] != 0xFFFFFFFFu ? 1u : 0u) : 0u;
+}
+
 // per leaf slot: range of sorted targets whose key (leaf slot, or sorted source position) falls in the leaf
 __global__ void k_leaf_ranges(const uint32_t *keys, size_t m, const int *key_lo, const int *key_hi, int n_leaves,
                               int *begin, int *end, int *tile_cnt) {

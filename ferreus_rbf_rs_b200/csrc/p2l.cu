@@ -24,7 +24,18 @@ template <int FAM, int NR, int PREG, bool FAST, bool FUSE>
 __global__ void __launch_bounds__(256, (NR * PREG <= (FUSE ? 8 : 16)) ? 2 : 1) k_p2l_grid(const P2LArgs a, const int nslices, const int cols, const int T) {
   const int ci = blockIdx.x;
   const int c = a.cells[ci];
-  if (!a.cell_flag[c]) return;
+  // P2L is wanted when the cell has targets below it; the fused M2P half when any X-list point is a target (a
+  // subset-of-sources target set carries exclusive target counts over the sorted positions)
+  const bool need_p2l = a.cell_flag[c] != 0;
+  if (!FUSE) {
+    if (!need_p2l) return;
+  } else if (!need_p2l) {
+    if (a.tgt_prefix == nullptr) return;  // every source is a target only when every cell is flagged
+    bool any = false;
+    for (long long e = a.x_ptr[ci]; e < a.x_ptr[ci + 1] && !any; ++e)
+      any = a.tgt_prefix[a.x_begin[e] + a.x_count[e]] != a.tgt_prefix[a.x_begin[e]];
+    if (!any) return;
+  }
   const int tid = threadIdx.x, nt = blockDim.x;
   const int p = a.p, P = a.P, dim = a.dim;
   extern __shared__ double sm[];
@@ -106,7 +117,9 @@ __global__ void __launch_bounds__(256, (NR * PREG <= (FUSE ? 8 : 16)) ? 2 : 1) k
   const int n_flush = nt - max(0, dim * T - nt);  // threads with at most one table row to build
   auto flush_m2p = [&](int first, int step, int m_done, int base_done) {
     for (int j = first; j < m_done; j += step) {
-      const size_t row = a.out_row[base_done + j];
+      const uint32_t row32 = a.out_row[base_done + j];
+      if (row32 == 0xFFFFFFFFu) continue;
+      const size_t row = row32;
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
         const double *pp = part + (size_t)r * cols * Ts + j;
@@ -158,7 +171,10 @@ __global__ void __launch_bounds__(256, (NR * PREG <= (FUSE ? 8 : 16)) ? 2 : 1) k
     __syncthreads();
     const int cur_base = tile_base;
     prefetch(m_next, next_base);
-    if (active) {
+    // a tile without targets contributes nothing when the cell itself has no targets either
+    const bool tile_wanted = !FUSE || need_p2l || a.tgt_prefix == nullptr ||
+                             a.tgt_prefix[cur_base + m] != a.tgt_prefix[cur_base];
+    if (active && tile_wanted) {
       const int kmax = (m + nslices - 1) / nslices;
       for (int k = 0; k < kmax; k += kP2LJB) {
         double axy[kP2LJB], wj[kP2LJB][NR], nx[kP2LJB];
@@ -207,7 +223,7 @@ __global__ void __launch_bounds__(256, (NR * PREG <= (FUSE ? 8 : 16)) ? 2 : 1) k
         }
       }
     }
-    m_done = m;
+    m_done = tile_wanted ? m : 0;
     base_done = cur_base;
     m_cur = m_next;
     tile_base = next_base;
@@ -216,6 +232,7 @@ __global__ void __launch_bounds__(256, (NR * PREG <= (FUSE ? 8 : 16)) ? 2 : 1) k
     __syncthreads();
     flush_m2p(tid, nt, m_done, base_done);
   }
+  if (FUSE && !need_p2l) return;
   // ---- sum the slices in a fixed order and add to the cell's local expansion
   double *red = sm;  // [nslices][P]
 #pragma unroll
