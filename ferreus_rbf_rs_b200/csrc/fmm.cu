@@ -463,6 +463,7 @@ void fb_tree::downward(const uint8_t *flags, const TargetSet *fuse_m2p) {
   if (!m2l_groups.empty()) {
     if (m2l_table_nrhs != nrhs) {  // CTA ranges depend on the number of right-hand sides
       std::vector<M2LGroupDev> tab;
+      std::vector<int> cta_group;
       long long cta = 0;
       for (const M2LGroup &g : m2l_groups) {
         M2LGroupDev t;
@@ -472,14 +473,17 @@ void fb_tree::downward(const uint8_t *flags, const TargetSet *fuse_m2p) {
         t.n_entries = (long long)g.n_entries;
         t.v_off = (long long)g.v_off;
         t.u_off = (long long)g.u_off;
+        const long long nct = (long long)((g.n_entries * (size_t)nrhs + m2l_nc - 1) / m2l_nc);
+        cta_group.insert(cta_group.end(), (size_t)nct, (int)tab.size());
         tab.push_back(t);
-        cta += (long long)((g.n_entries * (size_t)nrhs + m2l_nc - 1) / m2l_nc);
+        cta += nct;
       }
       FB_REQUIRE(cta < (1ll << 31), "too many M2L tiles");
       m2l_ctas = (unsigned)cta;
       d_m2l_table.reserve(tab.size() * sizeof(M2LGroupDev));
       FB_CUDA(cudaMemcpyAsync(d_m2l_table.p, tab.data(), tab.size() * sizeof(M2LGroupDev), cudaMemcpyHostToDevice,
                               stream));
+      d_m2l_cta_group.upload(cta_group, stream);
       FB_CUDA(cudaStreamSynchronize(stream));
       m2l_table_nrhs = nrhs;
     }
@@ -487,7 +491,7 @@ void fb_tree::downward(const uint8_t *flags, const TargetSet *fuse_m2p) {
 #define FB_M2L_LAUNCH(COMP, NCV)                                                                                   \
   do {                                                                                                             \
     set_smem(k_m2l<COMP, NCV>, m2l_smem);                                                                          \
-    FB_LAUNCH((k_m2l<COMP, NCV>), m2l_ctas, 256, m2l_smem, stream, tab, (int)m2l_groups.size(), d_m2l_tgt.p,       \
+    FB_LAUNCH((k_m2l<COMP, NCV>), m2l_ctas, 256, m2l_smem, stream, tab, d_m2l_cta_group.p, d_m2l_tgt.p,          \
               d_m2l_src.p, d_m2l_perm.p, d_oppool.p, d_perm_tab.p, d_inv_tab.p, P, m2l_P4, m2l_Pp, nrhs, flags,    \
               d_mult.p, d_loc.p);                                                                                  \
   } while (0)

@@ -167,6 +167,7 @@ struct fb_tree {
   size_t m2l_smem = 0;
   int m2l_nc = 32;  // (entry, rhs) columns per M2L CTA
   fb::DBuf<unsigned char> d_m2l_table;  // M2LGroupDev[] of the fused launch
+  fb::DBuf<int> d_m2l_cta_group;        // group of every CTA of that launch
   int m2l_table_nrhs = -1;
   unsigned m2l_ctas = 0;
   // timing

@@ -394,17 +394,12 @@ struct M2LGroupDev {  // one (level, reference vector) group of the fused M2L la
 };
 
 template <bool COMPRESSED, int NC>
-__global__ void __launch_bounds__(256, NC == 32 ? 2 : 1) k_m2l(const M2LGroupDev *groups, int n_groups, const int *e_tgt_all,
+__global__ void __launch_bounds__(256, NC == 32 ? 2 : 1) k_m2l(const M2LGroupDev *groups, const int *cta_group, const int *e_tgt_all,
                                                 const int *e_src_all, const int *e_perm_all, const double *pool,
                                                 const int *perm_tab, const int *inv_tab, int P, int P4, int Pp, int nrhs,
                                                 const uint8_t *flag, const double *mult, double *loc) {
   // all levels and reference vectors run in ONE launch: M2L at different levels is independent
-  int glo = 0, ghi = n_groups;
-  while (ghi - glo > 1) {
-    const int mid = (glo + ghi) >> 1;
-    if (groups[mid].cta_begin <= (int)blockIdx.x) glo = mid; else ghi = mid;
-  }
-  const M2LGroupDev g = groups[glo];
+  const M2LGroupDev g = groups[cta_group[blockIdx.x]];
   const int *e_tgt = e_tgt_all + g.entry_off, *e_src = e_src_all + g.entry_off, *e_perm = e_perm_all + g.entry_off;
   const size_t n_entries = (size_t)g.n_entries;
   const int rank_pad = g.rank_pad;

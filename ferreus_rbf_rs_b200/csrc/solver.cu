@@ -1079,7 +1079,10 @@ void fr_model::eval_tree(fb_tree *t, const double *targets, size_t mt, ptrdiff_t
     apply_affine(aff, targets, mt, rs, cs, ttg.data());
   }
   TargetSet ts = has_trend ? t->bin_targets(ttg.data(), mt, dim, 1, &bad) : t->bin_targets(targets, mt, rs, cs, &bad);
-  t->upload_weights(point_coeff.data(), n, n_cols, (ptrdiff_t)n_cols, 1);
+  // every caller has just uploaded the point coefficients into this tree (set_weights semantics, rbf.rs:684, 836):
+  // they stay resident, so repeated small-batch evaluate_targets calls move only the targets and the results
+  if (!t->have_weights || t->nrhs != (int)n_cols)
+    t->upload_weights(point_coeff.data(), n, n_cols, (ptrdiff_t)n_cols, 1);
   if (!leaves) t->downward(ts.cell_flag);
   t->leaf_pass(ts, out_grads != nullptr);
   t->fetch_output(mt, out_grads != nullptr, out_vals, out_grads, (ptrdiff_t)n_cols, 1);
