@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(kLeafWPC * 32, NR >= 4 ? 7 : 10) k_leaf_warp(c
         reg[1] = a.sy[s];
         reg[2] = a.sz[s];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) reg[3 + r] = a.w[(size_t)(a.rhs0 + r) * a.n + s];
+        for (int r = 0; r < NR; ++r) reg[3 + r] = a.w[(size_t)(a.rhs0 + r) * a.n + s] * kernel_weight_scale<FAM, FAST>();
       }
       c0 += kWarpTile;
       if (c0 >= rn) {
@@ -305,7 +305,8 @@ __global__ void __launch_bounds__(kLeafWPC * 32, NR >= 4 ? 7 : 10) k_leaf_warp(c
       __syncwarp();
 #pragma unroll
       for (int r = 0; r < NR; ++r)
-        for (int k = lane; k < plane; k += 32) mw[r * plane + k] = k < cn ? msrc[(size_t)r * P + s0 * slab + k] : 0.0;
+        for (int k = lane; k < plane; k += 32)
+          mw[r * plane + k] = k < cn ? msrc[(size_t)r * P + s0 * slab + k] * kernel_weight_scale<FAM, FAST>() : 0.0;
       __syncwarp();
       // kM2PQB columns at a time: independent kernel evaluations in flight inside every (uniformly predicated) i2
       // step; columns past nq re-read the last column's offsets against zero multipoles

@@ -155,21 +155,21 @@ __device__ __forceinline__ double seed_operand(double a) {
 }
 // ---- hot-loop variants -------------------------------------------------------------------------------
 // FAST = false: third-order step, ~1 ulp (measured 1.7e-16 max relative error, tools/fp64_ubench.cu).
-// FAST = true : second-order step r + r (1/2 - r y0 / 2): 3 FP64 operations instead of 5, relative error
+// FAST = true : second-order step r (3 - r y0) / 2: 3 FP64 operations instead of 5, relative error
 //               -1.5 d^2 with |d| <= 2^-20.1 the seed error: measured <= 1.24e-12.  Default; fb_set_sqrt_mode(0) or
 //               FB_SQRT=exact selects the third-order step.  The parity gates (1e-10 matvec, 1e-8 interpolant) hold
 //               in both modes (tests/test_gpu_fmm.py::test_sqrt_modes).
 __device__ __forceinline__ double half_of(double y) {  // y / 2 as an exponent decrement on the integer pipe
   return __hiloint2double(__double2hiint(y) - 0x00100000, __double2loint(y));
 }
+// FAST returns 2 sqrt(a) = r (3 - r y0): the factor 1/2 rides on the weights (kernel_weight_scale), which saves the
+// exponent fix-up of the seed — one instruction per pair in loops that are issue- as much as FP64-bound
+// (tools/fp64_ubench.cu: far body 2.40 -> 2.58 Tpair/s at 16 warps/SM)
 template <bool FAST, bool ZERO_OK>
 __device__ __forceinline__ double hot_sqrt(double a) {  // ZERO_OK: a == 0 -> exactly 0 (seed from max(a, 2^-1022))
   const double y0 = rsq64h(ZERO_OK ? seed_operand(a) : a);
   const double r = a * y0;
-  if (FAST) {
-    const double e = fma(-r, half_of(y0), 0.5);
-    return fma(r, e, r);
-  }
+  if (FAST) return r * fma(-r, y0, 3.0);
   const double e = fma(-r, y0, 1.0);
   const double c = fma(e, 0.375, 0.5);
   return fma(r * e, c, r);
@@ -220,6 +220,12 @@ template <int FAM>
 __device__ __forceinline__ void kernel_acc(double &acc, double mag, double w) {
   if (FAM == KF_LINEAR) acc -= mag * w;
   else acc += mag * w;
+}
+// kernel_mag<FAM, FAST, .> returns value / kernel_weight_scale<FAM, FAST>(): the callers stage weights (and the
+// multipoles of the M2P half) multiplied by this scale
+template <int FAM, bool FAST>
+__host__ __device__ constexpr double kernel_weight_scale() {
+  return (FAST && (FAM == KF_LINEAR || FAM == KF_CUBIC)) ? 0.5 : 1.0;
 }
 // families whose hot loop has a FAST variant (the others ignore the switch)
 template <int FAM>

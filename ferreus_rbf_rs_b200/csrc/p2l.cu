@@ -56,7 +56,9 @@ __global__ void __launch_bounds__(256, (NR * PREG <= (FUSE ? 8 : 16)) ? 2 : 1) k
     for (int r = 0; r < NR; ++r)
 #pragma unroll
       for (int il = 0; il < PREG; ++il)
-        mreg[r][il] = (active && il < p) ? a.mult[((size_t)c * a.nrhs + a.rhs0 + r) * P + q * p + il] : 0.0;
+        mreg[r][il] = (active && il < p) ? a.mult[((size_t)c * a.nrhs + a.rhs0 + r) * P + q * p + il] *
+                                               kernel_weight_scale<FAM, FAST>()
+                                         : 0.0;
   }
   const int i0 = dim == 3 ? q / p : q, i1 = dim == 3 ? q % p : 0;
   __shared__ double ncoord[3 * PREG];  // node coordinates of the cell per axis
@@ -101,7 +103,8 @@ __global__ void __launch_bounds__(256, (NR * PREG <= (FUSE ? 8 : 16)) ? 2 : 1) k
       if (it_d[k] < dim && it_j[k] < m)
         pc[k] = it_d[k] == 0 ? a.sx[base + it_j[k]] : (it_d[k] == 1 ? a.sy[base + it_j[k]] : a.sz[base + it_j[k]]);
 #pragma unroll
-    for (int r = 0; r < NR; ++r) pw[r] = tid < m ? a.w[(size_t)(a.rhs0 + r) * a.n + base + tid] : 0.0;
+    for (int r = 0; r < NR; ++r)
+      pw[r] = tid < m ? a.w[(size_t)(a.rhs0 + r) * a.n + base + tid] * kernel_weight_scale<FAM, FAST>() : 0.0;
     c0 += T;
     if (c0 >= rn) {
       ++e;
