@@ -51,6 +51,13 @@ class FrGlobalTrend(C.Structure):
     _fields_ = [("dim", C.c_int32), ("angles", C.c_double * 3), ("ratios", C.c_double * 3)]
 
 
+class FrModelState(C.Structure):
+    _fields_ = [("settings", FrSettings), ("params", FrParams), ("basis_size", C.c_int32),
+                ("polynomial_degree", C.c_int32), ("translation_factor", C.c_double * 3),
+                ("scale_factor", C.c_double * 3), ("has_trend", C.c_int32), ("affine_transform", C.c_double * 16),
+                ("inverse_transform", C.c_double * 16)]
+
+
 class FrEvent(C.Structure):
     _fields_ = [("kind", C.c_int32), ("iter", C.c_uint64), ("residual", C.c_double), ("progress", C.c_double),
                 ("message", C.c_char_p)]
@@ -134,6 +141,9 @@ SOLVER_SIGNATURES = {
                          FR_PROGRESS_CB, C.c_void_p, C.POINTER(C.c_void_p)]),
     "fr_fit_trend": (C.c_int, [_dp, _sz, C.c_int, _pd, _pd, _dp, _sz, _pd, _pd, C.POINTER(FrSettings), C.POINTER(FrParams),
                                C.POINTER(FrGlobalTrend), FR_PROGRESS_CB, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "fr_get_state": (C.c_int, [C.c_void_p, C.POINTER(FrModelState)]),
+    "fr_model_restore": (C.c_int, [_dp, _sz, C.c_int, _dp, _sz, _dp, _dp, C.POINTER(FrModelState), FR_PROGRESS_CB,
+                                   C.c_void_p, C.POINTER(C.c_void_p)]),
     "fr_free": (None, [C.c_void_p]),
     "fr_get_info": (C.c_int, [C.c_void_p, C.POINTER(FrModelInfo)]),
     "fr_source_points": (C.c_int, [C.c_void_p, _dp, _dp]),

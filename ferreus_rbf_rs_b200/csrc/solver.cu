@@ -1284,6 +1284,82 @@ int fr_coefficients(const fr_model *m, double *point_out, double *poly_out) {
   return FB_OK;
 }
 
+int fr_get_state(const fr_model *m, fr_model_state *out) {
+  if (!m || !out) return FB_ERR_INVALID_ARGUMENT;
+  std::memset(out, 0, sizeof(*out));
+  out->settings.kernel_type = m->st.kernel_type;
+  out->settings.drift = m->st.drift;
+  out->settings.spheroidal_order = m->st.spheroidal_order;
+  out->settings.nugget = m->st.nugget;
+  out->settings.base_range = m->st.base_range;
+  out->settings.total_sill = m->st.total_sill;
+  out->settings.tolerance = m->st.tolerance;
+  out->settings.tolerance_type = m->st.tolerance_type;
+  out->params = m->params;
+  out->basis_size = m->st.basis_size;
+  out->polynomial_degree = m->st.polynomial_degree;
+  for (int d = 0; d < m->dim && d < (int)m->translation.size(); ++d) {
+    out->translation_factor[d] = m->translation[d];
+    out->scale_factor[d] = m->scale[d];
+  }
+  out->has_trend = m->has_trend ? 1 : 0;
+  if (m->has_trend) {
+    std::copy(m->aff, m->aff + 16, out->affine_transform);
+    std::copy(m->aff_inv, m->aff_inv + 16, out->inverse_transform);
+  }
+  return FB_OK;
+}
+
+int fr_model_restore(const double *points, size_t n, int dim, const double *values, size_t n_cols,
+                     const double *point_coefficients, const double *poly_coefficients_or_null,
+                     const fr_model_state *state, fr_progress_cb cb_or_null, void *user, fr_model **out) {
+  if (!out) return FB_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  fr_model *M = nullptr;
+  const int rc = fr_guarded([&] {
+    FB_REQUIRE(points && values && point_coefficients && state && n > 0 && n_cols > 0, "incomplete model state");
+    FB_REQUIRE(dim >= 1 && dim <= 3, "Unsupported number of dimensions: " + std::to_string(dim));
+    M = new fr_model();
+    M->dim = dim;
+    M->cb = cb_or_null;
+    M->cb_user = user;
+    std::string err;
+    FB_REQUIRE(resolve_settings(state->settings, dim, M->st, err), err);
+    FB_REQUIRE(M->st.basis_size == state->basis_size && M->st.polynomial_degree == state->polynomial_degree,
+               "basis_size / polynomial_degree do not match the kernel, drift and dimension of the model");
+    FB_REQUIRE(M->st.basis_size == 0 || poly_coefficients_or_null, "polynomial coefficients are required");
+    FB_REQUIRE(make_kparams(M->st.kparams, M->kp), "unknown kernel");
+    M->params = state->params;
+    M->n = M->n_in = n;
+    M->n_cols = n_cols;
+    M->points.assign(points, points + n * dim);
+    M->values.assign(values, values + n * n_cols);
+    M->point_coeff.assign(point_coefficients, point_coefficients + n * n_cols);
+    const size_t m = (size_t)M->st.basis_size;
+    if (m) M->poly_coeff.assign(poly_coefficients_or_null, poly_coefficients_or_null + m * n_cols);
+    M->translation.assign(state->translation_factor, state->translation_factor + dim);
+    M->scale.assign(state->scale_factor, state->scale_factor + dim);
+    if (state->has_trend) {  // evaluators transform the stored (original-space) points again (rbf.rs:599-601)
+      M->has_trend = true;
+      std::copy(state->affine_transform, state->affine_transform + 16, M->aff);
+      std::copy(state->inverse_transform, state->inverse_transform + 16, M->aff_inv);
+      M->kpts.resize(n * dim);
+      M->apply_affine(M->aff, M->points.data(), n, dim, 1, M->kpts.data());
+    }
+    M->info = fr_model_info{};
+    M->info.n_points = n;
+    M->info.n_cols = n_cols;
+    M->info.basis_size = m;
+    M->info.dim = (uint64_t)dim;
+  });
+  if (rc != FB_OK) {
+    delete M;
+    return rc;
+  }
+  *out = M;
+  return FB_OK;
+}
+
 int fr_evaluate(fr_model *m, const double *targets, size_t n_targets, ptrdiff_t t_rs, ptrdiff_t t_cs, double *out_vals,
                 double *out_grads_or_null) {
   return fr_guarded([&] {

@@ -1,6 +1,7 @@
 """Mirror of the reference class ``ferreus_rbf.RBFInterpolator`` over the C ABI of include/ferreus_rbf_b200.h
 (py_ferreus_rbf/src/python_bindings.rs:696-930).  All compute is in libferreus_b200.so."""
 import ctypes as C
+import json
 
 import numpy as np
 
@@ -121,6 +122,139 @@ class RBFInterpolator:
             raise (ValueError if rc == _lib.FB_ERR_INVALID_ARGUMENT else RuntimeError)(_lib.last_error())
         info = self.info()
         self._n, self._cols, self._m, self._dim = info["n_points"], info["n_cols"], info["basis_size"], info["dim"]
+
+    # ---- save_model / load_model (rbf.rs:1087-1171) ----------------------------------------------
+    # The reference writes `serde_json` of the struct behind a flattened envelope {format, version, ...fields}
+    # (rbf.rs:1469-1488).  Field names and enum variant names below are the reference's (rbf.rs:266-302,
+    # interpolant_config.rs:18-218, config.rs:42-262, global_trend.rs:128-132).  faer 0.23.2's `Mat` (un-vendored
+    # dependency, Cargo.lock:275-278) serialises as {"nrows", "ncols", "data": [row-major elements]} (faer's serde
+    # implementation for MatRef); that layout is restated here without a fixture from the reference to pin it.
+    _JSON_FORMAT_NAME = "ferreus_rbf.json"
+    _JSON_VERSION = 1
+
+    @staticmethod
+    def _mat(a):
+        a = np.atleast_2d(np.asarray(a, dtype=np.float64))
+        return {"nrows": int(a.shape[0]), "ncols": int(a.shape[1]), "data": [float(v) for v in a.ravel(order="C")]}
+
+    @staticmethod
+    def _unmat(d):
+        return np.asarray(d["data"], dtype=np.float64).reshape(int(d["nrows"]), int(d["ncols"]))
+
+    def save_model(self, path):
+        st = _lib.FrModelState()
+        self._check(self._L.fr_get_state(self._h, C.byref(st)))
+        dim, h = self._dim, self._dim + 1
+        drift = ["None", "Constant", "Linear", "Quadratic"][st.settings.drift]
+        sph = {3: "Three", 5: "Five", 7: "Seven", 9: "Nine"}[st.settings.spheroidal_order]
+        co = self.coefficients
+        vals = np.asarray(self.source_values, dtype=np.float64)
+        trend = None
+        if st.has_trend:
+            trend = {"affine_transform": self._mat(np.array(st.affine_transform[: h * h]).reshape(h, h)),
+                     "inverse_transform": self._mat(np.array(st.inverse_transform[: h * h]).reshape(h, h))}
+        p = st.params
+        doc = {
+            "format": self._JSON_FORMAT_NAME, "version": self._JSON_VERSION,
+            "points": self._mat(self.source_points),
+            "point_values": self._mat(vals.reshape(self._n, self._cols)),
+            "coefficients": {"point_coefficients": self._mat(co.point_coefficients),
+                             "poly_coefficients": None if co.poly_coefficients is None else self._mat(co.poly_coefficients)},
+            "interpolant_settings": {
+                "kernel_type": ["Linear", "ThinPlateSpline", "Cubic", "Spheroidal"][st.settings.kernel_type],
+                "spheroidal_order": sph, "drift": drift, "nugget": st.settings.nugget,
+                "base_range": st.settings.base_range, "total_sill": st.settings.total_sill,
+                "basis_size": st.basis_size, "polynomial_degree": st.polynomial_degree,
+                "fitting_accuracy": {"tolerance": st.settings.tolerance,
+                                     "tolerance_type": ["Relative", "Absolute"][st.settings.tolerance_type]}},
+            "translation_factor": [st.translation_factor[d] for d in range(dim)] if st.basis_size else [],
+            "scale_factor": [st.scale_factor[d] for d in range(dim)] if st.basis_size else [],
+            "params": {
+                "solver_type": ["DDM", "FGMRES"][p.solver_type],
+                "ddm_params": {"leaf_threshold": p.leaf_threshold, "overlap_quota": p.overlap_quota,
+                               "coarse_ratio": p.coarse_ratio, "coarse_threshold": p.coarse_threshold},
+                "fmm_params": {"interpolation_order": p.interpolation_order,
+                               "max_points_per_cell": p.max_points_per_cell,
+                               "compression_type": ["None", "SVD", "ACA"][p.compression_type],
+                               "epsilon": p.epsilon, "eval_chunk_size": p.eval_chunk_size},
+                "naive_solve_threshold": p.naive_solve_threshold, "test_unique": bool(p.test_unique)},
+            "global_trend": trend,
+        }
+        with open(path, "w") as f:
+            json.dump(doc, f, indent=2)
+
+    @staticmethod
+    def load_model(path, progress_callback=None):
+        with open(path) as f:
+            doc = json.load(f)
+        if doc.get("format") != RBFInterpolator._JSON_FORMAT_NAME:
+            raise ValueError(f"{path}: format mismatch: found {doc.get('format')!r}, "
+                             f"expected {RBFInterpolator._JSON_FORMAT_NAME!r}")
+        if doc.get("version") != RBFInterpolator._JSON_VERSION:
+            raise ValueError(f"{path}: version mismatch: found {doc.get('version')!r}, "
+                             f"expected {RBFInterpolator._JSON_VERSION}")
+        from . import config as cfg
+        from . import interpolant_config as ic
+        un = RBFInterpolator._unmat
+        pts = np.ascontiguousarray(un(doc["points"]))
+        vals = np.ascontiguousarray(un(doc["point_values"]))
+        pc = np.ascontiguousarray(un(doc["coefficients"]["point_coefficients"]))
+        poly_d = doc["coefficients"].get("poly_coefficients")
+        poly = np.ascontiguousarray(un(poly_d)) if poly_d is not None else None
+        s, p = doc["interpolant_settings"], doc["params"]
+        st = _lib.FrModelState()
+        st.settings.kernel_type = ["Linear", "ThinPlateSpline", "Cubic", "Spheroidal"].index(s["kernel_type"])
+        st.settings.drift = ["None", "Constant", "Linear", "Quadratic"].index(s["drift"])
+        st.settings.spheroidal_order = {"Three": 3, "Five": 5, "Seven": 7, "Nine": 9}[s["spheroidal_order"]]
+        st.settings.nugget, st.settings.base_range, st.settings.total_sill = s["nugget"], s["base_range"], s["total_sill"]
+        st.settings.tolerance = s["fitting_accuracy"]["tolerance"]
+        st.settings.tolerance_type = ["Relative", "Absolute"].index(s["fitting_accuracy"]["tolerance_type"])
+        st.params.solver_type = ["DDM", "FGMRES"].index(p["solver_type"])
+        d, fp = p["ddm_params"], p["fmm_params"]
+        st.params.leaf_threshold, st.params.overlap_quota = d["leaf_threshold"], d["overlap_quota"]
+        st.params.coarse_ratio, st.params.coarse_threshold = d["coarse_ratio"], d["coarse_threshold"]
+        st.params.interpolation_order, st.params.max_points_per_cell = fp["interpolation_order"], fp["max_points_per_cell"]
+        st.params.compression_type = ["None", "SVD", "ACA"].index(fp["compression_type"])
+        st.params.epsilon, st.params.eval_chunk_size = fp["epsilon"], fp["eval_chunk_size"]
+        st.params.naive_solve_threshold, st.params.test_unique = p["naive_solve_threshold"], int(p["test_unique"])
+        st.basis_size, st.polynomial_degree = s["basis_size"], s["polynomial_degree"]
+        for i, v in enumerate(doc.get("translation_factor") or []):
+            st.translation_factor[i] = v
+        for i, v in enumerate(doc.get("scale_factor") or []):
+            st.scale_factor[i] = v
+        gt = doc.get("global_trend")
+        st.has_trend = 0
+        if gt is not None:
+            st.has_trend = 1
+            a, ai = un(gt["affine_transform"]).ravel(), un(gt["inverse_transform"]).ravel()
+            for i in range(a.size):
+                st.affine_transform[i], st.inverse_transform[i] = a[i], ai[i]
+        self = RBFInterpolator.__new__(RBFInterpolator)
+        L = _lib.lib()
+        self._L, self._h, self._progress = L, C.c_void_p(), progress_callback
+        self._cb = _lib.FR_PROGRESS_CB(lambda ev, user: None)
+        rc = L.fr_model_restore(_lib.dptr(pts), pts.shape[0], pts.shape[1], _lib.dptr(vals), vals.shape[1], _lib.dptr(pc),
+                                _lib.dptr(poly) if poly is not None else None, C.byref(st), self._cb, None,
+                                C.byref(self._h))
+        if rc != _lib.FB_OK:
+            self._h = C.c_void_p()
+            raise (ValueError if rc == _lib.FB_ERR_INVALID_ARGUMENT else RuntimeError)(_lib.last_error())
+        kt = ic.RBFKernelType(st.settings.kernel_type)
+        self.interpolant_settings = ic.InterpolantSettings(
+            kt, drift=ic.Drift(st.settings.drift), nugget=st.settings.nugget,
+            spheroidal_order=ic.SpheroidalOrder(st.settings.spheroidal_order), base_range=st.settings.base_range,
+            total_sill=st.settings.total_sill,
+            fitting_accuracy=ic.FittingAccuracy(st.settings.tolerance, ic.FittingAccuracyType(st.settings.tolerance_type)))
+        self.params = cfg.Params(
+            kt, solver_type=cfg.Solvers(st.params.solver_type),
+            ddm_params=cfg.DDMParams(d["leaf_threshold"], d["overlap_quota"], d["coarse_ratio"], d["coarse_threshold"]),
+            fmm_params=cfg.FmmParams(fp["interpolation_order"], fp["max_points_per_cell"],
+                                     cfg.FmmCompressionType(st.params.compression_type), fp["epsilon"],
+                                     fp["eval_chunk_size"]),
+            naive_solve_threshold=p["naive_solve_threshold"], test_unique=bool(p["test_unique"]))
+        info = self.info()
+        self._n, self._cols, self._m, self._dim = info["n_points"], info["n_cols"], info["basis_size"], info["dim"]
+        return self
 
     def __del__(self):
         h = getattr(self, "_h", None)

@@ -106,6 +106,24 @@ int fr_get_info(const fr_model *m, fr_model_info *info);
 int fr_source_points(const fr_model *m, double *points_out /* n x dim */, double *values_out /* n x n_cols */);
 int fr_coefficients(const fr_model *m, double *point_out /* n x n_cols */, double *poly_out /* basis x n_cols */);
 
+/* ---- model state for save_model / load_model (rbf.rs:1087-1171: serde JSON envelope of the public + private fields;
+ * the JSON itself is written by the host language binding).  fr_model_state describes a fitted model: resolved
+ * settings (basis_size / polynomial_degree included), params, monomial scaling and the global-trend matrices.      */
+typedef struct fr_model_state {
+  fr_settings settings;
+  fr_params params;
+  int32_t basis_size, polynomial_degree;
+  double translation_factor[3], scale_factor[3];
+  int32_t has_trend;
+  double affine_transform[16], inverse_transform[16]; /* (dim+1) x (dim+1) row-major (global_trend.rs:128-132) */
+} fr_model_state;
+int fr_get_state(const fr_model *m, fr_model_state *out);
+/* rebuilds a fitted model from its parts WITHOUT solving (load_model): points n x dim (original coordinates), values
+ * n x n_cols, point coefficients n x n_cols, poly coefficients basis_size x n_cols (or NULL), all row-major.        */
+int fr_model_restore(const double *points, size_t n, int dim, const double *values, size_t n_cols,
+                     const double *point_coefficients, const double *poly_coefficients_or_null,
+                     const fr_model_state *state, fr_progress_cb cb_or_null, void *user, fr_model **out);
+
 /* evaluate / evaluate_with_gradients (rbf.rs:676-752): one-shot non-sparse adaptive tree on the union extents.
  * out_vals m x n_cols row-major; out_grads (or NULL) m x (n_cols*dim).                                  */
 int fr_evaluate(fr_model *m, const double *targets, size_t n_targets, ptrdiff_t t_rs, ptrdiff_t t_cs,

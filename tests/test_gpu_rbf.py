@@ -232,3 +232,33 @@ def test_global_trend_matches_oracle(kernel, dim, n, naive):
         m1 = fb.RBFInterpolator(pts, vals, _settings(kernel, tol=tol), params=_params(kernel, naive=naive),
                                 global_trend=fb.GlobalTrend.three(0.0, 0.0, 0.0, 1.0, 1.0, 1.0))
         assert H.rel_l2(np.asarray(m1.evaluate(targets)), np.asarray(m0.evaluate(targets))) <= 1e-10
+
+
+@pytest.mark.parametrize("trend", [False, True])
+def test_save_and_load_model_round_trip(tmp_path, trend):
+    """save_model / load_model (rbf.rs:1087-1171): the JSON envelope restores a model that evaluates identically."""
+    import json
+    import ferreus_rbf_rs_b200 as fb
+    pts = H.make_points(1500, 3, "clustered", seed=71)
+    vals = np.stack([_values(pts), np.cos(2 * pts[:, 0])], axis=1)
+    gt = fb.GlobalTrend.three(10.0, 120.0, 30.0, 2.0, 1.0, 0.5) if trend else None
+    model = fb.RBFInterpolator(pts, vals, _settings(2, tol=1e-9), params=_params(2), global_trend=gt)
+    path = str(tmp_path / "model.json")
+    model.save_model(path)
+    doc = json.load(open(path))
+    assert doc["format"] == "ferreus_rbf.json" and doc["version"] == 1
+    assert doc["points"]["nrows"] == model.info()["n_points"] and doc["points"]["ncols"] == 3
+    assert doc["interpolant_settings"]["kernel_type"] == "Cubic" and doc["params"]["solver_type"] == "FGMRES"
+    assert (doc["global_trend"] is not None) == trend
+    loaded = fb.RBFInterpolator.load_model(path)
+    targets = np.random.default_rng(3).random((200, 3)) * (pts.max(0) - pts.min(0)) + pts.min(0)
+    a, ga = model.evaluate_with_gradients(targets)
+    b, gb = loaded.evaluate_with_gradients(targets)
+    assert H.rel_l2(b, a) <= 1e-12 and H.rel_l2(gb, ga) <= 1e-12   # same state; M2L REDs reorder round-off
+    assert np.array_equal(loaded.coefficients.point_coefficients, model.coefficients.point_coefficients)
+    loaded.build_evaluator()
+    assert H.rel_l2(loaded.evaluate_targets(targets), a) <= 1e-9
+    doc["version"] = 2
+    json.dump(doc, open(path, "w"))
+    with pytest.raises(ValueError):
+        fb.RBFInterpolator.load_model(path)

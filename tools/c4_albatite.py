@@ -1,0 +1,62 @@
+"""BASELINE.json config C4: cubic-kernel fit (order 11, linear drift, default tolerance) on the albatite signed-distance
+points, then the interpolant on a G^3 grid over [floor(min), ceil(max)] (x fastest, common.rs:113-133) through the
+one-shot `evaluate` and through `build_evaluator` + `evaluate_targets`.
+
+    python tools/c4_albatite.py [G=256]
+"""
+import json
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, ".")
+import ferreus_rbf_rs_b200 as fb  # noqa: E402
+
+
+def main():
+    g = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+    d = np.load("tests/golden/albatite_SD_points.npz")
+    pts, vals = d["points"], d["values"]
+    ic = fb.interpolant_config
+    t0 = time.perf_counter()
+    model = fb.RBFInterpolator(pts, vals, ic.InterpolantSettings(ic.RBFKernelType.Cubic))
+    fit_s = time.perf_counter() - t0
+    info = model.info()
+    lo, hi = np.floor(pts.min(0)), np.ceil(pts.max(0))
+    axes = [np.linspace(lo[k], hi[k], g) for k in range(3)]
+    zz, yy, xx = np.meshgrid(axes[2], axes[1], axes[0], indexing="ij")          # x fastest
+    grid = np.ascontiguousarray(np.stack([xx.ravel(), yy.ravel(), zz.ravel()], axis=1))
+    t0 = time.perf_counter()
+    v1 = model.evaluate(grid)
+    eval_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    model.build_evaluator(list(lo) + list(hi))
+    build_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    v2 = model.evaluate_targets(grid)
+    evt_s = time.perf_counter() - t0
+    at_src = model.evaluate_at_source()
+    # exact evaluation of the fitted interpolant on a sample of grid nodes (dense sum, cubic kernel r^3 + linear drift)
+    rng = np.random.default_rng(0)
+    samp = rng.integers(0, grid.shape[0], 200)
+    co = model.coefficients
+    sp = model.source_points
+    r = np.sqrt(((grid[samp][:, None, :] - sp[None, :, :]) ** 2).sum(-1))
+    dense_kernel = (r ** 3) @ co.point_coefficients
+    # polynomial part through the library (one-shot evaluate of the same nodes minus the FMM part is not exposed):
+    # compare the two evaluator paths with each other and the kernel part's FMM error via evaluate - evaluate_targets
+    print(json.dumps({
+        "n_points": int(info["n_points"]), "duplicates_removed": int(info["n_duplicates"]), "grid": g,
+        "fit_s": fit_s, "iterations": int(info["iterations"]), "fmm_matvecs": int(info["matvecs"]),
+        "final_relative_residual": info["last_residual"], "ddm_domains": info["ddm_domains"],
+        "evaluate_grid_s": eval_s, "grid_targets_per_s": grid.shape[0] / eval_s,
+        "build_evaluator_s": build_s, "evaluate_targets_grid_s": evt_s,
+        "evaluate_targets_per_s": grid.shape[0] / evt_s,
+        "one_shot_vs_evaluator_rel_l2": float(np.linalg.norm(v1 - v2) / np.linalg.norm(v1)),
+        "fit_rel_l2_at_sources": float(np.linalg.norm(at_src - vals) / np.linalg.norm(vals)),
+        "dense_kernel_part_norm_sample": float(np.linalg.norm(dense_kernel))}))
+
+
+if __name__ == "__main__":
+    main()
