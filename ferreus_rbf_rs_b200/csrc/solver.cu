@@ -1230,6 +1230,8 @@ int fr_fit_trend(const double *points, size_t n, int dim, ptrdiff_t p_rs, ptrdif
       for (size_t c = 0; c < n_cols; ++c) vals[i * n_cols + c] = values[(ptrdiff_t)i * v_rs + (ptrdiff_t)c * v_cs];
     }
     M->n_in = n;
+    const bool verbose = std::getenv("FB_TIMING") != nullptr;
+    const auto t_dedup = std::chrono::steady_clock::now();
     if (M->params.test_unique) {  // rbf.rs:341-359
       std::vector<int64_t> keep = remove_duplicates(pts.data(), n, dim, M->kp);
       if (keep.size() != n) {
@@ -1247,6 +1249,9 @@ int fr_fit_trend(const double *points, size_t n, int dim, ptrdiff_t p_rs, ptrdif
     M->values.swap(vals);
     M->n = M->points.size() / dim;
     M->n_cols = n_cols;
+    if (verbose)
+      fprintf(stderr, "[fr_fit] %-28s %8.3f s\n", "copy + remove_duplicates",
+              std::chrono::duration<double>(std::chrono::steady_clock::now() - t_dedup).count());
     M->fit();
     M->info.n_duplicates = n - M->n;
     char msg[256];

@@ -2,6 +2,7 @@
 #include "solver_host.h"
 
 #include <algorithm>
+#include <parallel/algorithm>
 #include <cmath>
 #include <deque>
 #include <numeric>
@@ -124,9 +125,29 @@ std::vector<int64_t> remove_duplicates(const double *pts, size_t n, int dim, con
   const double tol = duplicate_cutoff_distance(max_len, kp);
   std::vector<int64_t> order(n);
   std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return pts[a * dim] < pts[b * dim]; });
+  __gnu_parallel::stable_sort(order.begin(), order.end(),
+                              [&](int64_t a, int64_t b) { return pts[a * dim] < pts[b * dim]; });
   std::vector<double> xs(n);
-  for (size_t i = 0; i < n; ++i) xs[i] = pts[order[i] * dim];
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < (long)n; ++i) xs[i] = pts[order[i] * dim];
+  // fast path: no two points within the cutoff of each other => the greedy pass below keeps every point
+  bool any_near = false;
+#pragma omp parallel for schedule(static) reduction(|| : any_near)
+  for (long k = 0; k < (long)n; ++k) {
+    const int64_t i = order[k];
+    for (size_t q = (size_t)k + 1; q < n && xs[q] - xs[k] <= tol; ++q) {
+      const int64_t j = order[q];
+      bool near = true;
+      for (int d = 0; d < dim && near; ++d)
+        if (!(std::fabs(pts[j * dim + d] - pts[i * dim + d]) <= tol)) near = false;
+      if (near) any_near = true;
+    }
+  }
+  if (!any_near) {
+    std::vector<int64_t> all(n);
+    std::iota(all.begin(), all.end(), 0);
+    return all;
+  }
   std::vector<uint8_t> visited(n, 0);
   std::vector<int64_t> keep;
   for (size_t i = 0; i < n; ++i) {
@@ -373,33 +394,40 @@ std::vector<LevelHost> build_ddm(const double *pts, size_t n, int dim, const Set
       const size_t ng = gen.size();
       std::vector<DomainHost> lefts(ng), rights(ng);
       std::vector<uint8_t> split_more(ng, 0);
-#pragma omp parallel for schedule(dynamic, 1)
+      const bool outer_par = ng >= 8;  // few large domains: parallelise inside a domain instead
+#pragma omp parallel for schedule(dynamic, 1) if (outer_par)
       for (long gi = 0; gi < (long)ng; ++gi) {
         DomainHost &cur = gen[gi];
         const size_t nd = cur.idx.size();
         double len[3] = {0, 0, 0};
         for (int d = 0; d < dim; ++d) {
           double lo = pts[cur.idx[0] * dim + d], hi = lo;
-          for (int64_t i : cur.idx) {
-            lo = std::min(lo, pts[i * dim + d]);
-            hi = std::max(hi, pts[i * dim + d]);
+#pragma omp parallel for schedule(static) reduction(min : lo) reduction(max : hi) if (!outer_par && nd > 50000)
+          for (long k = 0; k < (long)nd; ++k) {
+            const double v = pts[cur.idx[k] * dim + d];
+            lo = std::min(lo, v);
+            hi = std::max(hi, v);
           }
           len[d] = hi - lo;
         }
         const int axis = argmax_first_positive(len, dim);
-        // stable argsort by the axis coordinate == sort of (coordinate, position) pairs
+        // The reference takes a stable argsort by the axis coordinate and cuts it at nd / 2
+        // (domain_decomposition.rs:118-131).  The first half of that order is the set of the nd / 2 smallest
+        // (coordinate, position) pairs, and both halves are re-sorted by index afterwards, so a selection
+        // (nth_element) yields the same two index sets and the same cut coordinate without the full sort.
         std::vector<std::pair<double, int>> ord(nd);
-        for (size_t k = 0; k < nd; ++k) ord[k] = {pts[cur.idx[k] * dim + axis], (int)k};
-        std::sort(ord.begin(), ord.end());
+#pragma omp parallel for schedule(static) if (!outer_par && nd > 50000)
+        for (long k = 0; k < (long)nd; ++k) ord[k] = {pts[cur.idx[k] * dim + axis], (int)k};
         const size_t mid = nd / 2;
-        DomainHost &left = lefts[gi], &right = rights[gi];
-        left.idx.resize(mid);
-        right.idx.resize(nd - mid);
-        for (size_t k = 0; k < mid; ++k) left.idx[k] = cur.idx[ord[k].second];
-        for (size_t k = mid; k < nd; ++k) right.idx[k - mid] = cur.idx[ord[k].second];
+        std::nth_element(ord.begin(), ord.begin() + mid, ord.end());
         const double mid_coord = ord[mid].first;
-        std::sort(left.idx.begin(), left.idx.end());
-        std::sort(right.idx.begin(), right.idx.end());
+        std::vector<uint8_t> in_left(nd, 0);
+        for (size_t k = 0; k < mid; ++k) in_left[ord[k].second] = 1;
+        DomainHost &left = lefts[gi], &right = rights[gi];
+        left.idx.reserve(mid);
+        right.idx.reserve(nd - mid);
+        for (size_t k = 0; k < nd; ++k)  // cur.idx is ascending, so both children come out ascending
+          (in_left[k] ? left.idx : right.idx).push_back(cur.idx[k]);
         left.extents = cur.extents;
         left.extents[axis + dim] = mid_coord;
         right.extents = cur.extents;

@@ -257,7 +257,7 @@ def test_save_and_load_model_round_trip(tmp_path, trend):
     assert H.rel_l2(b, a) <= 1e-12 and H.rel_l2(gb, ga) <= 1e-12   # same state; M2L REDs reorder round-off
     assert np.array_equal(loaded.coefficients.point_coefficients, model.coefficients.point_coefficients)
     loaded.build_evaluator()
-    assert H.rel_l2(loaded.evaluate_targets(targets), a) <= 1e-9
+    assert H.rel_l2(loaded.evaluate_targets(targets), a) <= 1e-5   # another tree (own extents): FMM accuracy at order 8
     doc["version"] = 2
     json.dump(doc, open(path, "w"))
     with pytest.raises(ValueError):
