@@ -146,7 +146,7 @@ def run_reference(args):
     val = args.n / (ms * 1e-3) / 1e6
     sample = (f"upward, M2L, P2L, L2L in full; leaf pass (P2P+M2P) on {detail['sample_leaves']} of "
               f"{detail['leaves']} target leaves scaled by pair count x{detail['leaf_scale']:.1f}")
-    line = {"impl": "reference", "metric": "bbfmm_matvec_throughput", "value": val, "unit": "Mpts/s", "n_gpus": 0,
+    line = {"impl": "reference", "metric": "bbfmm_matvec_throughput", "value": val, "unit": "Mpts/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.n, 1),

@@ -666,8 +666,14 @@ struct DeviceSolver {
     };
     if (coarse > 0) {
       for (int i = 0; i < coarse; ++i) {
-        matvec(sl.p, levels[i].get(), tmp.p);
-        sub_to(rg, tmp.p, res.p, nt);
+        if (i == 0) {
+          // sl is still exactly zero: A * 0 = 0 and rg - 0 = rg bit for bit, so the reference's first
+          // matvec_partial of the cycle (schwarz.rs:88-92) is skipped — it is the full-size one
+          FB_CUDA(cudaMemcpyAsync(res.p, rg, nt * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        } else {
+          matvec(sl.p, levels[i].get(), tmp.p);
+          sub_to(rg, tmp.p, res.p, nt);
+        }
         FB_CUDA(cudaMemsetAsync(s1.p, 0, nt * sizeof(double), s));
         solve_level(*levels[i], res.p, s1.p, 0, 0, s);
         if (m) {  // orthogonalise against the global polynomial space (schwarz.rs:111-117)
