@@ -122,6 +122,8 @@ struct fb_tree {
   fb::DBuf<uint32_t> d_perm, d_inv;           // sorted position -> source row, and inverse
   fb::DBuf<double> d_w;                       // weights, sorted, [rhs][n]
   fb::DBuf<double> d_w_user;                  // weights as uploaded [n][nrhs] row-major
+  std::vector<double> h_w_last;               // host copy of the last contiguous upload (skips the duplicate copy)
+  bool w_cache_valid = false;                 // false once d_w_user was written on the device (solver)
   fb::DBuf<double> d_mult, d_loc;             // [cell][rhs][P]
   fb::DBuf<double> d_ccx, d_ccy, d_ccz, d_chalf;
   fb::DBuf<int> d_cell_parent, d_cell_slot, d_cell_ptb, d_cell_pte;

@@ -639,6 +639,7 @@ struct DeviceSolver {
     tree->nrhs = 1;
     tree->d_w_user.reserve(n);
     FB_CUDA(cudaMemcpyAsync(tree->d_w_user.p, w, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    tree->w_cache_valid = false;  // the host copy of the last upload no longer describes d_w_user
     const bool all = lv == nullptr || lv->all_points;
     TargetSet ts = all ? tree->source_target_set() : lv->ts;
     tree->matvec_dev(ts);

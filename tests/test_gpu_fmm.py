@@ -304,3 +304,33 @@ def test_full_size_properties_1m():
     assert H.rel_l2(sub, y3[sample]) <= 1e-12                               # subset == rows of the full result
     gen = tree.evaluate(w3, pts[sample])
     assert H.rel_l2(gen, y3[sample]) <= 1e-12                               # re-binned targets == source fast path
+
+
+def test_repeated_weights_and_source_targets_are_recognised_by_content():
+    """The library skips the second transfer of a weight vector it already holds and of targets that are the source
+    points (both compared bytewise on the host).  The reference's call semantics must survive that: evaluate(w2, ..)
+    after set_weights(w1) uses w2 for P2P / P2L and w1's multipoles (bbfmm.rs:444-507), in-place edits are seen."""
+    n = 4000
+    pts = H.make_points(n, 3, "clustered", seed=81)
+    rng = np.random.default_rng(82)
+    w1, w2 = rng.random((n, 1)), rng.random((n, 1)) - 0.5
+    ot = H.oracle_tree(pts, 6, 0, True, True, 30, 2, 1e-6)
+    pt = H.product_tree(pts, 6, 0, True, True, 30, 2, 1e-6)
+
+    def ref(ws, we):
+        ot.set_weights(ws)
+        return ot.evaluate(we, pts)
+
+    pt.set_weights(w1)
+    assert H.rel_l2(np.asarray(pt.evaluate(w1, pts)).reshape(n, 1), ref(w1, w1)) <= MATVEC_TOL
+    assert H.rel_l2(np.asarray(pt.evaluate(w2, pts)).reshape(n, 1), ref(w1, w2)) <= MATVEC_TOL   # mixed, quirk (iv)
+    pt.set_weights(w2)                                                                              # already resident
+    assert H.rel_l2(np.asarray(pt.evaluate(w2, pts)).reshape(n, 1), ref(w2, w2)) <= MATVEC_TOL
+    w2 *= 3.0                                                                                       # edited in place
+    pt.set_weights(w2)
+    assert H.rel_l2(np.asarray(pt.evaluate(w2, pts)).reshape(n, 1), ref(w2, w2)) <= MATVEC_TOL
+    moved = pts.copy()
+    moved[17, 0] += 1e-9                                                                            # no longer the sources
+    got = np.asarray(pt.evaluate(w2, moved)).reshape(n, 1)
+    ot.set_weights(w2)
+    assert H.rel_l2(got, ot.evaluate(w2, moved)) <= MATVEC_TOL
