@@ -408,7 +408,10 @@ void fb_tree::build(const double *points, size_t n_, int dim_, ptrdiff_t rs, ptr
     m2l_Pp = P4;
     while (m2l_Pp % 16 != 4 && m2l_Pp % 16 != 12) m2l_Pp += 4;  // bank-conflict-free B fragments
     m2l_nc = 0;
+    const char *nc_env = std::getenv("FB_M2L_NC");  // experiment knob: cap the column tile
+    const int nc_cap = nc_env ? std::atoi(nc_env) : 32;
     for (int nc : {32, 16, 8}) {  // columns per CTA: the largest tile that fits in shared memory
+      if (nc > nc_cap) continue;
       const size_t need = sizeof(double) * ((size_t)nc * m2l_Pp + (size_t)max_rp * (nc + 4));
       if (need <= 220 * 1024) {
         m2l_nc = nc;

@@ -7,6 +7,8 @@ WANT = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__grid_
         'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
         'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+        'TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__t_sector_pipe_lsu_mem_global_op_ld_hit_rate.pct',
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
         'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
         'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
