@@ -354,7 +354,11 @@ __global__ void __launch_bounds__(kLeafWPC * 32, NR >= 4 ? 7 : 10) k_leaf_warp(c
   if (active) {
     const size_t row = a.ts.out_row[tb + lane];
 #pragma unroll
-    for (int r = 0; r < NR; ++r) a.out[row * a.nrhs + a.rhs0 + r] += acc[r];
+    for (int r = 0; r < NR; ++r) {
+      double *o = a.out + row * a.nrhs + a.rhs0 + r;
+      if (a.atomic_out) atomicAdd(o, acc[r]);
+      else *o += acc[r];
+    }
   }
 }
 

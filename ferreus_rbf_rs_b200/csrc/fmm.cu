@@ -62,6 +62,9 @@ fb_tree::~fb_tree() {
     if (e) cudaEventDestroy(e);
   for (auto &e : ev_mv)
     if (e) cudaEventDestroy(e);
+  if (ev_fork) cudaEventDestroy(ev_fork);
+  if (ev_join) cudaEventDestroy(ev_join);
+  if (stream2) cudaStreamDestroy(stream2);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -103,7 +106,16 @@ void fb_tree::build(const double *points, size_t n_, int dim_, ptrdiff_t rs, ptr
     t_lap = std::chrono::steady_clock::now();
   };
   FB_CUDA(cudaGetDevice(&device));
-  FB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  {
+    int prio_lo = 0, prio_hi = 0;
+    FB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    FB_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_hi));
+    FB_CUDA(cudaStreamCreateWithPriority(&stream2, cudaStreamNonBlocking, prio_lo));
+    FB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    FB_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    const char *ov = std::getenv("FB_OVERLAP");
+    overlap_p2p = ov && ov[0] == '1';  // measured slower on B200 (15.1 vs 13.6 ms), kept as an opt-in experiment
+  }
   for (auto &e : ev) FB_CUDA(cudaEventCreate(&e));
   for (auto &e : ev_mv) FB_CUDA(cudaEventCreate(&e));
 
@@ -487,11 +499,11 @@ void fb_tree::upward() {
 }
 
 // -------------------------------------------------------------------------------------- downward
-void fb_tree::downward(const uint8_t *flags, const TargetSet *fuse_m2p) {
+void fb_tree::downward(const uint8_t *flags, const TargetSet *fuse_m2p, bool out_zeroed, bool m2l_one_cta_per_sm) {
   const size_t nc = ht.ncells();
   const int p = order;
   d_loc.zero(nc * (size_t)nrhs * P, stream);
-  if (fuse_m2p) d_out.zero(fuse_m2p->m * (size_t)nrhs, stream);
+  if (fuse_m2p && !out_zeroed) d_out.zero(fuse_m2p->m * (size_t)nrhs, stream);
   if (timing) FB_CUDA(cudaEventRecord(ev[3], stream));
   // M2L (loop A of bbfmm.rs:781-832)
   const bool compressed = fparams.compression_type != FB_COMPRESSION_NONE;
@@ -523,10 +535,13 @@ void fb_tree::downward(const uint8_t *flags, const TargetSet *fuse_m2p) {
       m2l_table_nrhs = nrhs;
     }
     const M2LGroupDev *tab = reinterpret_cast<const M2LGroupDev *>(d_m2l_table.p);
+    // sharing the SM with the concurrent P2P kernel: ask for more than half of the shared memory so that one CTA
+    // (half of the registers) is resident per SM and the P2P CTAs fit beside it
+    const size_t m2l_smem_launch = m2l_one_cta_per_sm ? std::max(m2l_smem, (size_t)116 * 1024) : m2l_smem;
 #define FB_M2L_LAUNCH(COMP, NCV)                                                                                   \
   do {                                                                                                             \
-    set_smem(k_m2l<COMP, NCV>, m2l_smem);                                                                          \
-    FB_LAUNCH((k_m2l<COMP, NCV>), m2l_ctas, 256, m2l_smem, stream, tab, d_m2l_cta_group.p, d_m2l_tgt.p,          \
+    set_smem(k_m2l<COMP, NCV>, m2l_smem_launch);                                                                   \
+    FB_LAUNCH((k_m2l<COMP, NCV>), m2l_ctas, 256, m2l_smem_launch, stream, tab, d_m2l_cta_group.p, d_m2l_tgt.p,   \
               d_m2l_src.p, d_m2l_perm.p, d_oppool.p, d_perm_tab.p, d_inv_tab.p, P, m2l_P4, m2l_Pp, nrhs, flags,    \
               d_mult.p, d_loc.p);                                                                                  \
   } while (0)
@@ -591,18 +606,16 @@ void fb_tree::downward(const uint8_t *flags, const TargetSet *fuse_m2p) {
 }
 
 // ------------------------------------------------------------------------------------- leaf pass
-void fb_tree::leaf_pass(const TargetSet &ts, bool grads, bool m2p_done) {
+void fb_tree::launch_l2p(const TargetSet &ts, bool grads) {
   const int p = order;
-  if (!m2p_done) d_out.zero(ts.m * (size_t)nrhs, stream);
-  if (grads) d_gout.zero(ts.m * (size_t)nrhs * dim, stream);
-  if (timing) FB_CUDA(cudaEventRecord(ev[7], stream));
-  if (ts.max_tiles > 0) {
-    const size_t smem = sizeof(double) * ((size_t)p * p + P + (size_t)kTile * dim * p * (grads ? 2 : 1));
-    set_smem(k_l2p, smem);
-    FB_LAUNCH(k_l2p, ts.max_tiles, kTile, smem, stream, ts, d_leaf_cell.p, d_loc.p, d_ccx.p, d_ccy.p, d_ccz.p,
-              d_chalf.p, d_tnodes.p, p, dim, P, nrhs, d_out.p, grads ? d_gout.p : nullptr);
-  }
-  if (timing) FB_CUDA(cudaEventRecord(ev[8], stream));
+  if (ts.max_tiles <= 0) return;
+  const size_t smem = sizeof(double) * ((size_t)p * p + P + (size_t)kTile * dim * p * (grads ? 2 : 1));
+  set_smem(k_l2p, smem);
+  FB_LAUNCH(k_l2p, ts.max_tiles, kTile, smem, stream, ts, d_leaf_cell.p, d_loc.p, d_ccx.p, d_ccy.p, d_ccz.p,
+            d_chalf.p, d_tnodes.p, p, dim, P, nrhs, d_out.p, grads ? d_gout.p : nullptr);
+}
+
+void fb_tree::launch_p2p(const TargetSet &ts, bool grads, bool m2p_done, cudaStream_t s, bool atomic_out) {
   DirectArgs a{};
   a.ts = ts;
   a.u_ptr = d_u_ptr.p;
@@ -621,16 +634,27 @@ void fb_tree::leaf_pass(const TargetSet &ts, bool grads, bool m2p_done) {
   a.ccz = d_ccz.p;
   a.chalf = d_chalf.p;
   a.nodes = d_nodes.p;
-  a.p = p;
+  a.p = order;
   a.dim = dim;
   a.P = P;
   a.nrhs = nrhs;
   a.rhs0 = 0;
+  a.atomic_out = atomic_out ? 1 : 0;
   a.out = d_out.p;
   a.gout = grads ? d_gout.p : nullptr;
   a.kp = kp;
-  launch_leaf_direct(a, stream);
+  launch_leaf_direct(a, s);
+}
+
+void fb_tree::leaf_pass(const TargetSet &ts, bool grads, bool m2p_done) {
+  if (!m2p_done) d_out.zero(ts.m * (size_t)nrhs, stream);
+  if (grads) d_gout.zero(ts.m * (size_t)nrhs * dim, stream);
+  if (timing) FB_CUDA(cudaEventRecord(ev[7], stream));
+  launch_l2p(ts, grads);
+  if (timing) FB_CUDA(cudaEventRecord(ev[8], stream));
+  launch_p2p(ts, grads, m2p_done, stream, false);
   if (timing) FB_CUDA(cudaEventRecord(ev[9], stream));
+  last_overlapped = false;
 }
 
 // ----------------------------------------------------------------------------------- target sets
@@ -660,8 +684,32 @@ TargetSet fb_tree::source_target_set() {
 // targets = all sources: X is the transpose of W, so the P2L kernel applies the M2P half as well
 void fb_tree::evaluate_sources_fused(const TargetSet &ts) {
   const bool fuse = ht.adaptive && n_x_cells > 0 && ts.row_of_pos != nullptr;
-  downward(ts.cell_flag, fuse ? &ts : nullptr);
-  leaf_pass(ts, false, fuse);
+  if (!(fuse && overlap_p2p && !m2l_groups.empty())) {
+    downward(ts.cell_flag, fuse ? &ts : nullptr);
+    leaf_pass(ts, false, fuse);
+    return;
+  }
+  // Experiment (FB_OVERLAP=1): P2P needs only the sorted weights; M2L runs on the FP64 tensor pipe, P2P on the FP64
+  // FMA pipe, so the P2P kernel goes to a low-priority side stream and shares the SMs with M2L; its results and the
+  // fused M2P half are added with REDs, L2P joins last.  Result on B200: M2L at one CTA per SM (needed to leave
+  // registers for the P2P CTAs) slows from 2.9 to 4.8 ms and P2P then competes with the W/X pass for the FMA pipe:
+  // 15.1 ms against 13.6 ms for the serial order, so the serial order stays the default.
+  d_out.zero(ts.m * (size_t)nrhs, stream);
+  FB_CUDA(cudaEventRecord(ev_fork, stream));
+  FB_CUDA(cudaStreamWaitEvent(stream2, ev_fork, 0));
+  if (timing) FB_CUDA(cudaEventRecord(ev[10], stream2));
+  launch_p2p(ts, false, true, stream2, true);
+  if (timing) FB_CUDA(cudaEventRecord(ev[11], stream2));
+  FB_CUDA(cudaEventRecord(ev_join, stream2));
+  downward(ts.cell_flag, &ts, true, true);
+  FB_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
+  if (timing) FB_CUDA(cudaEventRecord(ev[7], stream));
+  launch_l2p(ts, false);
+  if (timing) {
+    FB_CUDA(cudaEventRecord(ev[8], stream));
+    FB_CUDA(cudaEventRecord(ev[9], stream));
+  }
+  last_overlapped = true;
 }
 
 // shared tail of bin_targets / subset_target_set: keys (leaf slot or sorted source position) -> TargetSet
@@ -891,7 +939,7 @@ static void collect_timing(fb_tree *t) {
   t->last_ms[3] = ms(4, 5);  // p2l
   t->last_ms[4] = ms(5, 6);  // l2l
   t->last_ms[5] = ms(7, 8);  // l2p
-  t->last_ms[6] = ms(8, 9);  // p2p + m2p
+  t->last_ms[6] = t->last_overlapped ? ms(10, 11) : ms(8, 9);  // p2p (+ m2p); overlapped: its own span on the side stream
   t->last_ms[7] = ms(0, 9);  // total
 }
 

@@ -50,6 +50,7 @@ struct DirectArgs {  // leaf pass: P2P over U ranges + M2P over W cells (bbfmm.r
   const double *ccx, *ccy, *ccz, *chalf;
   const double *nodes;  // p Chebyshev nodes
   int p, dim, P, nrhs, rhs0;
+  int atomic_out;  // 1: results are added with RED (the kernel runs concurrently with other writers of `out`)
   double *out;    // [m][nrhs]
   double *gout;   // [m][nrhs*dim] or null
   KParams kp;
@@ -104,6 +105,9 @@ struct M2LGroup {
 struct fb_tree {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // low-priority side stream: P2P (FP64 FMA pipe) under M2L (FP64 tensor pipe)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool overlap_p2p = false;
   int dim = 3, order = 0, P = 0;
   size_t n = 0;
   int nrhs = 1;
@@ -175,7 +179,8 @@ struct fb_tree {
   // timing
   bool timing = false;
   double last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  cudaEvent_t ev[10] = {};
+  cudaEvent_t ev[12] = {};
+  bool last_overlapped = false;
   cudaEvent_t ev_mv[2] = {};
   double last_matvec_ms = 0;
 
@@ -188,8 +193,11 @@ struct fb_tree {
   void upward();
   // fuse_m2p: the P2L kernel also applies the M2P transpose for that target set (ts.row_of_pos != null) into d_out
   // (zeroed here); leaf_pass(ts, false, m2p_done = true) must follow
-  void downward(const uint8_t *flags, const fb::TargetSet *fuse_m2p = nullptr);
+  void downward(const uint8_t *flags, const fb::TargetSet *fuse_m2p = nullptr, bool out_zeroed = false,
+                bool m2l_one_cta_per_sm = false);
   void leaf_pass(const fb::TargetSet &ts, bool grads, bool m2p_done = false);
+  void launch_l2p(const fb::TargetSet &ts, bool grads);
+  void launch_p2p(const fb::TargetSet &ts, bool grads, bool m2p_done, cudaStream_t s, bool atomic_out);
   void evaluate_sources_fused(const fb::TargetSet &ts);  // downward + leaf pass for targets that are source points
   fb::TargetSet source_target_set();
   fb::TargetSet bin_targets(const double *targets, size_t m, ptrdiff_t rs, ptrdiff_t cs, uint64_t *bad);
