@@ -204,94 +204,154 @@ __global__ void __launch_bounds__(256) k_dom_assemble(DomainTable t, const doubl
   }
 }
 
-// blocked right-looking Cholesky, one CTA per domain, lower triangle of a row-major mm x mm matrix in place
 constexpr int kNB = 32;
+constexpr int kPS = kNB + 4;
+__device__ __forceinline__ void chol_dmma884(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+// diagonal block kb (Cholesky by warp 0 in shared memory) and the panel below it (one thread per row):
+//   L[i, kb:kb+bs] = A[i, kb:kb+bs] Dk^-T
+__device__ __forceinline__ void chol_factor_panel(double *A, int n, int kb, int bs, double (*Dk)[kNB + 1], int *fail,
+                                                  int dom) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int e = tid; e < kNB * kNB; e += 256) {
+    const int r = e / kNB, c = e % kNB;
+    Dk[r][c] = (r < bs && c <= r) ? A[(size_t)(kb + r) * n + kb + c] : (r == c ? 1.0 : 0.0);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    for (int k = 0; k < bs; ++k) {
+      double dkk = Dk[k][k];
+      if (lane == 0 && !(dkk > 0.0)) atomicExch(fail, dom + 1);
+      dkk = sqrt(fmax(dkk, 1e-300));
+      __syncwarp();
+      if (lane == k) Dk[k][k] = dkk;
+      if (lane > k && lane < bs) Dk[lane][k] /= dkk;
+      __syncwarp();
+      if (lane > k && lane < bs) {
+        const double lk = Dk[lane][k];
+        for (int c = k + 1; c <= lane; ++c) Dk[lane][c] -= lk * Dk[c][k];
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < bs * bs; e += 256) {
+    const int r = e / bs, c = e % bs;
+    if (c <= r) A[(size_t)(kb + r) * n + kb + c] = Dk[r][c];
+  }
+  for (int i = kb + bs + tid; i < n; i += 256) {
+    double x[kNB];
+    double *row = A + (size_t)i * n + kb;
+#pragma unroll
+    for (int c = 0; c < kNB; ++c) x[c] = c < bs ? row[c] : 0.0;
+#pragma unroll
+    for (int c = 0; c < kNB; ++c) {
+      if (c < bs) {
+        double v = x[c];
+#pragma unroll
+        for (int k = 0; k < c; ++k) v -= x[k] * Dk[c][k];
+        x[c] = v / Dk[c][c];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < kNB; ++c)
+      if (c < bs) row[c] = x[c];
+  }
+}
+
+// trailing update of the tile column jb: A[ib.., jb..] -= P_i P_j^T for the lower tiles ib = ib_first, + ib_step, ...
+// (this warp's tiles); the whole CTA stages the j panel tile, every warp its own i panel tile.  C = P Pj^T runs on the
+// FP64 tensor cores: 4 x 4 tiles of m8n8k4, 8 k-steps (1.6x the FMA version on the 2048-domain level).
+__device__ __forceinline__ void chol_update_column(double *A, int n, int kb, int bs, int jb, double (*Pj)[kPS],
+                                                   double (*Pi)[kPS], int ib_first, int ib_step) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int bj = min(kNB, n - jb);
+  __syncthreads();
+  for (int e = tid; e < kNB * kNB; e += 256) {
+    const int r = e / kNB, c = e % kNB;
+    Pj[r][c] = (r < bj && c < bs) ? A[(size_t)(jb + r) * n + kb + c] : 0.0;
+  }
+  __syncthreads();
+  for (int ib = ib_first; ib < n; ib += ib_step) {
+    const int bi = min(kNB, n - ib);
+    double(*P)[kPS] = Pi + warp * kNB;
+    for (int r = 0; r < kNB; ++r) P[r][lane] = (r < bi && lane < bs) ? A[(size_t)(ib + r) * n + kb + lane] : 0.0;
+    __syncwarp();
+    const int g = lane >> 2, t4 = lane & 3;
+    double c[4][4][2];
+#pragma unroll
+    for (int a4 = 0; a4 < 4; ++a4)
+#pragma unroll
+      for (int b4 = 0; b4 < 4; ++b4) c[a4][b4][0] = c[a4][b4][1] = 0.0;
+#pragma unroll 2
+    for (int ks = 0; ks < kNB / 4; ++ks) {
+      double fa[4], fb4[4];
+#pragma unroll
+      for (int a4 = 0; a4 < 4; ++a4) fa[a4] = P[8 * a4 + g][4 * ks + t4];
+#pragma unroll
+      for (int b4 = 0; b4 < 4; ++b4) fb4[b4] = Pj[8 * b4 + g][4 * ks + t4];
+#pragma unroll
+      for (int a4 = 0; a4 < 4; ++a4)
+#pragma unroll
+        for (int b4 = 0; b4 < 4; ++b4) chol_dmma884(c[a4][b4][0], c[a4][b4][1], fa[a4], fb4[b4]);
+    }
+#pragma unroll
+    for (int a4 = 0; a4 < 4; ++a4) {
+      const int r = 8 * a4 + g;
+      if (r >= bi) continue;
+      double *row = A + (size_t)(ib + r) * n + jb;
+#pragma unroll
+      for (int b4 = 0; b4 < 4; ++b4)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int cc = 8 * b4 + 2 * t4 + h;
+          if (cc < bj && ib + r >= jb + cc) row[cc] -= c[a4][b4][h];  // lower triangle only
+        }
+    }
+    __syncwarp();
+  }
+}
+
+#define FB_CHOL_SMEM_VIEWS                                                                                          \
+  extern __shared__ double sm[];                                                                                    \
+  double(*Dk)[kNB + 1] = reinterpret_cast<double(*)[kNB + 1]>(sm);                       /* diagonal block */       \
+  /* panel tiles feed DMMA fragments: row stride kPS == 4 (mod 16): conflict-free fragment loads per half-warp */   \
+  double(*Pj)[kPS] = reinterpret_cast<double(*)[kPS]>(sm + kNB * (kNB + 1));              /* j panel tile */         \
+  double(*Pi)[kPS] = reinterpret_cast<double(*)[kPS]>(sm + kNB * (kNB + 1) + kNB * kPS);  /* 8 warps x i panel tile */
+
+// blocked right-looking Cholesky, one CTA per domain, lower triangle of a row-major mm x mm matrix in place
 __global__ void __launch_bounds__(256) k_cholesky(DomainTable t, double *lpool, int *fail) {
   const int d = blockIdx.x;
   const int n = (int)(t.pt_ptr[d + 1] - t.pt_ptr[d]) - t.rank[d];
   double *A = lpool + t.l_off[d];
-  extern __shared__ double sm[];
-  double(*Dk)[kNB + 1] = reinterpret_cast<double(*)[kNB + 1]>(sm);                          // diagonal block
-  double(*Pj)[kNB + 1] = reinterpret_cast<double(*)[kNB + 1]>(sm + kNB * (kNB + 1));        // panel rows of the j tile
-  double(*Pi)[kNB + 1] = reinterpret_cast<double(*)[kNB + 1]>(sm + 2 * kNB * (kNB + 1));    // 8 warps x panel rows of an i tile
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  FB_CHOL_SMEM_VIEWS
+  const int warp = threadIdx.x >> 5;
   for (int kb = 0; kb < n; kb += kNB) {
     const int bs = min(kNB, n - kb);
-    for (int e = tid; e < kNB * kNB; e += 256) {
-      const int r = e / kNB, c = e % kNB;
-      Dk[r][c] = (r < bs && c <= r) ? A[(size_t)(kb + r) * n + kb + c] : (r == c ? 1.0 : 0.0);
-    }
+    chol_factor_panel(A, n, kb, bs, Dk, fail, d);
     __syncthreads();
-    if (warp == 0) {
-      for (int k = 0; k < bs; ++k) {
-        double dkk = Dk[k][k];
-        if (lane == 0 && !(dkk > 0.0)) atomicExch(fail, d + 1);
-        dkk = sqrt(fmax(dkk, 1e-300));
-        __syncwarp();
-        if (lane == k) Dk[k][k] = dkk;
-        if (lane > k && lane < bs) Dk[lane][k] /= dkk;
-        __syncwarp();
-        if (lane > k && lane < bs) {
-          const double lk = Dk[lane][k];
-          for (int c = k + 1; c <= lane; ++c) Dk[lane][c] -= lk * Dk[c][k];
-        }
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    for (int e = tid; e < bs * bs; e += 256) {
-      const int r = e / bs, c = e % bs;
-      if (c <= r) A[(size_t)(kb + r) * n + kb + c] = Dk[r][c];
-    }
-    // panel: rows below the diagonal block, one thread per row:  L[i, kb:kb+bs] = A[i, kb:kb+bs] Dk^-T
-    for (int i = kb + bs + tid; i < n; i += 256) {
-      double x[kNB];
-      double *row = A + (size_t)i * n + kb;
-#pragma unroll
-      for (int c = 0; c < kNB; ++c) x[c] = c < bs ? row[c] : 0.0;
-#pragma unroll
-      for (int c = 0; c < kNB; ++c) {
-        if (c < bs) {
-          double v = x[c];
-#pragma unroll
-          for (int k = 0; k < c; ++k) v -= x[k] * Dk[c][k];
-          x[c] = v / Dk[c][c];
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < kNB; ++c)
-        if (c < bs) row[c] = x[c];
-    }
-    __syncthreads();
-    // trailing update: A[ib.., jb..] -= P_i P_j^T for the lower tiles; 8 warps take 8 i-tiles per j-tile
-    const int t0 = kb + bs;
-    for (int jb = t0; jb < n; jb += kNB) {
-      const int bj = min(kNB, n - jb);
-      __syncthreads();
-      for (int e = tid; e < kNB * kNB; e += 256) {
-        const int r = e / kNB, c = e % kNB;
-        Pj[r][c] = (r < bj && c < bs) ? A[(size_t)(jb + r) * n + kb + c] : 0.0;
-      }
-      __syncthreads();
-      for (int ib = jb + warp * kNB; ib < n; ib += 8 * kNB) {
-        const int bi = min(kNB, n - ib);
-        double(*P)[kNB + 1] = Pi + warp * kNB;
-        for (int r = 0; r < kNB; ++r) P[r][lane] = (r < bi && lane < bs) ? A[(size_t)(ib + r) * n + kb + lane] : 0.0;
-        __syncwarp();
-        if (lane < bj) {
-          for (int r = 0; r < bi; ++r) {
-            if (ib + r < jb + lane) continue;  // strictly upper part of the diagonal tile
-            double s = 0.0;
-#pragma unroll 8
-            for (int k = 0; k < kNB; ++k) s += P[r][k] * Pj[lane][k];
-            A[(size_t)(ib + r) * n + jb + lane] -= s;
-          }
-        }
-        __syncwarp();
-      }
-    }
+    for (int jb = kb + bs; jb < n; jb += kNB) chol_update_column(A, n, kb, bs, jb, Pj, Pi, jb + warp * kNB, 8 * kNB);
     __syncthreads();
   }
+}
+
+// the same factorisation of ONE large matrix (the coarse domain) spread over the GPU: per block column one small
+// launch for the diagonal block + panel and one grid for the trailing update
+__global__ void __launch_bounds__(256) k_chol_big_panel(double *A, int n, int kb, int *fail) {
+  extern __shared__ double sm[];
+  chol_factor_panel(A, n, kb, min(kNB, n - kb), reinterpret_cast<double(*)[kNB + 1]>(sm), fail, 0);
+}
+__global__ void __launch_bounds__(256) k_chol_big_update(double *A, int n, int kb) {
+  extern __shared__ double sm[];
+  double(*Pj)[kPS] = reinterpret_cast<double(*)[kPS]>(sm + kNB * (kNB + 1));
+  double(*Pi)[kPS] = reinterpret_cast<double(*)[kPS]>(sm + kNB * (kNB + 1) + kNB * kPS);
+  const int bs = min(kNB, n - kb);
+  const int jb = kb + bs + blockIdx.x * kNB;
+  const int ib = jb + (blockIdx.y * 8 + (threadIdx.x >> 5)) * kNB;
+  chol_update_column(A, n, kb, bs, jb, Pj, Pi, ib, n);  // at most one i tile per warp
 }
 
 // Domain::solve (domain.rs:393-467) + scatter of schwarz.rs:94-155, one CTA per domain.
@@ -567,12 +627,30 @@ struct DeviceSolver {
                 lv->qpool.p, scratch.p, lv->lpool.p);
     }
     FB_CUDA(cudaMemsetAsync(fail.p, 0, sizeof(int), stream));
-    const size_t smem = sizeof(double) * (size_t)(kNB + 1) * kNB * (2 + 8);
+    const size_t smem = sizeof(double) * ((size_t)(kNB + 1) * kNB + (size_t)kPS * kNB * (1 + 8));
     FB_CUDA(cudaFuncSetAttribute(k_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FB_LAUNCH(k_cholesky, (unsigned)nd, 256, smem, stream, t, lv->lpool.p, fail.p);
+    const auto t_ch = std::chrono::steady_clock::now();
+    if (nd == 1 && lv->max_mm >= 512) {  // one big matrix: spread every block column over the GPU
+      const int nn = lv->max_mm;
+      FB_CUDA(cudaFuncSetAttribute(k_chol_big_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      FB_CUDA(cudaFuncSetAttribute(k_chol_big_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      for (int kb = 0; kb < nn; kb += kNB) {
+        FB_LAUNCH(k_chol_big_panel, 1, 256, smem, stream, lv->lpool.p, nn, kb, fail.p);
+        const int ntile = (nn - (kb + kNB) + kNB - 1) / kNB;
+        if (ntile > 0) {
+          dim3 grid((unsigned)ntile, (unsigned)((ntile + 7) / 8));
+          FB_LAUNCH(k_chol_big_update, grid, 256, smem, stream, lv->lpool.p, nn, kb);
+        }
+      }
+    } else {
+      FB_LAUNCH(k_cholesky, (unsigned)nd, 256, smem, stream, t, lv->lpool.p, fail.p);
+    }
     int h_fail = 0;
     FB_CUDA(cudaMemcpyAsync(&h_fail, fail.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
     FB_CUDA(cudaStreamSynchronize(stream));
+    if (std::getenv("FB_TIMING"))
+      fprintf(stderr, "[fr_fit]   cholesky of %zu domains (+ queued assembly) %8.3f s\n", nd,
+              std::chrono::duration<double>(std::chrono::steady_clock::now() - t_ch).count());
     if (h_fail)
       throw Error(FB_ERR_INVALID_ARGUMENT,
                   "subdomain matrix Q^T A Q is not positive definite (domain " + std::to_string(h_fail - 1) +
@@ -642,7 +720,18 @@ struct DeviceSolver {
     tree->w_cache_valid = false;  // the host copy of the last upload no longer describes d_w_user
     const bool all = lv == nullptr || lv->all_points;
     TargetSet ts = all ? tree->source_target_set() : lv->ts;
+    static const bool verbose = std::getenv("FB_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0;
+    if (verbose) {
+      FB_CUDA(cudaStreamSynchronize(s));
+      t0 = std::chrono::steady_clock::now();
+    }
     tree->matvec_dev(ts);
+    if (verbose) {
+      FB_CUDA(cudaStreamSynchronize(s));
+      fprintf(stderr, "[fr_fit]   matvec on %9zu targets %8.3f ms\n", ts.m,
+              1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    }
     ++matvecs;
     const size_t cnt = all ? n : lv->n_level_pts;
     FB_LAUNCH(k_matvec_finish, nblk(cnt, 256), 256, 0, s, tree->d_out.p, all ? nullptr : lv->level_idx.p, cnt, w, n,
@@ -781,6 +870,8 @@ void fr_model::fit() {
   } else {
     tree.reset(make_tree(true, nullptr));  // adaptive, sparse, own extents (rbf.rs:456-467)
     lap("fmm tree + operators", t_lap);
+    // (building the DDM hierarchy on a second host thread meanwhile was tried: two OpenMP teams on the same cores
+    // made the whole fit's wall time erratic, 1.0 - 2.6 s, for a 0.15 s best-case gain)
     ddm = build_ddm(kp_ptr, n, dim, st, params, mono_ptr);
     lap("ddm hierarchy (host)", t_lap);
   }
