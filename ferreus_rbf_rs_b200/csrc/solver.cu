@@ -566,6 +566,15 @@ struct DeviceSolver {
 
   // ---- factorise one level on the device (domain.rs:322-382)
   void build_level(const LevelHost &lh, bool coarse, cudaStream_t stream) {
+    static const bool verbose = std::getenv("FB_TIMING") != nullptr;
+    auto t_sub = std::chrono::steady_clock::now();
+    auto sublap = [&](const char *what) {
+      if (!verbose) return;
+      cudaStreamSynchronize(stream);
+      fprintf(stderr, "[fr_fit]     %-26s %8.3f s\n", what,
+              std::chrono::duration<double>(std::chrono::steady_clock::now() - t_sub).count());
+      t_sub = std::chrono::steady_clock::now();
+    };
     auto lv = std::make_unique<LevelDev>();
     const size_t nd = lh.domains.size();
     std::vector<long long> pt_ptr(nd + 1, 0), q_off(nd, 0), l_off(nd, 0), s_off(nd, 0);
@@ -601,8 +610,10 @@ struct DeviceSolver {
     lv->pt_idx.upload(pt_idx, stream);
     lv->pt_mask.upload(pt_mask, stream);
     lv->qpool.upload(qpool, stream);
+    sublap("host tables + uploads");
     lv->lpool.reserve((size_t)lsize);
     scratch.reserve((size_t)std::max<long long>(ssize, 1));
+    sublap("factor pool allocation");
     DomainTable &t = lv->tab;
     t.n_domains = (int)nd;
     t.pt_ptr = lv->pt_ptr.p;
@@ -626,6 +637,7 @@ struct DeviceSolver {
       FB_LAUNCH(k_dom_assemble, dim3(tiles, tiles, cnt), 256, 0, stream, tt, px.p, py.p, pz.p, kp, M.st.nugget,
                 lv->qpool.p, scratch.p, lv->lpool.p);
     }
+    sublap("prep + assemble");
     FB_CUDA(cudaMemsetAsync(fail.p, 0, sizeof(int), stream));
     const size_t smem = sizeof(double) * ((size_t)(kNB + 1) * kNB + (size_t)kPS * kNB * (1 + 8));
     FB_CUDA(cudaFuncSetAttribute(k_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -672,6 +684,7 @@ struct DeviceSolver {
       lv->level_idx.upload(li, stream);
       lv->ts = tree->subset_target_set_dev(lv->level_idx.p, li.size(), lv->tb);
     }
+    sublap("level target set");
     levels.push_back(std::move(lv));
   }
 
