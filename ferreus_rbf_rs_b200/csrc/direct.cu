@@ -1,9 +1,10 @@
 // Direct-sum kernels of the leaf pass (FP64 FMA-pipe bound): P2P + M2P.  The downward-pass P2L (and its fused M2P
 // transpose) lives in p2l.cu.
-// Reference: particle_to_particle bbfmm.rs:1162-1251, multipole_to_particle :1254-1355,
-// particle_to_local :1001-1048.  One thread owns one target; source tiles of kTile points (or
-// Chebyshev nodes of a W cell, generated on the fly) are staged in shared memory and read back as
-// warp-wide broadcasts; the kernel function is evaluated once per pair for all right-hand sides.
+// Reference: particle_to_particle bbfmm.rs:1162-1251, multipole_to_particle :1254-1355.
+//   k_leaf_warp   values: one warp = 32 targets of a leaf, warp-private source tiles, the kernel function evaluated
+//                 once per pair for all right-hand sides (the hot path);
+//   k_leaf_direct values + gradients (evaluate_with_gradients): one thread per target, CTA-wide source tiles of kTile
+//                 points (or the Chebyshev nodes of a W cell, generated on the fly) broadcast from shared memory.
 #include "fmm.h"
 
 #include <algorithm>
