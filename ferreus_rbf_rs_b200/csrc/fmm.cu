@@ -447,14 +447,17 @@ void fb_tree::upload_weights(const double *w, size_t n_rows, size_t nrhs_, ptrdi
   const bool contiguous = cs == 1 && rs == (ptrdiff_t)nrhs_;
   // The reference API passes the weights twice per matvec (set_weights(w), then evaluate(w, ..): bbfmm.rs:383, 444);
   // the second copy is recognised on the host and neither re-uploaded nor re-sorted.
-  if (contiguous && w_cache_valid && (int)nrhs_ == nrhs && h_w_last.size() == cnt && d_w.cap >= cnt &&
-      same_bytes(w, h_w_last.data(), cnt * sizeof(double)))
+  if (contiguous && w_cache_valid && (int)nrhs_ == nrhs && h_w_last_cnt == cnt && d_w.cap >= cnt &&
+      same_bytes(w, h_w_last.p, cnt * sizeof(double)))
     return;
   d_w_user.reserve(cnt);
   if (contiguous) {
-    FB_CUDA(cudaMemcpyAsync(d_w_user.p, w, cnt * sizeof(double), cudaMemcpyHostToDevice, stream));
-    h_w_last.resize(cnt);
-    copy_bytes(h_w_last.data(), w, cnt * sizeof(double));
+    // user memory is pageable: gather it into the pinned cache with all host threads and send it from there
+    // (every API call ends with a stream synchronisation, so the previous transfer out of this buffer is complete)
+    h_w_last.reserve(cnt);
+    copy_bytes(h_w_last.p, w, cnt * sizeof(double));
+    h_w_last_cnt = cnt;
+    FB_CUDA(cudaMemcpyAsync(d_w_user.p, h_w_last.p, cnt * sizeof(double), cudaMemcpyHostToDevice, stream));
     w_cache_valid = true;
   } else {
     w_cache_valid = false;
@@ -884,9 +887,11 @@ void fb_tree::fetch_output(size_t m, bool grads, double *out_vals, double *out_g
                            ptrdiff_t o_cs) {
   auto fetch = [&](const double *dsrc, size_t cols, double *dst) {
     const size_t cnt = m * cols;
-    if (o_cs == 1 && o_rs == (ptrdiff_t)cols) {
-      FB_CUDA(cudaMemcpyAsync(dst, dsrc, cnt * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    if (o_cs == 1 && o_rs == (ptrdiff_t)cols) {  // device -> pinned staging -> user buffer (all host threads)
+      h_stage.reserve(cnt);
+      FB_CUDA(cudaMemcpyAsync(h_stage.p, dsrc, cnt * sizeof(double), cudaMemcpyDeviceToHost, stream));
       FB_CUDA(cudaStreamSynchronize(stream));
+      copy_bytes(dst, h_stage.p, cnt * sizeof(double));
     } else {
       h_stage.reserve(cnt);
       FB_CUDA(cudaMemcpyAsync(h_stage.p, dsrc, cnt * sizeof(double), cudaMemcpyDeviceToHost, stream));

@@ -126,7 +126,8 @@ struct fb_tree {
   fb::DBuf<uint32_t> d_perm, d_inv;           // sorted position -> source row, and inverse
   fb::DBuf<double> d_w;                       // weights, sorted, [rhs][n]
   fb::DBuf<double> d_w_user;                  // weights as uploaded [n][nrhs] row-major
-  std::vector<double> h_w_last;               // host copy of the last contiguous upload (skips the duplicate copy)
+  fb::PinnedBuf<double> h_w_last;             // pinned copy of the last contiguous upload (H2D source, duplicate test)
+  size_t h_w_last_cnt = 0;
   bool w_cache_valid = false;                 // false once d_w_user was written on the device (solver)
   fb::DBuf<double> d_mult, d_loc;             // [cell][rhs][P]
   fb::DBuf<double> d_ccx, d_ccy, d_ccz, d_chalf;
