@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(kLeafWPC * 32, NR >= 4 ? 7 : 10) k_leaf_warp(c
 
   // ---- P2P: warp-private tiles over the merged U ranges; a tile row is {x,y},{z,w0},{w1,w2},... so a source costs
   //      two 128-bit broadcast loads (one more per further pair of right-hand sides)
-  {
+  if (!a.skip_p2p) {
     constexpr int NC2 = (4 + NR) / 2;  // double2 components per source
     double2(*wt)[NC2][kWarpTile] = reinterpret_cast<double2(*)[NC2][kWarpTile]>(wsm);
     long long e = a.u_ptr[li];
@@ -396,6 +396,15 @@ static void leaf_direct_fam(DirectArgs a, cudaStream_t s) {
       FB_LAUNCH((k_leaf_direct<FAM, 1, true>), grid, kTile, 0, s, a);
     }
     return;
+  }
+  if (p2p_sym_applicable(a)) {  // targets == sources, 1 RHS: each unordered pair once; the warp kernel keeps the W lists
+    launch_p2p_sym(a, s);
+    if (!a.has_w) return;
+    a.skip_p2p = 1;
+  } else if (p2p_mma_applicable(a)) {  // opt-in experiment: squared distances on the FP64 tensor cores
+    launch_p2p_mma(a, s);
+    if (!a.has_w) return;
+    a.skip_p2p = 1;
   }
   int r = 0;
   while (r < a.nrhs) {

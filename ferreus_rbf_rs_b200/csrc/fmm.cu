@@ -308,6 +308,7 @@ void fb_tree::build(const double *points, size_t n_, int dim_, ptrdiff_t rs, ptr
     d_w_ptr.upload(w_ptr, stream);
     d_w_ptr_none.upload(std::vector<long long>(nl + 1, 0), stream);
     d_w_cell.upload(w_c, stream);
+    n_w_entries = (long long)w_c.size();
     std::vector<int> x_cells, x_b, x_c;
     std::vector<long long> x_ptr{0};
     for (size_t c = 0; c < nc; ++c) {
@@ -643,6 +644,8 @@ void fb_tree::launch_p2p(const TargetSet &ts, bool grads, bool m2p_done, cudaStr
   a.nrhs = nrhs;
   a.rhs0 = 0;
   a.atomic_out = atomic_out ? 1 : 0;
+  a.has_w = (!m2p_done && n_w_entries > 0) ? 1 : 0;
+  a.skip_p2p = 0;
   a.out = d_out.p;
   a.gout = grads ? d_gout.p : nullptr;
   a.kp = kp;
@@ -953,7 +956,7 @@ extern "C" {
 const char *fb_last_error(void) { return t_last_error.c_str(); }
 uint64_t fb_kernel_launch_count(void) { return g_launches.load(); }
 int fb_set_sqrt_mode(int fast) {
-  g_sqrt_mode.store(fast ? 1 : 0);
+  g_sqrt_mode.store(fast == 3 ? 3 : (fast ? 1 : 0));
   return FB_OK;
 }
 int fb_get_sqrt_mode(void) { return g_sqrt_mode.load(); }

@@ -51,6 +51,8 @@ struct DirectArgs {  // leaf pass: P2P over U ranges + M2P over W cells (bbfmm.r
   const double *nodes;  // p Chebyshev nodes
   int p, dim, P, nrhs, rhs0;
   int atomic_out;  // 1: results are added with RED (the kernel runs concurrently with other writers of `out`)
+  int has_w;       // 1: some leaf owns a W list that this call must apply (M2P)
+  int skip_p2p;    // 1: the U ranges were served by another kernel (p2p_sym.cu / p2p_mma.cu)
   double *out;    // [m][nrhs]
   double *gout;   // [m][nrhs*dim] or null
   KParams kp;
@@ -89,6 +91,10 @@ struct P2LArgs {  // bbfmm.rs:1001-1048
   }
 
 void launch_leaf_direct(const DirectArgs &a, cudaStream_t s);
+bool p2p_sym_applicable(const DirectArgs &a);           // p2p_sym.cu
+void launch_p2p_sym(const DirectArgs &a, cudaStream_t s);
+bool p2p_mma_applicable(const DirectArgs &a);           // p2p_mma.cu (opt-in experiment)
+void launch_p2p_mma(const DirectArgs &a, cudaStream_t s);
 void launch_p2l(const P2LArgs &a, cudaStream_t s);
 
 // ---- M2L work lists, one group per (level, reference vector) -----------------------------------
@@ -145,6 +151,7 @@ struct fb_tree {
   fb::DBuf<long long> d_u_ptr, d_w_ptr, d_x_ptr, d_w_ptr_none;
   fb::DBuf<int> d_u_begin, d_u_count, d_w_cell, d_x_begin, d_x_count, d_x_cells;
   int n_x_cells = 0;
+  long long n_w_entries = 0;
   int n_src_leaves = 0;
   // all-sources target set
   fb::DBuf<int> d_src_tl_begin, d_src_tl_end, d_src_tile_leaf, d_src_tile_off, d_src_ntiles;

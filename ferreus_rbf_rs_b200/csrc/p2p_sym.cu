@@ -1,0 +1,183 @@
+// Symmetric P2P for the matvec case targets == sources, one right-hand side (the solver's and the bench's hot call).
+// Reference: particle_to_particle bbfmm.rs:1162-1251 — there every (target, source) pair of the U lists is evaluated;
+// here each unordered pair is evaluated ONCE and serves both rows:
+//     out[t] += k(t, s) w[s]      and      out[s] += k(t, s) w[t]        (all registry kernels are symmetric).
+// U is a symmetric relation (adjacent leaves at any level + the leaf itself, linear_tree.rs:177-395 / :397-485), and the
+// sources are stored in Morton order, so "each unordered pair once" = a warp owning the 32 consecutive sorted positions
+// [tb, tb + cnt) of a leaf takes the part of the leaf's merged U ranges that lies AFTER its own chunk (symmetric
+// tiles), plus its own cnt x cnt diagonal block evaluated in full.
+//
+// Cost model (tools/fp64_ubench.cu, tools/dmma_bench.cu): the FP64 pipe is the only resource (DMMA shares it, MUFU.RSQ64H
+// serialises with it), 10 DFMA + 1 MUFU per evaluation = 7.2 clk per warp step on an SM.  The symmetric step adds one
+// DMUL (k w[t]) and, amortised, one DADD of the source-side reduction: 8.3 clk for TWO pairs — 1.75x fewer pipe cycles
+// per pair.  Source side: lane l parks k(t_l, s_j) w[t_l] in a warp-private shared-memory matrix part[j][l] (row stride
+// 33: conflict-free both ways); after the tile, lane j sums row j in a fixed order and issues one RED to out[s_j].
+// Target-side sums stay in registers and are added with one RED per target at the end (other warps' source-side REDs
+// hit the same rows concurrently).  Values are the reference's own per-pair values; only the summation order differs.
+#include "fmm.h"
+
+#include <cstdlib>
+
+namespace fb {
+
+constexpr int kSymWPC = 4;       // warps per CTA
+constexpr int kSymStride = 33;   // row stride of the partial-sum matrix (doubles)
+
+struct SymWarpSmem {
+  double2 st[2][2][32];           // double-buffered source tile: {x, y}, {z, w}
+  double part[32 * kSymStride];   // part[j][l] = k(t_l, s_j) w[t_l]
+};
+
+template <int FAM, bool FAST>
+__global__ void __launch_bounds__(kSymWPC * 32, 5) k_p2p_sym(const DirectArgs a) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long gw = (long long)blockIdx.x * kSymWPC + warp;
+  const int tile = (int)(gw >> 2), sub = (int)(gw & 3);
+  if (tile >= *a.ts.n_tiles_dev) return;
+  const int li = a.ts.tile_leaf[tile];
+  const int tb = a.ts.leaf_begin[li] + a.ts.tile_off[tile] + sub * 32;
+  const int cnt = min(32, a.ts.leaf_end[li] - tb);
+  if (cnt <= 0) return;
+  const int a_end = tb + cnt;
+  const bool active = lane < cnt;
+
+  extern __shared__ __align__(16) unsigned char dsm_raw[];
+  SymWarpSmem &sm = reinterpret_cast<SymWarpSmem *>(dsm_raw)[warp];
+
+  constexpr double kScale = kernel_weight_scale<FAM, FAST>();
+  double xt = 0, yt = 0, zt = 0, wt = 0;
+  if (active) {
+    xt = a.sx[tb + lane];
+    yt = a.sy[tb + lane];
+    zt = a.sz[tb + lane];
+    wt = a.w[tb + lane] * kScale;
+  }
+  double acc = 0.0;
+
+  // ---- diagonal block: the chunk against itself, every ordered pair (self term included, as the reference does)
+  sm.st[0][0][lane] = make_double2(xt, yt);
+  sm.st[0][1][lane] = make_double2(zt, wt);
+  __syncwarp();
+#pragma unroll 4
+  for (int j = 0; j < cnt; ++j) {
+    const double2 p0 = sm.st[0][0][j], p1 = sm.st[0][1][j];
+    const double dx = xt - p0.x, dy = yt - p0.y, dz = zt - p1.x;
+    double r2 = dx * dx;
+    r2 += dy * dy;
+    r2 += dz * dz;
+    kernel_acc<FAM>(acc, kernel_mag<FAM, FAST, true>(r2, a.kp), p1.y);
+  }
+  __syncwarp();
+
+  // ---- symmetric tiles: the part of the merged U ranges behind the chunk
+  long long e = a.u_ptr[li];
+  const long long e_end = a.u_ptr[li + 1];
+  int pos = 0, end = 0;  // current clipped range [pos, end)
+  auto next_range = [&]() {
+    while (e < e_end) {
+      const int b = a.u_begin[e], n = a.u_count[e];
+      ++e;
+      pos = max(b, a_end);
+      end = b + n;
+      if (pos < end) return;
+    }
+    pos = end = 0;
+  };
+  next_range();
+  double rx = 0, ry = 0, rz = 0, rw = 0;
+  int spos_next = 0;
+  auto fetch = [&](int &m) {  // this lane's element of the next tile, then advance
+    m = min(32, end - pos);
+    if (m <= 0) {
+      m = 0;
+      return;
+    }
+    spos_next = pos + lane;
+    if (lane < m) {
+      rx = a.sx[spos_next];
+      ry = a.sy[spos_next];
+      rz = a.sz[spos_next];
+      rw = a.w[spos_next] * kScale;
+    }
+    pos += m;
+    if (pos >= end) next_range();
+  };
+  auto stash = [&](int buf, int m) {
+    if (lane < m) {
+      sm.st[buf][0][lane] = make_double2(rx, ry);
+      sm.st[buf][1][lane] = make_double2(rz, rw);
+    }
+  };
+  int m_cur = 0, m_next = 0, buf = 0, spos_cur = 0;
+  fetch(m_cur);
+  spos_cur = spos_next;
+  stash(0, m_cur);
+  __syncwarp();
+  while (m_cur > 0) {
+    fetch(m_next);  // global loads of the next tile overlap the arithmetic below
+    const double2(*t)[32] = sm.st[buf];
+    double *pl = sm.part + lane;
+#pragma unroll 4
+    for (int j = 0; j < m_cur; ++j) {
+      const double2 p0 = t[0][j], p1 = t[1][j];
+      const double dx = xt - p0.x, dy = yt - p0.y, dz = zt - p1.x;
+      double r2 = dx * dx;
+      r2 += dy * dy;
+      r2 += dz * dz;
+      const double v = kernel_mag<FAM, FAST, true>(r2, a.kp);
+      kernel_acc<FAM>(acc, v, p1.y);
+      pl[j * kSymStride] = v * wt;
+    }
+    __syncwarp();
+    if (lane < m_cur) {  // source side: row `lane` of the partial sums, fixed order, one RED per source
+      const double *pr = sm.part + lane * kSymStride;
+      double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+      for (int l = 0; l < 32; l += 4) {
+        s0 += pr[l];
+        s1 += pr[l + 1];
+        s2 += pr[l + 2];
+        s3 += pr[l + 3];
+      }
+      const double s = (s0 + s1) + (s2 + s3);
+      atomicAdd(a.out + (size_t)a.ts.out_row[spos_cur] * a.nrhs + a.rhs0, FAM == KF_LINEAR ? -s : s);
+    }
+    buf ^= 1;
+    stash(buf, m_next);
+    __syncwarp();
+    m_cur = m_next;
+    spos_cur = spos_next;
+  }
+  if (active) atomicAdd(a.out + (size_t)a.ts.out_row[tb + lane] * a.nrhs + a.rhs0, acc);
+}
+
+template <int FAM>
+static void p2p_sym_fam(const DirectArgs &a, cudaStream_t s) {
+  const size_t smem = sizeof(SymWarpSmem) * kSymWPC;
+  const unsigned grid = (unsigned)(((long long)a.ts.max_tiles * 4 + kSymWPC - 1) / kSymWPC);
+  if (kernel_has_fast<FAM>() && a.kp.fast) {
+    constexpr bool F = kernel_has_fast<FAM>();
+    FB_CUDA(cudaFuncSetAttribute(k_p2p_sym<FAM, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FB_LAUNCH((k_p2p_sym<FAM, F>), grid, kSymWPC * 32, smem, s, a);
+  } else {
+    FB_CUDA(cudaFuncSetAttribute(k_p2p_sym<FAM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FB_LAUNCH((k_p2p_sym<FAM, false>), grid, kSymWPC * 32, smem, s, a);
+  }
+}
+
+// true when the symmetric kernel serves this call: values only, one right-hand side, targets = the tree's own sources
+bool p2p_sym_applicable(const DirectArgs &a) {
+  static const bool off = [] {
+    const char *v = std::getenv("FB_P2P_SYM");
+    return v && v[0] == '0';
+  }();
+  return !off && !a.gout && a.nrhs == 1 && a.ts.all_sources && a.ts.max_tiles > 0 && a.kp.fast != 3;
+}
+
+void launch_p2p_sym(const DirectArgs &a, cudaStream_t s) {
+#define CALL(F) p2p_sym_fam<F>(a, s)
+  FB_FAM_SWITCH(a.kp.fam, CALL)
+#undef CALL
+}
+
+}  // namespace fb

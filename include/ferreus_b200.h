@@ -73,7 +73,8 @@ int fb_set_device(int device);
  * 1 = second-order refinement of the hardware seed (default): relative error <= 1.3e-12 per kernel value (measured,
  *     tools/fp64_ubench.cu), two FP64 operations fewer per pair; 0 = third-order refinement, ~1 ulp.  Both keep the
  *     parity gates (matvec <= 1e-10, interpolant <= 1e-8).  The environment variable FB_SQRT=exact|fast sets the
- *     initial value.                                                                                             */
+ *     initial value.  3 = mode 1 plus an experiment: squared distances of the P2P sums (linear, cubic, spheroidal
+ *     kernels) from the FP64 tensor cores (csrc/p2p_mma.cu; measured 4 % faster only, not the default).            */
 int fb_set_sqrt_mode(int fast);
 int fb_get_sqrt_mode(void);
 

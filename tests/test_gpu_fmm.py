@@ -105,6 +105,99 @@ def test_matvec_matches_oracle(n, dim, kind, kernel, order, comp, nrhs, adaptive
     assert H.rel_l2(got4[::-1], ref) <= MATVEC_TOL
 
 
+@pytest.mark.parametrize("kernel,dim,adaptive,sparse,kind",
+                         [(0, 3, True, True, "clustered"), (0, 3, True, False, "uniform"), (0, 3, False, True, "uniform"),
+                          (1, 2, True, True, "uniform"), (2, 3, True, True, "near"), (3, 3, True, True, "clustered"),
+                          (6, 2, True, True, "clustered"), (7, 3, True, True, "uniform"), (8, 3, True, True, "near"),
+                          (9, 2, False, True, "uniform"), (0, 1, True, True, "uniform")])
+def test_p2p_symmetric_matches_full_lists(kernel, dim, adaptive, sparse, kind):
+    """targets == sources with one right-hand side runs the symmetric P2P kernel (csrc/p2p_sym.cu: each unordered pair
+    of the U lists evaluated once, both rows updated).  The same points passed in another order take the general path
+    (every ordered pair, bbfmm.rs:1162-1251); the two must agree to summation round-off, in both square-root modes,
+    on adaptive / uniform / non-sparse trees, ragged leaves, exact duplicates and near-coincident points."""
+    import ferreus_rbf_rs_b200 as fb
+    rng = np.random.default_rng(99)
+    n = 7000
+    if kind == "near":
+        base = H.make_points(n // 2, dim, "clustered", seed=6)
+        pts = np.concatenate([base, base + rng.standard_normal(base.shape) * 10.0 ** rng.uniform(-9, -3, (len(base), 1))])
+        pts[-40:] = pts[:40]
+    else:
+        pts = H.make_points(n, dim, kind, seed=6)
+    pts = np.ascontiguousarray(pts)
+    n = len(pts)
+    w = rng.random((n, 1)) - 0.5
+    order = 5
+    was = fb.get_sqrt_mode()
+    try:
+        for mode in (1, 0):
+            fb.set_sqrt_mode(mode)
+            pt = H.product_tree(pts, order, kernel, adaptive, sparse, 37, 0, 1e-8)
+            pt.set_weights(w)
+            sym = np.asarray(pt.evaluate(w, pts)).reshape(n, 1)
+            full = np.asarray(pt.evaluate(w, np.ascontiguousarray(pts[::-1]))).reshape(n, 1)[::-1]
+            # singular kernels on near-coincident points have huge rows: compare row by row, relative to the row's own
+            # magnitude plus the typical row magnitude (round-off scales with the sum of the terms, not with the result)
+            scale = np.abs(full) + np.median(np.abs(full))
+            assert (np.abs(sym - full) / scale).max() <= 1e-11
+            assert H.rel_l2(sym, full) <= 1e-12
+            # the solver's entry point (evaluate_at_sources) takes the same kernel
+            again = np.asarray(pt.evaluate_at_sources(w)).reshape(n, 1)
+            assert H.rel_l2(again, full) <= 1e-12
+    finally:
+        fb.set_sqrt_mode(was)
+    ot = H.oracle_tree(pts, order, kernel, adaptive, sparse, 37, 0, 1e-8)
+    ot.set_weights(w)
+    assert H.rel_l2(sym, ot.evaluate(w, pts)) <= MATVEC_TOL
+
+
+@pytest.mark.parametrize("kernel,dim,nrhs,kind", [(0, 3, 1, "near"), (0, 3, 3, "clustered"), (2, 3, 2, "uniform"),
+                                                  (3, 3, 4, "clustered"), (0, 2, 1, "uniform"), (5, 3, 8, "near"),
+                                                  (0, 3, 1, "offset")])
+def test_p2p_mma_matches_fma_path(kernel, dim, nrhs, kind):
+    """Opt-in mode 3: the P2P squared distances come from the FP64 tensor cores (csrc/p2p_mma.cu,
+    |t|^2 + |s|^2 - 2 t.s in warp-local coordinates, close pairs fixed up from coordinate differences).  It must
+    agree with the FMA-pipe kernels (mode 1) far inside the 1e-10 gate, on near-coincident points, ragged leaves and
+    coordinates far from the origin."""
+    import ferreus_rbf_rs_b200 as fb
+    n = 6000
+    rng = np.random.default_rng(77)
+    if kind == "near":  # pairs 1e-9 .. 1e-3 apart on top of a clustered cloud, plus exact duplicates
+        base = H.make_points(n // 2, dim, "clustered", seed=5)
+        pts = np.concatenate([base, base + rng.standard_normal(base.shape) * 10.0 ** rng.uniform(-9, -3, (len(base), 1))])
+        pts[-50:] = pts[:50]
+    elif kind == "offset":  # a small cloud far from the origin: cancellation must not depend on absolute coordinates
+        pts = 1.0e3 + 0.01 * rng.random((n, dim))
+    else:
+        pts = H.make_points(n, dim, kind, seed=5)
+    pts = np.ascontiguousarray(pts)
+    n = len(pts)
+    w = rng.random((n, nrhs)) - 0.5
+    order = 5
+    res = {}
+    was = fb.get_sqrt_mode()
+    try:
+        for mode in (3, 1, 0):
+            fb.set_sqrt_mode(mode)
+            pt = H.product_tree(pts, order, kernel, True, True, 40, 0, 1e-8)
+            pt.set_weights(w)
+            res[mode] = np.asarray(pt.evaluate(w, pts)).reshape(n, nrhs)
+            if mode == 3:  # general target set (no fused W/X pass): the same points in another order
+                res["general"] = np.asarray(pt.evaluate(w, np.ascontiguousarray(pts[::-1]))).reshape(n, nrhs)[::-1]
+    finally:
+        fb.set_sqrt_mode(was)
+    assert H.rel_l2(res[3], res[1]) <= 2e-12
+    assert H.rel_l2(res["general"], res[1]) <= 2e-12
+    assert H.rel_l2(res[3], res[0]) <= 2e-11
+    # per-row agreement, scaled by the row's own magnitude sum (an L2 norm would hide a wrong self pair)
+    ot = H.oracle_tree(pts, order, kernel, True, True, 40, 0, 1e-8)
+    ot.set_weights(w)
+    ref = ot.evaluate(w, pts)
+    assert H.rel_l2(res[3], ref) <= MATVEC_TOL
+    scale = np.abs(ref).max()
+    assert np.abs(res[3] - res[0]).max() <= 1e-10 * scale
+
+
 @pytest.mark.parametrize("kernel,order", [(0, 7), (2, 6), (6, 6)])
 def test_sqrt_modes(kernel, order):
     """fb_set_sqrt_mode: the default second-order square root (<= 1.3e-12 per kernel value) and the third-order one

@@ -50,6 +50,28 @@ __global__ void k_dmma16816(double *out, int iters) {
 }
 #endif
 
+// Do DMMA and DFMA overlap?  Per loop trip: 4 independent m8n8k4 products and NF independent DFMAs per lane (the P2P
+// tensor-core kernel's mix is 4 : 32).  If the pipes are separate the time is the max of the two, else the sum.
+template <int NF, int ND>
+__global__ void k_mix(double *out, int iters) {
+  double c[4][2], x[32];
+  for (int i = 0; i < 4; ++i) c[i][0] = c[i][1] = 0.0;
+  for (int i = 0; i < 32; ++i) x[i] = threadIdx.x * 1e-3 + i;
+  double a = threadIdx.x * 1e-3, b = threadIdx.x * 2e-3;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < ND; ++i)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+#pragma unroll
+    for (int i = 0; i < NF; ++i) x[i] = fma(x[i], 0.999999, 1e-9);
+  }
+  double s = 0;
+  for (int i = 0; i < 4; ++i) s += c[i][0] + c[i][1];
+  for (int i = 0; i < 32; ++i) s += x[i];
+  if (s == 1.2345) out[0] = s;
+}
+
 template <class F>
 double time_ms(F f) {
   cudaEvent_t e0, e1;
@@ -74,6 +96,15 @@ int main() {
   printf("DMMA m8n8k4 : %.2f TFLOP/s\n", 2.0 * 256 * 8 * iters * (double)blocks * (threads / 32) / (ms * 1e-3) / 1e12);
   ms = time_ms([&] { k_dmma16816<<<blocks, threads>>>(out, iters); });
   printf("DMMA m16n8k16: %.2f TFLOP/s\n", 2.0 * 2048 * 4 * iters * (double)blocks * (threads / 32) / (ms * 1e-3) / 1e12);
+  {
+    const int it2 = 2048;
+    const double ms_d = time_ms([&] { k_mix<0, 4><<<blocks, threads>>>(out, it2); });
+    const double ms_f = time_ms([&] { k_mix<32, 0><<<blocks, threads>>>(out, it2); });
+    const double ms_m = time_ms([&] { k_mix<32, 4><<<blocks, threads>>>(out, it2); });
+    const double ms_h = time_ms([&] { k_mix<16, 4><<<blocks, threads>>>(out, it2); });
+    printf("mix (4 DMMA : 32 DFMA per trip): DMMA only %.3f ms, DFMA only %.3f ms, both %.3f ms (sum %.3f, max %.3f); 4 : 16 -> %.3f ms\n",
+           ms_d, ms_f, ms_m, ms_d + ms_f, ms_d > ms_f ? ms_d : ms_f, ms_h);
+  }
   cudaError_t e = cudaGetLastError();
   printf("status: %s\n", cudaGetErrorString(e));
   return 0;
