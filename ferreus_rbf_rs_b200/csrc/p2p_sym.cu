@@ -25,47 +25,53 @@ constexpr int kSymStride = 33;   // row stride of the partial-sum matrix (double
 
 struct SymWarpSmem {
   double2 st[2][2][32];           // double-buffered source tile: {x, y}, {z, w}
-  double part[32 * kSymStride];   // part[j][l] = k(t_l, s_j) w[t_l]
+  double part[32 * kSymStride];   // part[j][l] = sum over the lane's targets of k(t, s_j) w[t]
 };
 
-template <int FAM, bool FAST>
-__global__ void __launch_bounds__(kSymWPC * 32, 5) k_p2p_sym(const DirectArgs a) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long gw = (long long)blockIdx.x * kSymWPC + warp;
-  const int tile = (int)(gw >> 2), sub = (int)(gw & 3);
-  if (tile >= *a.ts.n_tiles_dev) return;
-  const int li = a.ts.tile_leaf[tile];
-  const int tb = a.ts.leaf_begin[li] + a.ts.tile_off[tile] + sub * 32;
-  const int cnt = min(32, a.ts.leaf_end[li] - tb);
-  if (cnt <= 0) return;
-  const int a_end = tb + cnt;
-  const bool active = lane < cnt;
-
-  extern __shared__ __align__(16) unsigned char dsm_raw[];
-  SymWarpSmem &sm = reinterpret_cast<SymWarpSmem *>(dsm_raw)[warp];
-
+// A warp owns up to 64 consecutive sorted positions of a leaf, lane l the targets tb + l and (TWO) tb + 32 + l: every
+// staged source then serves two evaluations per lane, which halves the shared-memory traffic per pair (source broadcasts,
+// partial-sum stores and the row sums of the flush; ncu on the one-target version: l1tex 70 % busy, FP64 pipe 48 %) and
+// doubles the independent chains in flight.  Chunks of <= 32 targets take the one-target instantiation.
+template <int FAM, bool FAST, bool TWO>
+__device__ __forceinline__ void p2p_sym_body(const DirectArgs &a, SymWarpSmem &sm, const int li, const int tb,
+                                             const int cnt, const int lane) {
+  constexpr int NT = TWO ? 2 : 1;
   constexpr double kScale = kernel_weight_scale<FAM, FAST>();
-  double xt = 0, yt = 0, zt = 0, wt = 0;
-  if (active) {
-    xt = a.sx[tb + lane];
-    yt = a.sy[tb + lane];
-    zt = a.sz[tb + lane];
-    wt = a.w[tb + lane] * kScale;
+  const int a_end = tb + cnt;
+  double xt[NT], yt[NT], zt[NT], wt[NT], acc[NT];
+#pragma unroll
+  for (int u = 0; u < NT; ++u) {
+    const int i = 32 * u + lane;
+    xt[u] = yt[u] = zt[u] = wt[u] = acc[u] = 0.0;
+    if (i < cnt) {
+      xt[u] = a.sx[tb + i];
+      yt[u] = a.sy[tb + i];
+      zt[u] = a.sz[tb + i];
+      wt[u] = a.w[tb + i] * kScale;
+    }
   }
-  double acc = 0.0;
-
   // ---- diagonal block: the chunk against itself, every ordered pair (self term included, as the reference does)
-  sm.st[0][0][lane] = make_double2(xt, yt);
-  sm.st[0][1][lane] = make_double2(zt, wt);
+#pragma unroll
+  for (int h = 0; h < NT; ++h) {
+    sm.st[h][0][lane] = make_double2(xt[h], yt[h]);
+    sm.st[h][1][lane] = make_double2(zt[h], wt[h]);
+  }
   __syncwarp();
-#pragma unroll 4
-  for (int j = 0; j < cnt; ++j) {
-    const double2 p0 = sm.st[0][0][j], p1 = sm.st[0][1][j];
-    const double dx = xt - p0.x, dy = yt - p0.y, dz = zt - p1.x;
-    double r2 = dx * dx;
-    r2 += dy * dy;
-    r2 += dz * dz;
-    kernel_acc<FAM>(acc, kernel_mag<FAM, FAST, true>(r2, a.kp), p1.y);
+#pragma unroll
+  for (int h = 0; h < NT; ++h) {
+    const int mh = min(32, cnt - 32 * h);
+#pragma unroll 2
+    for (int j = 0; j < mh; ++j) {
+      const double2 p0 = sm.st[h][0][j], p1 = sm.st[h][1][j];
+#pragma unroll
+      for (int u = 0; u < NT; ++u) {
+        const double dx = xt[u] - p0.x, dy = yt[u] - p0.y, dz = zt[u] - p1.x;
+        double r2 = dx * dx;
+        r2 += dy * dy;
+        r2 += dz * dz;
+        kernel_acc<FAM>(acc[u], kernel_mag<FAM, FAST, true>(r2, a.kp), p1.y);
+      }
+    }
   }
   __syncwarp();
 
@@ -120,26 +126,30 @@ __global__ void __launch_bounds__(kSymWPC * 32, 5) k_p2p_sym(const DirectArgs a)
 #pragma unroll 4
     for (int j = 0; j < m_cur; ++j) {
       const double2 p0 = t[0][j], p1 = t[1][j];
-      const double dx = xt - p0.x, dy = yt - p0.y, dz = zt - p1.x;
-      double r2 = dx * dx;
-      r2 += dy * dy;
-      r2 += dz * dz;
-      const double v = kernel_mag<FAM, FAST, true>(r2, a.kp);
-      kernel_acc<FAM>(acc, v, p1.y);
-      pl[j * kSymStride] = v * wt;
+      double ps = 0.0;
+#pragma unroll
+      for (int u = 0; u < NT; ++u) {
+        const double dx = xt[u] - p0.x, dy = yt[u] - p0.y, dz = zt[u] - p1.x;
+        double r2 = dx * dx;
+        r2 += dy * dy;
+        r2 += dz * dz;
+        const double v = kernel_mag<FAM, FAST, true>(r2, a.kp);
+        kernel_acc<FAM>(acc[u], v, p1.y);
+        ps = u == 0 ? v * wt[0] : fma(v, wt[u], ps);
+      }
+      pl[j * kSymStride] = ps;
     }
     __syncwarp();
     if (lane < m_cur) {  // source side: row `lane` of the partial sums, fixed order, one RED per source
       const double *pr = sm.part + lane * kSymStride;
-      double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+      double sp[8];
 #pragma unroll
-      for (int l = 0; l < 32; l += 4) {
-        s0 += pr[l];
-        s1 += pr[l + 1];
-        s2 += pr[l + 2];
-        s3 += pr[l + 3];
-      }
-      const double s = (s0 + s1) + (s2 + s3);
+      for (int k = 0; k < 8; ++k) sp[k] = pr[k];
+#pragma unroll
+      for (int l = 8; l < 32; l += 8)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sp[k] += pr[l + k];
+      const double s = ((sp[0] + sp[1]) + (sp[2] + sp[3])) + ((sp[4] + sp[5]) + (sp[6] + sp[7]));
       atomicAdd(a.out + (size_t)a.ts.out_row[spos_cur] * a.nrhs + a.rhs0, FAM == KF_LINEAR ? -s : s);
     }
     buf ^= 1;
@@ -148,13 +158,34 @@ __global__ void __launch_bounds__(kSymWPC * 32, 5) k_p2p_sym(const DirectArgs a)
     m_cur = m_next;
     spos_cur = spos_next;
   }
-  if (active) atomicAdd(a.out + (size_t)a.ts.out_row[tb + lane] * a.nrhs + a.rhs0, acc);
+#pragma unroll
+  for (int u = 0; u < NT; ++u) {
+    const int i = 32 * u + lane;
+    if (i < cnt) atomicAdd(a.out + (size_t)a.ts.out_row[tb + i] * a.nrhs + a.rhs0, acc[u]);
+  }
+}
+
+template <int FAM, bool FAST>
+__global__ void __launch_bounds__(kSymWPC * 32, 4) k_p2p_sym(const DirectArgs a) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long gw = (long long)blockIdx.x * kSymWPC + warp;
+  const int tile = (int)(gw >> 1), sub = (int)(gw & 1);  // a tile holds <= kTile = 128 targets: two warps of <= 64
+  if (tile >= *a.ts.n_tiles_dev) return;
+  const int li = a.ts.tile_leaf[tile];
+  const int tb = a.ts.leaf_begin[li] + a.ts.tile_off[tile] + sub * 64;
+  const int cnt = min(64, a.ts.leaf_end[li] - tb);
+  if (cnt <= 0) return;
+  extern __shared__ __align__(16) unsigned char dsm_raw[];
+  SymWarpSmem &sm = reinterpret_cast<SymWarpSmem *>(dsm_raw)[warp];
+  if (cnt > 32) p2p_sym_body<FAM, FAST, true>(a, sm, li, tb, cnt, lane);
+  else p2p_sym_body<FAM, FAST, false>(a, sm, li, tb, cnt, lane);
 }
 
 template <int FAM>
 static void p2p_sym_fam(const DirectArgs &a, cudaStream_t s) {
+  static_assert(kTile == 128, "two 64-target warps per tile");
   const size_t smem = sizeof(SymWarpSmem) * kSymWPC;
-  const unsigned grid = (unsigned)(((long long)a.ts.max_tiles * 4 + kSymWPC - 1) / kSymWPC);
+  const unsigned grid = (unsigned)(((long long)a.ts.max_tiles * 2 + kSymWPC - 1) / kSymWPC);
   if (kernel_has_fast<FAM>() && a.kp.fast) {
     constexpr bool F = kernel_has_fast<FAM>();
     FB_CUDA(cudaFuncSetAttribute(k_p2p_sym<FAM, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
