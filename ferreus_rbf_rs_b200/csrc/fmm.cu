@@ -483,7 +483,8 @@ void fb_tree::upward() {
   const int p = order;
   if (timing) FB_CUDA(cudaEventRecord(ev[0], stream));
   const int nsl = n_src_leaves;
-  if (nsl > 0) {
+  if (nsl > 0 && !launch_p2m_fast(nsl, d_src_leaves.p, d_cell_ptb.p, d_cell_pte.p, d_sx.p, d_sy.p, d_sz.p, d_w.p, n,
+                                  d_ccx.p, d_ccy.p, d_ccz.p, d_chalf.p, d_tnodes.p, p, dim, nrhs, d_mult.p, stream)) {
     const size_t smem = sizeof(double) * ((size_t)p * p + 3 * (size_t)kP2MChunk * p);
     set_smem(k_p2m, smem);
     FB_LAUNCH(k_p2m, nsl, 256, smem, stream, d_src_leaves.p, d_cell_ptb.p, d_cell_pte.p, d_sx.p, d_sy.p, d_sz.p,
@@ -613,6 +614,9 @@ void fb_tree::downward(const uint8_t *flags, const TargetSet *fuse_m2p, bool out
 void fb_tree::launch_l2p(const TargetSet &ts, bool grads) {
   const int p = order;
   if (ts.max_tiles <= 0) return;
+  if (!grads && launch_l2p_fast(ts, d_leaf_cell.p, d_loc.p, d_ccx.p, d_ccy.p, d_ccz.p, d_chalf.p, d_tnodes.p, p, dim,
+                                nrhs, d_out.p, stream))
+    return;
   const size_t smem = sizeof(double) * ((size_t)p * p + P + (size_t)kTile * dim * p * (grads ? 2 : 1));
   set_smem(k_l2p, smem);
   FB_LAUNCH(k_l2p, ts.max_tiles, kTile, smem, stream, ts, d_leaf_cell.p, d_loc.p, d_ccx.p, d_ccy.p, d_ccz.p,

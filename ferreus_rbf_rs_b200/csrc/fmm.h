@@ -96,6 +96,14 @@ void launch_p2p_sym(const DirectArgs &a, cudaStream_t s);
 bool p2p_mma_applicable(const DirectArgs &a);           // p2p_mma.cu (opt-in experiment)
 void launch_p2p_mma(const DirectArgs &a, cudaStream_t s);
 void launch_p2l(const P2LArgs &a, cudaStream_t s);
+// transfers.cu: order / dimension templated P2M and L2P (values only); false = no instantiation, use the generic kernel
+bool launch_p2m_fast(int n_leaves, const int *leaves, const int *ptb, const int *pte, const double *sx, const double *sy,
+                     const double *sz, const double *w, size_t n, const double *ccx, const double *ccy,
+                     const double *ccz, const double *chalf, const double *tnodes, int p, int dim, int nrhs,
+                     double *mult, cudaStream_t s);
+bool launch_l2p_fast(const TargetSet &ts, const int *leaf_cell, const double *loc, const double *ccx, const double *ccy,
+                     const double *ccz, const double *chalf, const double *tnodes, int p, int dim, int nrhs,
+                     double *out, cudaStream_t s);
 
 // ---- M2L work lists, one group per (level, reference vector) -----------------------------------
 struct M2LGroup {
