@@ -37,7 +37,7 @@ sys.path.insert(0, ROOT)
 ORDER = 7
 KERNEL_FLOPS = {"linear": 1}  # c_k of SURVEY.md §8(d)
 # DRAM bytes per launch (read + write) from the committed ncu capture of the default workload (profiles/)
-NCU_DRAM_BYTES = {"k_p2l_grid": 74.585600e6 + 6.861056e6, "k_leaf_warp": 45.199360e6 + 2.131968e6,
+NCU_DRAM_BYTES = {"k_p2l_grid": 74.585600e6 + 6.861056e6, "k_p2p_sym": 45.108736e6 + 0.419840e6,
                   "k_m2l": 84.187136e6 + 6.039040e6}
 
 
@@ -364,15 +364,23 @@ def main():
                     "bound": "fp64", "achieved": wx_tf, "peak": peak, "unit": "TFLOP/s", "frac": wx_tf / peak,
                     "traffic": NCU_DRAM_BYTES["k_p2l_grid"] if n == 1_000_000 else None,
                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this "
-                                      "kernel at this workload (profiles/r1_s2b_ncu_full.txt); compute-bound: 81 MB",
+                                      "kernel at this workload (profiles/r1_final_ncu_full.txt); compute-bound: 81 MB",
                     "peak_source": "in-run DFMA micro-benchmark (fb_measure_fp64_tflops); MEASURED_PEAKS.json has no "
                                    "FP64 entry",
+                    "traffic_capture": "profiles/r1_final2_ncu_full.txt",
                     "algorithmic_flops_per_launch": wx_flops, "flops_per_pair": f_pair, "launch_ms": med["wx"],
                     "note": "algorithmic count = SURVEY.md §8(d): M2P and P2L pairs x 11 FLOP; the kernel evaluates the "
                             "symmetric kernel once per (point, node) and uses it for both passes",
-                    "p2p": {"kernel": "k_leaf_warp (P2P)", "achieved": p2p_tf, "frac": p2p_tf / peak,
+                    "p2p": {"kernel": "k_p2p_sym (P2P, targets == sources: each unordered U-list pair evaluated once, "
+                                      "both rows updated)",
+                            "achieved": p2p_tf, "frac": p2p_tf / peak,
                             "launch_ms": med["leaf"], "algorithmic_flops_per_launch": pairs_p2p * f_pair,
-                            "traffic": NCU_DRAM_BYTES["k_leaf_warp"] if n == 1_000_000 else None},
+                            "traffic": NCU_DRAM_BYTES["k_p2p_sym"] if n == 1_000_000 else None,
+                            "note": "algorithmic count = every ordered (target, source) pair of the reference's U lists "
+                                    "x 11 FLOP (SURVEY.md 8(d)); the kernel evaluates half of them"},
+                    "pipe_note": "FP64 tensor instructions (DMMA) share the DFMA datapath on B200 (tools/dmma_bench.cu mix "
+                                 "test, profiles/r1_dmma_dfma_mix.txt: 4 DMMA + 32 DFMA per trip take the sum of the two "
+                                 "times), so this one FP64 peak bounds P2P, W/X and M2L alike",
                     "direct_sums_total": {"achieved": direct_tf, "frac": direct_tf / peak}}
         stages = {"ms": med, "hbm_peak_gbs": hbm_peak,
                   "hbm_peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",

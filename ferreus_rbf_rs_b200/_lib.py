@@ -96,6 +96,8 @@ SIGNATURES = {
     "fb_last_error": (C.c_char_p, []),
     "fb_kernel_launch_count": (C.c_uint64, []),
     "fb_set_device": (C.c_int, [C.c_int]),
+    "fb_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "fb_host_free": (None, [C.c_void_p]),
     "fb_set_sqrt_mode": (C.c_int, [C.c_int]),
     "fb_get_sqrt_mode": (C.c_int, []),
     "fb_tree_new": (C.c_int, [_dp, _sz, C.c_int, _pd, _pd, C.c_int, C.POINTER(FbKernelParams), C.c_int, C.c_int,
@@ -181,6 +183,51 @@ def last_error():
 
 def dptr(a):
     return a.ctypes.data_as(_dp)
+
+
+class _PinnedPool:
+    """Result matrices backed by page-locked blocks (fb_host_alloc): the device -> host copy lands in them directly and a
+    block returns to the pool when the array that owns it is collected.  Small results and anything beyond the pool cap
+    use ordinary numpy memory."""
+    MIN_BYTES = 1 << 20
+    CAP_BYTES = 1 << 30
+
+    def __init__(self):
+        self.free = {}   # nbytes -> [ptr]
+        self.held = 0    # bytes currently owned by the pool (handed out or free)
+
+    def _release(self, ptr, nbytes):
+        self.free.setdefault(nbytes, []).append(ptr)
+
+    def empty(self, shape):
+        import weakref
+        import numpy as np
+        count = int(np.prod(shape))
+        nbytes = count * 8
+        if nbytes < self.MIN_BYTES:
+            return np.empty(shape)
+        lst = self.free.get(nbytes)
+        if lst:
+            ptr = lst.pop()
+        else:
+            if self.held + nbytes > self.CAP_BYTES:
+                for sz, ptrs in list(self.free.items()):   # drop cached blocks of other sizes first
+                    while ptrs:
+                        lib().fb_host_free(ptrs.pop())
+                        self.held -= sz
+                if self.held + nbytes > self.CAP_BYTES:
+                    return np.empty(shape)
+            ptr = lib().fb_host_alloc(nbytes)
+            if not ptr:
+                return np.empty(shape)
+            self.held += nbytes
+        block = (C.c_double * count).from_address(ptr)
+        fin = weakref.finalize(block, self._release, ptr, nbytes)
+        fin.atexit = False
+        return np.frombuffer(block, dtype=np.float64, count=count).reshape(shape)
+
+
+pinned = _PinnedPool()
 
 
 def strides_of(a):

@@ -86,7 +86,7 @@ def _as_matrix(obj, what):
 
 def _to_numpy(mat):
     """mat_to_numpy (python_bindings.rs:39-64): one column comes back 1-D."""
-    return mat[:, 0].copy() if mat.shape[1] == 1 else mat
+    return mat.reshape(mat.shape[0]) if mat.shape[1] == 1 else mat  # a view: no second copy of the result
 
 
 class FmmTree:
@@ -155,7 +155,7 @@ class FmmTree:
         w = _as_matrix(weights, "weights")
         x = _as_matrix(target_points, "target_points")
         m = x.shape[0]
-        out = np.zeros((m, self._nrhs))
+        out = _lib.pinned.empty((m, self._nrhs))  # the library writes every element
         g = np.zeros((m, self._nrhs * self._dim)) if grads else None
         bad = C.c_uint64(0)
         wr, wc = _lib.strides_of(w)
@@ -192,7 +192,7 @@ class FmmTree:
         if indices is not None:
             idx = np.ascontiguousarray(indices, dtype=np.uint64)
             m = idx.size
-        out = np.zeros((m, self._nrhs))
+        out = _lib.pinned.empty((m, self._nrhs))
         wr, wc = _lib.strides_of(w)
         rc = self._lib.fb_tree_evaluate_at_sources(
             self._h, _lib.dptr(w), w.shape[0], w.shape[1], wr, wc,

@@ -451,10 +451,12 @@ void fb_tree::upload_weights(const double *w, size_t n_rows, size_t nrhs_, ptrdi
   if (contiguous && w_cache_valid && (int)nrhs_ == nrhs && h_w_last_cnt == cnt && d_w.cap >= cnt &&
       same_bytes(w, h_w_last.p, cnt * sizeof(double)))
     return;
+  // fb_tree_set_weights returns without waiting for its transfer and upward pass: make sure nothing is still reading
+  // the staging buffers before they are rewritten (or reallocated)
+  FB_CUDA(cudaStreamSynchronize(stream));
   d_w_user.reserve(cnt);
   if (contiguous) {
     // user memory is pageable: gather it into the pinned cache with all host threads and send it from there
-    // (every API call ends with a stream synchronisation, so the previous transfer out of this buffer is complete)
     h_w_last.reserve(cnt);
     copy_bytes(h_w_last.p, w, cnt * sizeof(double));
     h_w_last_cnt = cnt;
@@ -892,9 +894,20 @@ void fb_tree::matvec_dev(const TargetSet &ts) {
 
 void fb_tree::fetch_output(size_t m, bool grads, double *out_vals, double *out_grads, ptrdiff_t o_rs,
                            ptrdiff_t o_cs) {
+  auto is_pinned = [](const void *p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+  };
   auto fetch = [&](const double *dsrc, size_t cols, double *dst) {
     const size_t cnt = m * cols;
-    if (o_cs == 1 && o_rs == (ptrdiff_t)cols) {  // device -> pinned staging -> user buffer (all host threads)
+    if (o_cs == 1 && o_rs == (ptrdiff_t)cols && cnt >= (1u << 14) && is_pinned(dst)) {  // fb_host_alloc'ed result
+      FB_CUDA(cudaMemcpyAsync(dst, dsrc, cnt * sizeof(double), cudaMemcpyDeviceToHost, stream));
+      FB_CUDA(cudaStreamSynchronize(stream));
+    } else if (o_cs == 1 && o_rs == (ptrdiff_t)cols) {  // device -> pinned staging -> user buffer (all host threads)
       h_stage.reserve(cnt);
       FB_CUDA(cudaMemcpyAsync(h_stage.p, dsrc, cnt * sizeof(double), cudaMemcpyDeviceToHost, stream));
       FB_CUDA(cudaStreamSynchronize(stream));
@@ -967,6 +980,17 @@ int fb_get_sqrt_mode(void) { return g_sqrt_mode.load(); }
 int fb_set_device(int device) {
   return guarded([&] { FB_CUDA(cudaSetDevice(device)); });
 }
+void *fb_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void fb_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
 
 int fb_tree_new(const double *points, size_t n, int dim, ptrdiff_t row_stride, ptrdiff_t col_stride,
                 int interpolation_order, const fb_kernel_params *kernel, int adaptive_tree, int sparse,
@@ -990,6 +1014,7 @@ int fb_tree_new(const double *points, size_t n, int dim, ptrdiff_t row_stride, p
 void fb_tree_free(fb_tree *t) {
   if (!t) return;
   cudaSetDevice(t->device);
+  cudaStreamSynchronize(t->stream);
   delete t;
 }
 
@@ -999,7 +1024,9 @@ int fb_tree_set_weights(fb_tree *t, const double *w, size_t n_rows, size_t nrhs,
     FB_CUDA(cudaSetDevice(t->device));
     t->upload_weights(w, n_rows, nrhs, rs, cs);
     t->upward();
-    FB_CUDA(cudaStreamSynchronize(t->stream));
+    // no synchronisation here: the weights were copied out of the caller's memory above, and the transfer + upward pass
+    // (0.5 ms at 1M points) run under the host-side work of the evaluate call that follows (target recognition);
+    // every call that hands results back synchronises the stream
   });
 }
 

@@ -69,6 +69,12 @@ const char *fb_last_error(void);
 uint64_t fb_kernel_launch_count(void);
 /* CUDA device used by handles created afterwards on this thread (default: current device) */
 int fb_set_device(int device);
+/* Page-locked host memory for result buffers (optional).  Every entry point accepts ordinary pageable memory; when an
+ * output pointer lies in memory obtained here the device -> host copy lands in it directly (no staging copy, no page
+ * faults of a freshly mapped buffer).  The reference returns freshly allocated matrices (bbfmm.rs:444-507); a binding
+ * can back them with these blocks.  fb_host_alloc returns NULL on failure.                                         */
+void *fb_host_alloc(size_t bytes);
+void fb_host_free(void *p);
 /* Square-root mode of the direct-sum hot loops (P2P, M2P, P2L) for trees and models built AFTER the call:
  * 1 = second-order refinement of the hardware seed (default): relative error <= 1.3e-12 per kernel value (measured,
  *     tools/fp64_ubench.cu), two FP64 operations fewer per pair; 0 = third-order refinement, ~1 ulp.  Both keep the
@@ -85,7 +91,9 @@ int fb_tree_new(const double *points, size_t n, int dim, ptrdiff_t row_stride, p
                 const double *extents_or_null, const fb_fmm_params *params_or_null, fb_tree **out);
 void fb_tree_free(fb_tree *t);
 
-/* FmmTree::set_weights (bbfmm.rs:383-401): upward pass P2M + M2M; only the first n rows are read. */
+/* FmmTree::set_weights (bbfmm.rs:383-401): upward pass P2M + M2M; only the first n rows are read.  The weights are
+ * copied before the call returns; the transfer and the upward pass are only enqueued (they overlap the host-side work
+ * of the next call), so a device failure in them is reported by the next call on this handle.                    */
 int fb_tree_set_weights(fb_tree *t, const double *w, size_t n_rows, size_t nrhs, ptrdiff_t row_stride,
                         ptrdiff_t col_stride);
 /* FmmTree::set_local_coefficients (bbfmm.rs:518-524): full downward pass. */
