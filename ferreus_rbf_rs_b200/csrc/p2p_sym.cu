@@ -166,7 +166,7 @@ __device__ __forceinline__ void p2p_sym_body(const DirectArgs &a, SymWarpSmem &s
 }
 
 template <int FAM, bool FAST>
-__global__ void __launch_bounds__(kSymWPC * 32, 4) k_p2p_sym(const DirectArgs a) {
+__global__ void __launch_bounds__(kSymWPC * 32, 5) k_p2p_sym(const DirectArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long gw = (long long)blockIdx.x * kSymWPC + warp;
   const int tile = (int)(gw >> 1), sub = (int)(gw & 1);  // a tile holds <= kTile = 128 targets: two warps of <= 64

@@ -47,7 +47,7 @@ __device__ __forceinline__ void cheb_weights(double x, const double *tn, double 
 constexpr int kP2MTChunk = 64;
 
 template <int PO, int DIM>
-__global__ void __launch_bounds__(256, 2) k_p2m_t(const int *leaves, const int *ptb, const int *pte, const double *sx,
+__global__ void __launch_bounds__(256, PO <= 8 ? 3 : 2) k_p2m_t(const int *leaves, const int *ptb, const int *pte, const double *sx,
                                                const double *sy, const double *sz, const double *w, size_t n,
                                                const double *ccx, const double *ccy, const double *ccz,
                                                const double *chalf, const double *tnodes, int nrhs, double *mult) {
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256, 2) k_p2m_t(const int *leaves, const int *
 }
 
 template <int PO, int DIM>
-__global__ void __launch_bounds__(kTile, 4) k_l2p_t(const TargetSet ts, const int *leaf_cell, const double *loc,
+__global__ void __launch_bounds__(kTile, PO <= 8 ? 6 : 4) k_l2p_t(const TargetSet ts, const int *leaf_cell, const double *loc,
                                                  const double *ccx, const double *ccy, const double *ccz,
                                                  const double *chalf, const double *tnodes, int nrhs, double *out) {
   constexpr int P1 = DIM > 1 ? PO : 1, P2 = DIM > 2 ? PO : 1;
