@@ -21,7 +21,7 @@ constexpr size_t kP2LFuseBytes = 48 * 1024;  // shared-memory budget of the fuse
                                              // those instantiations run one CTA per SM anyway)
 
 template <int FAM, int NR, int PREG, bool FAST, bool FUSE>
-__global__ void __launch_bounds__(256, (NR * PREG <= (FUSE ? 8 : 16)) ? 2 : 1) k_p2l_grid(const P2LArgs a, const int nslices, const int cols, const int T) {
+__global__ void __launch_bounds__(256, (NR * PREG <= 8) ? 3 : ((NR * PREG <= (FUSE ? 8 : 16)) ? 2 : 1)) k_p2l_grid(const P2LArgs a, const int nslices, const int cols, const int T) {
   const int ci = blockIdx.x;
   const int c = a.cells[ci];
   // P2L is wanted when the cell has targets below it; the fused M2P half when any X-list point is a target (a
