@@ -7,6 +7,8 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
+
 #include <cub/cub.cuh>
 #include <thrust/iterator/transform_iterator.h>
 
@@ -25,12 +27,26 @@ void set_last_error(const std::string &msg) { t_last_error = msg; }
 
 static inline unsigned nblocks(size_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
+// Host threads of the staging copies / comparisons below.  torchrun exports OMP_NUM_THREADS=1 to every rank, which would
+// serialise the 8-24 MB copies on the end-to-end path; they take an explicit team instead: FB_IO_THREADS, else the
+// machine's hardware threads divided among the ranks of this node (LOCAL_WORLD_SIZE), at most 16.
+int io_threads() {  // referenced from OpenMP clauses only (not static: the device front end would call it unused)
+  static const int n = [] {
+    if (const char *v = std::getenv("FB_IO_THREADS")) return std::max(1, std::atoi(v));
+    int ranks = 1;
+    if (const char *v = std::getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, std::atoi(v));
+    const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+    return std::max(1, std::min(16, hw / ranks));
+  }();
+  return n;
+}
+
 // bytewise equality of two host buffers, all host threads (24 MB in ~0.3 ms: cheaper than moving them over PCIe)
 static bool same_bytes(const void *a, const void *b, size_t bytes) {
   const size_t chunk = 1 << 18;
   const long nchunks = (long)((bytes + chunk - 1) / chunk);
   int differ = 0;
-#pragma omp parallel for schedule(static) reduction(| : differ)
+#pragma omp parallel for schedule(static) reduction(| : differ) num_threads(io_threads())
   for (long c = 0; c < nchunks; ++c) {
     const size_t off = (size_t)c * chunk, len = std::min(chunk, bytes - off);
     if (std::memcmp((const char *)a + off, (const char *)b + off, len) != 0) differ |= 1;
@@ -40,7 +56,7 @@ static bool same_bytes(const void *a, const void *b, size_t bytes) {
 static void copy_bytes(void *dst, const void *src, size_t bytes) {
   const size_t chunk = 1 << 18;
   const long nchunks = (long)((bytes + chunk - 1) / chunk);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(io_threads())
   for (long c = 0; c < nchunks; ++c) {
     const size_t off = (size_t)c * chunk, len = std::min(chunk, bytes - off);
     std::memcpy((char *)dst + off, (const char *)src + off, len);
