@@ -37,3 +37,15 @@ def test_invalid_arguments_are_reported_not_fatal():
     assert L.fb_tree_new(None, 0, 3, 3, 1, 5, None, 1, 1, None, None, ctypes.byref(out)) == _lib.FB_ERR_INVALID_ARGUMENT
     assert "source_points" in _lib.last_error()
     assert L.fb_tree_m2l_rank(None, 2, 0) == -1
+
+
+def test_pinned_pool_falls_back_without_a_device():
+    """_lib.pinned hands out ordinary numpy memory when fb_host_alloc cannot page-lock (no GPU in this container) and for
+    small results; either way the array is writable and has the requested shape."""
+    import numpy as np
+    from ferreus_rbf_rs_b200 import _lib
+    small = _lib.pinned.empty((10, 2))
+    big = _lib.pinned.empty((200_000, 1))
+    for a, shape in ((small, (10, 2)), (big, (200_000, 1))):
+        assert a.shape == shape and a.dtype == np.float64 and a.flags.writeable and a.flags.c_contiguous
+        a[:] = 1.0

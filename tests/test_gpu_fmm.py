@@ -427,3 +427,45 @@ def test_repeated_weights_and_source_targets_are_recognised_by_content():
     got = np.asarray(pt.evaluate(w2, moved)).reshape(n, 1)
     ot.set_weights(w2)
     assert H.rel_l2(got, ot.evaluate(w2, moved)) <= MATVEC_TOL
+
+
+def test_api_sequencing_async_set_weights_and_pooled_results():
+    """set_weights copies the weights before it returns and only enqueues its transfer and upward pass; results come
+    back in page-locked blocks from a pool.  The caller may overwrite its weight buffer right after set_weights, call
+    set_weights twice in a row, and hold several results at once without aliasing; a released block is reused."""
+    import gc
+    from ferreus_rbf_rs_b200 import _lib
+    n = 140_000  # > 1 MB per result column: the pooled path
+    pts = H.make_points(n, 3, "uniform", seed=3)
+    rng = np.random.default_rng(4)
+    w1, w2 = rng.random((n, 1)) - 0.5, rng.random((n, 1)) - 0.5
+    pt = H.product_tree(pts, 5, 0, True, True, 64, 2, 1e-6)
+    pt.set_weights(w1)
+    ref1 = np.array(pt.evaluate(w1, pts))
+    pt.set_weights(w2)
+    ref2 = np.array(pt.evaluate(w2, pts))
+    assert H.rel_l2(ref1, ref2) > 1e-3
+    # overwrite the caller's buffer right after set_weights: the library must already own a copy of the multipole input
+    scratch = w1.copy()
+    pt.set_weights(scratch)
+    scratch[:] = 7.0
+    got = np.array(pt.evaluate(w1, pts))  # evaluate's own w drives P2P / P2L; the multipoles come from set_weights
+    assert H.rel_l2(got, ref1) <= 1e-13
+    # two set_weights in a row: the second wins
+    pt.set_weights(w1)
+    pt.set_weights(w2)
+    assert H.rel_l2(np.array(pt.evaluate(w2, pts)), ref2) <= 1e-13
+    # results held together do not alias; a collected result's block is handed out again
+    pt.set_weights(w1)
+    a = pt.evaluate(w1, pts)
+    pt.set_weights(w2)
+    b = pt.evaluate(w2, pts)
+    assert H.rel_l2(a, ref1) <= 1e-13 and H.rel_l2(b, ref2) <= 1e-13
+    addr_a = a.ctypes.data
+    held = _lib.pinned.held
+    del a
+    gc.collect()
+    pt.set_weights(w1)
+    c = pt.evaluate(w1, pts)
+    assert c.ctypes.data == addr_a and _lib.pinned.held == held
+    assert H.rel_l2(c, ref1) <= 1e-13 and H.rel_l2(b, ref2) <= 1e-13
