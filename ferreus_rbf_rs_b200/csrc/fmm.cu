@@ -439,7 +439,7 @@ void fb_tree::build(const double *points, size_t n_, int dim_, ptrdiff_t rs, ptr
     m2l_nc = 0;
     const char *nc_env = std::getenv("FB_M2L_NC");  // experiment knob: cap the column tile
     const int nc_cap = nc_env ? std::atoi(nc_env) : 32;
-    for (int nc : {32, 16, 8}) {  // columns per CTA: the largest tile that fits in shared memory
+    for (int nc : {64, 32, 16, 8}) {  // columns per CTA: the largest tile that fits in shared memory
       if (nc > nc_cap) continue;
       const size_t need = sizeof(double) * ((size_t)nc * m2l_Pp + (size_t)max_rp * (nc + 4));
       if (need <= 220 * 1024) {
@@ -564,16 +564,18 @@ void fb_tree::downward(const uint8_t *flags, const TargetSet *fuse_m2p, bool out
 #define FB_M2L_LAUNCH(COMP, NCV)                                                                                   \
   do {                                                                                                             \
     set_smem(k_m2l<COMP, NCV>, m2l_smem_launch);                                                                   \
-    FB_LAUNCH((k_m2l<COMP, NCV>), m2l_ctas, 256, m2l_smem_launch, stream, tab, d_m2l_cta_group.p, d_m2l_tgt.p,   \
+    FB_LAUNCH((k_m2l<COMP, NCV>), m2l_ctas, (NCV) == 64 ? 512 : 256, m2l_smem_launch, stream, tab, d_m2l_cta_group.p, d_m2l_tgt.p,   \
               d_m2l_src.p, d_m2l_perm.p, d_oppool.p, d_perm_tab.p, d_inv_tab.p, P, m2l_P4, m2l_Pp, nrhs, flags,    \
               d_mult.p, d_loc.p);                                                                                  \
   } while (0)
     if (compressed) {
-      if (m2l_nc == 32) FB_M2L_LAUNCH(true, 32);
+      if (m2l_nc == 64) FB_M2L_LAUNCH(true, 64);
+      else if (m2l_nc == 32) FB_M2L_LAUNCH(true, 32);
       else if (m2l_nc == 16) FB_M2L_LAUNCH(true, 16);
       else FB_M2L_LAUNCH(true, 8);
     } else {
-      if (m2l_nc == 32) FB_M2L_LAUNCH(false, 32);
+      if (m2l_nc == 64) FB_M2L_LAUNCH(false, 64);
+      else if (m2l_nc == 32) FB_M2L_LAUNCH(false, 32);
       else if (m2l_nc == 16) FB_M2L_LAUNCH(false, 16);
       else FB_M2L_LAUNCH(false, 8);
     }

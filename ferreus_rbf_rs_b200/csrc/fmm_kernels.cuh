@@ -394,7 +394,7 @@ struct M2LGroupDev {  // one (level, reference vector) group of the fused M2L la
 };
 
 template <bool COMPRESSED, int NC>
-__global__ void __launch_bounds__(256, NC == 32 ? 2 : 1) k_m2l(const M2LGroupDev *groups, const int *cta_group, const int *e_tgt_all,
+__global__ void __launch_bounds__(NC == 64 ? 512 : 256, NC == 32 ? 2 : 1) k_m2l(const M2LGroupDev *groups, const int *cta_group, const int *e_tgt_all,
                                                 const int *e_src_all, const int *e_perm_all, const double *pool,
                                                 const int *perm_tab, const int *inv_tab, int P, int P4, int Pp, int nrhs,
                                                 const uint8_t *flag, const double *mult, double *loc) {
@@ -409,6 +409,8 @@ __global__ void __launch_bounds__(256, NC == 32 ? 2 : 1) k_m2l(const M2LGroupDev
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t ncols = n_entries * (size_t)nrhs;
   constexpr int kM2LCols = NC, kM2LColsPad = NC + 4;
+  constexpr int NW = NC == 64 ? 16 : 8;  // warps per CTA (NC = 64: one 512-thread CTA per SM, operator fragments re-read half as often)
+  constexpr int NH = (NC + 31) / 32;     // 32-column halves, each with its own run table
   constexpr int kNT = NC / 8;        // 8-column tiles
   const size_t col0 = (size_t)cta * kM2LCols;
   const int nc = (int)min((size_t)kM2LCols, ncols - col0);
@@ -416,7 +418,7 @@ __global__ void __launch_bounds__(256, NC == 32 ? 2 : 1) k_m2l(const M2LGroupDev
   double *Ys = Xs + (size_t)kM2LCols * Pp;                // [rank_pad][NC + 4]
   __shared__ int s_tgt[kM2LCols], s_rhs[kM2LCols], s_perm[kM2LCols], s_src[kM2LCols];
   __shared__ int s_list[kM2LCols], s_off[kM2LCols], s_len[kM2LCols];  // columns grouped by (target, rhs) run
-  __shared__ int s_runs[kM2LCols], s_nruns;                          // first column of every run
+  __shared__ int s_runs[kM2LCols], s_nruns[NH];                      // first column of every run, per half
   __shared__ int s_any;
   if (tid == 0) s_any = 0;
   __syncthreads();
@@ -438,11 +440,13 @@ __global__ void __launch_bounds__(256, NC == 32 ? 2 : 1) k_m2l(const M2LGroupDev
   }
   __syncthreads();
   if (!s_any) return;
-  if (warp == 0) {
+  if (warp < NH) {
     // runs of columns that add into the same (target, rhs): s_list holds the columns run by run; the first column
-    // of a run carries the run's offset and length, every other column length 0
-    const bool valid = lane < kM2LCols && s_tgt[lane] >= 0;
-    const int key = valid ? s_tgt[lane] * nrhs + s_rhs[lane] : -(lane + 1);
+    // of a run carries the run's offset and length, every other column length 0.  One warp per 32-column half; a run
+    // that crosses the halves is flushed as two
+    const int hb = warp * 32, col = hb + lane;
+    const bool valid = col < kM2LCols && s_tgt[col] >= 0;
+    const int key = valid ? s_tgt[col] * nrhs + s_rhs[col] : -(lane + 1);
     const unsigned same = __match_any_sync(0xffffffffu, key);
     const int first = __ffs(same) - 1;
     const int rank_in_run = __popc(same & ((1u << lane) - 1u));
@@ -454,16 +458,16 @@ __global__ void __launch_bounds__(256, NC == 32 ? 2 : 1) k_m2l(const M2LGroupDev
     }
     const bool is_first = valid && first == lane;
     const unsigned firsts = __ballot_sync(0xffffffffu, is_first);
-    if (lane < kM2LCols) {
-      if (valid) s_list[before + rank_in_run] = lane;
-      s_off[lane] = before;
-      s_len[lane] = is_first ? __popc(same) : 0;
-      if (is_first) s_runs[__popc(firsts & ((1u << lane) - 1u))] = lane;
+    if (col < kM2LCols) {
+      if (valid) s_list[hb + before + rank_in_run] = col;
+      s_off[col] = hb + before;
+      s_len[col] = is_first ? __popc(same) : 0;
+      if (is_first) s_runs[hb + __popc(firsts & ((1u << lane) - 1u))] = col;
     }
-    if (lane == 0) s_nruns = __popc(firsts);
+    if (lane == 0) s_nruns[warp] = __popc(firsts);
   }
   // stage permuted multipoles (zero padding up to P4 and for idle columns); 4 gathers in flight per lane
-  for (int c = warp; c < kM2LCols; c += 8) {
+  for (int c = warp; c < kM2LCols; c += NW) {
     double *dst = Xs + (size_t)c * Pp;
     if (s_tgt[c] >= 0) {
       const double *src = mult + ((size_t)s_src[c] * nrhs + s_rhs[c]) * P;
@@ -487,7 +491,7 @@ __global__ void __launch_bounds__(256, NC == 32 ? 2 : 1) k_m2l(const M2LGroupDev
   const int ar = lane >> 2, ak = lane & 3;  // fragment coordinates
   if (COMPRESSED) {
     // ---- Ys = Vt * Xs: warp -> column tile nt, reduction slice kh; rank tiles in chunks of kM2LChunk
-    constexpr int kKSplit = 8 / kNT;   // warps sharing one column tile split the P-long reduction
+    constexpr int kKSplit = NW / kNT;  // warps sharing one column tile split the P-long reduction
     const int nt = warp % kNT, kh = warp / kNT;
     const int mtiles = rank_pad >> 3;
     const int ksteps = P4 >> 2;
@@ -531,11 +535,11 @@ __global__ void __launch_bounds__(256, NC == 32 ? 2 : 1) k_m2l(const M2LGroupDev
   // operator fragments are read once per CTA (no reuse to hide their L2 latency behind): blocks of kM2LPre k-steps
   // are double buffered in registers, the next block's loads issued before the current block's DMMAs
   const int kblocks = (ksteps2 + kM2LPre - 1) / kM2LPre;
-  const int my_tiles = mt_total > warp ? (mt_total - warp + 7) / 8 : 0;
+  const int my_tiles = mt_total > warp ? (mt_total - warp + NW - 1) / NW : 0;
   const int nblocks = my_tiles * kblocks;
   double a_cur[kM2LPre], a_nxt[kM2LPre];
   auto load_block = [&](int blk, double (&dst)[kM2LPre]) {
-    const int mt = warp + 8 * (blk / kblocks), ks0 = (blk % kblocks) * kM2LPre;
+    const int mt = warp + NW * (blk / kblocks), ks0 = (blk % kblocks) * kM2LPre;
     const double *af = UF + ((size_t)mt * ksteps2 + ks0) * 32 + lane;
 #pragma unroll
     for (int u = 0; u < kM2LPre; ++u) dst[u] = ks0 + u < ksteps2 ? __ldg(af + (size_t)u * 32) : 0.0;
@@ -546,7 +550,7 @@ __global__ void __launch_bounds__(256, NC == 32 ? 2 : 1) k_m2l(const M2LGroupDev
   for (int i = 0; i < kNT; ++i) z[i][0] = z[i][1] = 0.0;
   for (int blk = 0; blk < nblocks; ++blk) {
     if (blk + 1 < nblocks) load_block(blk + 1, a_nxt);
-    const int mt = warp + 8 * (blk / kblocks), kb = blk % kblocks, ks0 = kb * kM2LPre;
+    const int mt = warp + NW * (blk / kblocks), kb = blk % kblocks, ks0 = kb * kM2LPre;
 #pragma unroll
     for (int u = 0; u < kM2LPre; ++u) {
       const int ks = ks0 + u;
@@ -586,10 +590,11 @@ __global__ void __launch_bounds__(256, NC == 32 ? 2 : 1) k_m2l(const M2LGroupDev
   __syncthreads();
   // ---- flush: L_tgt[i] += sum_{c in run} Zs[c][inv_perm_c[i]]; four gathers in flight per lane
   const int nchunks = (P + 31) >> 5;
-  const int nitems = s_nruns * nchunks;  // (run, 32-node chunk) pairs, dealt round-robin to the warps
-  for (int item = warp; item < nitems; item += 8) {
+  const int nruns0 = s_nruns[0], nruns = nruns0 + (NH > 1 ? s_nruns[NH - 1] : 0);
+  const int nitems = nruns * nchunks;  // (run, 32-node chunk) pairs, dealt round-robin to the warps
+  for (int item = warp; item < nitems; item += NW) {
     const int run = item / nchunks, i = (item - run * nchunks) * 32 + lane;
-    const int c0 = s_runs[run];
+    const int c0 = run < nruns0 ? s_runs[run] : s_runs[32 + run - nruns0];
     const int len = s_len[c0];
     const int *lst = s_list + s_off[c0];
     if (i < P) {
