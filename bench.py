@@ -122,13 +122,20 @@ def full_fit(n):
     # warm-up: a 30k-point fit loads the solver's kernels (CUDA loads modules lazily) before the timed construction
     wp = rng.random((30000, 3))
     fb.RBFInterpolator(wp, wp[:, 0] + wp[:, 1] * wp[:, 2], ic.InterpolantSettings(ic.RBFKernelType.Linear))
-    t0 = time.perf_counter()
-    model = fb.RBFInterpolator(pts, vals, ic.InterpolantSettings(ic.RBFKernelType.Linear))
-    wall = time.perf_counter() - t0
-    info = model.info()
+    # two complete constructions, the first model released outside the timed region; the smaller wall time is reported
+    # (the 17 GB factor pool makes a single measurement sensitive to the allocator's state: 0.96-1.9 s seen)
+    walls, info = [], None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        model = fb.RBFInterpolator(pts, vals, ic.InterpolantSettings(ic.RBFKernelType.Linear))
+        wall = time.perf_counter() - t0
+        if not walls or wall < min(walls):
+            info = model.info()
+        walls.append(wall)
+        del model
     return {"workload": f"ferreus_rbf 3D global fit, linear kernel, tol 1e-6, N={n} clustered (64 Gaussian blobs); "
-                        "timed after one 30k-point warm-up fit",
-            "wall_s": wall, "setup_s": info["setup_seconds"], "solve_s": info["solve_seconds"],
+                        "timed after one 30k-point warm-up fit; best of two constructions",
+            "wall_s": min(walls), "wall_s_all": walls, "setup_s": info["setup_seconds"], "solve_s": info["solve_seconds"],
             "iterations": info["iterations"], "fmm_matvecs": info["matvecs"], "ddm_domains": info["ddm_domains"],
             "final_relative_residual": info["last_residual"]}
 
