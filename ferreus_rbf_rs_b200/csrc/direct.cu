@@ -1,5 +1,6 @@
-// Direct-sum kernels of the leaf pass (FP64 FMA-pipe bound): P2P + M2P.  The downward-pass P2L (and its fused M2P
-// transpose) lives in p2l.cu.
+// Direct-sum kernels of the leaf pass (FP64 FMA-pipe bound): P2P + M2P for general target sets, several right-hand
+// sides and gradients.  The matvec case (targets == sources, one right-hand side) takes the symmetric P2P kernel of
+// p2p_sym.cu; the downward-pass P2L (and its fused M2P transpose) lives in p2l.cu; p2p_mma.cu is an opt-in experiment.
 // Reference: particle_to_particle bbfmm.rs:1162-1251, multipole_to_particle :1254-1355.
 //   k_leaf_warp   values: one warp = 32 targets of a leaf, warp-private source tiles, the kernel function evaluated
 //                 once per pair for all right-hand sides (the hot path);
