@@ -469,3 +469,22 @@ def test_api_sequencing_async_set_weights_and_pooled_results():
     c = pt.evaluate(w1, pts)
     assert c.ctypes.data == addr_a and _lib.pinned.held == held
     assert H.rel_l2(c, ref1) <= 1e-13 and H.rel_l2(b, ref2) <= 1e-13
+
+
+@pytest.mark.parametrize("order,dim", [(4, 3), (8, 3), (9, 3), (11, 3), (6, 2), (7, 2), (9, 2), (11, 2), (10, 3), (5, 2)])
+def test_templated_transfers_every_instantiation(order, dim):
+    """P2M / L2P are instantiated per (order, dim) in csrc/transfers.cu ((10, 3) and (5, 2) have no instantiation and
+    take the generic kernels): every one must reproduce the oracle's upward pass + leaf evaluation, several right-hand
+    sides, targets == sources and a separate target set."""
+    n = 1200 if order ** dim > 700 else 2500  # keeps the oracle's dense-operator side to a few seconds
+    pts = H.make_points(n, dim, "uniform", seed=31)
+    rng = np.random.default_rng(32)
+    w = rng.random((n, 2)) - 0.5
+    tg = np.ascontiguousarray(rng.random((700, dim)) * 0.98 + 0.01)
+    # dense M2L operators (compression none): no truncation choices between the two sides, the transfers are what differs
+    ot = H.oracle_tree(pts, order, 0, True, False, 60, 0, 1e-9)
+    ot.set_weights(w)
+    pt = H.product_tree(pts, order, 0, True, False, 60, 0, 1e-9)
+    pt.set_weights(w)
+    assert H.rel_l2(np.asarray(pt.evaluate(w, pts)).reshape(n, 2), ot.evaluate(w, pts)) <= MATVEC_TOL
+    assert H.rel_l2(np.asarray(pt.evaluate(w, tg)).reshape(700, 2), ot.evaluate(w, tg)) <= MATVEC_TOL
