@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kTile) k_leaf_direct(const DirectArgs a) {
         st.y[tid] = a.dim > 1 ? cy + h * a.nodes[i1] : 0.0;
         st.z[tid] = a.dim > 2 ? cz + h * a.nodes[i2] : 0.0;
 #pragma unroll
-        for (int r = 0; r < NR; ++r) st.w[r][tid] = a.mult[((size_t)c * a.nrhs + a.rhs0 + r) * P + nd];
+        for (int r = 0; r < NR; ++r) st.w[r][tid] = a.mult[((size_t)c * a.nrhs + a.rhs0 + r) * coef_stride(P) + nd];
       }
       __syncthreads();
       accumulate_tile<FAM, NR, GRAD>(st, m, xt, yt, zt, a.kp, acc, g);
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(kLeafWPC * 32, NR >= 4 ? 7 : 10) k_leaf_warp(c
           dzr[i] = oz * oz;
         }
     }
-    const double *msrc = a.mult + ((size_t)c * a.nrhs + a.rhs0) * P;
+    const double *msrc = a.mult + ((size_t)c * a.nrhs + a.rhs0) * coef_stride(P);
     for (int s0 = 0; s0 < p; s0 += slabs_per_chunk) {
       const int ns = min(slabs_per_chunk, p - s0);
       const int cn = ns * slab;  // nodes in this chunk
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(kLeafWPC * 32, NR >= 4 ? 7 : 10) k_leaf_warp(c
 #pragma unroll
       for (int r = 0; r < NR; ++r)
         for (int k = lane; k < plane; k += 32)
-          mw[r * plane + k] = k < cn ? msrc[(size_t)r * P + s0 * slab + k] * kernel_weight_scale<FAM, FAST>() : 0.0;
+          mw[r * plane + k] = k < cn ? msrc[(size_t)r * coef_stride(P) + s0 * slab + k] * kernel_weight_scale<FAM, FAST>() : 0.0;
       __syncwarp();
       // kM2PQB columns at a time: independent kernel evaluations in flight inside every (uniformly predicated) i2
       // step; columns past nq re-read the last column's offsets against zero multipoles

@@ -82,6 +82,7 @@ fb_tree::~fb_tree() {
   if (ev_join) cudaEventDestroy(ev_join);
   if (stream2) cudaStreamDestroy(stream2);
   if (stream) cudaStreamDestroy(stream);
+  if (m2l_plan) m2l_stream_free(m2l_plan);
 }
 
 // ------------------------------------------------------------------------------------------- build
@@ -368,8 +369,11 @@ void fb_tree::build(const double *points, size_t n_, int dim_, ptrdiff_t rs, ptr
     std::vector<int> it(ops.inv_perm.begin(), ops.inv_perm.end());
     d_inv_tab.upload(it, stream);
   }
-  // M2L groups: entries (target, source, permutation) per (level, reference vector), sorted by target
-  {
+  // M2L: the streaming kernel (m2l.cu) when the order fits its register-resident operator slices ...
+  if (m2l_stream_supported(P, fparams.compression_type) && ht.depth >= 2)
+    m2l_plan = m2l_stream_build(ht, ops, P, d_inv_tab.p, stream);
+  // ... else groups of entries (target, source, permutation) per (level, reference vector), sorted by target
+  if (!m2l_plan) {
     m2l_groups.clear();
     std::vector<double> pool;
     std::vector<int> e_tgt, e_src, e_perm;
@@ -497,7 +501,7 @@ void fb_tree::sort_weights() {
 // ---------------------------------------------------------------------------------------- upward
 void fb_tree::upward() {
   const size_t nc = ht.ncells();
-  d_mult.zero(nc * (size_t)nrhs * P, stream);
+  d_mult.zero(nc * (size_t)nrhs * coef_stride(P), stream);
   const int p = order;
   if (timing) FB_CUDA(cudaEventRecord(ev[0], stream));
   const int nsl = n_src_leaves;
@@ -525,12 +529,14 @@ void fb_tree::upward() {
 void fb_tree::downward(const uint8_t *flags, const TargetSet *fuse_m2p, bool out_zeroed, bool m2l_one_cta_per_sm) {
   const size_t nc = ht.ncells();
   const int p = order;
-  d_loc.zero(nc * (size_t)nrhs * P, stream);
+  d_loc.zero(nc * (size_t)nrhs * coef_stride(P), stream);
   if (fuse_m2p && !out_zeroed) d_out.zero(fuse_m2p->m * (size_t)nrhs, stream);
   if (timing) FB_CUDA(cudaEventRecord(ev[3], stream));
   // M2L (loop A of bbfmm.rs:781-832)
   const bool compressed = fparams.compression_type != FB_COMPRESSION_NONE;
-  if (!m2l_groups.empty()) {
+  if (m2l_plan) {
+    m2l_stream_launch(m2l_plan, nrhs, flags == d_flag_all.p ? nullptr : flags, d_mult.p, d_loc.p, stream);
+  } else if (!m2l_groups.empty()) {
     if (m2l_table_nrhs != nrhs) {  // CTA ranges depend on the number of right-hand sides
       std::vector<M2LGroupDev> tab;
       std::vector<int> cta_group;

@@ -11,6 +11,10 @@ namespace fb {
 
 constexpr int kMaxOrder = 16;   // Chebyshev nodes per axis supported by the device kernels
 constexpr int kTile = 128;      // targets per CTA in the direct-sum / L2P kernels
+// Multipoles / locals are stored [cell][rhs][Ps]: P = p^d coefficients padded to an even count, so every column
+// starts on a 16-byte boundary and its size is a multiple of 16 bytes (cp.async.bulk / cp.reduce.async.bulk in
+// m2l.cu).  The pad element is zeroed with the array and never written.
+__host__ __device__ __forceinline__ int coef_stride(int P) { return (P + 1) & ~1; }
 
 // ---- a target set binned into the leaves of a tree (sorted by leaf, Morton order) -------------
 struct TargetSet {
@@ -106,6 +110,14 @@ bool launch_l2p_fast(const TargetSet &ts, const int *leaf_cell, const double *lo
                      double *out, cudaStream_t s);
 
 // ---- M2L work lists, one group per (level, reference vector) -----------------------------------
+// m2l.cu: streaming M2L (TMA gathers / scatter-adds around register-resident operators); null plan = not applicable
+struct M2LStreamPlan;
+bool m2l_stream_supported(int P, int compression);
+M2LStreamPlan *m2l_stream_build(const HostTree &ht, const Operators &ops, int P, const int *d_inv_tab, cudaStream_t stream);
+void m2l_stream_launch(M2LStreamPlan *plan, int nrhs, const uint8_t *flag_or_null, const double *mult, double *loc,
+                       cudaStream_t stream);
+void m2l_stream_free(M2LStreamPlan *plan);
+
 struct M2LGroup {
   int level, ref, rank, rank_pad;
   size_t n_entries;
@@ -184,6 +196,7 @@ struct fb_tree {
   fb::DBuf<int> d_perm_tab, d_inv_tab;
   // M2L
   std::vector<fb::M2LGroup> m2l_groups;
+  fb::M2LStreamPlan *m2l_plan = nullptr;  // streaming kernel (m2l.cu) when applicable, else the grouped k_m2l below
   fb::DBuf<int> d_m2l_tgt, d_m2l_src, d_m2l_perm;
   int m2l_P4 = 0, m2l_Pp = 0;  // padded node counts of the M2L tiles
   size_t m2l_smem = 0;

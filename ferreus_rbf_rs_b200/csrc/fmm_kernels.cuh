@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(256) k_p2m(const int *leaves, const int *ptb, 
         if (dim > 2) s *= S[(2 * kP2MChunk + pt) * p + i2];
         acc += s * wr[pt];
       }
-      mult[((size_t)c * nrhs + r) * P + node] += acc;
+      mult[((size_t)c * nrhs + r) * coef_stride(P) + node] += acc;
     }
   }
 }
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(128) k_m2m(const int *parents, const int *chil
       const int ch = child_idx[k];
       const int slot = cell_slot[ch];
       __syncthreads();
-      const double *src = mult + ((size_t)ch * nrhs + r) * P;
+      const double *src = mult + ((size_t)ch * nrhs + r) * coef_stride(P);
       for (int i = tid; i < P; i += nt) b0[i] = src[i];
       __syncthreads();
       double *in = b0, *out = b1;
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(128) k_m2m(const int *parents, const int *chil
       for (int i = tid; i < P; i += nt) accp[i] += in[i];
     }
     __syncthreads();
-    double *dst = mult + ((size_t)parent * nrhs + r) * P;
+    double *dst = mult + ((size_t)parent * nrhs + r) * coef_stride(P);
     for (int i = tid; i < P; i += nt) dst[i] += accp[i];
   }
 }
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(128) k_l2l(int cell0, const int *cell_parent, 
   for (int i = tid; i < 2 * p * p; i += nt) A[i] = child_s[i];
   for (int r = 0; r < nrhs; ++r) {
     __syncthreads();
-    const double *src = loc + ((size_t)parent * nrhs + r) * P;
+    const double *src = loc + ((size_t)parent * nrhs + r) * coef_stride(P);
     for (int i = tid; i < P; i += nt) b0[i] = src[i];
     __syncthreads();
     double *in = b0, *out = b1;
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(128) k_l2l(int cell0, const int *cell_parent, 
       in = out;
       out = t;
     }
-    double *dst = loc + ((size_t)c * nrhs + r) * P;
+    double *dst = loc + ((size_t)c * nrhs + r) * coef_stride(P);
     for (int i = tid; i < P; i += nt) dst[i] += in[i];
   }
 }
@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(NC == 64 ? 512 : 256, NC == 32 ? 2 : 1) k_m2l(
   for (int c = warp; c < kM2LCols; c += NW) {
     double *dst = Xs + (size_t)c * Pp;
     if (s_tgt[c] >= 0) {
-      const double *src = mult + ((size_t)s_src[c] * nrhs + s_rhs[c]) * P;
+      const double *src = mult + ((size_t)s_src[c] * nrhs + s_rhs[c]) * coef_stride(P);
       const int *pm = perm_tab + (size_t)s_perm[c] * P;
       for (int j0 = lane; j0 < P4; j0 += 128) {
         int idx[4];
@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(NC == 64 ? 512 : 256, NC == 32 ? 2 : 1) k_m2l(
             const int tg = s_tgt[c];
             if (tg < 0) continue;
             const int *pm = perm_tab + (size_t)s_perm[c] * P;
-            atomicAdd(loc + ((size_t)tg * nrhs + s_rhs[c]) * P + __ldg(pm + m), z[nt][h]);  // L[perm[m]] += y[m]
+            atomicAdd(loc + ((size_t)tg * nrhs + s_rhs[c]) * coef_stride(P) + __ldg(pm + m), z[nt][h]);  // L[perm[m]] += y[m]
           }
         }
     }
@@ -612,7 +612,7 @@ __global__ void __launch_bounds__(NC == 64 ? 512 : 256, NC == 32 ? 2 : 1) k_m2l(
           if (k + u < len) v += x;
         }
       }
-      atomicAdd(loc + ((size_t)s_tgt[c0] * nrhs + s_rhs[c0]) * P + i, v);
+      atomicAdd(loc + ((size_t)s_tgt[c0] * nrhs + s_rhs[c0]) * coef_stride(P) + i, v);
     }
   }
 }
@@ -650,7 +650,7 @@ __global__ void __launch_bounds__(kTile) k_l2p(const TargetSet ts, const int *le
   const size_t row = active ? ts.out_row[tb + tid] : 0;
   for (int r = 0; r < nrhs; ++r) {
     __syncthreads();
-    const double *src = loc + ((size_t)c * nrhs + r) * P;
+    const double *src = loc + ((size_t)c * nrhs + r) * coef_stride(P);
     for (int i = tid; i < P; i += kTile) L[i] = src[i];
     __syncthreads();
     if (!active) continue;

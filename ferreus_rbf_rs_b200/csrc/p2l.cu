@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256, (NR * PREG <= 8) ? 3 : ((NR * PREG <= (FU
     for (int r = 0; r < NR; ++r)
 #pragma unroll
       for (int il = 0; il < PREG; ++il)
-        mreg[r][il] = (active && il < p) ? a.mult[((size_t)c * a.nrhs + a.rhs0 + r) * P + q * p + il] *
+        mreg[r][il] = (active && il < p) ? a.mult[((size_t)c * a.nrhs + a.rhs0 + r) * coef_stride(P) + q * p + il] *
                                                kernel_weight_scale<FAM, FAST>()
                                          : 0.0;
   }
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(256, (NR * PREG <= 8) ? 3 : ((NR * PREG <= (FU
     for (int nd = tid; nd < P; nd += nt) {
       double s = 0.0;
       for (int sl = 0; sl < nslices; ++sl) s += red[(size_t)sl * P + nd];
-      a.loc[((size_t)c * a.nrhs + a.rhs0 + r) * P + nd] += s;
+      a.loc[((size_t)c * a.nrhs + a.rhs0 + r) * coef_stride(P) + nd] += s;
     }
   }
 }

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256, PO <= 8 ? 3 : 2) k_p2m_t(const int *leave
     }
     __syncthreads();
     if (g == 0 && q < NQ) {
-      double *dst = mult + ((size_t)c * nrhs + r) * P + q * P2;
+      double *dst = mult + ((size_t)c * nrhs + r) * coef_stride(P) + q * P2;
 #pragma unroll
       for (int i2 = 0; i2 < P2; ++i2) {
         double s = acc[i2];
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(kTile, PO <= 8 ? 6 : 4) k_l2p_t(const TargetSe
   }
   for (int r = 0; r < nrhs; ++r) {
     __syncthreads();
-    const double *src = loc + ((size_t)c * nrhs + r) * P;
+    const double *src = loc + ((size_t)c * nrhs + r) * coef_stride(P);
     for (int i = tid; i < P; i += kTile) L[i] = src[i];
     __syncthreads();
     if (!active) continue;
