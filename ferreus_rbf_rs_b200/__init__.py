@@ -2,8 +2,8 @@
 graphic-goose/ferreus_rbf_rs.  The package is a thin host-side mirror of the reference's Python
 modules (``ferreus_bbfmm``, ``ferreus_rbf``) over the C ABI in ``include/ferreus_b200.h``."""
 from . import _lib  # noqa: F401
-from .bbfmm import (FmmKernelType, FmmParams, FmmTree, KernelParams, M2LCompressionType,  # noqa: F401
-                    SpheroidalOrder)
+from .bbfmm import (Communicator, FmmKernelType, FmmParams, FmmTree, KernelParams,  # noqa: F401
+                    M2LCompressionType, SpheroidalOrder)
 from . import config, interpolant_config, progress  # noqa: F401,E402
 from .rbf import Coefficients, GlobalTrend, RBFInterpolator  # noqa: F401,E402
 

@@ -127,6 +127,18 @@ SIGNATURES = {
     "fb_tree_morton_order": (C.c_int, [C.c_void_p, _u64p]),
     "fb_tree_set_target_subset": (C.c_int, [C.c_void_p, _u64p, _sz]),
     "fb_tree_result_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), _u64p, _u64p]),
+    "fb_comm_unique_id": (C.c_int, [_u8p]),
+    "fb_comm_init": (C.c_int, [_u8p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "fb_comm_free": (None, [C.c_void_p]),
+    "fb_comm_rank": (C.c_int, [C.c_void_p]),
+    "fb_comm_world_size": (C.c_int, [C.c_void_p]),
+    "fb_tree_shard": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fb_tree_shard_rows": (C.c_int, [C.c_void_p, C.c_int, _u64p, _u64p]),
+    "fb_tree_matvec_sharded": (C.c_int, [C.c_void_p]),
+    "fb_tree_sharded_timing": (C.c_int, [C.c_void_p, _dp]),
+    "fb_tree_sharded_result_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "fb_tree_sharded_download": (C.c_int, [C.c_void_p, _dp]),
+    "fb_partition_by_work": (C.c_int, [_dp, _sz, C.c_int, _u64p]),
     "fb_ops_new": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(FbKernelParams), C.c_int, C.c_double,
                              C.POINTER(C.c_void_p)]),
     "fb_ops_free": (None, [C.c_void_p]),

@@ -215,6 +215,30 @@ class FmmTree:
         self._check(self._lib.fb_tree_download_result(self._h, _lib.dptr(out), self._nrhs, 1))
         return _to_numpy(out)
 
+    # -- NCCL partition (csrc/comm.cu): one process per GPU ------------------------------------------------
+    def shard(self, comm):
+        """Partition this tree across the ranks of `comm` (a Communicator, or None to drop the partition)."""
+        self._check(self._lib.fb_tree_shard(self._h, comm._h if comm is not None else None))
+        self._comm = comm
+
+    def shard_rows(self, rank):
+        a, b = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.fb_tree_shard_rows(self._h, rank, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def matvec_sharded(self):
+        self._check(self._lib.fb_tree_matvec_sharded(self._h))
+
+    def sharded_timing(self):
+        ms = np.zeros(4)
+        self._check(self._lib.fb_tree_sharded_timing(self._h, _lib.dptr(ms)))
+        return dict(zip(("upward", "near_field_under_allreduce", "downward_leaf", "allgather"), ms.tolist()))
+
+    def sharded_download(self):
+        out = _lib.pinned.empty((self._n, self._nrhs))
+        self._check(self._lib.fb_tree_sharded_download(self._h, _lib.dptr(out)))
+        return _to_numpy(out)
+
     # -- sharding by Morton-contiguous leaf ranges (include/ferreus_b200.h, multi-GPU section) ---------
     def leaf_work(self):
         nl = self.info()["n_leaves"]
@@ -297,3 +321,46 @@ class FmmTree:
         vt = np.zeros(r * P)
         self._check(self._lib.fb_tree_m2l_operator(self._h, level, ref, _lib.dptr(u), _lib.dptr(vt)))
         return u.reshape((r, P)).T.copy(), vt.reshape((P, r)).T.copy()
+
+
+class Communicator:
+    """NCCL communicator of the partitioned matvec (fb_comm, include/ferreus_b200.h).  `exchange` broadcasts rank 0's
+    128-byte NCCL id to the other ranks: any callable bytes -> bytes, e.g. over torch.distributed or MPI."""
+
+    def __init__(self, rank, world_size, exchange=None):
+        L = _lib.lib()
+        ident = (C.c_uint8 * 128)()
+        if rank == 0:
+            rc = L.fb_comm_unique_id(ident)
+            if rc != 0:
+                raise RuntimeError(_lib.last_error())
+        if world_size > 1:
+            if exchange is None:
+                raise ValueError("world_size > 1 needs an `exchange` callable to broadcast the NCCL id")
+            raw = exchange(bytes(ident))
+            ident = (C.c_uint8 * 128).from_buffer_copy(raw)
+        h = C.c_void_p()
+        rc = L.fb_comm_init(ident, rank, world_size, C.byref(h))
+        if rc != 0:
+            raise RuntimeError(_lib.last_error())
+        self._h, self._L, self.rank, self.world_size = h, L, rank, world_size
+
+    @classmethod
+    def from_torch_distributed(cls, dist):
+        """ranks and the id broadcast taken from an initialised torch.distributed process group (any backend)"""
+        import torch
+        rank, world = dist.get_rank(), dist.get_world_size()
+
+        def exchange(raw):
+            dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+            t = torch.tensor(list(raw), dtype=torch.uint8, device=dev)
+            dist.broadcast(t, src=0)
+            return bytes(t.cpu().tolist())
+
+        return cls(rank, world, exchange)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._L.fb_comm_free(h)
+            self._h = None

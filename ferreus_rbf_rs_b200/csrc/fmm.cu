@@ -83,6 +83,7 @@ fb_tree::~fb_tree() {
   if (stream2) cudaStreamDestroy(stream2);
   if (stream) cudaStreamDestroy(stream);
   if (m2l_plan) m2l_stream_free(m2l_plan);
+  if (shard) fb_shard_free(shard);
 }
 
 // ------------------------------------------------------------------------------------------- build
@@ -499,17 +500,18 @@ void fb_tree::sort_weights() {
 }
 
 // ---------------------------------------------------------------------------------------- upward
-void fb_tree::upward() {
+void fb_tree::upward(const int *leaves, int n_leaves, const uint8_t *cell_flag) {
   const size_t nc = ht.ncells();
   d_mult.zero(nc * (size_t)nrhs * coef_stride(P), stream);
   const int p = order;
   if (timing) FB_CUDA(cudaEventRecord(ev[0], stream));
-  const int nsl = n_src_leaves;
-  if (nsl > 0 && !launch_p2m_fast(nsl, d_src_leaves.p, d_cell_ptb.p, d_cell_pte.p, d_sx.p, d_sy.p, d_sz.p, d_w.p, n,
+  const int nsl = leaves ? n_leaves : n_src_leaves;
+  const int *leaf_list = leaves ? leaves : d_src_leaves.p;
+  if (nsl > 0 && !launch_p2m_fast(nsl, leaf_list, d_cell_ptb.p, d_cell_pte.p, d_sx.p, d_sy.p, d_sz.p, d_w.p, n,
                                   d_ccx.p, d_ccy.p, d_ccz.p, d_chalf.p, d_tnodes.p, p, dim, nrhs, d_mult.p, stream)) {
     const size_t smem = sizeof(double) * ((size_t)p * p + 3 * (size_t)kP2MChunk * p);
     set_smem(k_p2m, smem);
-    FB_LAUNCH(k_p2m, nsl, 256, smem, stream, d_src_leaves.p, d_cell_ptb.p, d_cell_pte.p, d_sx.p, d_sy.p, d_sz.p,
+    FB_LAUNCH(k_p2m, nsl, 256, smem, stream, leaf_list, d_cell_ptb.p, d_cell_pte.p, d_sx.p, d_sy.p, d_sz.p,
               d_w.p, n, d_ccx.p, d_ccy.p, d_ccz.p, d_chalf.p, d_tnodes.p, p, dim, P, nrhs, d_mult.p);
   }
   if (timing) FB_CUDA(cudaEventRecord(ev[1], stream));
@@ -519,7 +521,7 @@ void fb_tree::upward() {
     const int np = parents_off[lvl + 1] - parents_off[lvl];
     if (np <= 0) continue;
     FB_LAUNCH(k_m2m, np, 128, smem, stream, d_parents.p + parents_off[lvl], d_child_ptr.p, d_child_idx.p,
-              d_cell_slot.p, d_child_s.p, p, dim, P, nrhs, d_mult.p);
+              d_cell_slot.p, d_child_s.p, p, dim, P, nrhs, cell_flag, d_mult.p);
   }
   if (timing) FB_CUDA(cudaEventRecord(ev[2], stream));
   have_weights = true;

@@ -127,6 +127,9 @@ struct M2LGroup {
 
 }  // namespace fb
 
+struct fb_shard;  // comm.cu: partition of the tree across the ranks of an fb_comm
+void fb_shard_free(fb_shard *s);
+
 // The opaque C handle
 struct fb_tree {
   int device = 0;
@@ -196,7 +199,8 @@ struct fb_tree {
   fb::DBuf<int> d_perm_tab, d_inv_tab;
   // M2L
   std::vector<fb::M2LGroup> m2l_groups;
-  fb::M2LStreamPlan *m2l_plan = nullptr;  // streaming kernel (m2l.cu) when applicable, else the grouped k_m2l below
+  fb::M2LStreamPlan *m2l_plan = nullptr;
+  fb_shard *shard = nullptr;  // multi-GPU partition (fb_tree_shard), null = the whole tree on this device  // streaming kernel (m2l.cu) when applicable, else the grouped k_m2l below
   fb::DBuf<int> d_m2l_tgt, d_m2l_src, d_m2l_perm;
   int m2l_P4 = 0, m2l_Pp = 0;  // padded node counts of the M2L tiles
   size_t m2l_smem = 0;
@@ -219,7 +223,8 @@ struct fb_tree {
              const fb_fmm_params *params);
   void upload_weights(const double *w, size_t n_rows, size_t nrhs_, ptrdiff_t rs, ptrdiff_t cs);
   void sort_weights();
-  void upward();
+  // P2M over `leaves` (null = every leaf with sources) and M2M over the cells flagged in `cell_flag` (null = all)
+  void upward(const int *leaves = nullptr, int n_leaves = 0, const uint8_t *cell_flag = nullptr);
   // fuse_m2p: the P2L kernel also applies the M2P transpose for that target set (ts.row_of_pos != null) into d_out
   // (zeroed here); leaf_pass(ts, false, m2p_done = true) must follow
   void downward(const uint8_t *flags, const fb::TargetSet *fuse_m2p = nullptr, bool out_zeroed = false,

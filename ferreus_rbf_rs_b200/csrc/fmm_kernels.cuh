@@ -287,7 +287,7 @@ __device__ __forceinline__ void tensor_axis(const double *in, double *out, const
 // (bbfmm.rs:742-772; M2M[c] = (S_x (x) S_y (x) S_z)^T, chebyshev.rs:196-241)
 __global__ void __launch_bounds__(128) k_m2m(const int *parents, const int *child_ptr, const int *child_idx,
                                              const int *cell_slot, const double *child_s, int p, int dim, int P,
-                                             int nrhs, double *mult) {
+                                             int nrhs, const uint8_t *flag, double *mult) {
   extern __shared__ double sm[];
   double *A = sm;              // 2*p*p
   double *b0 = A + 2 * p * p;  // P
@@ -295,6 +295,7 @@ __global__ void __launch_bounds__(128) k_m2m(const int *parents, const int *chil
   double *accp = b1 + P;       // P
   const int tid = threadIdx.x, nt = blockDim.x;
   const int parent = parents[blockIdx.x];
+  if (flag && !flag[parent]) return;  // sharded upward pass: no owned descendants, the multipole stays zero
   for (int i = tid; i < 2 * p * p; i += nt) A[i] = child_s[i];
   for (int r = 0; r < nrhs; ++r) {
     for (int i = tid; i < P; i += nt) accp[i] = 0.0;

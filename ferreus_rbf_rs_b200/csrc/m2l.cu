@@ -24,6 +24,7 @@
 #include <cstdlib>
 #include <map>
 #include <numeric>
+#include <type_traits>
 
 #include "fmm.h"
 
@@ -43,8 +44,9 @@ struct M2LItemDev {
 };
 
 struct M2LStreamArgs {
-  const M2LItemDev *items;
-  const int *cta_ptr;  // items of CTA b: [cta_ptr[b], cta_ptr[b + 1])
+  const M2LItemDev *items;  // longest first
+  int n_items;
+  int *next_item;  // work counter, zeroed before the launch: CTAs pull items as they finish (no static tail)
   const int *e_tgt, *e_src;
   const double *pool;
   const uint8_t *flag;  // per cell: subtree has targets; null = every cell
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_m2l_stream(const M2LStream
   const int Pc = a.Pc;
   double *stages = sm;                                  // [S][NC][Pc]
   double *Yb = stages + (size_t)S * NC * Pc;            // [2][24][YS]
-  __shared__ unsigned long long full[S], zfull[S];
+  __shared__ unsigned long long full[S], zfull[S], pbar[2], ybar[2];
   __shared__ int s_ncols[S], s_item[S];
   __shared__ long long s_tgtoff[S][NC];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -139,12 +141,15 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_m2l_stream(const M2LStream
       mbar_init(&full[s], 1);
       mbar_init(&zfull[s], NW);
     }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&pbar[b], NW);
+      mbar_init(&ybar[b], NW);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // stale shared memory must be finite: idle columns and pad rows are multiplied by zero operator entries
   for (int i = tid; i < S * NC * Pc + 2 * 24 * YS; i += blockDim.x) sm[i] = 0.0;
   __syncthreads();
-  const int item0 = a.cta_ptr[blockIdx.x], item1 = a.cta_ptr[blockIdx.x + 1];
   const unsigned col_bytes = (unsigned)a.Ps * 8u;
 
   if (warp == NW) {
@@ -171,7 +176,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_m2l_stream(const M2LStream
       __syncwarp();
       ++j;
     };
-    for (int it = item0; it < item1; ++it) {
+    for (;;) {
+      int it = 0;
+      if (lane == 0) it = atomicAdd(a.next_item, 1);
+      it = __shfl_sync(0xffffffffu, it, 0);
+      if (it >= a.n_items) break;
       const M2LItemDev im = a.items[it];
       const long long ncol_total = (long long)im.n_entries * a.nrhs;
       for (long long base = 0; base < ncol_total;) {
@@ -248,66 +257,67 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_m2l_stream(const M2LStream
       for (int ks = 0; ks < 2 * kStreamMaxMt; ++ks)
         A2[t][ks] = (t < mcnt && ks < KR) ? __ldg(uf + ((size_t)(warp + NW * t) * KR + ks) * 32) : 0.0;
   };
-  // first contraction of stage jj: partial Y over this warp's k-slice, parked in the rows of the stage it alone reads
-  auto gemm1 = [&](int jj) {
+  // first contraction of stage jj: partial Y over this warp's k-slice, parked in the rows of the stage it alone reads.
+  // The bodies are specialised on the rank tiles MT of the piece and run all KSW k-steps / MTW row tiles (slices one
+  // step short multiply zero fragments): a predicate around mma.sync costs a WARPSYNC + ISETP per pair of DMMAs, and
+  // the instruction stream next to the DMMAs is what keeps the FP64 pipe from saturating (profiles/r2_m2l_*).
+  auto gemm1 = [&](int jj, auto mt_c) {
+    constexpr int MT = decltype(mt_c)::value;
     double *st = stages + (size_t)(jj % S) * NC * Pc;
-    double y[kStreamMaxMt][2][2];
+    double y[MT][2][2];
 #pragma unroll
-    for (int m = 0; m < kStreamMaxMt; ++m) y[m][0][0] = y[m][0][1] = y[m][1][0] = y[m][1][1] = 0.0;
+    for (int m = 0; m < MT; ++m) y[m][0][0] = y[m][0][1] = y[m][1][0] = y[m][1][1] = 0.0;
     const double *bp = st + (size_t)ar * Pc + kb * 4 + ak;
 #pragma unroll
     for (int q = 0; q < KSW; ++q) {
-      if (q < kcnt) {
-        const double b0 = bp[q * 4], b1 = bp[(size_t)8 * Pc + q * 4];
+      const double b0 = bp[q * 4], b1 = bp[(size_t)8 * Pc + q * 4];
 #pragma unroll
-        for (int m = 0; m < kStreamMaxMt; ++m)
-          if (m < mt1) {
-            dmma(y[m][0][0], y[m][0][1], A1[m][q], b0);
-            dmma(y[m][1][0], y[m][1][1], A1[m][q], b1);
-          }
+      for (int m = 0; m < MT; ++m) {
+        dmma(y[m][0][0], y[m][0][1], A1[m][q], b0);
+        dmma(y[m][1][0], y[m][1][1], A1[m][q], b1);
       }
     }
     __syncwarp();  // every lane is done reading the slice before it is overwritten
     double *pp = st + kb * 4;
 #pragma unroll
-    for (int m = 0; m < kStreamMaxMt; ++m)
-      if (m < mt1) {
+    for (int m = 0; m < MT; ++m)
 #pragma unroll
-        for (int n = 0; n < 2; ++n)
+      for (int n = 0; n < 2; ++n)
 #pragma unroll
-          for (int h = 0; h < 2; ++h) pp[(size_t)(n * 8 + ak * 2 + h) * Pc + m * 8 + ar] = y[m][n][h];
-      }
+        for (int h = 0; h < 2; ++h) pp[(size_t)(n * 8 + ak * 2 + h) * Pc + m * 8 + ar] = y[m][n][h];
   };
-  // Y = sum of the 8 partial products, in a fixed order
+  // Y = sum of the NW partial products, in a fixed order
   auto reduce_y = [&](int jj, int mt) {
     const double *st = stages + (size_t)(jj % S) * NC * Pc;
     double *Y = Yb + (size_t)(jj & 1) * 24 * YS;
     const int rows = mt * 8, nel = rows * NC;
     for (int id = tid; id < nel; id += NW * 32) {
       const int rk = id % rows, c = id / rows;
-      double s = 0.0;
+      double v[NW];
 #pragma unroll
-      for (int w = 0; w < NW; ++w) s += st[(size_t)c * Pc + ((KS * w) / NW) * 4 + rk];
-      Y[rk * YS + c] = s;
+      for (int w = 0; w < NW; ++w) v[w] = st[(size_t)c * Pc + ((KS * w) / NW) * 4 + rk];
+#pragma unroll
+      for (int span = 1; span < NW; span *= 2)  // pairwise: a fixed order, log2(NW) dependent additions
+#pragma unroll
+        for (int w = 0; w + span < NW; w += 2 * span) v[w] += v[w + span];
+      Y[rk * YS + c] = v[0];
     }
   };
   // second contraction of stage jj: Z = U_t Y into the stage, then hand it to the producer
-  auto gemm2 = [&](int jj) {
+  auto gemm2 = [&](int jj, auto mt_c) {
+    constexpr int MT = decltype(mt_c)::value;
     double *st = stages + (size_t)(jj % S) * NC * Pc;
     const double *Y = Yb + (size_t)(jj & 1) * 24 * YS;
     double z[MTW][2][2];
 #pragma unroll
     for (int t = 0; t < MTW; ++t) z[t][0][0] = z[t][0][1] = z[t][1][0] = z[t][1][1] = 0.0;
 #pragma unroll
-    for (int ks = 0; ks < 2 * kStreamMaxMt; ++ks) {
-      if (ks < 2 * mt2) {
-        const double b0 = Y[(ks * 4 + ak) * YS + ar], b1 = Y[(ks * 4 + ak) * YS + 8 + ar];
+    for (int ks = 0; ks < 2 * MT; ++ks) {
+      const double b0 = Y[(ks * 4 + ak) * YS + ar], b1 = Y[(ks * 4 + ak) * YS + 8 + ar];
 #pragma unroll
-        for (int t = 0; t < MTW; ++t)
-          if (t < mcnt) {
-            dmma(z[t][0][0], z[t][0][1], A2[t][ks], b0);
-            dmma(z[t][1][0], z[t][1][1], A2[t][ks], b1);
-          }
+      for (int t = 0; t < MTW; ++t) {
+        dmma(z[t][0][0], z[t][0][1], A2[t][ks], b0);
+        dmma(z[t][1][0], z[t][1][1], A2[t][ks], b1);
       }
     }
 #pragma unroll
@@ -323,10 +333,24 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_m2l_stream(const M2LStream
     __syncwarp();
     if (lane == 0) mbar_arrive(&zfull[jj % S]);
   };
-  auto bar_mma = [] { asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory"); };
-
-  // software pipeline: iteration i runs the first contraction of stage i + 1 and the second of stage i, one CTA
-  // barrier per stage
+  // software pipeline: iteration i runs the first contraction of stage i + 1, the second of stage i and the partial-sum
+  // reduction of stage i + 1.  The MMA warps meet only through mbarriers they arrive on early and wait on late
+  // (pbar: partial sums of a stage complete; ybar: Y of a stage complete), so a warp that finishes its k-slice first
+  // goes straight on to its row tiles of the previous stage instead of idling at a CTA barrier.
+  auto run1 = [&](int jj) {
+    if (mt1 == 3) gemm1(jj, std::integral_constant<int, 3>());
+    else if (mt1 == 2) gemm1(jj, std::integral_constant<int, 2>());
+    else gemm1(jj, std::integral_constant<int, 1>());
+  };
+  auto run2 = [&](int jj) {
+    if (mt2 == 3) gemm2(jj, std::integral_constant<int, 3>());
+    else if (mt2 == 2) gemm2(jj, std::integral_constant<int, 2>());
+    else gemm2(jj, std::integral_constant<int, 1>());
+  };
+  auto warp_arrive = [&](unsigned long long *b) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(b);
+  };
   mbar_wait(&full[0], 0);
   int cur = s_item[0];
   if (cur < 0) return;
@@ -335,9 +359,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_m2l_stream(const M2LStream
     load_a1(im);
     item_g1 = cur;
   }
-  gemm1(0);
-  bar_mma();
+  run1(0);
+  warp_arrive(&pbar[0]);
+  mbar_wait(&pbar[0], 0);
   reduce_y(0, mt1);
+  warp_arrive(&ybar[0]);
   for (int i = 0;; ++i) {
     const int jn = i + 1;
     mbar_wait(&full[jn % S], (unsigned)((jn / S) & 1));
@@ -348,17 +374,20 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_m2l_stream(const M2LStream
         load_a1(im);
         item_g1 = nxt;
       }
-      gemm1(jn);
+      run1(jn);
+      warp_arrive(&pbar[jn & 1]);
     }
-    bar_mma();  // partial sums of stage i + 1 and Y of stage i are complete
-    if (nxt >= 0) reduce_y(jn, mt1);
     if (cur != item_g2) {
       const M2LItemDev im = a.items[cur];
       load_a2(im);
       item_g2 = cur;
     }
-    gemm2(i);
+    mbar_wait(&ybar[i & 1], (unsigned)((i >> 1) & 1));
+    run2(i);
     if (nxt < 0) break;
+    mbar_wait(&pbar[jn & 1], (unsigned)((jn >> 1) & 1));
+    reduce_y(jn, mt1);
+    warp_arrive(&ybar[jn & 1]);
     cur = nxt;
   }
 }
@@ -380,7 +409,8 @@ struct M2LStreamPlan {
   DBuf<int> d_tgt, d_src;
   DBuf<double> d_pool;
   DBuf<unsigned char> d_items;
-  DBuf<int> d_cta_ptr;
+  DBuf<int> d_counter;
+  int n_items = 0;
   int table_nrhs = -1;
   int n_ctas = 0;
   int P = 0, Ps = 0, Pc = 0, KS = 0, MTU = 0, nw = 0;
@@ -499,7 +529,7 @@ M2LStreamPlan *m2l_stream_build(const HostTree &ht, const Operators &ops, int P,
   return plan;
 }
 
-// work items of one launch: (piece, entry range), dealt to one persistent CTA per SM, longest first
+// work items of one launch: (piece, entry range), pulled by one persistent CTA per SM, longest first
 static void m2l_stream_items(M2LStreamPlan &pl, int nrhs, int sms, cudaStream_t stream) {
   struct Item {
     M2LItemDev d;
@@ -511,7 +541,7 @@ static void m2l_stream_items(M2LStreamPlan &pl, int nrhs, int sms, cudaStream_t 
     for (int pi : g.pieces) total += (double)g.n_entries * nrhs * pl.pieces[pi].mt;
   // an item should be long enough to amortise the operator load (~70 fragment loads per thread) and short enough to
   // balance: at most 1/4 of a CTA's share
-  const double max_cost = std::max(total / (4.0 * sms), 3.0 * 64.0);
+  const double max_cost = std::max(total / (6.0 * sms), 3.0 * 64.0);
   for (auto &g : pl.groups)
     for (int pi : g.pieces) {
       const auto &pc = pl.pieces[pi];
@@ -529,34 +559,15 @@ static void m2l_stream_items(M2LStreamPlan &pl, int nrhs, int sms, cudaStream_t 
         items.push_back(it);
       }
     }
-  std::vector<int> order(items.size());
-  std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return items[x].cost > items[y].cost; });
-  const int nb = std::max(1, std::min<int>(sms, (int)items.size()));
-  std::vector<std::vector<int>> bins(nb);
-  std::vector<std::pair<double, int>> heap;  // (load, bin), min-heap
-  for (int b = 0; b < nb; ++b) heap.push_back({0.0, b});
-  auto cmp = [](const std::pair<double, int> &x, const std::pair<double, int> &y) { return x > y; };
-  std::make_heap(heap.begin(), heap.end(), cmp);
-  for (int id : order) {
-    std::pop_heap(heap.begin(), heap.end(), cmp);
-    auto &top = heap.back();
-    bins[top.second].push_back(id);
-    top.first += items[id].cost;
-    std::push_heap(heap.begin(), heap.end(), cmp);
-  }
+  // longest first: the CTAs pull items from a counter as they finish
+  std::stable_sort(items.begin(), items.end(), [](const Item &x, const Item &y) { return x.cost > y.cost; });
   std::vector<M2LItemDev> flat;
-  std::vector<int> ptr{0};
-  for (auto &b : bins) {
-    // consecutive items of the same piece keep the operators in registers
-    std::stable_sort(b.begin(), b.end(), [&](int x, int y) { return items[x].d.v_off < items[y].d.v_off; });
-    for (int id : b) flat.push_back(items[id].d);
-    ptr.push_back((int)flat.size());
-  }
-  pl.n_ctas = nb;
+  for (auto &it : items) flat.push_back(it.d);
+  pl.n_items = (int)flat.size();
+  pl.n_ctas = std::max(1, std::min<int>(sms, pl.n_items));
   pl.d_items.reserve(flat.size() * sizeof(M2LItemDev));
   FB_CUDA(cudaMemcpyAsync(pl.d_items.p, flat.data(), flat.size() * sizeof(M2LItemDev), cudaMemcpyHostToDevice, stream));
-  pl.d_cta_ptr.upload(ptr, stream);
+  pl.d_counter.reserve(1);
   FB_CUDA(cudaStreamSynchronize(stream));
   pl.table_nrhs = nrhs;
 }
@@ -572,7 +583,9 @@ void m2l_stream_launch(M2LStreamPlan *plan, int nrhs, const uint8_t *flag_or_nul
   }
   M2LStreamArgs a{};
   a.items = reinterpret_cast<const M2LItemDev *>(pl.d_items.p);
-  a.cta_ptr = pl.d_cta_ptr.p;
+  a.n_items = pl.n_items;
+  a.next_item = pl.d_counter.p;
+  FB_CUDA(cudaMemsetAsync(pl.d_counter.p, 0, sizeof(int), stream));
   a.e_tgt = pl.d_tgt.p;
   a.e_src = pl.d_src.p;
   a.pool = pl.d_pool.p;

@@ -488,3 +488,35 @@ def test_templated_transfers_every_instantiation(order, dim):
     pt.set_weights(w)
     assert H.rel_l2(np.asarray(pt.evaluate(w, pts)).reshape(n, 2), ot.evaluate(w, pts)) <= MATVEC_TOL
     assert H.rel_l2(np.asarray(pt.evaluate(w, tg)).reshape(700, 2), ot.evaluate(w, tg)) <= MATVEC_TOL
+
+
+def test_nccl_partition_single_rank_matches_resident_matvec():
+    """csrc/comm.cu with a one-rank NCCL communicator: the partitioned step (owned-leaf upward pass, multipole
+    all-reduce, near field first, all-gather + scatter to the caller's row order) must reproduce the plain matvec;
+    the cut itself is the same as sharding.partition_by_work.  Ranks > 1 are checked by tools/sharded_bench.py and
+    bench.py --gpus N against the unpartitioned result on every rank."""
+    import ctypes as C
+    import ferreus_rbf_rs_b200 as fb
+    from ferreus_rbf_rs_b200 import _lib, sharding
+    n = 30000
+    pts = H.make_points(n, 3, "clustered", seed=61)
+    w = np.random.default_rng(62).random((n, 2)) - 0.5
+    pt = H.product_tree(pts, 6, 0, True, True, 64, 2, 1e-6)
+    pt.upload_weights(w)
+    pt.matvec_resident()
+    ref = np.array(pt.download_result()).reshape(n, 2)
+    comm = fb.Communicator(0, 1)
+    pt.shard(comm)
+    assert pt.shard_rows(0) == (0, n)
+    pt.matvec_sharded()
+    got = np.array(pt.sharded_download()).reshape(n, 2)
+    assert H.rel_l2(got, ref) <= 1e-13
+    t = pt.sharded_timing()
+    assert all(v >= 0 for v in t.values()) and t["downward_leaf"] > 0
+    pt.shard(None)
+    pt.matvec_resident()
+    assert H.rel_l2(np.array(pt.download_result()).reshape(n, 2), ref) <= 1e-13
+    _, work = pt.leaf_work()
+    b = np.zeros(6, dtype=np.uint64)
+    assert _lib.lib().fb_partition_by_work(_lib.dptr(work), work.size, 5, b.ctypes.data_as(C.POINTER(C.c_uint64))) == 0
+    assert np.array_equal(b.astype(np.int64), sharding.partition_by_work(work, 5))
