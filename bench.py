@@ -18,8 +18,10 @@ One "step" = one matvec = set_weights(w) + evaluate(w, targets = sources) on a p
 * `cpu_baseline`: the oracle port (oracle/fast.py + oracle/csrc/oracle_passes.c, OpenMP) on this host.
 * `sqrt_exact`: the same resident matvec with the third-order (~1 ulp) square root (fb_set_sqrt_mode(0)); the
              default is the second-order one (<= 1.3e-12 per kernel value, see include/ferreus_b200.h).
-N > 1: one process per GPU (torchrun), each rank owns an independent 1M-point tree (weak scaling, no
-data-path collective; see DESIGN.md "multi-GPU").
+N > 1: one process per GPU (torchrun), ONE shared 1M-point cloud partitioned by Morton-contiguous leaf ranges
+(csrc/comm.cu): owned-leaf upward pass, ncclAllReduce of the multipoles under the near-field pass, downward / leaf passes
+for the owned targets, ncclAllGather of the result rows.  `value` = N / (device time of that step, max over ranks):
+strong scaling.  Every rank checks the partitioned result against the unpartitioned matvec on its own GPU.
 """
 import argparse
 import json
@@ -168,13 +170,16 @@ def run_reference(args):
 
 
 def workload_config(n, n_gpus):
-    return {"workload": f"ferreus_bbfmm 3D LinearRbf matvec, N={n} uniform points in the unit cube per GPU, "
+    par = ("one GPU" if n_gpus == 1 else
+           f"one {n}-point cloud partitioned over {n_gpus} GPUs by Morton-contiguous leaf ranges balanced by work; "
+           "ncclAllReduce of the multipoles (under the near-field pass) + ncclAllGather of the result rows per matvec")
+    return {"workload": f"ferreus_bbfmm 3D LinearRbf matvec, N={n} uniform points in the unit cube, "
                         f"Chebyshev order {ORDER}, 1 RHS, adaptive sparse tree, 256 pts/leaf, ACA eps=1e-{ORDER} "
                         "(BASELINE.md headline H)",
-            "points_per_gpu": n, "order": ORDER, "nrhs": 1, "kernel": "LinearRbf", "compression": "ACA",
+            "points": n, "order": ORDER, "nrhs": 1, "kernel": "LinearRbf", "compression": "ACA",
             "sqrt_mode": "second-order (default; <= 1.3e-12 per kernel value; sqrt_exact holds the ~1 ulp variant)",
             "l2_policy": "256 MiB buffer written between timed iterations (L2 flush)",
-            "parallelism": f"{n_gpus} independent trees (one per GPU), no data-path collective"}
+            "parallelism": par}
 
 
 def main():
@@ -223,7 +228,7 @@ def main():
     L.fb_set_device(local_rank)
 
     n = args.n
-    pts, w = make_workload(n, 1000 + rank)
+    pts, w = make_workload(n, 1000)  # the same cloud on every rank: N > 1 partitions it
     t0 = time.perf_counter()
     tree = fb.FmmTree(pts, ORDER, fb.KernelParams(fb.FmmKernelType.LinearRbf), True, True)
     build_s = time.perf_counter() - t0
@@ -231,6 +236,26 @@ def main():
     tree.set_timing(True)
     tree.upload_weights(w)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    partition_err = None
+    if world > 1:
+        comm = fb.Communicator.from_torch_distributed(dist)
+        tree.matvec_resident()
+        unpartitioned = np.array(tree.download_result()).reshape(n, -1)
+        tree.shard(comm)
+        tree.matvec_sharded()
+        got = np.array(tree.sharded_download()).reshape(n, -1)
+        partition_err = float(np.linalg.norm(got - unpartitioned) / np.linalg.norm(unpartitioned))
+        assert partition_err <= 1e-12, f"rank {rank}: partitioned matvec differs from the unpartitioned one: {partition_err}"
+        del got, unpartitioned
+
+    def step():
+        if world > 1:
+            tree.matvec_sharded()
+            t = tree.sharded_timing()
+            t.update({"k_" + k: v for k, v in tree.last_timing().items()})  # this rank's per-kernel times
+            return sum(v for k, v in t.items() if not k.startswith("k_")), t
+        tree.matvec_resident()
+        return tree.last_matvec_ms(), tree.last_timing()
 
     def barrier():
         torch.cuda.synchronize()
@@ -240,7 +265,7 @@ def main():
 
     launches0 = L.fb_kernel_launch_count()
     for _ in range(args.warmup):
-        tree.matvec_resident()
+        step()
     launches_per_step = (L.fb_kernel_launch_count() - launches0) // max(args.warmup, 1)
 
     sampler = ClockSampler(local_rank)
@@ -253,9 +278,11 @@ def main():
     for _ in range(args.steps):
         flush.fill_(1)
         torch.cuda.synchronize()
-        tree.matvec_resident()
-        dev_ms.append(tree.last_matvec_ms())
-        stage_ms.append(tree.last_timing())
+        if world > 1:
+            dist.barrier()
+        ms, st = step()
+        dev_ms.append(ms)
+        stage_ms.append(st)
     barrier()
     wall_s = time.perf_counter() - wall0
     total_ms = float(np.sum(dev_ms))
@@ -284,69 +311,46 @@ def main():
     #      every step, as in a solver: set_weights(w) uploads them, evaluate(w, points) recognises on the host that
     #      w is the vector just set and that the targets are the source points, so neither is sent again.
     w_alt = [w, np.ascontiguousarray(w[::-1])]
-    for i in range(2):
+
+    def e2e_step(i):
+        if world > 1:  # host weights in, partitioned matvec, full result out to the host on every rank
+            tree.upload_weights(w_alt[i % 2])
+            tree.matvec_sharded()
+            return tree.sharded_download()
         tree.set_weights(w_alt[i % 2])
-        tree.evaluate(w_alt[i % 2], pts)
+        return tree.evaluate(w_alt[i % 2], pts)
+
+    for i in range(2):
+        e2e_step(i)
     barrier()
     e0 = time.perf_counter()
     for i in range(args.steps):
-        tree.set_weights(w_alt[i % 2])
-        out = tree.evaluate(w_alt[i % 2], pts)
+        out = e2e_step(i)
     barrier()
     e2e_s = time.perf_counter() - e0
     clocks = sampler.finish()
 
-    # ---- strong scaling (extra, N > 1): ONE shared cloud, Morton-contiguous leaf ranges per rank, result
-    #      slices all-gathered over NCCL (ferreus_rbf_rs_b200/sharding.py)
-    strong = None
-    if world > 1:
-        from ferreus_rbf_rs_b200.sharding import ShardedMatvec
-        spts, sw = make_workload(n, 1000)
-        stree = fb.FmmTree(spts, ORDER, fb.KernelParams(fb.FmmKernelType.LinearRbf), True, True)
-        sm = ShardedMatvec(stree, rank, world)
-        stree.set_target_subset(sm.my_rows)
-        stree.upload_weights(sw)
-        sizes = [r.size for r in sm.rows]
-        pad = max(sizes)
-        send = torch.zeros(pad, dtype=torch.float64, device="cuda")
-        recv = torch.zeros(pad * world, dtype=torch.float64, device="cuda")
-
-        class _Dev:
-            def __init__(self, ptr, cnt):
-                self.__cuda_array_interface__ = {"shape": (cnt,), "typestr": "<f8", "data": (ptr, False),
-                                                 "version": 3, "strides": None}
-
-        def strong_step():
-            stree.matvec_resident()
-            ptr, rows, cols = stree.result_device()
-            send[: rows * cols].copy_(torch.as_tensor(_Dev(ptr, rows * cols), device="cuda"))
-            dist.all_gather_into_tensor(recv, send)
-
-        for _ in range(args.warmup):
-            strong_step()
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0 = time.perf_counter()
-        for _ in range(args.steps):
-            strong_step()
-        barrier()
-        strong_s = time.perf_counter() - s0
-        full = torch.zeros(n, dtype=torch.float64, device="cuda")
-        for r in range(world):
-            full[torch.from_numpy(sm.rows[r]).cuda()] = recv[r * pad: r * pad + sizes[r]]
-        strong = {"wall_ms_per_step": strong_s / args.steps * 1e3, "rows_per_rank": sizes,
-                  "checksum": float(full.sum().item())}
-
-    tms = torch.tensor([total_ms, e2e_s * 1e3, (strong or {}).get("wall_ms_per_step", 0.0)], dtype=torch.float64,
-                       device="cuda")
+    tms = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    per_rank = None
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    total_ms_max, e2e_ms_max, strong_ms_max = [float(v) for v in tms.tolist()]
+        med_r = {k: float(np.median([s_[k] for s_ in stage_ms])) for k in stage_ms[0]}
+        a, b = tree.shard_rows(rank)
+        kernel_keys = ["p2m", "m2m", "m2l", "wx", "l2l", "l2p", "leaf"]
+        mine = torch.tensor([float(b - a), med_r["upward"], med_r["near_field_under_allreduce"], med_r["downward_leaf"],
+                             med_r["allgather"], partition_err] + [med_r["k_" + k] for k in kernel_keys],
+                            dtype=torch.float64, device="cuda")
+        allv = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        names = ["rows", "upward_ms", "near_field_under_allreduce_ms", "downward_leaf_ms", "allgather_ms",
+                 "rel_l2_vs_unpartitioned"] + ["kernel_" + k + "_ms" for k in kernel_keys]
+        per_rank = [dict(zip(names, v.cpu().tolist())) for v in allv]
+    total_ms_max, e2e_ms_max = [float(v) for v in tms.tolist()]
 
     if rank == 0:
         ms_per_step = total_ms_max / args.steps
-        value = world * n / (ms_per_step * 1e-3) / 1e6
-        e2e_val = world * n / (e2e_ms_max / args.steps * 1e-3) / 1e6
+        value = n / (ms_per_step * 1e-3) / 1e6
+        e2e_val = n / (e2e_ms_max / args.steps * 1e-3) / 1e6
         # ---- roofline of the dominant kernel
         fp64_peak = np.zeros(1)
         L.fb_measure_fp64_tflops(_lib.dptr(fp64_peak))
@@ -361,12 +365,16 @@ def main():
         pairs_p2p = info["p2p_pairs"]
         pairs_m2p = info["m2p_pairs"] * P
         pairs_p2l = info["p2l_pairs"] * P
-        med = {k: float(np.median([s[k] for s in stage_ms])) for k in stage_ms[0]}
+        if world == 1:
+            med = {k: float(np.median([s[k] for s in stage_ms])) for k in stage_ms[0]}
+        else:  # slowest rank per kernel: the time the whole-job FLOP counts below are divided by
+            med = {k: max(r["kernel_" + k + "_ms"] for r in per_rank) for k in kernel_keys}
+            med["total"] = ms_per_step
         wx_flops = (pairs_m2p + pairs_p2l) * f_pair
         wx_tf = wx_flops / max(med["wx"] * 1e-3, 1e-9) / 1e12
         p2p_tf = pairs_p2p * f_pair / max(med["leaf"] * 1e-3, 1e-9) / 1e12
         direct_tf = (wx_flops + pairs_p2p * f_pair) / max((med["wx"] + med["leaf"]) * 1e-3, 1e-9) / 1e12
-        peak = float(fp64_peak[0])
+        peak = float(fp64_peak[0]) * world  # whole-job FLOPs against the FP64 peak of all GPUs used
         roofline = {"kernel": "k_p2l_grid<FUSE> (W/X pass: P2L + M2P transpose, one kernel evaluation per pair)",
                     "bound": "fp64", "achieved": wx_tf, "peak": peak, "unit": "TFLOP/s", "frac": wx_tf / peak,
                     "traffic": NCU_DRAM_BYTES["k_p2l_grid"] if n == 1_000_000 else None,
@@ -395,23 +403,25 @@ def main():
                             "m2l_entries": info["n_v"]}}
         line = {"metric": "bbfmm_matvec_throughput", "value": value, "unit": "Mpts/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(n, world),
-                "e2e": {"value": e2e_val, "unit": "Mpts/s", "h2d_bytes_per_step": int(w.nbytes),
-                        "d2h_bytes_per_step": int(out.nbytes), "api": "FmmTree.set_weights + FmmTree.evaluate",
-                        "note": "weights alternate between two vectors; the second copy of w (evaluate) and the "
-                                "targets (== source points) are compared on the host instead of being re-sent"},
+                "e2e": {"value": e2e_val, "unit": "Mpts/s", "h2d_bytes_per_step": int(w.nbytes) * world,
+                        "d2h_bytes_per_step": int(out.nbytes) * world,
+                        "api": ("FmmTree.set_weights + FmmTree.evaluate" if world == 1 else
+                                "FmmTree.upload_weights + FmmTree.matvec_sharded + FmmTree.sharded_download on every rank"),
+                        "note": "weights alternate between two vectors; N = 1: the second copy of w (evaluate) and the "
+                                "targets (== source points) are compared on the host instead of being re-sent; N > 1: "
+                                "every rank uploads the full weight vector and downloads the full result"},
                 "gpu_launches": int(launches_per_step * args.steps),
                 "clocks": clocks, "roofline": roofline, "stages": stages, "sqrt_exact": exact,
                 "tree": {"build_s": build_s, "cells": info["n_cells"], "leaves": info["n_leaves"],
                          "depth": info["depth"]},
                 "wall_s_timed_region": wall_s}
-        if strong is not None:
-            line["strong_scaling"] = {
-                "what": "one shared N-point cloud, tree replicated, targets split by Morton-contiguous leaf ranges "
-                        "balanced by work, result slices all-gathered over NCCL (wall clock incl. the collective)",
-                "ms_per_matvec": strong_ms_max, "value": n / (strong_ms_max * 1e-3) / 1e6, "unit": "Mpts/s",
-                "rows_per_rank": strong["rows_per_rank"]}
+        if per_rank is not None:
+            line["partition"] = {"per_rank": per_rank,
+                                 "what": "device time per stage and per kernel on every rank (median over the timed steps); "
+                                         "near_field_under_allreduce = P2P of the owned targets with the multipole "
+                                         "all-reduce running beside it on a second stream"}
         if world == 1 and not args.no_fit:
             line["fit"] = full_fit(n)
         if world == 1 and not args.no_cpu_baseline:

@@ -143,11 +143,14 @@ struct fb_shard {
   TargetBuffers tb;
   TargetSet ts{};
   DBuf<unsigned long long> d_rows;
+  std::vector<int> level_lo, level_hi;  // per level: the cells with owned targets are the ids [lo, hi)
+  M2LItemTable *m2l_table = nullptr;    // M2L work items of that share
   double last_ms[4] = {0, 0, 0, 0};   // upward, all-reduce wait, downward + leaf, all-gather + scatter
   cudaEvent_t ev[5] = {};
   ~fb_shard() {
     for (auto &e : ev)
       if (e) cudaEventDestroy(e);
+    if (m2l_table) m2l_stream_table_free(m2l_table);
   }
 };
 
@@ -249,6 +252,16 @@ int fb_tree_shard(fb_tree *t, fb_comm *comm) {
       const int c = ht.leaves[l];
       if (ht.pt_end[c] > ht.pt_begin[c]) owned.push_back(c);
     }
+    // ancestors of a contiguous leaf range are one contiguous id range per level
+    sh->level_lo.assign(ht.depth + 1, INT32_MAX);
+    sh->level_hi.assign(ht.depth + 1, 0);
+    for (int c0 : owned)
+      for (int c = c0; c >= 0; c = ht.parent[c]) {
+        const int lv = ht.level[c];
+        if (c >= sh->level_lo[lv] && c < sh->level_hi[lv]) break;  // the rest of the chain is already inside
+        sh->level_lo[lv] = std::min(sh->level_lo[lv], c);
+        sh->level_hi[lv] = std::max(sh->level_hi[lv], c + 1);
+      }
     sh->n_owned_leaves = (int)owned.size();
     sh->d_owned_leaves.upload(owned, t->stream);
     // owned rows (Morton order) as the target subset: cell flags, leaf tiles, fused W/X row map
@@ -297,13 +310,22 @@ int fb_tree_matvec_sharded(fb_tree *t) {
     }
     if (p2p_first) {
       t->d_out.zero(std::max(sh.ts.m, sh.max_rows) * (size_t)t->nrhs, s);
+      if (t->timing) FB_CUDA(cudaEventRecord(t->ev[10], s));
       t->launch_p2p(sh.ts, false, fuse, s, false);
+      if (t->timing) FB_CUDA(cudaEventRecord(t->ev[11], s));
     }
     if (cm.world > 1) FB_CUDA(cudaStreamWaitEvent(s, cm.ev_done, 0));
     FB_CUDA(cudaEventRecord(sh.ev[2], s));
+    if (t->m2l_plan && (!sh.m2l_table || m2l_stream_table_nrhs(sh.m2l_table) != t->nrhs)) {
+      if (sh.m2l_table) m2l_stream_table_free(sh.m2l_table);
+      sh.m2l_table = nullptr;
+      sh.m2l_table = m2l_stream_table_new(t->m2l_plan, t->nrhs, sh.level_lo.data(), sh.level_hi.data(), s);
+    }
     if (p2p_first) {
-      t->downward(sh.ts.cell_flag, fuse ? &sh.ts : nullptr, true);
+      t->downward(sh.ts.cell_flag, fuse ? &sh.ts : nullptr, true, false, sh.m2l_table);
+      if (t->timing) FB_CUDA(cudaEventRecord(t->ev[7], s));
       t->launch_l2p(sh.ts, false);
+      if (t->timing) FB_CUDA(cudaEventRecord(t->ev[8], s));
     } else {
       t->d_out.reserve(sh.max_rows * (size_t)t->nrhs);
       t->evaluate_sources_fused(sh.ts);
@@ -329,6 +351,21 @@ int fb_tree_matvec_sharded(fb_tree *t) {
       sh.last_ms[k] = ms;
     }
     t->last_out_rows = t->n;
+    if (t->timing && p2p_first) {  // per-kernel times of this rank's share, same slots as fb_tree_last_timing
+      auto ms = [&](int a, int b) {
+        float v = 0;
+        cudaEventElapsedTime(&v, t->ev[a], t->ev[b]);
+        return (double)v;
+      };
+      t->last_ms[0] = ms(0, 1);
+      t->last_ms[1] = ms(1, 2);
+      t->last_ms[2] = ms(3, 4);
+      t->last_ms[3] = ms(4, 5);
+      t->last_ms[4] = ms(5, 6);
+      t->last_ms[5] = ms(7, 8);
+      t->last_ms[6] = ms(10, 11);
+      t->last_ms[7] = sh.last_ms[0] + sh.last_ms[1] + sh.last_ms[2] + sh.last_ms[3];
+    }
   });
 }
 

@@ -515,20 +515,23 @@ void fb_tree::upward(const int *leaves, int n_leaves, const uint8_t *cell_flag) 
               d_w.p, n, d_ccx.p, d_ccy.p, d_ccz.p, d_chalf.p, d_tnodes.p, p, dim, P, nrhs, d_mult.p);
   }
   if (timing) FB_CUDA(cudaEventRecord(ev[1], stream));
-  const size_t smem = sizeof(double) * (2 * (size_t)p * p + 3 * (size_t)P);
+  int cpar = 1 << dim;  // children in flight per parent: all of them unless p^d is too large for shared memory
+  while (cpar > 1 && sizeof(double) * (2 * (size_t)p * p + 2 * (size_t)cpar * P) > 200 * 1024) cpar >>= 1;
+  const size_t smem = sizeof(double) * (2 * (size_t)p * p + 2 * (size_t)cpar * P);
   set_smem(k_m2m, smem);
   for (int lvl = ht.depth - 1; lvl >= 1; --lvl) {  // bbfmm.rs:675-687
     const int np = parents_off[lvl + 1] - parents_off[lvl];
     if (np <= 0) continue;
-    FB_LAUNCH(k_m2m, np, 128, smem, stream, d_parents.p + parents_off[lvl], d_child_ptr.p, d_child_idx.p,
-              d_cell_slot.p, d_child_s.p, p, dim, P, nrhs, cell_flag, d_mult.p);
+    FB_LAUNCH(k_m2m, np, 256, smem, stream, d_parents.p + parents_off[lvl], d_child_ptr.p, d_child_idx.p,
+              d_cell_slot.p, d_child_s.p, p, dim, P, nrhs, cell_flag, cpar, d_mult.p);
   }
   if (timing) FB_CUDA(cudaEventRecord(ev[2], stream));
   have_weights = true;
 }
 
 // -------------------------------------------------------------------------------------- downward
-void fb_tree::downward(const uint8_t *flags, const TargetSet *fuse_m2p, bool out_zeroed, bool m2l_one_cta_per_sm) {
+void fb_tree::downward(const uint8_t *flags, const TargetSet *fuse_m2p, bool out_zeroed, bool m2l_one_cta_per_sm,
+                       const M2LItemTable *m2l_table) {
   const size_t nc = ht.ncells();
   const int p = order;
   d_loc.zero(nc * (size_t)nrhs * coef_stride(P), stream);
@@ -537,7 +540,7 @@ void fb_tree::downward(const uint8_t *flags, const TargetSet *fuse_m2p, bool out
   // M2L (loop A of bbfmm.rs:781-832)
   const bool compressed = fparams.compression_type != FB_COMPRESSION_NONE;
   if (m2l_plan) {
-    m2l_stream_launch(m2l_plan, nrhs, flags == d_flag_all.p ? nullptr : flags, d_mult.p, d_loc.p, stream);
+    m2l_stream_launch(m2l_plan, nrhs, flags == d_flag_all.p ? nullptr : flags, m2l_table, d_mult.p, d_loc.p, stream);
   } else if (!m2l_groups.empty()) {
     if (m2l_table_nrhs != nrhs) {  // CTA ranges depend on the number of right-hand sides
       std::vector<M2LGroupDev> tab;

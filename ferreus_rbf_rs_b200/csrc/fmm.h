@@ -114,8 +114,13 @@ bool launch_l2p_fast(const TargetSet &ts, const int *leaf_cell, const double *lo
 struct M2LStreamPlan;
 bool m2l_stream_supported(int P, int compression);
 M2LStreamPlan *m2l_stream_build(const HostTree &ht, const Operators &ops, int P, const int *d_inv_tab, cudaStream_t stream);
-void m2l_stream_launch(M2LStreamPlan *plan, int nrhs, const uint8_t *flag_or_null, const double *mult, double *loc,
-                       cudaStream_t stream);
+struct M2LItemTable;  // work items restricted to the cells [level_lo, level_hi) of every level (a rank's share)
+M2LItemTable *m2l_stream_table_new(M2LStreamPlan *plan, int nrhs, const int *level_lo, const int *level_hi,
+                                   cudaStream_t stream);
+int m2l_stream_table_nrhs(const M2LItemTable *t);
+void m2l_stream_table_free(M2LItemTable *t);
+void m2l_stream_launch(M2LStreamPlan *plan, int nrhs, const uint8_t *flag_or_null, const M2LItemTable *table_or_null,
+                       const double *mult, double *loc, cudaStream_t stream);
 void m2l_stream_free(M2LStreamPlan *plan);
 
 struct M2LGroup {
@@ -228,7 +233,7 @@ struct fb_tree {
   // fuse_m2p: the P2L kernel also applies the M2P transpose for that target set (ts.row_of_pos != null) into d_out
   // (zeroed here); leaf_pass(ts, false, m2p_done = true) must follow
   void downward(const uint8_t *flags, const fb::TargetSet *fuse_m2p = nullptr, bool out_zeroed = false,
-                bool m2l_one_cta_per_sm = false);
+                bool m2l_one_cta_per_sm = false, const fb::M2LItemTable *m2l_table = nullptr);
   void leaf_pass(const fb::TargetSet &ts, bool grads, bool m2p_done = false);
   void launch_l2p(const fb::TargetSet &ts, bool grads);
   void launch_p2p(const fb::TargetSet &ts, bool grads, bool m2p_done, cudaStream_t s, bool atomic_out);

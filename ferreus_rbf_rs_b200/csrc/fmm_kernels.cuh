@@ -283,45 +283,53 @@ __device__ __forceinline__ void tensor_axis(const double *in, double *out, const
   }
 }
 
-// M2M: one CTA per parent; M_parent += M2M[child_index] * M_child, sum-factorised over the axes
-// (bbfmm.rs:742-772; M2M[c] = (S_x (x) S_y (x) S_z)^T, chebyshev.rs:196-241)
-__global__ void __launch_bounds__(128) k_m2m(const int *parents, const int *child_ptr, const int *child_idx,
+// M2M: one CTA per parent, one WARP per child (all children in flight: the pass is a chain of dependent shared-memory
+// sweeps, latency not work — 42-59 us per level with the children taken one after the other, and the upward pass is a
+// fixed cost of every partitioned matvec); M_parent += M2M[child_index] * M_child, sum-factorised over the axes, the
+// children's contributions added in child order (bbfmm.rs:742-772; M2M[c] = (S_x (x) S_y (x) S_z)^T, chebyshev.rs:196-241)
+__global__ void __launch_bounds__(256) k_m2m(const int *parents, const int *child_ptr, const int *child_idx,
                                              const int *cell_slot, const double *child_s, int p, int dim, int P,
-                                             int nrhs, const uint8_t *flag, double *mult) {
+                                             int nrhs, const uint8_t *flag, int cpar, double *mult) {
   extern __shared__ double sm[];
   double *A = sm;              // 2*p*p
-  double *b0 = A + 2 * p * p;  // P
-  double *b1 = b0 + P;         // P
-  double *accp = b1 + P;       // P
-  const int tid = threadIdx.x, nt = blockDim.x;
+  double *buf = A + 2 * p * p;  // [cpar children][2][P]
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int parent = parents[blockIdx.x];
   if (flag && !flag[parent]) return;  // sharded upward pass: no owned descendants, the multipole stays zero
   for (int i = tid; i < 2 * p * p; i += nt) A[i] = child_s[i];
+  const int k0 = child_ptr[parent], nch = child_ptr[parent + 1] - k0;
+  const int Ps = coef_stride(P);
   for (int r = 0; r < nrhs; ++r) {
-    for (int i = tid; i < P; i += nt) accp[i] = 0.0;
-    for (int k = child_ptr[parent]; k < child_ptr[parent + 1]; ++k) {
-      const int ch = child_idx[k];
-      const int slot = cell_slot[ch];
+    double *dst = mult + ((size_t)parent * nrhs + r) * Ps;
+    for (int c0 = 0; c0 < nch; c0 += cpar) {  // cpar children at a time (all 2^dim unless p^d is too large for that)
+      const int nb = min(cpar, nch - c0);
       __syncthreads();
-      const double *src = mult + ((size_t)ch * nrhs + r) * coef_stride(P);
-      for (int i = tid; i < P; i += nt) b0[i] = src[i];
-      __syncthreads();
-      double *in = b0, *out = b1;
-      for (int d = 0; d < dim; ++d) {
-        int stride = 1;
-        for (int e = d + 1; e < dim; ++e) stride *= p;
-        const int h = (slot >> d) & 1;  // bit d of the child index = half along axis d (chebyshev.rs:183-192)
-        tensor_axis(in, out, A + h * p * p, p, P, stride, true, tid, nt);
-        __syncthreads();
-        double *t = in;
-        in = out;
-        out = t;
+      if (warp < nb) {
+        const int ch = child_idx[k0 + c0 + warp];
+        const int slot = cell_slot[ch];
+        double *in = buf + (size_t)warp * 2 * P, *out = in + P;
+        const double *src = mult + ((size_t)ch * nrhs + r) * Ps;
+        for (int i = lane; i < P; i += 32) in[i] = src[i];
+        __syncwarp();
+        for (int d = 0; d < dim; ++d) {
+          int stride = 1;
+          for (int e = d + 1; e < dim; ++e) stride *= p;
+          const int h = (slot >> d) & 1;  // bit d of the child index = half along axis d (chebyshev.rs:183-192)
+          tensor_axis(in, out, A + h * p * p, p, P, stride, true, lane, 32);
+          __syncwarp();
+          double *t = in;
+          in = out;
+          out = t;
+        }
       }
-      for (int i = tid; i < P; i += nt) accp[i] += in[i];
+      __syncthreads();
+      // the transformed child c sits in buf[c][dim & 1]
+      for (int i = tid; i < P; i += nt) {
+        double acc = 0.0;
+        for (int c = 0; c < nb; ++c) acc += buf[((size_t)c * 2 + (dim & 1)) * P + i];
+        dst[i] += acc;
+      }
     }
-    __syncthreads();
-    double *dst = mult + ((size_t)parent * nrhs + r) * coef_stride(P);
-    for (int i = tid; i < P; i += nt) dst[i] += accp[i];
   }
 }
 

@@ -393,6 +393,12 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_m2l_stream(const M2LStream
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
+// work items of one launch for one (nrhs, target restriction)
+struct M2LItemTable {
+  DBuf<unsigned char> d_items;
+  int n_items = 0, n_ctas = 0, nrhs = -1;
+};
+
 struct M2LStreamPlan {
   struct Group {
     int level, tix;
@@ -406,13 +412,11 @@ struct M2LStreamPlan {
   };
   std::vector<Group> groups;
   std::vector<Piece> pieces;
+  std::vector<int> h_tgt;  // target cell of every entry (ascending inside a group): per-rank subranges are cut from it
   DBuf<int> d_tgt, d_src;
   DBuf<double> d_pool;
-  DBuf<unsigned char> d_items;
   DBuf<int> d_counter;
-  int n_items = 0;
-  int table_nrhs = -1;
-  int n_ctas = 0;
+  M2LItemTable all;  // every entry
   int P = 0, Ps = 0, Pc = 0, KS = 0, MTU = 0, nw = 0;
   size_t smem = 0;
 };
@@ -515,6 +519,7 @@ M2LStreamPlan *m2l_stream_build(const HostTree &ht, const Operators &ops, int P,
   }
   if (plan->groups.empty()) return nullptr;
   plan->d_tgt.upload(e_tgt, stream);
+  plan->h_tgt = e_tgt;
   plan->d_src.upload(e_src, stream);
   plan->d_pool.reserve((size_t)pool_size);
   DBuf<double> d_dense;
@@ -530,25 +535,44 @@ M2LStreamPlan *m2l_stream_build(const HostTree &ht, const Operators &ops, int P,
 }
 
 // work items of one launch: (piece, entry range), pulled by one persistent CTA per SM, longest first
-static void m2l_stream_items(M2LStreamPlan &pl, int nrhs, int sms, cudaStream_t stream) {
+// level_lo / level_hi (per level, or null): only entries whose target cell id lies in [lo, hi) of its level — the cells
+// with targets of a Morton-contiguous leaf range form one such range per level, so a rank's share is a subrange of
+// every group and needs no per-entry flag test
+static void m2l_stream_items(M2LStreamPlan &pl, M2LItemTable &tab, int nrhs, int sms, const int *level_lo,
+                             const int *level_hi, cudaStream_t stream) {
   struct Item {
     M2LItemDev d;
     double cost;
   };
-  std::vector<Item> items;
+  struct Span {
+    int e0, e1;
+  };
+  std::vector<Span> spans(pl.groups.size());
   double total = 0;
-  for (auto &g : pl.groups)
-    for (int pi : g.pieces) total += (double)g.n_entries * nrhs * pl.pieces[pi].mt;
-  // an item should be long enough to amortise the operator load (~70 fragment loads per thread) and short enough to
-  // balance: at most 1/4 of a CTA's share
+  for (size_t gi = 0; gi < pl.groups.size(); ++gi) {
+    const auto &g = pl.groups[gi];
+    int e0 = 0, e1 = g.n_entries;
+    if (level_lo) {
+      const int *b = pl.h_tgt.data() + g.entry_off, *e = b + g.n_entries;
+      e0 = (int)(std::lower_bound(b, e, level_lo[g.level]) - b);
+      e1 = (int)(std::lower_bound(b, e, level_hi[g.level]) - b);
+      e1 = std::max(e1, e0);  // a level without owned cells has lo > hi
+    }
+    spans[gi] = {e0, e1};
+    for (int pi : g.pieces) total += (double)(e1 - e0) * nrhs * pl.pieces[pi].mt;
+  }
+  std::vector<Item> items;
+  // an item should be long enough to amortise the operator load (~50 fragment loads per thread) and short enough to
+  // balance the tail: at most 1/6 of a CTA's share
   const double max_cost = std::max(total / (6.0 * sms), 3.0 * 64.0);
-  for (auto &g : pl.groups)
+  for (size_t gi = 0; gi < pl.groups.size(); ++gi) {
+    const auto &g = pl.groups[gi];
     for (int pi : g.pieces) {
       const auto &pc = pl.pieces[pi];
       const double per_entry = (double)nrhs * pc.mt;
       const int chunk = std::max(1, (int)(max_cost / per_entry));
-      for (int e0 = 0; e0 < g.n_entries; e0 += chunk) {
-        const int ne = std::min(chunk, g.n_entries - e0);
+      for (int e0 = spans[gi].e0; e0 < spans[gi].e1; e0 += chunk) {
+        const int ne = std::min(chunk, spans[gi].e1 - e0);
         Item it;
         it.d.entry_off = g.entry_off + e0;
         it.d.n_entries = ne;
@@ -559,37 +583,61 @@ static void m2l_stream_items(M2LStreamPlan &pl, int nrhs, int sms, cudaStream_t 
         items.push_back(it);
       }
     }
+  }
   // longest first: the CTAs pull items from a counter as they finish
   std::stable_sort(items.begin(), items.end(), [](const Item &x, const Item &y) { return x.cost > y.cost; });
   std::vector<M2LItemDev> flat;
   for (auto &it : items) flat.push_back(it.d);
-  pl.n_items = (int)flat.size();
-  pl.n_ctas = std::max(1, std::min<int>(sms, pl.n_items));
-  pl.d_items.reserve(flat.size() * sizeof(M2LItemDev));
-  FB_CUDA(cudaMemcpyAsync(pl.d_items.p, flat.data(), flat.size() * sizeof(M2LItemDev), cudaMemcpyHostToDevice, stream));
+  tab.n_items = (int)flat.size();
+  tab.n_ctas = std::max(1, std::min<int>(sms, tab.n_items));
+  tab.d_items.reserve(flat.size() * sizeof(M2LItemDev));
+  FB_CUDA(cudaMemcpyAsync(tab.d_items.p, flat.data(), flat.size() * sizeof(M2LItemDev), cudaMemcpyHostToDevice, stream));
   pl.d_counter.reserve(1);
   FB_CUDA(cudaStreamSynchronize(stream));
-  pl.table_nrhs = nrhs;
+  tab.nrhs = nrhs;
 }
 
-void m2l_stream_launch(M2LStreamPlan *plan, int nrhs, const uint8_t *flag_or_null, const double *mult, double *loc,
-                       cudaStream_t stream) {
-  M2LStreamPlan &pl = *plan;
-  if (pl.table_nrhs != nrhs) {
-    int dev = 0, sms = 148;
-    FB_CUDA(cudaGetDevice(&dev));
-    FB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    m2l_stream_items(pl, nrhs, sms, stream);
+static int device_sms() {
+  int dev = 0, sms = 148;
+  FB_CUDA(cudaGetDevice(&dev));
+  FB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  return sms;
+}
+
+M2LItemTable *m2l_stream_table_new(M2LStreamPlan *plan, int nrhs, const int *level_lo, const int *level_hi,
+                                   cudaStream_t stream) {
+  auto *t = new M2LItemTable();
+  try {
+    m2l_stream_items(*plan, *t, nrhs, device_sms(), level_lo, level_hi, stream);
+  } catch (...) {
+    delete t;
+    throw;
   }
+  return t;
+}
+int m2l_stream_table_nrhs(const M2LItemTable *t) { return t->nrhs; }
+void m2l_stream_table_free(M2LItemTable *t) { delete t; }
+
+void m2l_stream_launch(M2LStreamPlan *plan, int nrhs, const uint8_t *flag_or_null, const M2LItemTable *table_or_null,
+                       const double *mult, double *loc, cudaStream_t stream) {
+  M2LStreamPlan &pl = *plan;
+  const M2LItemTable *tp = table_or_null;
+  if (!tp) {
+    if (pl.all.nrhs != nrhs) m2l_stream_items(pl, pl.all, nrhs, device_sms(), nullptr, nullptr, stream);
+    tp = &pl.all;
+  }
+  FB_REQUIRE(tp->nrhs == nrhs, "M2L item table built for another number of right-hand sides");
+  if (tp->n_items == 0) return;
+  const M2LItemTable &tb = *tp;
   M2LStreamArgs a{};
-  a.items = reinterpret_cast<const M2LItemDev *>(pl.d_items.p);
-  a.n_items = pl.n_items;
+  a.items = reinterpret_cast<const M2LItemDev *>(tb.d_items.p);
+  a.n_items = tb.n_items;
   a.next_item = pl.d_counter.p;
   FB_CUDA(cudaMemsetAsync(pl.d_counter.p, 0, sizeof(int), stream));
   a.e_tgt = pl.d_tgt.p;
   a.e_src = pl.d_src.p;
   a.pool = pl.d_pool.p;
-  a.flag = flag_or_null;
+  a.flag = table_or_null ? nullptr : flag_or_null;  // a restricted table is already exact
   a.mult = mult;
   a.loc = loc;
   a.P = pl.P;
@@ -601,7 +649,7 @@ void m2l_stream_launch(M2LStreamPlan *plan, int nrhs, const uint8_t *flag_or_nul
 #define FB_STREAM_LAUNCH(NWV)                                                                                     \
   do {                                                                                                            \
     FB_CUDA(cudaFuncSetAttribute(k_m2l_stream<NWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));  \
-    FB_LAUNCH((k_m2l_stream<NWV>), pl.n_ctas, ((NWV) + 1) * 32, pl.smem, stream, a);                              \
+    FB_LAUNCH((k_m2l_stream<NWV>), tb.n_ctas, ((NWV) + 1) * 32, pl.smem, stream, a);                              \
   } while (0)
   if (pl.nw == 8)
     FB_STREAM_LAUNCH(8);

@@ -102,6 +102,7 @@ struct DomainTable {  // one DDM level on the device
   const long long *q_off;    // offset of Q_top (rank x mm, row-major) in the q pool
   const long long *l_off;    // offset of the mm x mm factor in the factor pool
   const long long *s_off;    // offset of the 2 x rank x mm assembly scratch (A12, C)
+  const uint8_t *use_inverse;  // per domain: the factor slot holds the explicit inverse (indefinite Q^T A Q), or null
 };
 
 __device__ __forceinline__ double kval_rt(double r2, const KParams &kp) {
@@ -213,8 +214,8 @@ __device__ __forceinline__ void chol_dmma884(double &d0, double &d1, double a, d
 }
 // diagonal block kb (Cholesky by warp 0 in shared memory) and the panel below it (one thread per row):
 //   L[i, kb:kb+bs] = A[i, kb:kb+bs] Dk^-T
-__device__ __forceinline__ void chol_factor_panel(double *A, int n, int kb, int bs, double (*Dk)[kNB + 1], int *fail,
-                                                  int dom) {
+__device__ __forceinline__ void chol_factor_panel(double *A, int n, int kb, int bs, double (*Dk)[kNB + 1],
+                                                  uint8_t *fail, int dom) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int e = tid; e < kNB * kNB; e += 256) {
     const int r = e / kNB, c = e % kNB;
@@ -224,7 +225,7 @@ __device__ __forceinline__ void chol_factor_panel(double *A, int n, int kb, int 
   if (warp == 0) {
     for (int k = 0; k < bs; ++k) {
       double dkk = Dk[k][k];
-      if (lane == 0 && !(dkk > 0.0)) atomicExch(fail, dom + 1);
+      if (lane == 0 && !(dkk > 0.0)) fail[dom] = 1;
       dkk = sqrt(fmax(dkk, 1e-300));
       __syncwarp();
       if (lane == k) Dk[k][k] = dkk;
@@ -323,7 +324,7 @@ __device__ __forceinline__ void chol_update_column(double *A, int n, int kb, int
   double(*Pi)[kPS] = reinterpret_cast<double(*)[kPS]>(sm + kNB * (kNB + 1) + kNB * kPS);  /* 8 warps x i panel tile */
 
 // blocked right-looking Cholesky, one CTA per domain, lower triangle of a row-major mm x mm matrix in place
-__global__ void __launch_bounds__(256) k_cholesky(DomainTable t, double *lpool, int *fail) {
+__global__ void __launch_bounds__(256) k_cholesky(DomainTable t, double *lpool, uint8_t *fail) {
   const int d = blockIdx.x;
   const int n = (int)(t.pt_ptr[d + 1] - t.pt_ptr[d]) - t.rank[d];
   double *A = lpool + t.l_off[d];
@@ -340,7 +341,7 @@ __global__ void __launch_bounds__(256) k_cholesky(DomainTable t, double *lpool, 
 
 // the same factorisation of ONE large matrix (the coarse domain) spread over the GPU: per block column one small
 // launch for the diagonal block + panel and one grid for the trailing update
-__global__ void __launch_bounds__(256) k_chol_big_panel(double *A, int n, int kb, int *fail) {
+__global__ void __launch_bounds__(256) k_chol_big_panel(double *A, int n, int kb, uint8_t *fail) {
   extern __shared__ double sm[];
   chol_factor_panel(A, n, kb, min(kNB, n - kb), reinterpret_cast<double(*)[kNB + 1]>(sm), fail, 0);
 }
@@ -382,8 +383,23 @@ __global__ void __launch_bounds__(256) k_dom_solve(DomainTable t, const double *
     x[j] = v;
   }
   __syncthreads();
+  const bool inverse = t.use_inverse != nullptr && t.use_inverse[d] != 0;
+  if (inverse) {
+    // Cholesky failed for this domain (Q^T A Q indefinite; domain.rs:63-68 falls back to a pivoted factorisation): the
+    // slot holds the explicit inverse, gamma = Inv rhs.  d_rest (dv[rk..n)) is dead once rhs is formed: it takes gamma
+    for (int r = warp; r < mm; r += 8) {
+      const double *row = L + (size_t)r * mm;
+      double sacc = 0.0;
+      for (int c = lane; c < mm; c += 32) sacc += row[c] * x[c];
+      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, o);
+      if (lane == 0) dv[rk + r] = sacc;
+    }
+    __syncthreads();
+    for (int j = tid; j < mm; j += 256) x[j] = dv[rk + j];
+    __syncthreads();
+  }
   // forward substitution L y = rhs
-  for (int kb = 0; kb < mm; kb += 32) {
+  for (int kb = 0; !inverse && kb < mm; kb += 32) {
     const int bs = min(32, mm - kb);
     for (int r = warp; r < bs; r += 8) {
       const double *row = L + (size_t)(kb + r) * mm;
@@ -405,7 +421,7 @@ __global__ void __launch_bounds__(256) k_dom_solve(DomainTable t, const double *
     __syncthreads();
   }
   // backward substitution L^T gamma = y
-  for (int kb = ((mm - 1) / 32) * 32; kb >= 0; kb -= 32) {
+  for (int kb = ((mm - 1) / 32) * 32; !inverse && kb >= 0; kb -= 32) {
     const int bs = min(32, mm - kb);
     double s = 0.0;
     if (lane < bs)
@@ -474,6 +490,8 @@ struct LevelDev {
   DBuf<int> pt_idx, rank;
   DBuf<uint8_t> pt_mask;
   DBuf<double> qpool, lpool;
+  DBuf<uint8_t> use_inverse;  // all zero unless a domain needed the indefinite fallback
+  int n_fallback = 0;
   DBuf<unsigned long long> level_idx;  // point_indices of the level (matvec_partial target set)
   size_t n_level_pts = 0;
   TargetBuffers tb;
@@ -531,6 +549,44 @@ double progress_from_rel(double current_res, double start_res, double target_res
   return (std::log10(start_res) - std::log10(current_res)) / (std::log10(start_res) - std::log10(target_res));
 }
 
+// inverse of a dense n x n matrix (row-major) by Gauss-Jordan elimination with partial pivoting; false when singular
+static bool invert_pivoted(const std::vector<double> &a_in, int n, std::vector<double> &inv) {
+  std::vector<double> a(a_in);
+  inv.assign((size_t)n * n, 0.0);
+  for (int i = 0; i < n; ++i) inv[(size_t)i * n + i] = 1.0;
+  double amax = 0.0;
+  for (double v : a) amax = std::max(amax, std::fabs(v));
+  for (int k = 0; k < n; ++k) {
+    int piv = k;
+    for (int i = k + 1; i < n; ++i)
+      if (std::fabs(a[(size_t)i * n + k]) > std::fabs(a[(size_t)piv * n + k])) piv = i;
+    if (!(std::fabs(a[(size_t)piv * n + k]) > 1e-14 * amax)) return false;
+    if (piv != k)
+      for (int c = 0; c < n; ++c) {
+        std::swap(a[(size_t)k * n + c], a[(size_t)piv * n + c]);
+        std::swap(inv[(size_t)k * n + c], inv[(size_t)piv * n + c]);
+      }
+    const double d = 1.0 / a[(size_t)k * n + k];
+    for (int c = 0; c < n; ++c) {
+      a[(size_t)k * n + c] *= d;
+      inv[(size_t)k * n + c] *= d;
+    }
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i) {
+      if (i == k) continue;
+      const double f = a[(size_t)i * n + k];
+      if (f == 0.0) continue;
+      double *ai = &a[(size_t)i * n], *ii = &inv[(size_t)i * n];
+      const double *ak = &a[(size_t)k * n], *ik = &inv[(size_t)k * n];
+      for (int c = 0; c < n; ++c) {
+        ai[c] -= f * ak[c];
+        ii[c] -= f * ik[c];
+      }
+    }
+  }
+  return true;
+}
+
 struct DeviceSolver {
   fr_model &M;
   fb_tree *tree;
@@ -539,7 +595,7 @@ struct DeviceSolver {
   DBuf<double> px, py, pz, P, Qp, proj, scalar;
   DBuf<unsigned long long> umax;
   std::vector<std::unique_ptr<LevelDev>> levels;
-  DBuf<int> fail;
+  DBuf<uint8_t> fail;  // per domain: Cholesky met a non-positive pivot
   DBuf<double> scratch;
   uint64_t matvecs = 0;
 
@@ -561,7 +617,59 @@ struct DeviceSolver {
     pz.upload(z, stream);
     scalar.reserve(16);
     umax.reserve(1);
-    fail.reserve(1);
+  }
+
+  // ---- Cholesky of every slot of a level's factor pool; domains whose Q^T A Q is not positive definite take the
+  //      reference's fallback (domain.rs:63-68: faer's Bunch-Kaufman LBL^T, linalg.rs:514-616): the matrix is assembled
+  //      again, inverted on the host with a pivoted elimination and the explicit inverse stored in the slot
+  //      (DomainTable::use_inverse); both solve the same symmetric indefinite system.
+  template <class Reassemble>
+  void factorise_pool(LevelDev &lv, const std::vector<int> &mms, const std::vector<long long> &l_off,
+                      Reassemble &&reassemble, cudaStream_t stream) {
+    const size_t nd = mms.size();
+    fail.reserve(nd);
+    lv.use_inverse.reserve(nd);
+    FB_CUDA(cudaMemsetAsync(fail.p, 0, nd, stream));
+    FB_CUDA(cudaMemsetAsync(lv.use_inverse.p, 0, nd, stream));
+    lv.tab.use_inverse = lv.use_inverse.p;
+    const size_t smem = sizeof(double) * ((size_t)(kNB + 1) * kNB + (size_t)kPS * kNB * (1 + 8));
+    FB_CUDA(cudaFuncSetAttribute(k_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (nd == 1 && lv.max_mm >= 512) {  // one big matrix: spread every block column over the GPU
+      const int nn = (int)lv.max_mm;
+      FB_CUDA(cudaFuncSetAttribute(k_chol_big_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      FB_CUDA(cudaFuncSetAttribute(k_chol_big_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      for (int kb = 0; kb < nn; kb += kNB) {
+        FB_LAUNCH(k_chol_big_panel, 1, 256, smem, stream, lv.lpool.p, nn, kb, fail.p);
+        const int ntile = (nn - (kb + kNB) + kNB - 1) / kNB;
+        if (ntile > 0) {
+          dim3 grid((unsigned)ntile, (unsigned)((ntile + 7) / 8));
+          FB_LAUNCH(k_chol_big_update, grid, 256, smem, stream, lv.lpool.p, nn, kb);
+        }
+      }
+    } else {
+      FB_LAUNCH(k_cholesky, (unsigned)nd, 256, smem, stream, lv.tab, lv.lpool.p, fail.p);
+    }
+    std::vector<uint8_t> h_fail(nd, 0);
+    FB_CUDA(cudaMemcpyAsync(h_fail.data(), fail.p, nd, cudaMemcpyDeviceToHost, stream));
+    FB_CUDA(cudaStreamSynchronize(stream));
+    std::vector<double> a, inv;
+    for (size_t d = 0; d < nd; ++d) {
+      if (!h_fail[d]) continue;
+      const int mm = mms[d];
+      reassemble(d);
+      a.resize((size_t)mm * mm);
+      FB_CUDA(cudaMemcpyAsync(a.data(), lv.lpool.p + l_off[d], a.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+      FB_CUDA(cudaStreamSynchronize(stream));
+      for (int i = 0; i < mm; ++i)  // the slot holds the lower triangle
+        for (int j = i + 1; j < mm; ++j) a[(size_t)i * mm + j] = a[(size_t)j * mm + i];
+      if (!invert_pivoted(a, mm, inv))
+        throw Error(FB_ERR_INVALID_ARGUMENT, "subdomain matrix Q^T A Q is singular (domain " + std::to_string(d) + ")");
+      FB_CUDA(cudaMemcpyAsync(lv.lpool.p + l_off[d], inv.data(), inv.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+      const uint8_t one = 1;
+      FB_CUDA(cudaMemcpyAsync(lv.use_inverse.p + d, &one, 1, cudaMemcpyHostToDevice, stream));
+      FB_CUDA(cudaStreamSynchronize(stream));
+      ++lv.n_fallback;
+    }
   }
 
   // ---- factorise one level on the device (domain.rs:322-382)
@@ -638,35 +746,26 @@ struct DeviceSolver {
                 lv->qpool.p, scratch.p, lv->lpool.p);
     }
     sublap("prep + assemble");
-    FB_CUDA(cudaMemsetAsync(fail.p, 0, sizeof(int), stream));
-    const size_t smem = sizeof(double) * ((size_t)(kNB + 1) * kNB + (size_t)kPS * kNB * (1 + 8));
-    FB_CUDA(cudaFuncSetAttribute(k_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const auto t_ch = std::chrono::steady_clock::now();
-    if (nd == 1 && lv->max_mm >= 512) {  // one big matrix: spread every block column over the GPU
-      const int nn = lv->max_mm;
-      FB_CUDA(cudaFuncSetAttribute(k_chol_big_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      FB_CUDA(cudaFuncSetAttribute(k_chol_big_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      for (int kb = 0; kb < nn; kb += kNB) {
-        FB_LAUNCH(k_chol_big_panel, 1, 256, smem, stream, lv->lpool.p, nn, kb, fail.p);
-        const int ntile = (nn - (kb + kNB) + kNB - 1) / kNB;
-        if (ntile > 0) {
-          dim3 grid((unsigned)ntile, (unsigned)((ntile + 7) / 8));
-          FB_LAUNCH(k_chol_big_update, grid, 256, smem, stream, lv->lpool.p, nn, kb);
-        }
-      }
-    } else {
-      FB_LAUNCH(k_cholesky, (unsigned)nd, 256, smem, stream, t, lv->lpool.p, fail.p);
-    }
-    int h_fail = 0;
-    FB_CUDA(cudaMemcpyAsync(&h_fail, fail.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    FB_CUDA(cudaStreamSynchronize(stream));
+    auto reassemble = [&](size_t d) {  // one domain's Q^T A Q again (its slot was overwritten by the failed attempt)
+      DomainTable tt = t;
+      tt.pt_ptr += d;
+      tt.rank += d;
+      tt.q_off += d;
+      tt.l_off += d;
+      tt.s_off += d;
+      tt.n_domains = 1;
+      FB_LAUNCH(k_dom_prep, 1, 128, 0, stream, tt, px.p, py.p, pz.p, kp, M.st.nugget, lv->qpool.p, scratch.p);
+      FB_LAUNCH(k_dom_assemble, dim3(tiles, tiles, 1), 256, 0, stream, tt, px.p, py.p, pz.p, kp, M.st.nugget,
+                lv->qpool.p, scratch.p, lv->lpool.p);
+    };
+    std::vector<int> mms(nd);
+    for (size_t d = 0; d < nd; ++d) mms[d] = (int)(lh.domains[d].idx.size() - lh.domains[d].rank);
+    factorise_pool(*lv, mms, l_off, reassemble, stream);
     if (std::getenv("FB_TIMING"))
-      fprintf(stderr, "[fr_fit]   cholesky of %zu domains (+ queued assembly) %8.3f s\n", nd,
-              std::chrono::duration<double>(std::chrono::steady_clock::now() - t_ch).count());
-    if (h_fail)
-      throw Error(FB_ERR_INVALID_ARGUMENT,
-                  "subdomain matrix Q^T A Q is not positive definite (domain " + std::to_string(h_fail - 1) +
-                      "); the reference's Bunch-Kaufman fallback (domain.rs:63-68) is not implemented");
+      fprintf(stderr, "[fr_fit]   cholesky of %zu domains (+ queued assembly) %8.3f s%s\n", nd,
+              std::chrono::duration<double>(std::chrono::steady_clock::now() - t_ch).count(),
+              lv->n_fallback ? " (indefinite fallback used)" : "");
     if (coarse && !lh.domains.empty() && lh.domains[0].solve_for_poly) {
       const DomainHost &dh = lh.domains[0];
       const int nn = (int)dh.idx.size();
