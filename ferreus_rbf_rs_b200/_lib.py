@@ -166,6 +166,8 @@ SOLVER_SIGNATURES = {
     "fr_evaluate_at_source": (C.c_int, [C.c_void_p, C.c_int, _dp]),
     "fr_build_evaluator": (C.c_int, [C.c_void_p, _dp]),
     "fr_evaluate_targets": (C.c_int, [C.c_void_p, _dp, _sz, _pd, _pd, _dp, _dp]),
+    "fr_dense_spd_solve": (C.c_int, [_dp, C.c_int, _dp, C.c_int, _dp, _i32p]),
+    "fr_evaluate_monomials": (C.c_int, [_dp, _sz, C.c_int, C.c_int, _dp, _dp, _dp, _i32p]),
     "fr_ddm_level": (C.c_int, [C.c_void_p, C.c_int, _u64p, _u64p, _u64p, _u64p, _u64p, _u8p]),
 }
 

@@ -355,12 +355,18 @@ __global__ void __launch_bounds__(256) k_chol_big_update(double *A, int n, int k
   chol_update_column(A, n, kb, bs, jb, Pj, Pi, ib, n);  // at most one i tile per warp
 }
 
-// Domain::solve (domain.rs:393-467) + scatter of schwarz.rs:94-155, one CTA per domain.
+// Domain::solve (domain.rs:393-467) + scatter of schwarz.rs:94-155, one CTA of kSolveThreads threads per domain.
 //   mode 0: fine level — write internal points only;  mode 1: coarse — write all points (+ polynomial tail)
-__global__ void __launch_bounds__(256) k_dom_solve(DomainTable t, const double *qpool, const double *lpool,
-                                                   const double *res, double *out, int mode, int add_poly,
-                                                   const double *a_special, const double *sp_inv, size_t n_total,
-                                                   int basis) {
+// The two substitutions are chains of 2 x mm / 32 dependent block steps; a step is a row-block x vector product (read
+// straight from HBM) and a 32 x 32 triangular solve.  With 8 warps a step took ~30 us (four rows per warp, one after the
+// other) and a 978-point domain 2 ms — 6.4 ms for the 2048-domain level against 1.2 ms of factor streaming; 32 warps
+// give every row of the block its own warp and four independent partial sums per lane.
+constexpr int kSolveThreads = 1024;
+constexpr int kSolveWarps = kSolveThreads / 32;
+__global__ void __launch_bounds__(kSolveThreads) k_dom_solve(DomainTable t, const double *qpool, const double *lpool,
+                                                             const double *res, double *out, int mode, int add_poly,
+                                                             const double *a_special, const double *sp_inv,
+                                                             size_t n_total, int basis) {
   const int d = blockIdx.x;
   const int rk = t.rank[d];
   const long long p0 = t.pt_ptr[d];
@@ -372,12 +378,13 @@ __global__ void __launch_bounds__(256) k_dom_solve(DomainTable t, const double *
   extern __shared__ double sm[];
   double *dv = sm;        // n gathered residuals
   double *x = dv + n;     // mm rhs / solution
-  double *red = x + mm;   // 8 x 32 partial sums
-  double *top = red + 256;  // rk
+  double *red = x + mm;   // kSolveWarps x 32 partial sums
+  double *top = red + kSolveWarps * 32;  // rk
+  __shared__ double Dg[32][33];          // the diagonal block of the current step (lower triangle)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < n; i += 256) dv[i] = res[idx[i]];
+  for (int i = tid; i < n; i += kSolveThreads) dv[i] = res[idx[i]];
   __syncthreads();
-  for (int j = tid; j < mm; j += 256) {  // rhs = Q^T d_special + d_rest
+  for (int j = tid; j < mm; j += kSolveThreads) {  // rhs = Q^T d_special + d_rest
     double v = dv[rk + j];
     for (int a = 0; a < rk; ++a) v += Q[(size_t)a * mm + j] * dv[a];
     x[j] = v;
@@ -387,7 +394,7 @@ __global__ void __launch_bounds__(256) k_dom_solve(DomainTable t, const double *
   if (inverse) {
     // Cholesky failed for this domain (Q^T A Q indefinite; domain.rs:63-68 falls back to a pivoted factorisation): the
     // slot holds the explicit inverse, gamma = Inv rhs.  d_rest (dv[rk..n)) is dead once rhs is formed: it takes gamma
-    for (int r = warp; r < mm; r += 8) {
+    for (int r = warp; r < mm; r += kSolveWarps) {
       const double *row = L + (size_t)r * mm;
       double sacc = 0.0;
       for (int c = lane; c < mm; c += 32) sacc += row[c] * x[c];
@@ -395,26 +402,35 @@ __global__ void __launch_bounds__(256) k_dom_solve(DomainTable t, const double *
       if (lane == 0) dv[rk + r] = sacc;
     }
     __syncthreads();
-    for (int j = tid; j < mm; j += 256) x[j] = dv[rk + j];
+    for (int j = tid; j < mm; j += kSolveThreads) x[j] = dv[rk + j];
     __syncthreads();
   }
-  // forward substitution L y = rhs
+  // forward substitution L y = rhs: row r of the block belongs to warp r
   for (int kb = 0; !inverse && kb < mm; kb += 32) {
     const int bs = min(32, mm - kb);
-    for (int r = warp; r < bs; r += 8) {
-      const double *row = L + (size_t)(kb + r) * mm;
-      double s = 0.0;
-      for (int c = lane; c < kb; c += 32) s += row[c] * x[c];
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-      if (lane == 0) red[r] = s;
+    if (warp < bs) {
+      const double *row = L + (size_t)(kb + warp) * mm;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int c = lane;
+      for (; c + 96 < kb; c += 128) {
+        s0 += row[c] * x[c];
+        s1 += row[c + 32] * x[c + 32];
+        s2 += row[c + 64] * x[c + 64];
+        s3 += row[c + 96] * x[c + 96];
+      }
+      for (; c < kb; c += 32) s0 += row[c] * x[c];
+      Dg[warp][lane] = lane <= warp ? row[kb + lane] : 0.0;  // the block's own triangle, staged for the serial part
+      double sacc = (s0 + s1) + (s2 + s3);
+      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, o);
+      if (lane == 0) red[warp] = sacc;
     }
     __syncthreads();
     if (warp == 0) {
       double v = lane < bs ? x[kb + lane] - red[lane] : 0.0;
       for (int k = 0; k < bs; ++k) {
-        const double piv = __shfl_sync(0xffffffffu, v, k) / L[(size_t)(kb + k) * mm + kb + k];
+        const double piv = __shfl_sync(0xffffffffu, v, k) / Dg[k][k];
         if (lane == k) v = piv;
-        if (lane > k && lane < bs) v -= L[(size_t)(kb + lane) * mm + kb + k] * piv;
+        if (lane > k && lane < bs) v -= Dg[lane][k] * piv;
       }
       if (lane < bs) x[kb + lane] = v;
     }
@@ -423,51 +439,60 @@ __global__ void __launch_bounds__(256) k_dom_solve(DomainTable t, const double *
   // backward substitution L^T gamma = y
   for (int kb = ((mm - 1) / 32) * 32; !inverse && kb >= 0; kb -= 32) {
     const int bs = min(32, mm - kb);
-    double s = 0.0;
-    if (lane < bs)
-      for (int j = kb + bs + warp; j < mm; j += 8) s += L[(size_t)j * mm + kb + lane] * x[j];
-    red[warp * 32 + lane] = s;
+    double sacc = 0.0;
+    if (lane < bs) {
+      double s0 = 0.0, s1 = 0.0;
+      int j = kb + bs + warp;
+      for (; j + kSolveWarps < mm; j += 2 * kSolveWarps) {
+        s0 += L[(size_t)j * mm + kb + lane] * x[j];
+        s1 += L[(size_t)(j + kSolveWarps) * mm + kb + lane] * x[j + kSolveWarps];
+      }
+      if (j < mm) s0 += L[(size_t)j * mm + kb + lane] * x[j];
+      sacc = s0 + s1;
+    }
+    red[warp * 32 + lane] = sacc;
+    if (warp < bs) Dg[warp][lane] = lane <= warp ? L[(size_t)(kb + warp) * mm + kb + lane] : 0.0;
     __syncthreads();
     if (warp == 0) {
       double acc = 0.0;
-      for (int w = 0; w < 8; ++w) acc += red[w * 32 + lane];
+      for (int w = 0; w < kSolveWarps; ++w) acc += red[w * 32 + lane];
       double v = lane < bs ? x[kb + lane] - acc : 0.0;
       for (int k = bs - 1; k >= 0; --k) {
-        const double piv = __shfl_sync(0xffffffffu, v, k) / L[(size_t)(kb + k) * mm + kb + k];
+        const double piv = __shfl_sync(0xffffffffu, v, k) / Dg[k][k];
         if (lane == k) v = piv;
-        if (lane < k) v -= L[(size_t)(kb + k) * mm + kb + lane] * piv;
+        if (lane < k) v -= Dg[k][lane] * piv;
       }
       if (lane < bs) x[kb + lane] = v;
     }
     __syncthreads();
   }
   // lambda_top = Q gamma
-  for (int a = warp; a < rk; a += 8) {
-    double s = 0.0;
-    for (int j = lane; j < mm; j += 32) s += Q[(size_t)a * mm + j] * x[j];
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if (lane == 0) top[a] = s;
+  for (int a = warp; a < rk; a += kSolveWarps) {
+    double sacc = 0.0;
+    for (int j = lane; j < mm; j += 32) sacc += Q[(size_t)a * mm + j] * x[j];
+    for (int o = 16; o > 0; o >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, o);
+    if (lane == 0) top[a] = sacc;
   }
   __syncthreads();
-  for (int i = tid; i < n; i += 256) {
+  for (int i = tid; i < n; i += kSolveThreads) {
     const double lam = i < rk ? top[i] : x[i - rk];
     if (mode == 1 || mask[i]) out[idx[i]] = lam;
   }
   if (mode == 1 && add_poly && rk > 0 && a_special) {
     // r = d_special - A_special lambda;  poly = sp_mono^-1 r  (domain.rs:446-463)
     __syncthreads();
-    for (int a = warp; a < rk; a += 8) {
+    for (int a = warp; a < rk; a += kSolveWarps) {
       const double *row = a_special + (size_t)a * n;
-      double s = 0.0;
-      for (int i = lane; i < n; i += 32) s += row[i] * (i < rk ? top[i] : x[i - rk]);
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-      if (lane == 0) red[a] = dv[a] - s;
+      double sacc = 0.0;
+      for (int i = lane; i < n; i += 32) sacc += row[i] * (i < rk ? top[i] : x[i - rk]);
+      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, o);
+      if (lane == 0) red[a] = dv[a] - sacc;
     }
     __syncthreads();
     if (tid < rk) {
-      double s = 0.0;
-      for (int b = 0; b < rk; ++b) s += sp_inv[tid * rk + b] * red[b];
-      out[n_total - rk + tid] = s;  // schwarz.rs:147-152: tail rows
+      double sacc = 0.0;
+      for (int b = 0; b < rk; ++b) sacc += sp_inv[tid * rk + b] * red[b];
+      out[n_total - rk + tid] = sacc;  // schwarz.rs:147-152: tail rows
     }
   }
 }
@@ -788,9 +813,15 @@ struct DeviceSolver {
   }
 
   void solve_level(const LevelDev &lv, const double *res, double *out, int mode, int add_poly, cudaStream_t stream) {
-    const size_t smem = sizeof(double) * (lv.max_n + lv.max_mm + 256 + 32);
+    const size_t smem = sizeof(double) * (lv.max_n + lv.max_mm + kSolveWarps * 32 + 32);
+    // the gathered residual and the solution of a domain live in shared memory (227 KB per CTA on sm_100a)
+    if (smem > 227 * 1024)
+      throw Error(FB_ERR_INVALID_ARGUMENT,
+                  "a subdomain of " + std::to_string(lv.max_n) + " points exceeds the shared-memory budget of the batched "
+                  "subdomain solve (about 14300 points per domain): lower naive_solve_threshold / "
+                  "DDMParams.coarse_threshold / DDMParams.leaf_threshold below that");
     FB_CUDA(cudaFuncSetAttribute(k_dom_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
-    FB_LAUNCH(k_dom_solve, (unsigned)lv.n_domains, 256, smem, stream, lv.tab, lv.qpool.p, lv.lpool.p, res, out, mode,
+    FB_LAUNCH(k_dom_solve, (unsigned)lv.n_domains, kSolveThreads, smem, stream, lv.tab, lv.qpool.p, lv.lpool.p, res, out, mode,
               add_poly, lv.solve_for_poly ? lv.a_special.p : nullptr, lv.solve_for_poly ? lv.sp_inv.p : nullptr, nt,
               (int)m);
   }
@@ -1638,6 +1669,89 @@ int fr_evaluate_targets(fr_model *m, const double *targets, size_t n_targets, pt
     FB_REQUIRE(m->evaluator != nullptr, "build_evaluator must be called before evaluate_targets");
     m->eval_tree(m->evaluator.get(), targets, n_targets, t_rs, t_cs, true, false, out_vals, out_grads_or_null);
   });
+}
+
+// x = A^-1 b for a dense symmetric matrix through the subdomain machinery (k_cholesky / k_chol_big_* and k_dom_solve on a
+// one-domain level without special points; indefinite matrices take the fallback of factorise_pool): the entry point of
+// the reference's reproducible known-answer tests linalg.rs:638-764 (make_spd) against the device factorisation.
+int fr_dense_spd_solve(const double *a, int n, const double *b, int nrhs, double *x, int *used_fallback) {
+  return fr_guarded([&] {
+    FB_REQUIRE(a && b && x && n > 0 && nrhs > 0, "fr_dense_spd_solve: bad arguments");
+    fr_model dummy;
+    DeviceSolver S(dummy, nullptr);
+    cudaStream_t stream = nullptr;
+    FB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    S.s = stream;
+    S.n = (size_t)n;
+    S.m = 0;
+    S.nt = (size_t)n;
+    try {
+      LevelDev lv;
+      std::vector<long long> pt_ptr{0, n}, zero{0};
+      std::vector<int> idx(n), rank{0};
+      std::vector<uint8_t> mask(n, 1);
+      for (int i = 0; i < n; ++i) idx[i] = i;
+      lv.n_domains = 1;
+      lv.max_n = lv.max_mm = (size_t)n;
+      lv.pt_ptr.upload(pt_ptr, stream);
+      lv.q_off.upload(zero, stream);
+      lv.l_off.upload(zero, stream);
+      lv.s_off.upload(zero, stream);
+      lv.rank.upload(rank, stream);
+      lv.pt_idx.upload(idx, stream);
+      lv.pt_mask.upload(mask, stream);
+      lv.qpool.reserve(1);
+      lv.lpool.reserve((size_t)n * n);
+      DomainTable &t = lv.tab;
+      t.n_domains = 1;
+      t.pt_ptr = lv.pt_ptr.p;
+      t.pt_idx = lv.pt_idx.p;
+      t.pt_mask = lv.pt_mask.p;
+      t.rank = lv.rank.p;
+      t.q_off = lv.q_off.p;
+      t.l_off = lv.l_off.p;
+      t.s_off = lv.s_off.p;
+      auto upload_a = [&](size_t) {
+        FB_CUDA(cudaMemcpyAsync(lv.lpool.p, a, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, stream));
+      };
+      upload_a(0);
+      S.factorise_pool(lv, std::vector<int>{n}, std::vector<long long>{0}, upload_a, stream);
+      if (used_fallback) *used_fallback = lv.n_fallback;
+      DBuf<double> db, dx;
+      db.reserve((size_t)n);
+      dx.reserve((size_t)n);
+      std::vector<double> col(n);
+      for (int r = 0; r < nrhs; ++r) {
+        for (int i = 0; i < n; ++i) col[i] = b[(size_t)i * nrhs + r];
+        FB_CUDA(cudaMemcpyAsync(db.p, col.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        S.solve_level(lv, db.p, dx.p, 1, 0, stream);
+        FB_CUDA(cudaMemcpyAsync(col.data(), dx.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        FB_CUDA(cudaStreamSynchronize(stream));
+        for (int i = 0; i < n; ++i) x[(size_t)i * nrhs + r] = col[i];
+      }
+    } catch (...) {
+      cudaStreamDestroy(stream);
+      throw;
+    }
+    cudaStreamDestroy(stream);
+  });
+}
+
+// monomial basis of `n` points (polynomials.rs:15-62), host only: degree -1 .. 2, columns [1, x, y, z, x^2, xy, xz, y^2,
+// yz, z^2]; out is n x basis row-major, basis = C(dim + degree, degree) is returned through basis_out
+int fr_evaluate_monomials(const double *points, size_t n, int dim, int degree, const double *translation,
+                          const double *scale, double *out, int *basis_out) {
+  if (!points || dim < 1 || dim > 3 || degree < -1 || degree > 2) return FB_ERR_INVALID_ARGUMENT;
+  int basis = 0;
+  if (degree == 0) basis = 1;
+  if (degree == 1) basis = 1 + dim;
+  if (degree == 2) basis = (dim + 1) * (dim + 2) / 2;
+  if (basis_out) *basis_out = basis;
+  if (!out || basis == 0) return FB_OK;
+  std::vector<double> tr(dim, 0.0), sc(dim, 1.0);
+  evaluate_monomials(points, nullptr, n, dim, degree, basis, translation ? translation : tr.data(),
+                     scale ? scale : sc.data(), out);
+  return FB_OK;
 }
 
 int fr_ddm_level(const fr_model *m, int level, uint64_t *n_domains, uint64_t *n_level_points, uint64_t *level_points,

@@ -141,6 +141,16 @@ int fr_evaluate_targets(fr_model *m, const double *targets, size_t n_targets, pt
 int fr_ddm_level(const fr_model *m, int level, uint64_t *n_domains, uint64_t *n_level_points,
                  uint64_t *level_points, uint64_t *dom_ptr, uint64_t *dom_idx, uint8_t *dom_internal);
 
+/* ---- entry points of the reference's reproducible known-answer tests --------------------------------------------
+ * fr_dense_spd_solve: x = A^-1 b for a dense symmetric n x n matrix (row-major) through the batched subdomain kernels
+ * (blocked Cholesky with the DMMA trailing update, forward / backward substitution; an indefinite matrix takes the
+ * fallback of domain.rs:63-68) -- linalg.rs:638-764 (make_spd) runs against it.  b, x: n x nrhs row-major.
+ * fr_evaluate_monomials: polynomials.rs:15-62 / its tests :163-239 (column order [1, x, y, z, x^2, xy, xz, y^2, yz, z^2]);
+ * host only, translation / scale may be NULL (0 / 1).                                                               */
+int fr_dense_spd_solve(const double *a, int n, const double *b, int nrhs, double *x, int *used_fallback_or_null);
+int fr_evaluate_monomials(const double *points, size_t n, int dim, int degree, const double *translation_or_null,
+                          const double *scale_or_null, double *out, int *basis_out);
+
 #ifdef __cplusplus
 }
 #endif

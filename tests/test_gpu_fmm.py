@@ -65,6 +65,8 @@ MATVEC_CASES = [
     (3000, 3, "clustered", 5, 5, 2, 8, True, True, 30),
     (3000, 3, "clustered", 8, 5, 0, 1, True, True, 30),
     (3000, 3, "clustered", 9, 5, 2, 5, True, True, 30),
+    (3000, 3, "clustered", 4, 5, 2, 2, True, True, 30),    # Spheroidal5 (pw == 2)
+    (3000, 2, "uniform", 6, 6, 1, 1, True, True, 30),      # Spheroidal9, SVD compression
     (1500, 3, "uniform", 2, 10, 2, 1, True, True, 60),     # P = 1000: M2L tile of 16 columns
     (1200, 3, "uniform", 2, 12, 0, 1, True, True, 80),     # P = 1728 uncompressed: M2L tile of 8 columns
 ]
@@ -520,3 +522,27 @@ def test_nccl_partition_single_rank_matches_resident_matvec():
     b = np.zeros(6, dtype=np.uint64)
     assert _lib.lib().fb_partition_by_work(_lib.dptr(work), work.size, 5, b.ctypes.data_as(C.POINTER(C.c_uint64))) == 0
     assert np.array_equal(b.astype(np.int64), sharding.partition_by_work(work, 5))
+
+
+@pytest.mark.parametrize("kernel", [4, 5, 6, 8, 9])
+def test_gradients_remaining_kernels_match_oracle(kernel):
+    """values + gradients at separate targets for the kernels test_targets_and_gradients_match_oracle leaves out:
+    Spheroidal5 / 7 / 9 and the 1 / r^2, 1 / r^4 kernels (rbf_kernels.rs:245-317, non_rbf_kernels.rs:20-163)."""
+    n, m = 3000, 800
+    pts = H.make_points(n, 3, "clustered", seed=121)
+    rng = np.random.default_rng(122)
+    # singular kernels: keep the targets a cell away from the sources so the comparison is not dominated by 1 / r^5
+    targets = np.clip(pts[rng.integers(0, n, m)] + 0.02 * rng.standard_normal((m, 3)), pts.min(axis=0), pts.max(axis=0))
+    w = rng.random((n, 2)) - 0.5
+    ext = list(np.minimum(pts.min(0), targets.min(0))) + list(np.maximum(pts.max(0), targets.max(0)))
+    ot = H.oracle_tree(pts, 5, kernel, True, False, 30, 2, 1e-5, extents=ext)
+    pt = H.product_tree(pts, 5, kernel, True, False, 30, 2, 1e-5, extents=np.array(ext))
+    ot.set_weights(w)
+    pt.set_weights(w)
+    rv, rg = ot.evaluate(w, targets, with_gradients=True)
+    gv, gg = pt.evaluate_with_gradients(w, targets)
+    assert H.rel_l2(gv, rv) <= MATVEC_TOL
+    assert H.rel_l2(gg, rg) <= 1e-9
+    # row-wise as well: the singular kernels have a few huge rows that would hide the others in a norm
+    scale = np.abs(rg) + np.median(np.abs(rg))
+    assert (np.abs(np.asarray(gg) - rg) / scale).max() <= 1e-8

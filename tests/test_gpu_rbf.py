@@ -262,3 +262,92 @@ def test_save_and_load_model_round_trip(tmp_path, trend):
     json.dump(doc, open(path, "w"))
     with pytest.raises(ValueError):
         fb.RBFInterpolator.load_model(path)
+
+
+@pytest.mark.parametrize("kernel,dim,n", [(0, 3, 2400), (1, 2, 2400)])
+def test_absolute_tolerance_fit_matches_oracle(kernel, dim, n):
+    """FittingAccuracyType.Absolute (iterative_solvers.rs:57, 137-163): beta and the restart test use the max-norm of the
+    residual, the in-loop test the 2-norm estimate |g[j + 1]| un-normalised.  Same stopping iteration as the oracle
+    at a loose tolerance (the mixed norms decide where it stops), same interpolant at a tight one."""
+    import ferreus_rbf_rs_b200 as fb
+    from oracle import rbf as orbf
+    ic = fb.interpolant_config
+    pts = H.make_points(n, dim, "uniform", seed=131)
+    vals = 50.0 * _values(pts)          # |values| well above 1: absolute and relative tolerances differ by that factor
+    for tol, interp_tol in ((1e-3, 1e-5), (1e-9, INTERP_TOL)):
+        st = ic.InterpolantSettings(ic.RBFKernelType(kernel),
+                                    fitting_accuracy=ic.FittingAccuracy(tol, ic.FittingAccuracyType.Absolute))
+        model = fb.RBFInterpolator(pts, vals, st, params=_params(kernel))
+        s = orbf.InterpolantSettings(kernel, tolerance=tol, tolerance_type=orbf.ABSOLUTE)
+        p = orbf.Params(kernel, solver_type=1, leaf_threshold=128, coarse_threshold=300, naive_solve_threshold=100,
+                        interpolation_order=8, max_points_per_cell=40, epsilon=1e-10)
+        om = orbf.RBFInterpolator(pts, vals, s, p)
+        info = model.info()
+        assert info["last_residual"] < tol
+        assert abs(info["iterations"] - om.iterations) <= 1
+        targets = np.random.default_rng(1).random((300, dim)) * (pts.max(0) - pts.min(0)) + pts.min(0)
+        got = np.asarray(model.evaluate(targets)).reshape(-1, 1)
+        assert H.rel_l2(got, om.evaluate(targets)) <= interp_tol
+    # the absolute test is un-normalised: the same tolerance read as Relative stops (much) earlier
+    st_rel = ic.InterpolantSettings(ic.RBFKernelType(kernel),
+                                    fitting_accuracy=ic.FittingAccuracy(1e-3, ic.FittingAccuracyType.Relative))
+    rel_its = fb.RBFInterpolator(pts, vals, st_rel, params=_params(kernel)).info()["iterations"]
+    st_abs = ic.InterpolantSettings(ic.RBFKernelType(kernel),
+                                    fitting_accuracy=ic.FittingAccuracy(1e-3, ic.FittingAccuracyType.Absolute))
+    abs_its = fb.RBFInterpolator(pts, vals, st_abs, params=_params(kernel)).info()["iterations"]
+    assert abs_its >= rel_its
+
+
+@pytest.mark.parametrize("kernel,dim,n", [(0, 3, 2600), (2, 3, 2600), (1, 2, 2600)])
+def test_ddm_overlap_order_matches_oracle(kernel, dim, n):
+    """domain_decomposition.rs:236-311: the overlap points of a leaf are the nearest internal points of its neighbour
+    leaves in ascending point-to-box distance, appended after the internal points.  Domain::factorise then moves the
+    special points to the front (domain.rs:219-260); everything else keeps the order, which is compared here
+    element by element (test_ddm_hierarchy_bit_exact compares the sets)."""
+    import ferreus_rbf_rs_b200 as fb
+    from oracle import rbf as orbf
+    pts = H.make_points(n, dim, "clustered", seed=141)
+    vals = _values(pts)
+    model = fb.RBFInterpolator(pts, vals, _settings(kernel, tol=1e-2), params=_params(kernel, order=5, eps=1e-5))
+    s = orbf.InterpolantSettings(kernel)
+    s.set_basis_size(dim)
+    keep = orbf.remove_duplicates(pts, s.kernel())
+    ddm = orbf.DDMTree(pts[keep], s, 128, 0.5, 0.125, 300, factorise=False)
+    checked = 0
+    for li, lvl in enumerate(ddm.levels):
+        _, ptr, idx, internal = model.ddm_level(li)
+        for d, dom in enumerate(lvl.leaf_domains):
+            mine = idx[int(ptr[d]):int(ptr[d + 1])].astype(np.int64).tolist()
+            ref = [int(v) for v in dom.idx]
+            ok = False
+            for rk in range(0, s.basis_size + 1):      # rk special points were moved to the front
+                front = set(mine[:rk])
+                if len(front) == rk and mine[rk:] == [v for v in ref if v not in front]:
+                    ok = True
+                    break
+            assert ok, f"level {li} domain {d}: point order differs from the oracle's"
+            # internal flags follow their points
+            k = min(len(dom.mask), len(dom.idx))
+            ref_int = {int(v) for v, mk in zip(dom.idx[:k], dom.mask[:k]) if mk}
+            assert {v for v, f in zip(mine, internal[int(ptr[d]):int(ptr[d + 1])]) if f} == ref_int
+            checked += 1
+    assert checked >= 10
+
+
+def test_indefinite_subdomain_falls_back_like_the_reference():
+    """domain.rs:63-68: when the Cholesky factorisation of Q^T A Q fails the reference silently switches to its
+    Bunch-Kaufman LBL^T; here the domain is inverted by a pivoted elimination instead.  A negative nugget makes the
+    spheroidal kernel matrix indefinite; the fit must solve (K + nugget I) lambda = f all the same."""
+    import ferreus_rbf_rs_b200 as fb
+    from oracle import kernels as okern
+    ic = fb.interpolant_config
+    n = 700
+    pts = H.make_points(n, 3, "uniform", seed=151)
+    vals = _values(pts).reshape(-1, 1)
+    st = ic.InterpolantSettings(ic.RBFKernelType.Spheroidal, nugget=-0.4, base_range=0.5, total_sill=0.5)
+    model = fb.RBFInterpolator(pts, vals, st)          # n < naive_solve_threshold: one dense domain
+    k = okern.Kernel(3, 0.5, 0.5).matrix(pts, pts) - 0.4 * np.eye(n)
+    ev = np.linalg.eigvalsh(k)
+    assert ev[0] < -1e-3 and ev[-1] > 1e-3             # indefinite: the Cholesky path cannot have been taken
+    lam = np.linalg.solve(k, vals)
+    assert H.rel_l2(model.coefficients.point_coefficients, lam) <= 1e-8

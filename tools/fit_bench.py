@@ -1,5 +1,5 @@
 """Full RBF fit wall time (BASELINE.json config C3 recipe): clustered 3-D points, linear kernel, tol 1e-6,
-default Params.  Usage: python tools/fit_bench.py N [kernel]"""
+default Params.  Usage: python tools/fit_bench.py N [kernel] [reps]"""
 import json
 import sys
 import time
@@ -19,6 +19,7 @@ def f1_3d(p):  # smooth analytic test function (stand-in for rbf_test_functions.
 def main():
     n = int(sys.argv[1])
     kernel = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
     rng = np.random.default_rng(0)
     centres = rng.random((64, 3))
     pts = centres[rng.integers(0, 64, n)] + 0.02 * rng.standard_normal((n, 3))
@@ -29,7 +30,7 @@ def main():
     fb.RBFInterpolator(wp, f1_3d(wp), ic.InterpolantSettings(ic.RBFKernelType(kernel)))
     events = []
     walls = []
-    for rep in range(3):
+    for rep in range(reps):
         events.clear()
         t0 = time.perf_counter()
         model = fb.RBFInterpolator(pts, vals, ic.InterpolantSettings(ic.RBFKernelType(kernel)),
