@@ -38,9 +38,14 @@ sys.path.insert(0, ROOT)
 
 ORDER = 7
 KERNEL_FLOPS = {"linear": 1}  # c_k of SURVEY.md §8(d)
-# DRAM bytes per launch (read + write) from the committed ncu capture of the default workload (profiles/)
-NCU_DRAM_BYTES = {"k_p2l_grid": 74.585600e6 + 6.861056e6, "k_p2p_sym": 45.108736e6 + 0.419840e6,
-                  "k_m2l": 84.187136e6 + 6.039040e6}
+# DRAM bytes per launch (read + write) from the committed ncu captures of the default workload: profiles/ncu_traffic.json
+# names the capture every figure comes from
+try:
+    _TRAFFIC = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+except Exception:
+    _TRAFFIC = {}
+NCU_DRAM_BYTES = {k: v["bytes"] for k, v in _TRAFFIC.items() if isinstance(v, dict)}
+NCU_CAPTURE = {k: v["capture"] for k, v in _TRAFFIC.items() if isinstance(v, dict)}
 
 
 def make_workload(n, seed):
@@ -96,12 +101,21 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def cpu_baseline(pts, w, leaf_fraction):
     """Oracle port on the host cores (kind = "port": restatement of the reference algorithm, not the Rust
-    binary — no cargo/rustc on this image)."""
+    binary — no cargo/rustc on this image).  torchrun exports OMP_NUM_THREADS=1: the OpenMP team is set explicitly
+    to every core this process may run on, as the reference's rayon pool would be."""
     from oracle import bbfmm as obb
     from oracle import fast
     from oracle import kernels as okern
+    fast.lib().orc_set_num_threads(host_threads())
     t0 = time.perf_counter()
     ot = obb.FmmTree(pts, ORDER, okern.Kernel(okern.LINEAR), True, True, None,
                      obb.FmmParams(256, 2, 10.0 ** -ORDER, 1024))
@@ -124,47 +138,56 @@ def full_fit(n):
     # warm-up: a 30k-point fit loads the solver's kernels (CUDA loads modules lazily) before the timed construction
     wp = rng.random((30000, 3))
     fb.RBFInterpolator(wp, wp[:, 0] + wp[:, 1] * wp[:, 2], ic.InterpolantSettings(ic.RBFKernelType.Linear))
-    # two complete constructions, the first model released outside the timed region; the smaller wall time is reported
-    # (the 17 GB factor pool makes a single measurement sensitive to the allocator's state: 0.96-1.9 s seen)
-    walls, info = [], None
-    for _ in range(2):
+    # three complete constructions, each model released outside the timed region; the MEDIAN wall time is reported
+    walls, infos = [], []
+    for _ in range(3):
         t0 = time.perf_counter()
         model = fb.RBFInterpolator(pts, vals, ic.InterpolantSettings(ic.RBFKernelType.Linear))
-        wall = time.perf_counter() - t0
-        if not walls or wall < min(walls):
-            info = model.info()
-        walls.append(wall)
+        walls.append(time.perf_counter() - t0)
+        infos.append(model.info())
         del model
+    mid = int(np.argsort(walls)[1])
+    info = infos[mid]
     return {"workload": f"ferreus_rbf 3D global fit, linear kernel, tol 1e-6, N={n} clustered (64 Gaussian blobs); "
-                        "timed after one 30k-point warm-up fit; best of two constructions",
-            "wall_s": min(walls), "wall_s_all": walls, "setup_s": info["setup_seconds"], "solve_s": info["solve_seconds"],
+                        "timed after one 30k-point warm-up fit; median of three constructions",
+            "wall_s": walls[mid], "wall_s_all": walls, "setup_s": info["setup_seconds"], "solve_s": info["solve_seconds"],
             "iterations": info["iterations"], "fmm_matvecs": info["matvecs"], "ddm_domains": info["ddm_domains"],
             "final_relative_residual": info["last_residual"]}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port, all host threads) on the same workload."""
+    """--impl reference: the reference's CPU algorithm (oracle port, all host threads) on the same workload.  Every
+    step is one complete, fully timed 1M-point matvec (upward pass, M2L, P2L, L2L and the whole leaf pass; nothing is
+    extrapolated).  A step takes several seconds, so the number of steps actually run is bounded by a wall-clock
+    budget (REF_BUDGET_S) and reported in `steps`."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    budget_s = float(os.environ.get("REF_BUDGET_S", "150"))
+    t_begin = time.perf_counter()
     pts, w = make_workload(args.n, 1000)
     ff, build_s, cores = cpu_baseline(pts, w, args.cpu_leaf_fraction)
     times = []
-    detail = None
-    for it in range(args.warmup + args.steps):
-        sec, detail = ff.timed_matvec_estimate(w, args.cpu_leaf_fraction, seed=it)
-        if it >= args.warmup:
+    warm = min(args.warmup, 1)
+    for it in range(warm + args.steps):
+        t0 = time.perf_counter()
+        ff.matvec(w)
+        sec = time.perf_counter() - t0
+        if it >= warm:
             times.append(sec)
+        if times and time.perf_counter() - t_begin + sec > budget_s:
+            break
     ms = 1e3 * float(np.mean(times))
     val = args.n / (ms * 1e-3) / 1e6
-    sample = (f"upward, M2L, P2L, L2L in full; leaf pass (P2P+M2P) on {detail['sample_leaves']} of "
-              f"{detail['leaves']} target leaves scaled by pair count x{detail['leaf_scale']:.1f}")
+    sample = (f"{len(times)} complete 1M-point matvecs of the oracle port (oracle/fast.py + oracle/csrc/oracle_passes.c, "
+              f"OpenMP, {cores} threads), every stage timed in full; {args.steps} steps requested, bounded by a "
+              f"{budget_s:.0f} s budget")
     line = {"impl": "reference", "metric": "bbfmm_matvec_throughput", "value": val, "unit": "Mpts/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "steps": len(times), "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.n, 1),
             "cpu_baseline": {"value": val, "unit": "Mpts/s", "cores": cores, "kind": "port", "sample": sample,
-                             "tree_build_s": build_s},
+                             "tree_build_s": build_s, "step_seconds": times},
             "e2e": {"value": val, "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -352,8 +375,12 @@ def main():
         value = n / (ms_per_step * 1e-3) / 1e6
         e2e_val = n / (e2e_ms_max / args.steps * 1e-3) / 1e6
         # ---- roofline of the dominant kernel
-        fp64_peak = np.zeros(1)
+        fp64_peak, dmma_peak = np.zeros(1), np.zeros(1)
         L.fb_measure_fp64_tflops(_lib.dptr(fp64_peak))
+        L.fb_measure_fp64_dmma_tflops(_lib.dptr(dmma_peak))
+        fp64_peak[0] = max(fp64_peak[0], dmma_peak[0])  # one FP64 datapath: the higher of the two readings is the peak
+        m2l_flops = np.zeros(1)
+        L.fb_tree_m2l_flops(tree._h, _lib.dptr(m2l_flops))
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -377,12 +404,12 @@ def main():
         peak = float(fp64_peak[0]) * world  # whole-job FLOPs against the FP64 peak of all GPUs used
         roofline = {"kernel": "k_p2l_grid<FUSE> (W/X pass: P2L + M2P transpose, one kernel evaluation per pair)",
                     "bound": "fp64", "achieved": wx_tf, "peak": peak, "unit": "TFLOP/s", "frac": wx_tf / peak,
-                    "traffic": NCU_DRAM_BYTES["k_p2l_grid"] if n == 1_000_000 else None,
+                    "traffic": NCU_DRAM_BYTES.get("k_p2l_grid") if n == 1_000_000 and world == 1 else None,
                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this "
-                                      "kernel at this workload (profiles/r1_final_ncu_full.txt); compute-bound: 81 MB",
-                    "peak_source": "in-run DFMA micro-benchmark (fb_measure_fp64_tflops); MEASURED_PEAKS.json has no "
-                                   "FP64 entry",
-                    "traffic_capture": "profiles/r1_final2_ncu_full.txt",
+                                      "kernel at this workload; compute-bound: 81 MB",
+                    "peak_source": "in-run DFMA and DMMA micro-benchmarks (fb_measure_fp64_tflops / "
+                                   "fb_measure_fp64_dmma_tflops), the higher reading; MEASURED_PEAKS.json has no FP64 entry",
+                    "traffic_capture": NCU_CAPTURE.get("k_p2l_grid"),
                     "algorithmic_flops_per_launch": wx_flops, "flops_per_pair": f_pair, "launch_ms": med["wx"],
                     "note": "algorithmic count = SURVEY.md §8(d): M2P and P2L pairs x 11 FLOP; the kernel evaluates the "
                             "symmetric kernel once per (point, node) and uses it for both passes",
@@ -390,13 +417,28 @@ def main():
                                       "both rows updated)",
                             "achieved": p2p_tf, "frac": p2p_tf / peak,
                             "launch_ms": med["leaf"], "algorithmic_flops_per_launch": pairs_p2p * f_pair,
-                            "traffic": NCU_DRAM_BYTES["k_p2p_sym"] if n == 1_000_000 else None,
+                            "traffic": NCU_DRAM_BYTES.get("k_p2p_sym") if n == 1_000_000 and world == 1 else None,
+                            "traffic_capture": NCU_CAPTURE.get("k_p2p_sym"),
                             "note": "algorithmic count = every ordered (target, source) pair of the reference's U lists "
                                     "x 11 FLOP (SURVEY.md 8(d)); the kernel evaluates half of them"},
                     "pipe_note": "FP64 tensor instructions (DMMA) share the DFMA datapath on B200 (tools/dmma_bench.cu mix "
                                  "test, profiles/r1_dmma_dfma_mix.txt: 4 DMMA + 32 DFMA per trip take the sum of the two "
                                  "times), so this one FP64 peak bounds P2P, W/X and M2L alike",
-                    "direct_sums_total": {"achieved": direct_tf, "frac": direct_tf / peak}}
+                    "direct_sums_total": {"achieved": direct_tf, "frac": direct_tf / peak},
+                    "m2l": {"kernel": "k_m2l_stream (TMA bulk gathers, register-resident operator slices, DMMA, TMA "
+                                      "scatter-adds)",
+                            "achieved": float(m2l_flops[0]) / max(med["m2l"] * 1e-3, 1e-9) / 1e12,
+                            "frac": float(m2l_flops[0]) / max(med["m2l"] * 1e-3, 1e-9) / 1e12 / peak,
+                            "launch_ms": med["m2l"], "algorithmic_flops_per_launch": float(m2l_flops[0]),
+                            "traffic": NCU_DRAM_BYTES.get("k_m2l_stream") if n == 1_000_000 and world == 1 else None,
+                            "traffic_capture": NCU_CAPTURE.get("k_m2l_stream"),
+                            "note": "algorithmic count = sum over V-list entries of 4 r P with the reference's truncation "
+                                    "ranks r (SURVEY.md 8(d)); rank tiles are padded to 8"},
+                    "stage_fractions": {k: med[k] / max(med["total"], 1e-9) for k in med if k != "total"},
+                    "peaks": {"dfma_tflops": float(fp64_peak[0]) if dmma_peak[0] <= fp64_peak[0] else None,
+                              "dmma_tflops": float(dmma_peak[0]), "per_gpu_peak_used": float(fp64_peak[0]),
+                              "measured": "in this run, after the timed region, 8 repetitions each (the first two bring the "
+                                          "clocks up), best of the rest"}}
         stages = {"ms": med, "hbm_peak_gbs": hbm_peak,
                   "hbm_peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                   "pairs": {"p2p": pairs_p2p, "m2p_nodes": pairs_m2p, "p2l_nodes": pairs_p2l,
@@ -426,13 +468,18 @@ def main():
             line["fit"] = full_fit(n)
         if world == 1 and not args.no_cpu_baseline:
             ff, cpu_build_s, cores = cpu_baseline(pts, w, args.cpu_leaf_fraction)
-            sec, detail = ff.timed_matvec_estimate(w, args.cpu_leaf_fraction)
-            # parity spot check of the timed GPU result against the oracle on the sampled leaves is in tests/
+            t0 = time.perf_counter()
+            cpu_out = ff.matvec(w)
+            sec = time.perf_counter() - t0
+            # the timed CPU result doubles as a parity check of the timed GPU path (bar: 1e-10, tests/test_gpu_configs.py)
+            tree.set_weights(w)
+            gpu_out = np.asarray(tree.evaluate(w, pts)).reshape(n, 1)
             line["cpu_baseline"] = {
                 "value": n / sec / 1e6, "unit": "Mpts/s", "cores": cores, "kind": "port",
-                "sample": (f"oracle port (OpenMP): upward, M2L, P2L, L2L in full; leaf pass on {detail['sample_leaves']} "
-                           f"of {detail['leaves']} leaves scaled x{detail['leaf_scale']:.1f} by pair count"),
-                "seconds_per_matvec": sec, "tree_build_s": cpu_build_s}
+                "sample": "one complete 1M-point matvec of the oracle port (OpenMP over cells / leaves like the "
+                          "reference's rayon loops), every stage timed in full, nothing extrapolated",
+                "seconds_per_matvec": sec, "tree_build_s": cpu_build_s,
+                "rel_l2_gpu_vs_cpu": float(np.linalg.norm(gpu_out - cpu_out) / np.linalg.norm(cpu_out))}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -100,6 +100,7 @@ SIGNATURES = {
     "fb_host_free": (None, [C.c_void_p]),
     "fb_set_sqrt_mode": (C.c_int, [C.c_int]),
     "fb_get_sqrt_mode": (C.c_int, []),
+    "fb_trim_memory": (C.c_uint64, []),
     "fb_tree_new": (C.c_int, [_dp, _sz, C.c_int, _pd, _pd, C.c_int, C.POINTER(FbKernelParams), C.c_int, C.c_int,
                               _dp, C.POINTER(FbFmmParams), C.POINTER(C.c_void_p)]),
     "fb_tree_free": (None, [C.c_void_p]),
@@ -117,6 +118,8 @@ SIGNATURES = {
     "fb_tree_last_timing": (C.c_int, [C.c_void_p, _dp]),
     "fb_tree_last_matvec_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "fb_measure_fp64_tflops": (C.c_int, [_dp]),
+    "fb_measure_fp64_dmma_tflops": (C.c_int, [_dp]),
+    "fb_tree_m2l_flops": (C.c_int, [C.c_void_p, _dp]),
     "fb_tree_source_points": (C.c_int, [C.c_void_p, _dp, _pd, _pd]),
     "fb_tree_get_info": (C.c_int, [C.c_void_p, C.POINTER(FbTreeInfo)]),
     "fb_tree_dump_cells": (C.c_int, [C.c_void_p, _u64p, _u8p, _u64p, _u64p]),

@@ -43,6 +43,14 @@ extern std::atomic<uint64_t> g_launches;
     FB_CUDA(cudaGetLastError());                                          \
   } while (0)
 
+// Device memory comes from a per-process cache (fmm.cu): a released block is kept and handed out again to the next
+// request of a similar size, so repeated fits / tree builds do not pay cudaMalloc / cudaFree (tens of ms each for the
+// multi-GB factor pools, and the source of 0.9-1.9 s swings of the 1M-point fit).  dev_free synchronises the device
+// first, exactly like the cudaFree it replaces; fb_trim_memory() returns the cache to the driver.
+void *dev_alloc(size_t bytes);
+void dev_free(void *p);
+size_t dev_cache_trim();
+
 template <class T>
 struct DBuf {  // device buffer, grows on demand, never shrinks
   T *p = nullptr;
@@ -51,14 +59,14 @@ struct DBuf {  // device buffer, grows on demand, never shrinks
   DBuf(const DBuf &) = delete;
   DBuf &operator=(const DBuf &) = delete;
   ~DBuf() {
-    if (p) cudaFree(p);
+    if (p) dev_free(p);
   }
   void reserve(size_t n) {
     if (n <= cap) return;
-    if (p) cudaFree(p);
+    if (p) dev_free(p);
     p = nullptr;
     cap = 0;
-    FB_CUDA(cudaMalloc((void **)&p, (n ? n : 1) * sizeof(T)));
+    p = static_cast<T *>(dev_alloc((n ? n : 1) * sizeof(T)));
     cap = n ? n : 1;
   }
   void upload(const std::vector<T> &h, cudaStream_t s) {

@@ -7,7 +7,10 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <thread>
+#include <unordered_map>
 
 #include <cub/cub.cuh>
 #include <thrust/iterator/transform_iterator.h>
@@ -26,6 +29,94 @@ static thread_local std::string t_last_error;
 void set_last_error(const std::string &msg) { t_last_error = msg; }
 
 static inline unsigned nblocks(size_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+// ---- device memory cache (see common.h) ------------------------------------------------------------------------------
+namespace {
+struct DevCache {
+  std::mutex mu;
+  std::multimap<size_t, void *> free_blocks[16];            // per device: size -> block
+  std::unordered_map<void *, std::pair<size_t, int>> live;  // block -> (size, device)
+  size_t cached_bytes = 0;
+};
+DevCache &dev_cache() {
+  static DevCache *c = new DevCache();  // never destroyed: blocks may be released during static destruction
+  return *c;
+}
+size_t round_block(size_t bytes) {
+  if (bytes <= (1u << 20)) return (bytes + 511) & ~(size_t)511;
+  return (bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+}
+void trim_locked(DevCache &c) {
+  for (auto &m : c.free_blocks) {
+    for (auto &kv : m) cudaFree(kv.second);
+    m.clear();
+  }
+  c.cached_bytes = 0;
+}
+}  // namespace
+
+void *dev_alloc(size_t bytes) {
+  DevCache &c = dev_cache();
+  const size_t want = round_block(bytes);
+  int dev = 0;
+  FB_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(c.mu);
+  auto &m = c.free_blocks[dev & 15];
+  auto it = m.lower_bound(want);
+  // reuse a cached block unless it would waste more than a quarter of itself
+  if (it != m.end() && it->first - want <= it->first / 4) {
+    void *p = it->second;
+    c.cached_bytes -= it->first;
+    c.live[p] = {it->first, dev};
+    m.erase(it);
+    return p;
+  }
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {  // out of memory: give the cache back and try once more
+    cudaGetLastError();
+    trim_locked(c);
+    e = cudaMalloc(&p, want);
+  }
+  if (e != cudaSuccess)
+    throw Error(FB_ERR_CUDA, std::string("cudaMalloc of ") + std::to_string(want) + " bytes: " + cudaGetErrorString(e));
+  c.live[p] = {want, dev};
+  return p;
+}
+
+void dev_free(void *p) {
+  if (!p) return;
+  DevCache &c = dev_cache();
+  cudaDeviceSynchronize();  // nothing queued may still touch the block (the semantics of the cudaFree this replaces)
+  std::lock_guard<std::mutex> lock(c.mu);
+  auto it = c.live.find(p);
+  if (it == c.live.end()) {
+    cudaFree(p);
+    return;
+  }
+  const size_t sz = it->second.first;
+  const int dev = it->second.second;
+  c.live.erase(it);
+  static const bool off = [] {
+    const char *v = std::getenv("FB_NO_MEMORY_CACHE");
+    return v && v[0] == '1';
+  }();
+  if (off) {
+    cudaFree(p);
+    return;
+  }
+  c.free_blocks[dev & 15].emplace(sz, p);
+  c.cached_bytes += sz;
+}
+
+size_t dev_cache_trim() {
+  DevCache &c = dev_cache();
+  cudaDeviceSynchronize();
+  std::lock_guard<std::mutex> lock(c.mu);
+  const size_t b = c.cached_bytes;
+  trim_locked(c);
+  return b;
+}
 
 // Host threads of the staging copies / comparisons below.  torchrun exports OMP_NUM_THREADS=1 to every rank, which would
 // serialise the 8-24 MB copies on the end-to-end path; they take an explicit team instead: FB_IO_THREADS, else the
@@ -371,8 +462,10 @@ void fb_tree::build(const double *points, size_t n_, int dim_, ptrdiff_t rs, ptr
     d_inv_tab.upload(it, stream);
   }
   // M2L: the streaming kernel (m2l.cu) when the order fits its register-resident operator slices ...
+  lap("leaf list packing + upload");
   if (m2l_stream_supported(P, fparams.compression_type) && ht.depth >= 2)
     m2l_plan = m2l_stream_build(ht, ops, P, d_inv_tab.p, stream);
+  lap("M2L stream plan");
   // ... else groups of entries (target, source, permutation) per (level, reference vector), sorted by target
   if (!m2l_plan) {
     m2l_groups.clear();
@@ -1006,6 +1099,7 @@ int fb_set_sqrt_mode(int fast) {
   return FB_OK;
 }
 int fb_get_sqrt_mode(void) { return g_sqrt_mode.load(); }
+uint64_t fb_trim_memory(void) { return (uint64_t)fb::dev_cache_trim(); }
 int fb_set_device(int device) {
   return guarded([&] { FB_CUDA(cudaSetDevice(device)); });
 }
@@ -1261,9 +1355,9 @@ int fb_measure_fp64_tflops(double *tflops_out) {
     cudaEvent_t e0, e1;
     FB_CUDA(cudaEventCreate(&e0));
     FB_CUDA(cudaEventCreate(&e1));
-    const int iters = 8192, blocks = sms * 8, threads = 256;
+    const int iters = 16384, blocks = sms * 8, threads = 256;
     double best = 0;
-    for (int rep = 0; rep < 5; ++rep) {
+    for (int rep = 0; rep < 8; ++rep) {  // the first repetitions also bring the clocks up
       FB_CUDA(cudaEventRecord(e0, 0));
       FB_LAUNCH(k_dfma_peak, blocks, threads, 0, 0, out.p, iters, 0.999999, 1e-9);
       FB_CUDA(cudaEventRecord(e1, 0));
@@ -1271,7 +1365,79 @@ int fb_measure_fp64_tflops(double *tflops_out) {
       float ms = 0;
       FB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
       const double fl = 2.0 * 16.0 * iters * (double)blocks * threads;
-      best = std::max(best, fl / (ms * 1e-3) / 1e12);
+      if (rep >= 2) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops_out = best;
+  });
+}
+
+// algorithmic FLOPs of one M2L pass per right-hand side: sum over the V-list entries of 4 r P for the
+// compressed operators (2 P^2 uncompressed), r the rank of the entry's (level, reference vector) operator
+int fb_tree_m2l_flops(const fb_tree *t, double *flops_out) {
+  if (!t || !flops_out) return FB_ERR_INVALID_ARGUMENT;
+  const fb::HostTree &ht = t->ht;
+  const bool compressed = t->fparams.compression_type != FB_COMPRESSION_NONE;
+  double fl = 0.0;
+  for (int lvl = 2; lvl <= ht.depth; ++lvl)
+    for (int c = ht.level_ptr[lvl]; c < ht.level_ptr[lvl + 1]; ++c) {
+      uint32_t ac[3];
+      ht.anchor(c, ac);
+      for (long long e = ht.v_ptr[c]; e < ht.v_ptr[c + 1]; ++e) {
+        uint32_t as[3];
+        ht.anchor(ht.v_idx[e], as);
+        int tix = 0;
+        for (int d = 0; d < t->dim; ++d) tix = tix * 7 + ((int)ac[d] - (int)as[d] + 3);
+        const int r = t->ops.m2l[lvl - 2][t->ops.ref_lookup[tix]].rank;
+        fl += compressed ? 4.0 * r * t->P : 2.0 * (double)t->P * t->P;
+      }
+    }
+  *flops_out = fl;
+  return FB_OK;
+}
+
+// FP64 tensor-instruction peak of the current device (mma.sync m8n8k4, 6 independent chains per warp)
+__global__ void k_dmma_peak(double *out, int iters) {
+  double c[6][2];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) c[i][0] = c[i][1] = 0.0;
+  const double a = threadIdx.x * 1e-3, b = threadIdx.x * 2e-3;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c[i][0]), "+d"(c[i][1])
+                   : "d"(a), "d"(b));
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) s += c[i][0] + c[i][1];
+  if (s == 12345.678) out[0] = s;
+}
+
+int fb_measure_fp64_dmma_tflops(double *tflops_out) {
+  return guarded([&] {
+    FB_REQUIRE(tflops_out, "null argument");
+    int dev = 0, sms = 0;
+    FB_CUDA(cudaGetDevice(&dev));
+    FB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    fb::DBuf<double> out;
+    out.reserve(1);
+    cudaEvent_t e0, e1;
+    FB_CUDA(cudaEventCreate(&e0));
+    FB_CUDA(cudaEventCreate(&e1));
+    const int iters = 16384, blocks = sms * 4, threads = 256;
+    double best = 0;
+    for (int rep = 0; rep < 8; ++rep) {  // the first repetitions also bring the clocks up
+      FB_CUDA(cudaEventRecord(e0, 0));
+      FB_LAUNCH(k_dmma_peak, blocks, threads, 0, 0, out.p, iters);
+      FB_CUDA(cudaEventRecord(e1, 0));
+      FB_CUDA(cudaEventSynchronize(e1));
+      float ms = 0;
+      FB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      const double fl = 512.0 * 6.0 * iters * (double)blocks * (threads / 32);
+      if (rep >= 2) best = std::max(best, fl / (ms * 1e-3) / 1e12);
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);

@@ -517,6 +517,10 @@ struct LevelDev {
   DBuf<double> qpool, lpool;
   DBuf<uint8_t> use_inverse;  // all zero unless a domain needed the indefinite fallback
   int n_fallback = 0;
+  DBuf<uint8_t> fail;         // per domain: Cholesky met a non-positive pivot
+  std::vector<int> h_mms;     // order of every domain's Q^T A Q (host copy, for the fallback)
+  std::vector<long long> h_l_off;
+  unsigned tiles = 0;
   DBuf<unsigned long long> level_idx;  // point_indices of the level (matvec_partial target set)
   size_t n_level_pts = 0;
   TargetBuffers tb;
@@ -620,11 +624,17 @@ struct DeviceSolver {
   DBuf<double> px, py, pz, P, Qp, proj, scalar;
   DBuf<unsigned long long> umax;
   std::vector<std::unique_ptr<LevelDev>> levels;
-  DBuf<uint8_t> fail;  // per domain: Cholesky met a non-positive pivot
   DBuf<double> scratch;
   uint64_t matvecs = 0;
 
+  cudaStream_t upload_stream = nullptr;
+  cudaEvent_t upload_done = nullptr;
+
   DeviceSolver(fr_model &model, fb_tree *t) : M(model), tree(t), s(t ? t->stream : nullptr) {}
+  ~DeviceSolver() {
+    if (upload_done) cudaEventDestroy(upload_done);
+    if (upload_stream) cudaStreamDestroy(upload_stream);
+  }
 
   void upload_points(cudaStream_t stream) {
     n = M.n;
@@ -648,13 +658,11 @@ struct DeviceSolver {
   //      reference's fallback (domain.rs:63-68: faer's Bunch-Kaufman LBL^T, linalg.rs:514-616): the matrix is assembled
   //      again, inverted on the host with a pivoted elimination and the explicit inverse stored in the slot
   //      (DomainTable::use_inverse); both solve the same symmetric indefinite system.
-  template <class Reassemble>
-  void factorise_pool(LevelDev &lv, const std::vector<int> &mms, const std::vector<long long> &l_off,
-                      Reassemble &&reassemble, cudaStream_t stream) {
-    const size_t nd = mms.size();
-    fail.reserve(nd);
+  void factorise_launch(LevelDev &lv, cudaStream_t stream) {  // asynchronous: nothing here waits for the device
+    const size_t nd = lv.h_mms.size();
+    lv.fail.reserve(nd);
     lv.use_inverse.reserve(nd);
-    FB_CUDA(cudaMemsetAsync(fail.p, 0, nd, stream));
+    FB_CUDA(cudaMemsetAsync(lv.fail.p, 0, nd, stream));
     FB_CUDA(cudaMemsetAsync(lv.use_inverse.p, 0, nd, stream));
     lv.tab.use_inverse = lv.use_inverse.p;
     const size_t smem = sizeof(double) * ((size_t)(kNB + 1) * kNB + (size_t)kPS * kNB * (1 + 8));
@@ -664,7 +672,7 @@ struct DeviceSolver {
       FB_CUDA(cudaFuncSetAttribute(k_chol_big_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       FB_CUDA(cudaFuncSetAttribute(k_chol_big_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       for (int kb = 0; kb < nn; kb += kNB) {
-        FB_LAUNCH(k_chol_big_panel, 1, 256, smem, stream, lv.lpool.p, nn, kb, fail.p);
+        FB_LAUNCH(k_chol_big_panel, 1, 256, smem, stream, lv.lpool.p, nn, kb, lv.fail.p);
         const int ntile = (nn - (kb + kNB) + kNB - 1) / kNB;
         if (ntile > 0) {
           dim3 grid((unsigned)ntile, (unsigned)((ntile + 7) / 8));
@@ -672,24 +680,31 @@ struct DeviceSolver {
         }
       }
     } else {
-      FB_LAUNCH(k_cholesky, (unsigned)nd, 256, smem, stream, lv.tab, lv.lpool.p, fail.p);
+      FB_LAUNCH(k_cholesky, (unsigned)nd, 256, smem, stream, lv.tab, lv.lpool.p, lv.fail.p);
     }
+  }
+
+  template <class Reassemble>
+  void factorise_finish(LevelDev &lv, Reassemble &&reassemble, cudaStream_t stream) {
+    const size_t nd = lv.h_mms.size();
     std::vector<uint8_t> h_fail(nd, 0);
-    FB_CUDA(cudaMemcpyAsync(h_fail.data(), fail.p, nd, cudaMemcpyDeviceToHost, stream));
+    FB_CUDA(cudaMemcpyAsync(h_fail.data(), lv.fail.p, nd, cudaMemcpyDeviceToHost, stream));
     FB_CUDA(cudaStreamSynchronize(stream));
     std::vector<double> a, inv;
     for (size_t d = 0; d < nd; ++d) {
       if (!h_fail[d]) continue;
-      const int mm = mms[d];
+      const int mm = lv.h_mms[d];
       reassemble(d);
       a.resize((size_t)mm * mm);
-      FB_CUDA(cudaMemcpyAsync(a.data(), lv.lpool.p + l_off[d], a.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+      FB_CUDA(cudaMemcpyAsync(a.data(), lv.lpool.p + lv.h_l_off[d], a.size() * sizeof(double), cudaMemcpyDeviceToHost,
+                              stream));
       FB_CUDA(cudaStreamSynchronize(stream));
       for (int i = 0; i < mm; ++i)  // the slot holds the lower triangle
         for (int j = i + 1; j < mm; ++j) a[(size_t)i * mm + j] = a[(size_t)j * mm + i];
       if (!invert_pivoted(a, mm, inv))
         throw Error(FB_ERR_INVALID_ARGUMENT, "subdomain matrix Q^T A Q is singular (domain " + std::to_string(d) + ")");
-      FB_CUDA(cudaMemcpyAsync(lv.lpool.p + l_off[d], inv.data(), inv.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+      FB_CUDA(cudaMemcpyAsync(lv.lpool.p + lv.h_l_off[d], inv.data(), inv.size() * sizeof(double), cudaMemcpyHostToDevice,
+                              stream));
       const uint8_t one = 1;
       FB_CUDA(cudaMemcpyAsync(lv.use_inverse.p + d, &one, 1, cudaMemcpyHostToDevice, stream));
       FB_CUDA(cudaStreamSynchronize(stream));
@@ -697,14 +712,28 @@ struct DeviceSolver {
     }
   }
 
+  // ---- Cholesky of every slot of a level's factor pool; domains whose Q^T A Q is not positive definite take the
+  //      reference's fallback (domain.rs:63-68: faer's Bunch-Kaufman LBL^T, linalg.rs:514-616): the matrix is assembled
+  //      again, inverted on the host with a pivoted elimination and the explicit inverse stored in the slot
+  //      (DomainTable::use_inverse); both solve the same symmetric indefinite system.
+  template <class Reassemble>
+  void factorise_pool(LevelDev &lv, const std::vector<int> &mms, const std::vector<long long> &l_off,
+                      Reassemble &&reassemble, cudaStream_t stream) {
+    lv.h_mms = mms;
+    lv.h_l_off = l_off;
+    factorise_launch(lv, stream);
+    factorise_finish(lv, reassemble, stream);
+  }
+
   // ---- factorise one level on the device (domain.rs:322-382)
-  void build_level(const LevelHost &lh, bool coarse, cudaStream_t stream) {
+  // queue the whole factorisation of a level (tables, assembly, Cholesky) without waiting for the device: the host goes on
+  // building the next DDM level / the FMM tree meanwhile (fit())
+  void build_level_launch(const LevelHost &lh, bool coarse, cudaStream_t stream) {
     static const bool verbose = std::getenv("FB_TIMING") != nullptr;
     auto t_sub = std::chrono::steady_clock::now();
     auto sublap = [&](const char *what) {
       if (!verbose) return;
-      cudaStreamSynchronize(stream);
-      fprintf(stderr, "[fr_fit]     %-26s %8.3f s\n", what,
+      fprintf(stderr, "[fr_fit]     %-26s %8.3f s (host, queued)\n", what,
               std::chrono::duration<double>(std::chrono::steady_clock::now() - t_sub).count());
       t_sub = std::chrono::steady_clock::now();
     };
@@ -735,14 +764,22 @@ struct DeviceSolver {
       lv->max_mm = std::max(lv->max_mm, mm);
     }
     lv->n_domains = (int)nd;
-    lv->pt_ptr.upload(pt_ptr, stream);
-    lv->q_off.upload(q_off, stream);
-    lv->l_off.upload(l_off, stream);
-    lv->s_off.upload(s_off, stream);
-    lv->rank.upload(rank, stream);
-    lv->pt_idx.upload(pt_idx, stream);
-    lv->pt_mask.upload(pt_mask, stream);
-    lv->qpool.upload(qpool, stream);
+    // the tables are pageable host memory: such a copy holds the host until the stream reaches it, i.e. until the previous
+    // level's factorisation is done.  They go through an otherwise idle stream; the factorisation stream waits for them.
+    if (!upload_stream) {
+      FB_CUDA(cudaStreamCreateWithFlags(&upload_stream, cudaStreamNonBlocking));
+      FB_CUDA(cudaEventCreateWithFlags(&upload_done, cudaEventDisableTiming));
+    }
+    lv->pt_ptr.upload(pt_ptr, upload_stream);
+    lv->q_off.upload(q_off, upload_stream);
+    lv->l_off.upload(l_off, upload_stream);
+    lv->s_off.upload(s_off, upload_stream);
+    lv->rank.upload(rank, upload_stream);
+    lv->pt_idx.upload(pt_idx, upload_stream);
+    lv->pt_mask.upload(pt_mask, upload_stream);
+    lv->qpool.upload(qpool, upload_stream);
+    FB_CUDA(cudaEventRecord(upload_done, upload_stream));
+    FB_CUDA(cudaStreamWaitEvent(stream, upload_done, 0));
     sublap("host tables + uploads");
     lv->lpool.reserve((size_t)lsize);
     scratch.reserve((size_t)std::max<long long>(ssize, 1));
@@ -771,45 +808,52 @@ struct DeviceSolver {
                 lv->qpool.p, scratch.p, lv->lpool.p);
     }
     sublap("prep + assemble");
-    const auto t_ch = std::chrono::steady_clock::now();
+    lv->tiles = tiles;
+    lv->h_mms.resize(nd);
+    for (size_t d = 0; d < nd; ++d) lv->h_mms[d] = (int)(lh.domains[d].idx.size() - lh.domains[d].rank);
+    lv->h_l_off = l_off;
+    factorise_launch(*lv, stream);
+    if (coarse && !lh.domains.empty() && lh.domains[0].solve_for_poly) {
+      const DomainHost &dh = lh.domains[0];
+      const int nn = (int)dh.idx.size();
+      lv->solve_for_poly = true;
+      lv->a_special.reserve((size_t)dh.rank * nn);
+      lv->sp_inv.upload(dh.sp_inv, upload_stream);
+      FB_CUDA(cudaEventRecord(upload_done, upload_stream));
+      FB_CUDA(cudaStreamWaitEvent(stream, upload_done, 0));
+      FB_LAUNCH(k_special_rows, nblk(nn, 128), 128, 0, stream, lv->pt_idx.p, nn, dh.rank, px.p, py.p, pz.p, kp,
+                M.st.nugget, lv->a_special.p);
+    }
+    lv->n_level_pts = lh.point_indices.size();
+    lv->all_points = lv->n_level_pts == n;
+    levels.push_back(std::move(lv));
+  }
+
+  // wait for the queued factorisations, run the indefinite fallback where Cholesky failed, bin the level's points as
+  // the target set of its partial matvecs (needs the FMM tree)
+  void finish_level(size_t l, const LevelHost &lh, cudaStream_t stream) {
+    LevelDev &lv = *levels[l];
+    const KParams kp = M.kp;
     auto reassemble = [&](size_t d) {  // one domain's Q^T A Q again (its slot was overwritten by the failed attempt)
-      DomainTable tt = t;
+      DomainTable tt = lv.tab;
       tt.pt_ptr += d;
       tt.rank += d;
       tt.q_off += d;
       tt.l_off += d;
       tt.s_off += d;
       tt.n_domains = 1;
-      FB_LAUNCH(k_dom_prep, 1, 128, 0, stream, tt, px.p, py.p, pz.p, kp, M.st.nugget, lv->qpool.p, scratch.p);
-      FB_LAUNCH(k_dom_assemble, dim3(tiles, tiles, 1), 256, 0, stream, tt, px.p, py.p, pz.p, kp, M.st.nugget,
-                lv->qpool.p, scratch.p, lv->lpool.p);
+      FB_LAUNCH(k_dom_prep, 1, 128, 0, stream, tt, px.p, py.p, pz.p, kp, M.st.nugget, lv.qpool.p, scratch.p);
+      FB_LAUNCH(k_dom_assemble, dim3(lv.tiles, lv.tiles, 1), 256, 0, stream, tt, px.p, py.p, pz.p, kp, M.st.nugget,
+                lv.qpool.p, scratch.p, lv.lpool.p);
     };
-    std::vector<int> mms(nd);
-    for (size_t d = 0; d < nd; ++d) mms[d] = (int)(lh.domains[d].idx.size() - lh.domains[d].rank);
-    factorise_pool(*lv, mms, l_off, reassemble, stream);
-    if (std::getenv("FB_TIMING"))
-      fprintf(stderr, "[fr_fit]   cholesky of %zu domains (+ queued assembly) %8.3f s%s\n", nd,
-              std::chrono::duration<double>(std::chrono::steady_clock::now() - t_ch).count(),
-              lv->n_fallback ? " (indefinite fallback used)" : "");
-    if (coarse && !lh.domains.empty() && lh.domains[0].solve_for_poly) {
-      const DomainHost &dh = lh.domains[0];
-      const int nn = (int)dh.idx.size();
-      lv->solve_for_poly = true;
-      lv->a_special.reserve((size_t)dh.rank * nn);
-      lv->sp_inv.upload(dh.sp_inv, stream);
-      FB_LAUNCH(k_special_rows, nblk(nn, 128), 128, 0, stream, lv->pt_idx.p, nn, dh.rank, px.p, py.p, pz.p, kp,
-                M.st.nugget, lv->a_special.p);
-    }
-    // target set of matvec_partial for this level
-    lv->n_level_pts = lh.point_indices.size();
-    lv->all_points = lv->n_level_pts == n;
-    if (tree && !lv->all_points) {
+    factorise_finish(lv, reassemble, stream);
+    if (std::getenv("FB_TIMING") && lv.n_fallback)
+      fprintf(stderr, "[fr_fit]   level %zu: indefinite fallback used for %d domain(s)\n", l, lv.n_fallback);
+    if (tree && !lv.all_points) {
       std::vector<unsigned long long> li(lh.point_indices.begin(), lh.point_indices.end());
-      lv->level_idx.upload(li, stream);
-      lv->ts = tree->subset_target_set_dev(lv->level_idx.p, li.size(), lv->tb);
+      lv.level_idx.upload(li, stream);
+      lv.ts = tree->subset_target_set_dev(lv.level_idx.p, li.size(), lv.tb);
     }
-    sublap("level target set");
-    levels.push_back(std::move(lv));
   }
 
   void solve_level(const LevelDev &lv, const double *res, double *out, int mode, int add_poly, cudaStream_t stream) {
@@ -999,52 +1043,56 @@ void fr_model::fit() {
     t0 = clk::now();
   };
   auto t_lap = clk::now();
-  if (naive) {  // single dense domain (rbf.rs:423-454)
-    LevelHost lh;
-    lh.point_indices.resize(n);
-    for (size_t i = 0; i < n; ++i) lh.point_indices[i] = (int64_t)i;
-    DomainHost d;
-    d.idx = lh.point_indices;
-    d.mask.assign(n, 1);
-    d.prepare(kp_ptr, dim, st, true, mono_ptr);
-    lh.domains.push_back(std::move(d));
-    ddm.clear();
-    ddm.push_back(std::move(lh));
-  } else {
-    tree.reset(make_tree(true, nullptr));  // adaptive, sparse, own extents (rbf.rs:456-467)
-    lap("fmm tree + operators", t_lap);
-    // (building the DDM hierarchy on a second host thread meanwhile was tried: two OpenMP teams on the same cores
-    // made the whole fit's wall time erratic, 1.0 - 2.6 s, for a 0.15 s best-case gain)
-    ddm = build_ddm(kp_ptr, n, dim, st, params, mono_ptr);
-    lap("ddm hierarchy (host)", t_lap);
-  }
-  cudaStream_t stream = nullptr;
-  std::unique_ptr<DeviceSolver> solver(new DeviceSolver(*this, tree.get()));
-  bool own_stream = false;
-  if (!tree) {
-    FB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    own_stream = true;
-    solver->s = stream;
-  } else {
-    stream = tree->stream;
-  }
+  // Setup order: the device factorises a DDM level (assembly + batched Cholesky, ~0.15 s for the finest level of a
+  // 1M-point fit) while the host builds the next level and then the FMM tree (~0.15 s of host work): the hierarchy comes
+  // first, every finished level is queued on a setup stream at once, the tree is built under it.
+  cudaStream_t setup_stream = nullptr;
+  FB_CUDA(cudaStreamCreateWithFlags(&setup_stream, cudaStreamNonBlocking));
+  std::unique_ptr<DeviceSolver> solver(new DeviceSolver(*this, nullptr));
+  solver->s = setup_stream;
+  cudaStream_t stream = setup_stream;
   try {
     DeviceSolver &S = *solver;
-    S.upload_points(stream);
+    S.upload_points(setup_stream);
     if (m && !naive) {
       std::vector<double> Pm(n * m), Qm(n * m);
       evaluate_monomials(mono_ptr ? mono_ptr : points.data(), nullptr, n, dim, st.polynomial_degree, (int)m, translation.data(),
                          scale.data(), Pm.data());
       thin_q_rowmajor(Pm.data(), n, (int)m, Qm.data());
-      S.P.upload(Pm, stream);
-      S.Qp.upload(Qm, stream);
+      S.P.upload(Pm, setup_stream);
+      S.Qp.upload(Qm, setup_stream);
       S.proj.reserve(m);
     }
-    lap("monomials / thin Q / upload", t_lap);
-    for (size_t l = 0; l < ddm.size(); ++l) {
-      S.build_level(ddm[l], l + 1 == ddm.size(), stream);
-      lap("factorise level", t_lap);
+    lap("points / monomials / thin Q", t_lap);
+    if (naive) {  // single dense domain (rbf.rs:423-454)
+      LevelHost lh;
+      lh.point_indices.resize(n);
+      for (size_t i = 0; i < n; ++i) lh.point_indices[i] = (int64_t)i;
+      DomainHost d;
+      d.idx = lh.point_indices;
+      d.mask.assign(n, 1);
+      d.prepare(kp_ptr, dim, st, true, mono_ptr);
+      lh.domains.push_back(std::move(d));
+      ddm.clear();
+      ddm.push_back(std::move(lh));
+      S.build_level_launch(ddm[0], true, setup_stream);
+    } else {
+      const LevelCallback queue_level = [&](size_t, const LevelHost &level, bool is_coarse) {
+        S.build_level_launch(level, is_coarse, setup_stream);
+      };
+      ddm = build_ddm(kp_ptr, n, dim, st, params, mono_ptr, &queue_level);
+      lap("ddm hierarchy (host) + queued factorisations", t_lap);
+      tree.reset(make_tree(true, nullptr));  // adaptive, sparse, own extents (rbf.rs:456-467)
+      lap("fmm tree + operators", t_lap);
+      S.tree = tree.get();
     }
+    FB_CUDA(cudaStreamSynchronize(setup_stream));
+    if (tree) {  // from here on everything runs on the tree's stream
+      stream = tree->stream;
+      S.s = stream;
+    }
+    for (size_t l = 0; l < ddm.size(); ++l) S.finish_level(l, ddm[l], stream);
+    lap("factorisations finished + level target sets", t_lap);
     info.ddm_levels = ddm.size();
     for (size_t l = 0; l < ddm.size() && l < 8; ++l) info.ddm_domains[l] = ddm[l].domains.size();
     const auto t_setup = clk::now();
@@ -1172,11 +1220,11 @@ void fr_model::fit() {
     info.solve_seconds = std::chrono::duration<double>(clk::now() - t_setup).count();
   } catch (...) {
     solver.reset();
-    if (own_stream) cudaStreamDestroy(stream);
+    cudaStreamDestroy(setup_stream);
     throw;
   }
   solver.reset();
-  if (own_stream) cudaStreamDestroy(stream);
+  cudaStreamDestroy(setup_stream);
   if (has_trend) {  // rbf.rs:579-581 and 599-601: public points = inverse transform; evaluators transform them again
     points.swap(mono_pts);
     apply_affine(aff, points.data(), n, dim, 1, kpts.data());

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <parallel/algorithm>
+#include <chrono>
 #include <cmath>
 #include <deque>
 #include <numeric>
@@ -366,8 +367,26 @@ static int argmax_first_positive(const double *v, int n) {  // ferreus_rbf_utils
 }
 
 std::vector<LevelHost> build_ddm(const double *pts, size_t n, int dim, const Settings &s, const fr_params &p,
-                                 const double *mono_pts) {
+                                 const double *mono_pts, const LevelCallback *on_level) {
   std::vector<LevelHost> levels;
+  static const bool verbose = std::getenv("FB_TIMING") != nullptr;
+  auto t_lap = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (verbose)
+      fprintf(stderr, "[fr_fit]     ddm %-24s %8.3f s\n", what,
+              std::chrono::duration<double>(std::chrono::steady_clock::now() - t_lap).count());
+    t_lap = std::chrono::steady_clock::now();
+  };
+  // host part of the factorisations (special points, Q_top), parallel over domains (domain_decomposition.rs:314), as soon
+  // as a level is complete; the caller may then queue that level's device factorisation while the next level is built
+  auto finish = [&](LevelHost &level, bool is_coarse) {
+    std::vector<DomainHost> &doms = level.domains;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (long i = 0; i < (long)doms.size(); ++i) doms[i].prepare(pts, dim, s, is_coarse && s.basis_size != 0, mono_pts);
+    lap("prepare (special points, Q)");
+    if (on_level) (*on_level)(levels.size(), level, is_coarse);
+    lap("queue level on the device");
+  };
   std::vector<int64_t> active(n);
   std::iota(active.begin(), active.end(), 0);
   while (active.size() > p.coarse_threshold) {
@@ -419,15 +438,45 @@ std::vector<LevelHost> build_ddm(const double *pts, size_t n, int dim, const Set
 #pragma omp parallel for schedule(static) if (!outer_par && nd > 50000)
         for (long k = 0; k < (long)nd; ++k) ord[k] = {pts[cur.idx[k] * dim + axis], (int)k};
         const size_t mid = nd / 2;
-        std::nth_element(ord.begin(), ord.begin() + mid, ord.end());
+        if (!outer_par && nd > 100000)  // the first generations: few, large domains
+          __gnu_parallel::nth_element(ord.begin(), ord.begin() + mid, ord.end());
+        else
+          std::nth_element(ord.begin(), ord.begin() + mid, ord.end());
         const double mid_coord = ord[mid].first;
         std::vector<uint8_t> in_left(nd, 0);
-        for (size_t k = 0; k < mid; ++k) in_left[ord[k].second] = 1;
         DomainHost &left = lefts[gi], &right = rights[gi];
-        left.idx.reserve(mid);
-        right.idx.reserve(nd - mid);
-        for (size_t k = 0; k < nd; ++k)  // cur.idx is ascending, so both children come out ascending
-          (in_left[k] ? left.idx : right.idx).push_back(cur.idx[k]);
+        if (!outer_par && nd > 100000) {
+          // the first generations are a handful of huge domains: mark and split with all threads (a stable partition by
+          // per-chunk counts), cur.idx is ascending, so both children come out ascending
+#pragma omp parallel for schedule(static)
+          for (long k = 0; k < (long)mid; ++k) in_left[ord[k].second] = 1;
+          left.idx.resize(mid);
+          right.idx.resize(nd - mid);
+          const int nchunk = 64;
+          std::vector<size_t> cnt_l(nchunk + 1, 0);
+          const size_t per = (nd + nchunk - 1) / nchunk;
+#pragma omp parallel for schedule(static)
+          for (int c = 0; c < nchunk; ++c) {
+            size_t cl = 0;
+            for (size_t k = c * per; k < std::min(nd, (c + 1) * per); ++k) cl += in_left[k];
+            cnt_l[c + 1] = cl;
+          }
+          for (int c = 0; c < nchunk; ++c) cnt_l[c + 1] += cnt_l[c];
+#pragma omp parallel for schedule(static)
+          for (int c = 0; c < nchunk; ++c) {
+            size_t wl = cnt_l[c], wr = std::min(nd, c * per) - cnt_l[c];
+            for (size_t k = c * per; k < std::min(nd, (c + 1) * per); ++k) {
+              if (in_left[k]) left.idx[wl++] = cur.idx[k];
+              else right.idx[wr++] = cur.idx[k];
+            }
+          }
+        } else {
+          for (size_t k = 0; k < mid; ++k) in_left[ord[k].second] = 1;
+          left.idx.reserve(mid);
+          right.idx.reserve(nd - mid);
+          for (size_t k = 0; k < nd; ++k)  // cur.idx is ascending, so both children come out ascending
+            (in_left[k] ? left.idx : right.idx).push_back(cur.idx[k]);
+        }
         left.extents = cur.extents;
         left.extents[axis + dim] = mid_coord;
         right.extents = cur.extents;
@@ -450,6 +499,7 @@ std::vector<LevelHost> build_ddm(const double *pts, size_t n, int dim, const Set
       }
       gen.swap(next_gen);
     }
+    lap("bisection");
     const size_t nl = level.domains.size();
     const size_t num_coarse =
         (size_t)std::ceil(std::ceil((double)active.size() * p.coarse_ratio) / (double)nl);
@@ -508,10 +558,15 @@ std::vector<LevelHost> build_ddm(const double *pts, size_t n, int dim, const Set
         }
         dist[k] = std::sqrt(r2);
       }
+      // the reference takes a stable argsort of the distances and keeps the first `take` (domain_decomposition.rs:289-298):
+      // the same prefix, in the same order, comes from selecting the `take` smallest (distance, position) pairs and
+      // sorting only those
       std::vector<int> ord(nidx.size());
       std::iota(ord.begin(), ord.end(), 0);
-      std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return dist[a] < dist[b]; });
       const size_t take = std::min(num_overlap, nidx.size());
+      auto before = [&](int a, int b) { return dist[a] < dist[b] || (dist[a] == dist[b] && a < b); };
+      if (take < ord.size()) std::nth_element(ord.begin(), ord.begin() + take, ord.end(), before);
+      std::sort(ord.begin(), ord.begin() + take, before);
       for (size_t k = 0; k < take; ++k) overlap[i].push_back(nidx[ord[k]]);
     }
     std::vector<int64_t> next;
@@ -522,6 +577,8 @@ std::vector<LevelHost> build_ddm(const double *pts, size_t n, int dim, const Set
       dm.mask.insert(dm.mask.end(), overlap[i].size(), 0);
     }
     std::sort(next.begin(), next.end());
+    lap("coarse points + overlap");
+    finish(level, false);
     levels.push_back(std::move(level));
     active.swap(next);
   }
@@ -531,14 +588,8 @@ std::vector<LevelHost> build_ddm(const double *pts, size_t n, int dim, const Set
   cd.idx = active;
   cd.mask.assign(active.size(), 1);
   coarse.domains.push_back(std::move(cd));
+  finish(coarse, true);
   levels.push_back(std::move(coarse));
-  // host part of the factorisations (special points, Q_top), parallel over domains (domain_decomposition.rs:314)
-  for (size_t l = 0; l < levels.size(); ++l) {
-    const bool is_coarse = l + 1 == levels.size();
-    std::vector<DomainHost> &doms = levels[l].domains;
-#pragma omp parallel for schedule(dynamic, 4)
-    for (long i = 0; i < (long)doms.size(); ++i) doms[i].prepare(pts, dim, s, is_coarse && s.basis_size != 0, mono_pts);
-  }
   return levels;
 }
 

@@ -3,6 +3,7 @@
 // common.rs:246-320, preconditioning/domain_decomposition.rs:67-346, domain.rs:153-383 (host part).
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -50,8 +51,11 @@ struct LevelHost {
 };
 
 // DDMTree::new without the factorisations (domain_decomposition.rs:67-346)
+// on_level(l, level, is_coarse) is called as soon as level l is complete (its domains prepared), before the next level
+// is built
+using LevelCallback = std::function<void(size_t, const LevelHost &, bool)>;
 std::vector<LevelHost> build_ddm(const double *pts, size_t n, int dim, const Settings &s, const fr_params &p,
-                                 const double *mono_pts = nullptr);
+                                 const double *mono_pts = nullptr, const LevelCallback *on_level = nullptr);
 
 // thin Q of an n x m matrix (row-major in, row-major out), rbf.rs:493-495
 void thin_q_rowmajor(const double *a, size_t n, int m, double *q);

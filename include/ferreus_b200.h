@@ -83,6 +83,10 @@ void fb_host_free(void *p);
  *     kernels) from the FP64 tensor cores (csrc/p2p_mma.cu; measured 4 % faster only, not the default).            */
 int fb_set_sqrt_mode(int fast);
 int fb_get_sqrt_mode(void);
+/* Device memory released by trees / models is cached for the next allocation of a similar size (repeated fits do not
+ * pay cudaMalloc / cudaFree again); fb_trim_memory hands the cache back to the driver and returns the bytes released.
+ * FB_NO_MEMORY_CACHE=1 in the environment disables the cache.                                                        */
+uint64_t fb_trim_memory(void);
 
 /* FmmTree::new  (ferreus_rbf_utils/src/utils.rs:392-421 -> ferreus_bbfmm/src/bbfmm.rs:272-353).
  * points: n x dim (dim 1..3).  extents: NULL or [mins..., maxs...] (2*dim doubles).            */
@@ -127,6 +131,10 @@ int fb_tree_download_result(fb_tree *t, double *out_vals, ptrdiff_t o_rs, ptrdif
 /* per-pass device time (ms, CUDA events) of the last fb_tree_matvec_resident call when timing is
  * enabled with fb_tree_set_timing(t, 1).  names: p2m m2m m2l p2l l2l l2p p2p_m2p total          */
 int fb_tree_set_timing(fb_tree *t, int enabled);
+/* algorithmic FLOPs of one M2L pass per right-hand side: sum over V-list entries of 4 r P (2 P^2 uncompressed) */
+int fb_tree_m2l_flops(const fb_tree *t, double *flops_out);
+/* FP64 peak of the tensor instruction (mma.sync m8n8k4) next to fb_measure_fp64_tflops (DFMA): same datapath on B200 */
+int fb_measure_fp64_dmma_tflops(double *tflops_out);
 /* device time (ms, CUDA events on the handle's stream) of the last fb_tree_matvec_resident call */
 int fb_tree_last_matvec_ms(fb_tree *t, double *ms_out);
 /* FP64 FMA-pipe peak of the current device (TFLOP/s): in-run DFMA micro-benchmark, CUDA-event timed */

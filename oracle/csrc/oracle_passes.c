@@ -49,6 +49,10 @@ static inline double kval(const orc_kernel *k, double r2) {
 
 double orc_kernel_value(const orc_kernel *k, double r2) { return kval(k, r2); }
 
+void orc_set_num_threads(int n) {
+  if (n > 0) omp_set_num_threads(n);
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
@@ -228,5 +232,121 @@ void orc_m2l(int P, int nrhs, int n_tgt, const int64_t *tgt_cell, const int64_t 
       }
     }
     free(x); free(y); free(z);
+  }
+}
+
+/* ---- Chebyshev transfers (added round 2: the upward pass, L2L and L2P were Python loops over cells) ---------------
+ * S_n(x)[m] = (2 sum_k T_k(x) T_k(x_m) - 1) / p   (chebyshev.rs:114-127), T by the three-term recurrence (:47-110);
+ * tensor weights with axis 0 slowest (chebyshev.rs:894-906).  tn[m * p + k] = T_k(node_m).                         */
+static void cheb_sn(int p, double x, const double *tn, double *s) {
+  double T[32];
+  T[0] = 1.0;
+  if (p > 1) T[1] = x;
+  for (int k = 2; k < p; ++k) T[k] = 2.0 * x * T[k - 1] - T[k - 2];
+  for (int m = 0; m < p; ++m) {
+    double acc = 0.0;
+    for (int k = 0; k < p; ++k) acc += T[k] * tn[m * p + k];
+    s[m] = (acc * 2.0 - 1.0) / (double)p;
+  }
+}
+
+static void tensor_weights(int p, int dim, const double *pt, const double *center, double half, const double *tn,
+                           double *S /* p^dim */) {
+  double s[3][32];
+  for (int d = 0; d < dim; ++d) cheb_sn(p, (pt[d] - center[d]) / half, tn, s[d]);
+  if (dim == 1) {
+    for (int i = 0; i < p; ++i) S[i] = s[0][i];
+  } else if (dim == 2) {
+    for (int i = 0; i < p; ++i)
+      for (int j = 0; j < p; ++j) S[i * p + j] = s[0][i] * s[1][j];
+  } else {
+    for (int i = 0; i < p; ++i)
+      for (int j = 0; j < p; ++j) {
+        const double sij = s[0][i] * s[1][j];
+        for (int k = 0; k < p; ++k) S[(i * p + j) * p + k] = sij * s[2][k];
+      }
+  }
+}
+
+/* P2M (bbfmm.rs:691-739): M[cell][rhs][:] += sum_{points of the leaf} S(point) w[point][rhs] */
+void orc_p2m(int p, int dim, int P, int nrhs, int n_leaves, const int64_t *leaf_cell, const int64_t *t_ptr,
+             const int64_t *t_idx, const double *src, const double *w, const double *center, const double *half,
+             const double *tn, double *M) {
+#pragma omp parallel
+  {
+    double *S = (double *)malloc(sizeof(double) * (size_t)P);
+#pragma omp for schedule(dynamic, 4)
+    for (int l = 0; l < n_leaves; ++l) {
+      const int64_t c = leaf_cell[l];
+      double *Mc = M + (size_t)c * nrhs * P;
+      for (int64_t e = t_ptr[l]; e < t_ptr[l + 1]; ++e) {
+        const int64_t i = t_idx[e];
+        tensor_weights(p, dim, src + (size_t)i * dim, center + (size_t)c * dim, half[c], tn, S);
+        for (int r = 0; r < nrhs; ++r) {
+          const double wr = w[(size_t)i * nrhs + r];
+          double *Mr = Mc + (size_t)r * P;
+          for (int k = 0; k < P; ++k) Mr[k] += S[k] * wr;
+        }
+      }
+    }
+    free(S);
+  }
+}
+
+/* L2P (bbfmm.rs:1358-1440, values): out[point][rhs] += S(point) . L[cell][rhs][:] */
+void orc_l2p(int p, int dim, int P, int nrhs, int n_leaves, const int64_t *leaf_cell, const int64_t *t_ptr,
+             const int64_t *t_idx, const double *src, const double *center, const double *half, const double *tn,
+             const double *L, double *out) {
+#pragma omp parallel
+  {
+    double *S = (double *)malloc(sizeof(double) * (size_t)P);
+#pragma omp for schedule(dynamic, 4)
+    for (int l = 0; l < n_leaves; ++l) {
+      const int64_t c = leaf_cell[l];
+      const double *Lc = L + (size_t)c * nrhs * P;
+      for (int64_t e = t_ptr[l]; e < t_ptr[l + 1]; ++e) {
+        const int64_t i = t_idx[e];
+        tensor_weights(p, dim, src + (size_t)i * dim, center + (size_t)c * dim, half[c], tn, S);
+        for (int r = 0; r < nrhs; ++r) {
+          const double *Lr = Lc + (size_t)r * P;
+          double acc = 0.0;
+          for (int k = 0; k < P; ++k) acc += S[k] * Lr[k];
+          out[(size_t)i * nrhs + r] += acc;
+        }
+      }
+    }
+    free(S);
+  }
+}
+
+/* one level of M2M (bbfmm.rs:742-772): M[parent] += M2M[slot(child)] M[child]; parents of the level are independent.
+ * one level of L2L (bbfmm.rs:1051-1086): L[child] += M2M[slot(child)]^T L[parent]; children are independent.
+ * m2m: [2^dim][P][P] row-major; up != 0 selects M2M.                                                                */
+void orc_transfer_level(int P, int nrhs, int up, int n_parents, const int64_t *parents, const int64_t *child_ptr,
+                        const int64_t *child_idx, const int64_t *child_slot, const double *m2m, double *X) {
+#pragma omp parallel for schedule(dynamic, 2)
+  for (int q = 0; q < n_parents; ++q) {
+    const int64_t par = parents[q];
+    for (int64_t e = child_ptr[q]; e < child_ptr[q + 1]; ++e) {
+      const int64_t ch = child_idx[e];
+      const double *A = m2m + (size_t)child_slot[ch] * P * P;
+      for (int r = 0; r < nrhs; ++r) {
+        double *xp = X + ((size_t)par * nrhs + r) * P, *xc = X + ((size_t)ch * nrhs + r) * P;
+        if (up) {
+          for (int i = 0; i < P; ++i) {
+            double acc = 0.0;
+            const double *row = A + (size_t)i * P;
+            for (int j = 0; j < P; ++j) acc += row[j] * xc[j];
+            xp[i] += acc;
+          }
+        } else {
+          for (int i = 0; i < P; ++i) {
+            const double v = xp[i];
+            const double *row = A + (size_t)i * P;
+            for (int j = 0; j < P; ++j) xc[j] += row[j] * v;
+          }
+        }
+      }
+    }
   }
 }

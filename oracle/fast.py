@@ -144,9 +144,44 @@ class FastFmm:
         self.children = {self.index[k]: [self.index[c] for c in ch] for k, ch in L.children.items() if ch}
         self.child_slot = np.array([morton.get_child_index(k, self.dim) for k in self.keys], dtype=np.int64)
         self.m2m = [np.ascontiguousarray(m) for m in ops.m2m]
+        # C transfers (oracle_passes.c: orc_p2m / orc_l2p / orc_transfer_level): per-leaf cell ids, T_k(node_m) table,
+        # per level the parents with their children as CSR
+        self.leaf_cell = np.array([self.index[k] for k in self.leaf_keys], dtype=np.int64)
+        self.tn = np.ascontiguousarray(tree.ops.polynomial_nodes, dtype=np.float64)
+        self.m2m_all = np.ascontiguousarray(np.stack(self.m2m), dtype=np.float64)
+        self.level_transfers = {}
+        for lvl, cells in L.level_cells_map.items():
+            par = [self.index[k] for k in cells if self.children.get(self.index[k])]
+            ptr, idx = [0], []
+            for pi in par:
+                idx.extend(self.children[pi])
+                ptr.append(len(idx))
+            self.level_transfers[lvl] = (np.array(par, dtype=np.int64), np.array(ptr, dtype=np.int64),
+                                         np.array(idx, dtype=np.int64))
 
     # ------------------------------------------------------------------------------------
     def upward(self, w):
+        nrhs = w.shape[1]
+        M = np.zeros((self.nc, nrhs, self.P))
+        l = lib()
+        wc = np.ascontiguousarray(w)
+        l.orc_p2m(self.p, self.dim, self.P, nrhs, len(self.leaf_keys), _p(self.leaf_cell, C.c_int64),
+                  _p(self.t_ptr, C.c_int64), _p(self.t_idx, C.c_int64), _p(self.src, C.c_double), _p(wc, C.c_double),
+                  _p(self.center, C.c_double), _p(self.half, C.c_double), _p(self.tn, C.c_double), _p(M, C.c_double))
+        for lvl in range(self.t.depth - 1, 0, -1):
+            self._transfer(lvl, M, up=1, nrhs=nrhs)
+        return M
+
+    def _transfer(self, lvl, X, up, nrhs):
+        par, ptr, idx = self.level_transfers.get(lvl, (None, None, None))
+        if par is None or len(par) == 0:
+            return
+        lib().orc_transfer_level(self.P, nrhs, up, len(par), _p(par, C.c_int64), _p(ptr, C.c_int64),
+                                 _p(idx, C.c_int64), _p(self.child_slot, C.c_int64), _p(self.m2m_all, C.c_double),
+                                 _p(X, C.c_double))
+
+    def upward_numpy(self, w):
+        """the same pass with numpy per cell (the round-1 implementation; kept as the cross-check of the C version)"""
         t = self.t
         nrhs = w.shape[1]
         M = np.zeros((self.nc, nrhs, self.P))
@@ -177,12 +212,8 @@ class FastFmm:
                       _p(self.x_ptr, C.c_int64), _p(self.x_idx, C.c_int64), _p(self.src, C.c_double),
                       _p(wc, C.c_double), _p(self.center, C.c_double), _p(self.half, C.c_double), self.P,
                       _p(self.nodes_nd, C.c_double), _p(Lc, C.c_double))
-        t = self.t
-        for lvl in range(1, t.depth + 1):
-            for k in t.lists.level_cells_map.get(lvl, []):
-                i = self.index[k]
-                for c in self.children.get(i, []):
-                    Lc[c] += Lc[i] @ self.m2m[self.child_slot[c]]
+        for lvl in range(1, self.t.depth + 1):
+            self._transfer(lvl, Lc, up=0, nrhs=nrhs)
         return Lc
 
     def leaf_pass(self, w, M, Lc, leaf_subset=None):
@@ -207,13 +238,11 @@ class FastFmm:
                             _p(wc, C.c_double), _p(wp, C.c_int64), _p(wi, C.c_int64), _p(self.center, C.c_double),
                             _p(self.half, C.c_double), _p(Mc, C.c_double), self.P, _p(self.nodes_nd, C.c_double),
                             _p(out, C.c_double))
-        for s in sel:
-            k = self.leaf_keys[s]
-            i = self.index[k]
-            idx = t.lists.leaf_source_indices[k]
-            S, _ = chebyshev.get_approximation_coefficients(self.p, self.src[idx], self.center[i], 2 * self.half[i],
-                                                            t.ops.polynomial_nodes, self.dim)
-            out[idx] += S @ Lc[i].T
+        Lcc = np.ascontiguousarray(Lc)
+        lcell = np.ascontiguousarray(self.leaf_cell[sel])
+        lib().orc_l2p(self.p, self.dim, self.P, nrhs, len(sel), _p(lcell, C.c_int64), _p(tp, C.c_int64), _p(ti, C.c_int64),
+                      _p(self.src, C.c_double), _p(self.center, C.c_double), _p(self.half, C.c_double),
+                      _p(self.tn, C.c_double), _p(Lcc, C.c_double), _p(out, C.c_double))
         return out
 
     def matvec(self, w):

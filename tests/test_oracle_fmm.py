@@ -106,3 +106,19 @@ def test_m2m_reproduces_polynomials():
         child_nodes_in_parent = (nodes + (1 if c else -1)) * 0.5
         # L2L = M2M^T interpolates parent node values to child nodes
         assert np.allclose(m2m[c].T @ f(nodes), f(child_nodes_in_parent), atol=1e-13)
+
+
+@pytest.mark.parametrize("n,dim,kernel,order,nrhs", [(4000, 3, 0, 5, 2), (3000, 2, 1, 6, 1), (1500, 1, 7, 6, 3)])
+def test_c_transfers_match_the_numpy_restatement(n, dim, kernel, order, nrhs):
+    """oracle/csrc/oracle_passes.c orc_p2m / orc_transfer_level / orc_l2p (the upward pass, L2L and L2P of the CPU
+    baseline) against the per-cell numpy restatement and the pure-Python oracle matvec."""
+    from oracle import fast
+    from tests import helpers as H
+    pts = H.make_points(n, dim, "clustered", seed=3)
+    w = np.random.default_rng(1).random((n, nrhs)) - 0.5
+    ot = H.oracle_tree(pts, order, kernel, True, True, 30, 2, 1e-6)
+    ff = fast.FastFmm(ot)
+    M, M2 = ff.upward(w), ff.upward_numpy(w)
+    assert np.abs(M - M2).max() <= 1e-13 * np.abs(M2).max()
+    ot.set_weights(w)
+    assert H.rel_l2(ff.matvec(w), ot.evaluate(w, pts)) <= 1e-13
