@@ -20,8 +20,9 @@ One "step" = one matvec = set_weights(w) + evaluate(w, targets = sources) on a p
              default is the second-order one (<= 1.3e-12 per kernel value, see include/ferreus_b200.h).
 N > 1: one process per GPU (torchrun), ONE shared 1M-point cloud partitioned by Morton-contiguous leaf ranges
 (csrc/comm.cu): owned-leaf upward pass, ncclAllReduce of the multipoles under the near-field pass, downward / leaf passes
-for the owned targets, ncclAllGather of the result rows.  `value` = N / (device time of that step, max over ranks):
-strong scaling.  Every rank checks the partitioned result against the unpartitioned matvec on its own GPU.
+of the share (every kernel evaluation of the unpartitioned matvec is made by exactly one rank: the symmetric halves for
+foreign rows travel in the result), ncclAllReduce of the full-length result.  `value` = N / (device time of that step, max
+over ranks): strong scaling.  Every rank checks the partitioned result against the unpartitioned matvec on its own GPU.
 """
 import argparse
 import json
@@ -195,7 +196,7 @@ def run_reference(args):
 def workload_config(n, n_gpus):
     par = ("one GPU" if n_gpus == 1 else
            f"one {n}-point cloud partitioned over {n_gpus} GPUs by Morton-contiguous leaf ranges balanced by work; "
-           "ncclAllReduce of the multipoles (under the near-field pass) + ncclAllGather of the result rows per matvec")
+           "ncclAllReduce of the multipoles (under the near-field pass) + ncclAllReduce of the full-length result per matvec")
     return {"workload": f"ferreus_bbfmm 3D LinearRbf matvec, N={n} uniform points in the unit cube, "
                         f"Chebyshev order {ORDER}, 1 RHS, adaptive sparse tree, 256 pts/leaf, ACA eps=1e-{ORDER} "
                         "(BASELINE.md headline H)",
@@ -360,12 +361,12 @@ def main():
         med_r = {k: float(np.median([s_[k] for s_ in stage_ms])) for k in stage_ms[0]}
         a, b = tree.shard_rows(rank)
         kernel_keys = ["p2m", "m2m", "m2l", "wx", "l2l", "l2p", "leaf"]
-        mine = torch.tensor([float(b - a), med_r["upward"], med_r["near_field_under_allreduce"], med_r["downward_leaf"],
-                             med_r["allgather"], partition_err] + [med_r["k_" + k] for k in kernel_keys],
+        mine = torch.tensor([float(b - a), med_r["near_field"], med_r["multipole_wait"], med_r["downward_leaf"],
+                             med_r["result_allreduce"], partition_err] + [med_r["k_" + k] for k in kernel_keys],
                             dtype=torch.float64, device="cuda")
         allv = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allv, mine)
-        names = ["rows", "upward_ms", "near_field_under_allreduce_ms", "downward_leaf_ms", "allgather_ms",
+        names = ["rows", "near_field_ms", "multipole_wait_ms", "downward_leaf_ms", "result_allreduce_ms",
                  "rel_l2_vs_unpartitioned"] + ["kernel_" + k + "_ms" for k in kernel_keys]
         per_rank = [dict(zip(names, v.cpu().tolist())) for v in allv]
     total_ms_max, e2e_ms_max = [float(v) for v in tms.tolist()]
@@ -462,8 +463,9 @@ def main():
         if per_rank is not None:
             line["partition"] = {"per_rank": per_rank,
                                  "what": "device time per stage and per kernel on every rank (median over the timed steps); "
-                                         "near_field_under_allreduce = P2P of the owned targets with the multipole "
-                                         "all-reduce running beside it on a second stream"}
+                                         "near_field = weight sort + symmetric P2P of the owned chunks, with the owned-leaf "
+                                         "upward pass and the multipole all-reduce running beside it on a second stream; "
+                                         "multipole_wait = what is left of those two when the P2P is done"}
         if world == 1 and not args.no_fit:
             line["fit"] = full_fit(n)
         if world == 1 and not args.no_cpu_baseline:

@@ -221,6 +221,11 @@ class FmmTree:
         self._check(self._lib.fb_tree_shard(self._h, comm._h if comm is not None else None))
         self._comm = comm
 
+    def shard_as(self, comm, rank, world, exact=False):
+        """Profiling / test aid: the share of `rank` of `world` ranks on a world-1 communicator (fb_tree_shard_as)."""
+        self._check(self._lib.fb_tree_shard_as(self._h, comm._h, rank, world, 1 if exact else 0))
+        self._comm = comm
+
     def shard_rows(self, rank):
         a, b = C.c_uint64(), C.c_uint64()
         self._check(self._lib.fb_tree_shard_rows(self._h, rank, C.byref(a), C.byref(b)))
@@ -232,7 +237,7 @@ class FmmTree:
     def sharded_timing(self):
         ms = np.zeros(4)
         self._check(self._lib.fb_tree_sharded_timing(self._h, _lib.dptr(ms)))
-        return dict(zip(("upward", "near_field_under_allreduce", "downward_leaf", "allgather"), ms.tolist()))
+        return dict(zip(("near_field", "multipole_wait", "downward_leaf", "result_allreduce"), ms.tolist()))
 
     def sharded_download(self):
         out = _lib.pinned.empty((self._n, self._nrhs))

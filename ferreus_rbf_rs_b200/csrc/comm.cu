@@ -2,16 +2,20 @@
 // NCCL over NVLink for the two exchange steps.  The reference is single-process rayon (bbfmm.rs:669, 682, 788, 841,
 // 1122 are its parallel loops); this file is what replaces "one rayon pool" when the tree spans several B200s.
 //
-//   ownership   leaves in Morton order, cut into `world` contiguous ranges of nearly equal estimated work
-//               (fb_tree_leaf_work); a rank owns the points of its range as sources AND as targets.  Tree topology and
-//               point coordinates are replicated (24 B per point), coefficients and results are not.
+//   ownership   leaves in Morton order, cut into `world` contiguous ranges of nearly equal estimated work; a rank owns
+//               the points of its range.  Tree topology and point coordinates are replicated (24 B per point), the
+//               work is not: every kernel evaluation of the unpartitioned matvec is made by exactly one rank.
 //   upward      P2M over the OWNED leaves only, M2M over the cells that have owned descendants: every rank holds the
 //               exact multipoles of the cells inside its range and a partial sum for the cells that span ranks;
 //   exchange 1  ncclAllReduce(sum) of the multipole array completes the spanning cells and hands every rank the halo
 //               multipoles its V / W lists need, on a side stream UNDER the near-field pass (P2P needs no multipoles);
-//   downward    M2L / P2L / L2L restricted to cells with owned targets, L2P / M2P for owned targets;
-//   exchange 2  ncclAllGather of the owned result rows (padded to the largest share) + one scatter kernel: the full
-//               result, replicated, in the caller's row order — the next Krylov vector needs exactly that.
+//   near field  symmetric P2P (p2p_sym.cu) for the chunks of the owned range against ALL sources behind them: the
+//               source-side sums of rows another rank owns are added into this rank's copy of the full-length result;
+//   downward    M2L / L2L / L2P for the cells / targets of the share; the fused W/X kernel (p2l.cu) for the cells with
+//               owned targets — its M2P half, applied by the owner of the cell's first point, also reaches foreign rows;
+//   exchange 2  ncclAllReduce(sum) of the full-length result (8 N nrhs bytes): owned rows + the symmetric halves other
+//               ranks computed for them = the full A w, replicated, in the caller's row order — the next Krylov vector
+//               needs exactly that.
 // NCCL is loaded at run time (dlopen of the copy already in the process, else libnccl.so.2): the single-GPU drop-in
 // has no link-time dependency on it.
 #include <dlfcn.h>
@@ -96,18 +100,6 @@ void partition_by_work(const double *work, size_t n, int parts, uint64_t *bounds
   }
 }
 
-// full result in the caller's row order from the gathered, padded, Morton-ordered shares
-__global__ void k_scatter_gathered(const double *gathered, const int *shard_pos, int world, size_t max_rows, int nrhs,
-                                   const uint32_t *perm, size_t n, double *full) {
-  const size_t pos = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (pos >= n) return;
-  int r = 0;
-  while (r + 1 < world && (size_t)shard_pos[r + 1] <= pos) ++r;
-  const double *src = gathered + ((size_t)r * max_rows + (pos - (size_t)shard_pos[r])) * nrhs;
-  double *dst = full + (size_t)perm[pos] * nrhs;
-  for (int k = 0; k < nrhs; ++k) dst[k] = src[k];
-}
-
 __global__ void k_iota_u64(const uint32_t *perm, size_t begin, size_t count, unsigned long long *out) {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i < count) out[i] = perm[begin + i];
@@ -133,19 +125,18 @@ struct fb_comm {
 // per-tree state of the partition (fb_tree::shard)
 struct fb_shard {
   fb_comm *comm = nullptr;
+  bool full_upward = false;           // emulated share with every multipole formed locally: the owned rows come out exact
+  int rank = 0, world = 1;            // the share this process computes: the communicator's, or an emulated one (fb_tree_shard_as)
   std::vector<uint64_t> leaf_bounds;  // world + 1 boundaries into the Morton leaf sequence
   std::vector<int> pos;               // world + 1 boundaries into the sorted point order
-  size_t max_rows = 0;                // largest share
-  DBuf<int> d_pos;
   DBuf<int> d_owned_leaves;           // cells of the owned leaves that hold sources (P2M grid)
   int n_owned_leaves = 0;
-  DBuf<double> d_gather, d_full;
   TargetBuffers tb;
   TargetSet ts{};
   DBuf<unsigned long long> d_rows;
   std::vector<int> level_lo, level_hi;  // per level: the cells with owned targets are the ids [lo, hi)
   M2LItemTable *m2l_table = nullptr;    // M2L work items of that share
-  double last_ms[4] = {0, 0, 0, 0};   // upward, all-reduce wait, downward + leaf, all-gather + scatter
+  double last_ms[4] = {0, 0, 0, 0};   // near field, rest of upward pass + multipole all-reduce, downward + leaf, result all-reduce
   cudaEvent_t ev[5] = {};
   ~fb_shard() {
     for (auto &e : ev)
@@ -203,7 +194,12 @@ int fb_comm_init(const uint8_t *id128, int rank, int world_size, fb_comm **out) 
     ncclUniqueId id;
     std::memcpy(&id, id128, sizeof(id));
     FB_NCCL(nccl().CommInitRank(&c->comm, world_size, id, rank));
-    FB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    // highest priority: the collective's CTAs must become resident while the near-field kernel it runs under is still
+    // feeding the SMs, not after that kernel's last wave (a default-priority stream measured exactly that: 0.68 ms for
+    // 0.48 ms of P2P at 8 ranks)
+    int prio_lo = 0, prio_hi = 0;
+    FB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    FB_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
     FB_CUDA(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
     FB_CUDA(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
   });
@@ -224,7 +220,41 @@ void fb_comm_free(fb_comm *c) {
 int fb_comm_rank(const fb_comm *c) { return c ? c->rank : -1; }
 int fb_comm_world_size(const fb_comm *c) { return c ? c->world : -1; }
 
-int fb_tree_shard(fb_tree *t, fb_comm *comm) {
+// Estimated work of every leaf under the ownership rules above, in units of one direct-sum kernel evaluation
+// (calibrated on the 1M-point headline workload: symmetric P2P 1.16 ps, W/X 0.74 ps per evaluation, M2L 1.75 ns per entry
+// at P = 343): the P2P evaluations of a leaf are the pairs with the sources BEHIND it (one RHS: p2p_sym.cu) or all its
+// ordered pairs; a cell's X-list work and M2L entries are pushed down to its leaves.
+static void share_work(const fb_tree &t, uint64_t *leaf_ptr, double *work) {
+  const HostTree &ht = t.ht;
+  const size_t nl = ht.leaves.size(), nc = ht.ncells();
+  const bool sym = t.nrhs == 1;
+  std::vector<double> down(nc, 0.0);
+  for (size_t c = 1; c < nc; ++c) {
+    double nx = 0;
+    for (long long e = ht.x_ptr[c]; e < ht.x_ptr[c + 1]; ++e) nx += ht.pt_end[ht.x_idx[e]] - ht.pt_begin[ht.x_idx[e]];
+    down[c] += nx * t.P + (double)(ht.v_ptr[c + 1] - ht.v_ptr[c]) * 7.0 * t.P;
+    const int nch = ht.child_ptr[c + 1] - ht.child_ptr[c];
+    for (int k = ht.child_ptr[c]; k < ht.child_ptr[c + 1]; ++k) down[ht.child_idx[k]] += down[c] / nch;
+  }
+  for (size_t l = 0; l < nl; ++l) {
+    const int c = ht.leaves[l];
+    leaf_ptr[l] = (uint64_t)ht.pt_begin[c];
+    const double nt = ht.pt_end[c] - ht.pt_begin[c];
+    double nsrc = 0;
+    for (long long e = ht.u_ptr[c]; e < ht.u_ptr[c + 1]; ++e) {
+      const int u = ht.u_idx[e];
+      if (!sym || ht.pt_begin[u] >= ht.pt_begin[c]) nsrc += ht.pt_end[u] - ht.pt_begin[u];
+    }
+    // (the M2P evaluations of the leaf's W list ride on the X-list evaluations of those cells)
+    work[l] = (sym ? 1.6 : 1.0) * nt * nsrc + down[c] + 0.3 * nt * t.P + 1.0;
+  }
+  leaf_ptr[nl] = (uint64_t)t.n;
+}
+
+// as_world > 0: take the share of rank `as_rank` of `as_world` ranks with a world-1 communicator — the per-rank kernel
+// times of an N-GPU partition measured on one GPU (tools/shard_emulate.py); the collectives degenerate to copies, so
+// the owned rows are exact only with `exact` != 0 (every multipole formed locally: the upward time is then the unpartitioned one)
+static int shard_impl(fb_tree *t, fb_comm *comm, int as_rank, int as_world, int exact) {
   return guarded([&] {
     FB_REQUIRE(t, "null tree");
     FB_CUDA(cudaSetDevice(t->device));
@@ -236,19 +266,26 @@ int fb_tree_shard(fb_tree *t, fb_comm *comm) {
     FB_REQUIRE(comm->device == t->device, "the communicator and the tree live on different devices");
     std::unique_ptr<fb_shard> sh(new fb_shard());
     sh->comm = comm;
+    sh->rank = comm->rank;
+    sh->world = comm->world;
+    if (as_world > 0) {
+      FB_REQUIRE(comm->world == 1 && as_rank >= 0 && as_rank < as_world, "emulated shares need a world-1 communicator");
+      sh->rank = as_rank;
+      sh->world = as_world;
+      sh->full_upward = exact != 0;
+    }
+    const int world = sh->world, rank = sh->rank;
     const HostTree &ht = t->ht;
     const size_t nl = ht.leaves.size();
     std::vector<uint64_t> leaf_ptr(nl + 1);
     std::vector<double> work(nl);
-    FB_REQUIRE(fb_tree_leaf_work(t, leaf_ptr.data(), work.data()) == FB_OK, "leaf work");
-    sh->leaf_bounds.resize(comm->world + 1);
-    partition_by_work(work.data(), nl, comm->world, sh->leaf_bounds.data());
-    sh->pos.resize(comm->world + 1);
-    for (int r = 0; r <= comm->world; ++r) sh->pos[r] = (int)leaf_ptr[sh->leaf_bounds[r]];
-    for (int r = 0; r < comm->world; ++r) sh->max_rows = std::max(sh->max_rows, (size_t)(sh->pos[r + 1] - sh->pos[r]));
-    sh->d_pos.upload(sh->pos, t->stream);
+    share_work(*t, leaf_ptr.data(), work.data());
+    sh->leaf_bounds.resize(world + 1);
+    partition_by_work(work.data(), nl, world, sh->leaf_bounds.data());
+    sh->pos.resize(world + 1);
+    for (int r = 0; r <= world; ++r) sh->pos[r] = (int)leaf_ptr[sh->leaf_bounds[r]];
     std::vector<int> owned;
-    for (uint64_t l = sh->leaf_bounds[comm->rank]; l < sh->leaf_bounds[comm->rank + 1]; ++l) {
+    for (uint64_t l = sh->leaf_bounds[rank]; l < sh->leaf_bounds[rank + 1]; ++l) {
       const int c = ht.leaves[l];
       if (ht.pt_end[c] > ht.pt_begin[c]) owned.push_back(c);
     }
@@ -265,19 +302,33 @@ int fb_tree_shard(fb_tree *t, fb_comm *comm) {
     sh->n_owned_leaves = (int)owned.size();
     sh->d_owned_leaves.upload(owned, t->stream);
     // owned rows (Morton order) as the target subset: cell flags, leaf tiles, fused W/X row map
-    const size_t p0 = (size_t)sh->pos[comm->rank], cnt = (size_t)sh->pos[comm->rank + 1] - p0;
+    const size_t p0 = (size_t)sh->pos[rank], cnt = (size_t)sh->pos[rank + 1] - p0;
     FB_REQUIRE(cnt > 0, "a rank owns no points: more ranks than leaves with work");
     sh->d_rows.reserve(cnt);
     FB_LAUNCH(k_iota_u64, (unsigned)((cnt + 255) / 256), 256, 0, t->stream, t->d_perm.p, p0, cnt, sh->d_rows.p);
     sh->ts = t->subset_target_set_dev(sh->d_rows.p, cnt, sh->tb);
+    // the rows were listed in Morton order, so target i of the set is the source at sorted position p0 + i; the result
+    // buffer of a partitioned matvec has a row for every source (foreign rows receive the symmetric halves), so the
+    // set's row maps are the global ones
+    const TargetSet all = t->source_target_set();
+    sh->ts.own_lo = (int)p0;
+    sh->ts.own_hi = (int)(p0 + cnt);
+    sh->ts.out_row = all.out_row + p0;
+    sh->ts.row_of_pos = all.row_of_pos;
+    sh->ts.tgt_prefix = nullptr;
     for (auto &e : sh->ev) FB_CUDA(cudaEventCreate(&e));
     FB_CUDA(cudaStreamSynchronize(t->stream));
     t->shard = sh.release();
   });
 }
 
+int fb_tree_shard(fb_tree *t, fb_comm *comm) { return shard_impl(t, comm, 0, 0, 0); }
+int fb_tree_shard_as(fb_tree *t, fb_comm *comm, int rank, int world, int exact) {
+  return shard_impl(t, comm, rank, world, exact);
+}
+
 int fb_tree_shard_rows(const fb_tree *t, int rank, uint64_t *begin_pos, uint64_t *end_pos) {
-  if (!t || !t->shard || rank < 0 || rank >= t->shard->comm->world) return FB_ERR_INVALID_ARGUMENT;
+  if (!t || !t->shard || rank < 0 || rank >= t->shard->world) return FB_ERR_INVALID_ARGUMENT;
   if (begin_pos) *begin_pos = (uint64_t)t->shard->pos[rank];
   if (end_pos) *end_pos = (uint64_t)t->shard->pos[rank + 1];
   return FB_OK;
@@ -293,56 +344,55 @@ int fb_tree_matvec_sharded(fb_tree *t) {
     fb_comm &cm = *sh.comm;
     cudaStream_t s = t->stream;
     const size_t nc = t->ht.ncells();
+    const size_t out_count = t->n * (size_t)t->nrhs;
     FB_CUDA(cudaEventRecord(sh.ev[0], s));
     t->sort_weights();
-    t->upward(sh.d_owned_leaves.p, sh.n_owned_leaves, sh.ts.cell_flag);
-    FB_CUDA(cudaEventRecord(sh.ev[1], s));
-    // exchange 1 under the near-field pass
-    const bool fuse = t->ht.adaptive && t->n_x_cells > 0 && sh.ts.row_of_pos != nullptr;
-    const bool p2p_first = fuse || t->n_w_entries == 0;  // the near-field kernel then needs no multipoles
+    // The near-field pass needs the sorted weights and nothing else, so it runs on the main stream while the upward pass
+    // (P2M, then one small M2M launch per level: latency-bound on a rank's share) and exchange 1 run beside it on the
+    // communicator's stream.
+    const bool fuse = t->ht.adaptive && t->n_x_cells > 0;
     const size_t mult_count = nc * (size_t)t->nrhs * coef_stride(t->P);
+    FB_CUDA(cudaEventRecord(cm.ev_ready, s));
+    FB_CUDA(cudaStreamWaitEvent(cm.stream, cm.ev_ready, 0));
+    {
+      struct StreamSwap {  // fb_tree's passes launch on t->stream
+        fb_tree *t;
+        cudaStream_t saved;
+        StreamSwap(fb_tree *t_, cudaStream_t other) : t(t_), saved(t_->stream) { t->stream = other; }
+        ~StreamSwap() { t->stream = saved; }
+      } swap(t, cm.stream);
+      if (sh.full_upward) t->upward();
+      else t->upward(sh.d_owned_leaves.p, sh.n_owned_leaves, sh.ts.cell_flag);
+    }
     if (cm.world > 1) {
-      FB_CUDA(cudaEventRecord(cm.ev_ready, s));
-      FB_CUDA(cudaStreamWaitEvent(cm.stream, cm.ev_ready, 0));
       FB_NCCL(nccl().AllReduce(t->d_mult.p, t->d_mult.p, mult_count, ncclDouble, ncclSum, cm.comm, cm.stream));
-      FB_CUDA(cudaEventRecord(cm.ev_done, cm.stream));
       g_launches.fetch_add(1);
     }
-    if (p2p_first) {
-      t->d_out.zero(std::max(sh.ts.m, sh.max_rows) * (size_t)t->nrhs, s);
-      if (t->timing) FB_CUDA(cudaEventRecord(t->ev[10], s));
-      t->launch_p2p(sh.ts, false, fuse, s, false);
-      if (t->timing) FB_CUDA(cudaEventRecord(t->ev[11], s));
-    }
-    if (cm.world > 1) FB_CUDA(cudaStreamWaitEvent(s, cm.ev_done, 0));
+    FB_CUDA(cudaEventRecord(cm.ev_done, cm.stream));
+    // this rank's copy of the full-length result: owned rows + the symmetric halves it computes for foreign rows
+    t->d_out.zero(out_count, s);
+    if (t->timing) FB_CUDA(cudaEventRecord(t->ev[10], s));
+    t->launch_p2p(sh.ts, false, true, s, false);  // U lists only
+    if (t->timing) FB_CUDA(cudaEventRecord(t->ev[11], s));
+    FB_CUDA(cudaEventRecord(sh.ev[1], s));
+    FB_CUDA(cudaStreamWaitEvent(s, cm.ev_done, 0));
     FB_CUDA(cudaEventRecord(sh.ev[2], s));
     if (t->m2l_plan && (!sh.m2l_table || m2l_stream_table_nrhs(sh.m2l_table) != t->nrhs)) {
       if (sh.m2l_table) m2l_stream_table_free(sh.m2l_table);
       sh.m2l_table = nullptr;
       sh.m2l_table = m2l_stream_table_new(t->m2l_plan, t->nrhs, sh.level_lo.data(), sh.level_hi.data(), s);
     }
-    if (p2p_first) {
-      t->downward(sh.ts.cell_flag, fuse ? &sh.ts : nullptr, true, false, sh.m2l_table);
-      if (t->timing) FB_CUDA(cudaEventRecord(t->ev[7], s));
-      t->launch_l2p(sh.ts, false);
-      if (t->timing) FB_CUDA(cudaEventRecord(t->ev[8], s));
-    } else {
-      t->d_out.reserve(sh.max_rows * (size_t)t->nrhs);
-      t->evaluate_sources_fused(sh.ts);
-    }
+    t->downward(sh.ts.cell_flag, fuse ? &sh.ts : nullptr, true, false, sh.m2l_table);
+    if (t->timing) FB_CUDA(cudaEventRecord(t->ev[7], s));
+    t->launch_l2p(sh.ts, false);
+    if (t->timing) FB_CUDA(cudaEventRecord(t->ev[8], s));
+    if (!fuse && t->n_w_entries > 0) t->launch_p2p(sh.ts, false, false, s, false, true);  // W lists on their own
     FB_CUDA(cudaEventRecord(sh.ev[3], s));
-    // exchange 2: owned rows -> full result on every rank
-    const size_t share = sh.max_rows * (size_t)t->nrhs;
-    sh.d_gather.reserve(share * cm.world);
-    sh.d_full.reserve(t->n * (size_t)t->nrhs);
+    // exchange 2: partial full-length results -> A w on every rank
     if (cm.world > 1) {
-      FB_NCCL(nccl().AllGather(t->d_out.p, sh.d_gather.p, share, ncclDouble, cm.comm, s));
+      FB_NCCL(nccl().AllReduce(t->d_out.p, t->d_out.p, out_count, ncclDouble, ncclSum, cm.comm, s));
       g_launches.fetch_add(1);
-    } else {
-      FB_CUDA(cudaMemcpyAsync(sh.d_gather.p, t->d_out.p, share * sizeof(double), cudaMemcpyDeviceToDevice, s));
     }
-    FB_LAUNCH(k_scatter_gathered, (unsigned)((t->n + 255) / 256), 256, 0, s, sh.d_gather.p, sh.d_pos.p, cm.world,
-              sh.max_rows, t->nrhs, t->d_perm.p, t->n, sh.d_full.p);
     FB_CUDA(cudaEventRecord(sh.ev[4], s));
     FB_CUDA(cudaStreamSynchronize(s));
     for (int k = 0; k < 4; ++k) {
@@ -351,7 +401,7 @@ int fb_tree_matvec_sharded(fb_tree *t) {
       sh.last_ms[k] = ms;
     }
     t->last_out_rows = t->n;
-    if (t->timing && p2p_first) {  // per-kernel times of this rank's share, same slots as fb_tree_last_timing
+    if (t->timing) {  // per-kernel times of this rank's share, same slots as fb_tree_last_timing
       auto ms = [&](int a, int b) {
         float v = 0;
         cudaEventElapsedTime(&v, t->ev[a], t->ev[b]);
@@ -377,7 +427,7 @@ int fb_tree_sharded_timing(const fb_tree *t, double *ms_out4) {
 
 int fb_tree_sharded_result_device(const fb_tree *t, const double **dev_ptr) {
   if (!t || !t->shard || !dev_ptr) return FB_ERR_INVALID_ARGUMENT;
-  *dev_ptr = t->shard->d_full.p;
+  *dev_ptr = t->d_out.p;
   return FB_OK;
 }
 
@@ -385,7 +435,7 @@ int fb_tree_sharded_download(fb_tree *t, double *out_vals) {
   return guarded([&] {
     FB_REQUIRE(t && t->shard && out_vals, "null argument");
     FB_CUDA(cudaSetDevice(t->device));
-    FB_CUDA(cudaMemcpyAsync(out_vals, t->shard->d_full.p, t->n * (size_t)t->nrhs * sizeof(double), cudaMemcpyDeviceToHost,
+    FB_CUDA(cudaMemcpyAsync(out_vals, t->d_out.p, t->n * (size_t)t->nrhs * sizeof(double), cudaMemcpyDeviceToHost,
                             t->stream));
     FB_CUDA(cudaStreamSynchronize(t->stream));
   });

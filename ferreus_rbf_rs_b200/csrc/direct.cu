@@ -398,7 +398,9 @@ static void leaf_direct_fam(DirectArgs a, cudaStream_t s) {
     }
     return;
   }
-  if (p2p_sym_applicable(a)) {  // targets == sources, 1 RHS: each unordered pair once; the warp kernel keeps the W lists
+  if (a.skip_p2p) {  // W lists only
+    if (!a.has_w) return;
+  } else if (p2p_sym_applicable(a)) {  // targets == sources, 1 RHS: each unordered pair once; the warp kernel keeps the W lists
     launch_p2p_sym(a, s);
     if (!a.has_w) return;
     a.skip_p2p = 1;

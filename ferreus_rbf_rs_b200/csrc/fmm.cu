@@ -418,31 +418,50 @@ void fb_tree::build(const double *points, size_t n_, int dim_, ptrdiff_t rs, ptr
     d_w_ptr_none.upload(std::vector<long long>(nl + 1, 0), stream);
     d_w_cell.upload(w_c, stream);
     n_w_entries = (long long)w_c.size();
+    // one CTA per X cell (p2l.cu), dispatched in blockIdx order: the cells are listed by descending source count so that
+    // the long lists start first and the short ones fill the tail of the grid (a rank's share of a partitioned tree is
+    // only a couple of waves deep)
     std::vector<int> x_cells, x_b, x_c;
     std::vector<long long> x_ptr{0};
-    for (size_t c = 0; c < nc; ++c) {
-      if (ht.x_ptr[c + 1] == ht.x_ptr[c]) continue;
-      rng.clear();
-      for (long long e = ht.x_ptr[c]; e < ht.x_ptr[c + 1]; ++e) {
-        const int x = ht.x_idx[e];
-        if (ht.pt_end[x] > ht.pt_begin[x]) {
-          rng.emplace_back(ht.pt_begin[x], ht.pt_end[x]);
-          p2l_pairs += ht.pt_end[x] - ht.pt_begin[x];
+    {
+      struct XCell {
+        int cell;
+        long long count;
+        std::vector<std::pair<int, int>> ranges;
+      };
+      std::vector<XCell> xs;
+      for (size_t c = 0; c < nc; ++c) {
+        if (ht.x_ptr[c + 1] == ht.x_ptr[c]) continue;
+        rng.clear();
+        long long cnt = 0;
+        for (long long e = ht.x_ptr[c]; e < ht.x_ptr[c + 1]; ++e) {
+          const int x = ht.x_idx[e];
+          if (ht.pt_end[x] > ht.pt_begin[x]) {
+            rng.emplace_back(ht.pt_begin[x], ht.pt_end[x]);
+            cnt += ht.pt_end[x] - ht.pt_begin[x];
+          }
         }
+        if (rng.empty()) continue;
+        p2l_pairs += (uint64_t)cnt;
+        std::sort(rng.begin(), rng.end());
+        XCell xc{(int)c, cnt, {}};
+        for (auto &r : rng) {
+          if (!xc.ranges.empty() && xc.ranges.back().first + xc.ranges.back().second == r.first)
+            xc.ranges.back().second += r.second - r.first;
+          else
+            xc.ranges.emplace_back(r.first, r.second - r.first);
+        }
+        xs.push_back(std::move(xc));
       }
-      if (rng.empty()) continue;
-      std::sort(rng.begin(), rng.end());
-      const size_t start = x_b.size();
-      for (auto &r : rng) {
-        if (x_b.size() > start && x_b.back() + x_c.back() == r.first)
-          x_c.back() += r.second - r.first;
-        else {
+      std::stable_sort(xs.begin(), xs.end(), [](const XCell &a, const XCell &b) { return a.count > b.count; });
+      for (const XCell &xc : xs) {
+        for (auto &r : xc.ranges) {
           x_b.push_back(r.first);
-          x_c.push_back(r.second - r.first);
+          x_c.push_back(r.second);
         }
+        x_cells.push_back(xc.cell);
+        x_ptr.push_back((long long)x_b.size());
       }
-      x_cells.push_back((int)c);
-      x_ptr.push_back((long long)x_b.size());
     }
     n_x_cells = (int)x_cells.size();
     d_x_cells.upload(x_cells, stream);
@@ -612,7 +631,9 @@ void fb_tree::upward(const int *leaves, int n_leaves, const uint8_t *cell_flag) 
   while (cpar > 1 && sizeof(double) * (2 * (size_t)p * p + 2 * (size_t)cpar * P) > 200 * 1024) cpar >>= 1;
   const size_t smem = sizeof(double) * (2 * (size_t)p * p + 2 * (size_t)cpar * P);
   set_smem(k_m2m, smem);
-  for (int lvl = ht.depth - 1; lvl >= 1; --lvl) {  // bbfmm.rs:675-687
+  // bbfmm.rs:675-687 goes up to the level-1 parents; their multipoles are never read (V, W and X lists only hold cells
+  // of level >= 2: every level-1 cell touches every other), so the last, eight-cell launch is left out
+  for (int lvl = ht.depth - 1; lvl >= 2; --lvl) {
     const int np = parents_off[lvl + 1] - parents_off[lvl];
     if (np <= 0) continue;
     FB_LAUNCH(k_m2m, np, 256, smem, stream, d_parents.p + parents_off[lvl], d_child_ptr.p, d_child_idx.p,
@@ -717,6 +738,11 @@ void fb_tree::downward(const uint8_t *flags, const TargetSet *fuse_m2p, bool out
       a.out = d_out.p;
       a.out_row = fuse_m2p->row_of_pos;
       a.tgt_prefix = fuse_m2p->tgt_prefix;
+      if (fuse_m2p->own_hi > fuse_m2p->own_lo && !fuse_m2p->all_sources) {  // a rank's share of a partitioned tree
+        a.cell_ptb = d_cell_ptb.p;
+        a.own_lo = fuse_m2p->own_lo;
+        a.own_hi = fuse_m2p->own_hi;
+      }
     }
     launch_p2l(a, stream);
   }
@@ -724,7 +750,9 @@ void fb_tree::downward(const uint8_t *flags, const TargetSet *fuse_m2p, bool out
   // L2L (loop B of bbfmm.rs:834-856): children at levels 2..depth
   const size_t smem = sizeof(double) * (2 * (size_t)p * p + 2 * (size_t)P);
   set_smem(k_l2l, smem);
-  for (int lvl = 2; lvl <= ht.depth; ++lvl) {
+  // (level-1 locals are identically zero — no M2L or P2L reaches that level — so the children of level 2 have nothing
+  // to inherit and the loop starts one level further down)
+  for (int lvl = 3; lvl <= ht.depth; ++lvl) {
     const int c0 = ht.level_ptr[lvl], cnt = ht.level_ptr[lvl + 1] - c0;
     if (cnt <= 0) continue;
     FB_LAUNCH(k_l2l, cnt, 128, smem, stream, c0, d_cell_parent.p, d_cell_slot.p, flags, d_child_s.p, p, dim, P, nrhs,
@@ -747,7 +775,8 @@ void fb_tree::launch_l2p(const TargetSet &ts, bool grads) {
             d_chalf.p, d_tnodes.p, p, dim, P, nrhs, d_out.p, grads ? d_gout.p : nullptr);
 }
 
-void fb_tree::launch_p2p(const TargetSet &ts, bool grads, bool m2p_done, cudaStream_t s, bool atomic_out) {
+void fb_tree::launch_p2p(const TargetSet &ts, bool grads, bool m2p_done, cudaStream_t s, bool atomic_out,
+                         bool w_only) {
   DirectArgs a{};
   a.ts = ts;
   a.u_ptr = d_u_ptr.p;
@@ -773,7 +802,8 @@ void fb_tree::launch_p2p(const TargetSet &ts, bool grads, bool m2p_done, cudaStr
   a.rhs0 = 0;
   a.atomic_out = atomic_out ? 1 : 0;
   a.has_w = (!m2p_done && n_w_entries > 0) ? 1 : 0;
-  a.skip_p2p = 0;
+  a.skip_p2p = w_only ? 1 : 0;
+  a.sym_row = ts.own_hi > ts.own_lo ? d_src_out_row.p : nullptr;  // filled by source_target_set()
   a.out = d_out.p;
   a.gout = grads ? d_gout.p : nullptr;
   a.kp = kp;
@@ -811,6 +841,8 @@ TargetSet fb_tree::source_target_set() {
   ts.max_tiles = src_tiles;
   ts.cell_flag = d_flag_all.p;
   ts.all_sources = true;
+  ts.own_lo = 0;
+  ts.own_hi = (int)n;
   ts.row_of_pos = d_src_out_row.p;
   return ts;
 }

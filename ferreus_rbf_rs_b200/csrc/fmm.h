@@ -26,6 +26,10 @@ struct TargetSet {
   const int *n_tiles_dev = nullptr;                        // device scalar: number of valid tiles
   int max_tiles = 0;                                       // launch bound for the tile grid
   bool all_sources = false;                                // the tree's own source set
+  // targets = the sources at the sorted positions [own_lo, own_hi), in that order (target i = position own_lo + i): every
+  // source, or the Morton-contiguous share of a rank (comm.cu: `out` then has a row for EVERY source and out_row /
+  // row_of_pos name those global rows).  Enables the symmetric P2P (p2p_sym.cu); 0, 0 = neither
+  int own_lo = 0, own_hi = 0;
   // targets that are source points (all of them, or a duplicate-free subset): enables the fused W/X pass
   const uint32_t *row_of_pos = nullptr;  // per sorted source position: output row, 0xFFFFFFFF when not a target
   const uint32_t *tgt_prefix = nullptr;  // n + 1 exclusive counts of targets over the sorted positions; null = all
@@ -57,6 +61,7 @@ struct DirectArgs {  // leaf pass: P2P over U ranges + M2P over W cells (bbfmm.r
   int atomic_out;  // 1: results are added with RED (the kernel runs concurrently with other writers of `out`)
   int has_w;       // 1: some leaf owns a W list that this call must apply (M2P)
   int skip_p2p;    // 1: the U ranges were served by another kernel (p2p_sym.cu / p2p_mma.cu)
+  const uint32_t *sym_row;  // symmetric P2P: output row of EVERY sorted source position (null: kernel not applicable)
   double *out;    // [m][nrhs]
   double *gout;   // [m][nrhs*dim] or null
   KParams kp;
@@ -80,6 +85,10 @@ struct P2LArgs {  // bbfmm.rs:1001-1048
   double *out;              // [n][nrhs]
   const uint32_t *out_row;  // output row of each sorted source position (0xFFFFFFFF: not a target)
   const uint32_t *tgt_prefix;  // n + 1 exclusive target counts over the sorted positions, or null (every source)
+  // partitioned tree: the M2P half of a cell is applied by the rank that owns the cell's first point (sorted position
+  // cell_ptb[c] in [own_lo, own_hi)), for all of the cell's X-list points — foreign rows travel in the result all-reduce
+  const int *cell_ptb;
+  int own_lo, own_hi;
 };
 
 // kernel family -> template argument
@@ -236,7 +245,9 @@ struct fb_tree {
                 bool m2l_one_cta_per_sm = false, const fb::M2LItemTable *m2l_table = nullptr);
   void leaf_pass(const fb::TargetSet &ts, bool grads, bool m2p_done = false);
   void launch_l2p(const fb::TargetSet &ts, bool grads);
-  void launch_p2p(const fb::TargetSet &ts, bool grads, bool m2p_done, cudaStream_t s, bool atomic_out);
+  // m2p_done: the W lists are (or will be) applied elsewhere; w_only: the U lists are
+  void launch_p2p(const fb::TargetSet &ts, bool grads, bool m2p_done, cudaStream_t s, bool atomic_out,
+                  bool w_only = false);
   void evaluate_sources_fused(const fb::TargetSet &ts);  // downward + leaf pass for targets that are source points
   fb::TargetSet source_target_set();
   fb::TargetSet bin_targets(const double *targets, size_t m, ptrdiff_t rs, ptrdiff_t cs, uint64_t *bad);

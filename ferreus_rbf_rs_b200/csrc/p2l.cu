@@ -27,6 +27,9 @@ __global__ void __launch_bounds__(256, (NR * PREG <= 8) ? 3 : ((NR * PREG <= (FU
   // P2L is wanted when the cell has targets below it; the fused M2P half when any X-list point is a target (a
   // subset-of-sources target set carries exclusive target counts over the sorted positions)
   const bool need_p2l = a.cell_flag[c] != 0;
+  // partitioned tree: one rank applies the M2P half of a cell (the owner of its first point); the others that hold
+  // targets below the cell run the P2L half alone
+  const bool do_m2p = FUSE && (a.cell_ptb == nullptr || (a.cell_ptb[c] >= a.own_lo && a.cell_ptb[c] < a.own_hi));
   if (!FUSE) {
     if (!need_p2l) return;
   } else if (!need_p2l) {
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(256, (NR * PREG <= 8) ? 3 : ((NR * PREG <= (FU
 #pragma unroll
       for (int r = 0; r < NR; ++r) wts[r * T + tid] = pw[r];
     }
-    if (FUSE && m_done > 0) {  // the threads that built one row (or none) flush the previous tile's M2P sums
+    if (FUSE && do_m2p && m_done > 0) {  // the threads that built one row (or none) flush the previous tile's M2P sums
       if (n_flush >= 32) {
         if (tid >= nt - n_flush) flush_m2p(tid - (nt - n_flush), n_flush, m_done, base_done);
       } else {
@@ -218,7 +221,7 @@ __global__ void __launch_bounds__(256, (NR * PREG <= 8) ? 3 : ((NR * PREG <= (FU
                 if (FUSE) kernel_acc<FAM>(tp[u][r], v[u], mreg[r][il]);
               }
           }
-        if (FUSE) {
+        if (FUSE && do_m2p) {
 #pragma unroll
           for (int u = 0; u < kP2LJB; ++u)
 #pragma unroll
@@ -231,7 +234,7 @@ __global__ void __launch_bounds__(256, (NR * PREG <= 8) ? 3 : ((NR * PREG <= (FU
     m_cur = m_next;
     tile_base = next_base;
   }
-  if (FUSE) {
+  if (FUSE && do_m2p) {
     __syncthreads();
     flush_m2p(tid, nt, m_done, base_done);
   }

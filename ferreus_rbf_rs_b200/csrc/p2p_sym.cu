@@ -1,4 +1,7 @@
 // Symmetric P2P for the matvec case targets == sources, one right-hand side (the solver's and the bench's hot call).
+// In a partitioned tree (comm.cu) a rank runs it for the chunks of its own Morton range [own_lo, own_hi) only: a chunk
+// still takes ALL sources behind it, whoever owns them, and the source-side sums of foreign rows travel in the result
+// all-reduce — every unordered pair of the whole cloud is evaluated exactly once across the ranks, nothing twice.
 // Reference: particle_to_particle bbfmm.rs:1162-1251 — there every (target, source) pair of the U lists is evaluated;
 // here each unordered pair is evaluated ONCE and serves both rows:
 //     out[t] += k(t, s) w[s]      and      out[s] += k(t, s) w[t]        (all registry kernels are symmetric).
@@ -16,6 +19,7 @@
 // hit the same rows concurrently).  Values are the reference's own per-pair values; only the summation order differs.
 #include "fmm.h"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace fb {
@@ -32,9 +36,11 @@ struct SymWarpSmem {
 // staged source then serves two evaluations per lane, which halves the shared-memory traffic per pair (source broadcasts,
 // partial-sum stores and the row sums of the flush; ncu on the one-target version: l1tex 70 % busy, FP64 pipe 48 %) and
 // doubles the independent chains in flight.  Chunks of <= 32 targets take the one-target instantiation.
+// split > 1 (grids too small to fill the GPU, e.g. one rank's share): `split` warps share a chunk, warp `part` takes
+// every split-th source tile (part 0 also the diagonal block); all sums leave through REDs, so nothing else changes.
 template <int FAM, bool FAST, bool TWO>
 __device__ __forceinline__ void p2p_sym_body(const DirectArgs &a, SymWarpSmem &sm, const int li, const int tb,
-                                             const int cnt, const int lane) {
+                                             const int cnt, const int lane, const int split, const int part) {
   constexpr int NT = TWO ? 2 : 1;
   constexpr double kScale = kernel_weight_scale<FAM, FAST>();
   const int a_end = tb + cnt;
@@ -59,7 +65,7 @@ __device__ __forceinline__ void p2p_sym_body(const DirectArgs &a, SymWarpSmem &s
   __syncwarp();
 #pragma unroll
   for (int h = 0; h < NT; ++h) {
-    const int mh = min(32, cnt - 32 * h);
+    const int mh = part == 0 ? min(32, cnt - 32 * h) : 0;
 #pragma unroll 2
     for (int j = 0; j < mh; ++j) {
       const double2 p0 = sm.st[h][0][j], p1 = sm.st[h][1][j];
@@ -92,21 +98,29 @@ __device__ __forceinline__ void p2p_sym_body(const DirectArgs &a, SymWarpSmem &s
   next_range();
   double rx = 0, ry = 0, rz = 0, rw = 0;
   int spos_next = 0;
-  auto fetch = [&](int &m) {  // this lane's element of the next tile, then advance
-    m = min(32, end - pos);
-    if (m <= 0) {
-      m = 0;
-      return;
+  int skip = part;  // tiles to pass over before the next one of this warp
+  auto fetch = [&](int &m) {  // this lane's element of the next tile of this warp, then advance
+    for (;;) {
+      m = min(32, end - pos);
+      if (m <= 0) {
+        m = 0;
+        return;
+      }
+      const bool mine = skip == 0;
+      skip = mine ? split - 1 : skip - 1;
+      if (mine) {
+        spos_next = pos + lane;
+        if (lane < m) {
+          rx = a.sx[spos_next];
+          ry = a.sy[spos_next];
+          rz = a.sz[spos_next];
+          rw = a.w[spos_next] * kScale;
+        }
+      }
+      pos += m;
+      if (pos >= end) next_range();
+      if (mine) return;
     }
-    spos_next = pos + lane;
-    if (lane < m) {
-      rx = a.sx[spos_next];
-      ry = a.sy[spos_next];
-      rz = a.sz[spos_next];
-      rw = a.w[spos_next] * kScale;
-    }
-    pos += m;
-    if (pos >= end) next_range();
   };
   auto stash = [&](int buf, int m) {
     if (lane < m) {
@@ -150,7 +164,7 @@ __device__ __forceinline__ void p2p_sym_body(const DirectArgs &a, SymWarpSmem &s
 #pragma unroll
         for (int k = 0; k < 8; ++k) sp[k] += pr[l + k];
       const double s = ((sp[0] + sp[1]) + (sp[2] + sp[3])) + ((sp[4] + sp[5]) + (sp[6] + sp[7]));
-      atomicAdd(a.out + (size_t)a.ts.out_row[spos_cur] * a.nrhs + a.rhs0, FAM == KF_LINEAR ? -s : s);
+      atomicAdd(a.out + (size_t)a.sym_row[spos_cur] * a.nrhs + a.rhs0, FAM == KF_LINEAR ? -s : s);
     }
     buf ^= 1;
     stash(buf, m_next);
@@ -161,38 +175,44 @@ __device__ __forceinline__ void p2p_sym_body(const DirectArgs &a, SymWarpSmem &s
 #pragma unroll
   for (int u = 0; u < NT; ++u) {
     const int i = 32 * u + lane;
-    if (i < cnt) atomicAdd(a.out + (size_t)a.ts.out_row[tb + i] * a.nrhs + a.rhs0, acc[u]);
+    if (i < cnt) atomicAdd(a.out + (size_t)a.sym_row[tb + i] * a.nrhs + a.rhs0, acc[u]);
   }
 }
 
 template <int FAM, bool FAST>
-__global__ void __launch_bounds__(kSymWPC * 32, 5) k_p2p_sym(const DirectArgs a) {
+__global__ void __launch_bounds__(kSymWPC * 32, 5) k_p2p_sym(const DirectArgs a, const int split) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long gw = (long long)blockIdx.x * kSymWPC + warp;
-  const int tile = (int)(gw >> 1), sub = (int)(gw & 1);  // a tile holds <= kTile = 128 targets: two warps of <= 64
+  const long long chunk = gw / split;
+  const int part = (int)(gw - chunk * split);
+  const int tile = (int)(chunk >> 1), sub = (int)(chunk & 1);  // a tile holds <= kTile = 128 targets: two warps of <= 64
   if (tile >= *a.ts.n_tiles_dev) return;
   const int li = a.ts.tile_leaf[tile];
-  const int tb = a.ts.leaf_begin[li] + a.ts.tile_off[tile] + sub * 64;
-  const int cnt = min(64, a.ts.leaf_end[li] - tb);
+  // target i of the set is the source at the sorted position own_lo + i
+  const int tb = a.ts.own_lo + a.ts.leaf_begin[li] + a.ts.tile_off[tile] + sub * 64;
+  const int cnt = min(64, a.ts.own_lo + a.ts.leaf_end[li] - tb);
   if (cnt <= 0) return;
   extern __shared__ __align__(16) unsigned char dsm_raw[];
   SymWarpSmem &sm = reinterpret_cast<SymWarpSmem *>(dsm_raw)[warp];
-  if (cnt > 32) p2p_sym_body<FAM, FAST, true>(a, sm, li, tb, cnt, lane);
-  else p2p_sym_body<FAM, FAST, false>(a, sm, li, tb, cnt, lane);
+  if (cnt > 32) p2p_sym_body<FAM, FAST, true>(a, sm, li, tb, cnt, lane, split, part);
+  else p2p_sym_body<FAM, FAST, false>(a, sm, li, tb, cnt, lane, split, part);
 }
 
 template <int FAM>
 static void p2p_sym_fam(const DirectArgs &a, cudaStream_t s) {
   static_assert(kTile == 128, "two 64-target warps per tile");
   const size_t smem = sizeof(SymWarpSmem) * kSymWPC;
-  const unsigned grid = (unsigned)(((long long)a.ts.max_tiles * 2 + kSymWPC - 1) / kSymWPC);
+  // about three waves of warps (148 SMs x 20 resident warps) keep the uneven chunks from leaving SMs idle at the end
+  const long long chunks = std::max<long long>(1, (long long)(a.ts.m / 64));
+  const int split = (int)std::min<long long>(8, std::max<long long>(1, (148 * 20 * 3) / chunks));
+  const unsigned grid = (unsigned)(((long long)a.ts.max_tiles * 2 * split + kSymWPC - 1) / kSymWPC);
   if (kernel_has_fast<FAM>() && a.kp.fast) {
     constexpr bool F = kernel_has_fast<FAM>();
     FB_CUDA(cudaFuncSetAttribute(k_p2p_sym<FAM, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FB_LAUNCH((k_p2p_sym<FAM, F>), grid, kSymWPC * 32, smem, s, a);
+    FB_LAUNCH((k_p2p_sym<FAM, F>), grid, kSymWPC * 32, smem, s, a, split);
   } else {
     FB_CUDA(cudaFuncSetAttribute(k_p2p_sym<FAM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FB_LAUNCH((k_p2p_sym<FAM, false>), grid, kSymWPC * 32, smem, s, a);
+    FB_LAUNCH((k_p2p_sym<FAM, false>), grid, kSymWPC * 32, smem, s, a, split);
   }
 }
 
@@ -202,7 +222,8 @@ bool p2p_sym_applicable(const DirectArgs &a) {
     const char *v = std::getenv("FB_P2P_SYM");
     return v && v[0] == '0';
   }();
-  return !off && !a.gout && a.nrhs == 1 && a.ts.all_sources && a.ts.max_tiles > 0 && a.kp.fast != 3;
+  return !off && !a.gout && a.nrhs == 1 && a.ts.own_hi > a.ts.own_lo && a.sym_row != nullptr && a.ts.max_tiles > 0 &&
+         a.kp.fast != 3;
 }
 
 void launch_p2p_sym(const DirectArgs &a, cudaStream_t s) {

@@ -182,11 +182,14 @@ int fb_tree_result_device(fb_tree *t, const double **dev_ptr, uint64_t *n_rows, 
 /* ---- NCCL partition (csrc/comm.cu): one process per GPU, the reference's rayon loops (bbfmm.rs:669, 682, 788, 841,
  * 1122) split across devices.  Every rank builds the same tree from the same points and calls fb_tree_shard with its
  * communicator: the Morton leaf sequence is cut into world_size contiguous ranges of nearly equal estimated work, a rank
- * owns the points of its range as sources and as targets.  fb_tree_matvec_sharded then runs P2M / M2M over the owned
- * part, completes the multipoles with ncclAllReduce (under the near-field pass), runs M2L / P2L / L2L / L2P / M2P for
- * the owned targets and ncclAllGather's the result rows: the full A w, in the caller's row order, replicated, stays in
- * device memory (fb_tree_sharded_result_device) or is copied out (fb_tree_sharded_download).  Weights: all N rows,
- * uploaded with fb_tree_upload_weights on every rank.  NCCL is dlopen'ed on first use.                              */
+ * owns the points of its range.  fb_tree_matvec_sharded then runs P2M / M2M over the owned part, completes the
+ * multipoles with ncclAllReduce (under the near-field pass), runs M2L / L2L / L2P for the owned cells / targets, the
+ * symmetric P2P for the owned chunks and the fused P2L + M2P pass for the owned cells (every kernel evaluation of the
+ * unpartitioned matvec is made by exactly one rank; symmetric halves that belong to foreign rows are added into the
+ * rank's full-length partial result) and ncclAllReduce's that result: the full A w, in the caller's row order,
+ * replicated, stays in device memory (fb_tree_sharded_result_device) or is copied out (fb_tree_sharded_download).
+ * Weights: all N rows, uploaded with fb_tree_upload_weights on every rank (before fb_tree_shard: the work model of the
+ * cut depends on the number of right-hand sides).  NCCL is dlopen'ed on first use.                                    */
 typedef struct fb_comm fb_comm;
 int fb_comm_unique_id(uint8_t *id_out128);                       /* rank 0; broadcast the 128 bytes out of band   */
 int fb_comm_init(const uint8_t *id128, int rank, int world_size, fb_comm **out);  /* on the current device        */
@@ -194,9 +197,13 @@ void fb_comm_free(fb_comm *c);
 int fb_comm_rank(const fb_comm *c);
 int fb_comm_world_size(const fb_comm *c);
 int fb_tree_shard(fb_tree *t, fb_comm *comm_or_null);            /* NULL drops the partition                      */
+/* profiling / test aid: with a world-1 communicator, take the share rank `rank` of `world` ranks would own — the per-rank
+ * kernel times of an N-GPU partition on one GPU.  The collectives degenerate to copies: exact = 0 forms the owned
+ * multipoles only (faithful times, partial sums in the result), exact = 1 forms all of them (owned rows exact)       */
+int fb_tree_shard_as(fb_tree *t, fb_comm *comm, int rank, int world, int exact);
 int fb_tree_shard_rows(const fb_tree *t, int rank, uint64_t *begin_pos, uint64_t *end_pos);  /* Morton positions  */
 int fb_tree_matvec_sharded(fb_tree *t);
-int fb_tree_sharded_timing(const fb_tree *t, double *ms_out4);   /* upward, near field under all-reduce, downward + leaf, all-gather */
+int fb_tree_sharded_timing(const fb_tree *t, double *ms_out4);   /* near field (upward pass + multipole all-reduce beside it), rest of those two, downward + leaf, result all-reduce */
 int fb_tree_sharded_result_device(const fb_tree *t, const double **dev_ptr);
 int fb_tree_sharded_download(fb_tree *t, double *out_vals /* n x nrhs row-major */);
 /* the cut itself (host only): n_parts + 1 boundaries into the leaf sequence */

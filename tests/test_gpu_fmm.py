@@ -524,6 +524,39 @@ def test_nccl_partition_single_rank_matches_resident_matvec():
     assert np.array_equal(b.astype(np.int64), sharding.partition_by_work(work, 5))
 
 
+@pytest.mark.parametrize("nrhs,world", [(1, 3), (1, 5), (2, 3)])
+def test_shares_of_a_partition_add_up_to_the_matvec(nrhs, world):
+    """fb_tree_shard_as (exact mode) on a world-1 communicator: the full-length partial results of the `world` shares
+    add up to the unpartitioned matvec (what the result all-reduce of csrc/comm.cu computes).  One right-hand side takes
+    the symmetric P2P restricted to the chunks of the owned Morton range (source-side sums reach foreign rows), two take
+    the general kernel; the fused W/X kernel applies a cell's M2P half on the rank that owns the cell's first point."""
+    import ferreus_rbf_rs_b200 as fb
+    n = 40000
+    pts = H.make_points(n, 3, "clustered", seed=71)
+    w = np.random.default_rng(72).random((n, nrhs)) - 0.5
+    pt = H.product_tree(pts, 6, 0, True, True, 64, 2, 1e-6)
+    pt.upload_weights(w)
+    pt.matvec_resident()
+    ref = np.array(pt.download_result()).reshape(n, nrhs)
+    comm = fb.Communicator(0, 1)
+    total = np.zeros((n, nrhs))
+    ends = []
+    for r in range(world):
+        pt.shard_as(comm, r, world, exact=True)
+        a, b = pt.shard_rows(r)
+        assert b > a
+        ends.append((a, b))
+        pt.matvec_sharded()
+        part = np.array(pt.sharded_download()).reshape(n, nrhs)
+        assert H.rel_l2(part, ref) > 1e-3  # a share is not the whole
+        total += part
+    assert ends[0][0] == 0 and ends[-1][1] == n and all(ends[i][1] == ends[i + 1][0] for i in range(world - 1))
+    assert H.rel_l2(total, ref) <= 1e-13
+    pt.shard(None)
+    pt.matvec_resident()
+    assert H.rel_l2(np.array(pt.download_result()).reshape(n, nrhs), ref) <= 1e-13
+
+
 @pytest.mark.parametrize("kernel", [4, 5, 6, 8, 9])
 def test_gradients_remaining_kernels_match_oracle(kernel):
     """values + gradients at separate targets for the kernels test_targets_and_gradients_match_oracle leaves out:
