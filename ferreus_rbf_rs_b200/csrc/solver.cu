@@ -497,6 +497,160 @@ __global__ void __launch_bounds__(kSolveThreads) k_dom_solve(DomainTable t, cons
   }
 }
 
+// ---- the single coarse domain (n ~ 2000) -----------------------------------------------------------------------------
+// k_dom_solve gives a domain one CTA: its two substitutions are chains of 2 x mm / 32 dependent steps, 3.5 ms for the
+// coarse domain of the 1M-point fit, three times per preconditioner cycle.  For a one-domain level the triangular factor
+// is inverted once at setup (X = L^-1, kept with its transpose), and Domain::solve becomes two triangular matrix-vector
+// products spread over the whole GPU:  gamma = X^T (X rhs)  — the same L^-T L^-1 rhs, a few rounding errors apart.
+__global__ void k_tri_inv_diag(const double *L, int n, double *X) {  // X[kb.., kb..] = L[kb.., kb..]^-1, one warp per block
+  const int kb = blockIdx.x * kNB, bs = min(kNB, n - kb), lane = threadIdx.x;
+  __shared__ double D[kNB][kNB + 1];
+  for (int r = 0; r < bs; ++r) D[r][lane] = (lane < bs && lane <= r) ? L[(size_t)(kb + r) * n + kb + lane] : 0.0;
+  __syncwarp();
+  if (lane < bs) {  // column `lane` of the inverse by forward substitution
+    double x[kNB];
+#pragma unroll
+    for (int r = 0; r < kNB; ++r) x[r] = 0.0;
+#pragma unroll
+    for (int r = 0; r < kNB; ++r) {
+      if (r < bs && r >= lane) {
+        double v = r == lane ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < kNB; ++k)
+          if (k < r && k >= lane) v -= D[r][k] * x[k];
+        x[r] = v / D[r][r];
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kNB; ++r)
+      if (r < bs) X[(size_t)(kb + r) * n + kb + lane] = r >= lane ? x[r] : 0.0;
+  }
+}
+
+// block column j of X = L^-1 below the diagonal, one CTA per block column:  X_ij = -X_ii sum_{k=j}^{i-1} L_ik X_kj
+__global__ void __launch_bounds__(256) k_tri_inv_column(const double *L, int n, double *X) {
+  const int jb = blockIdx.x * kNB, bj = min(kNB, n - jb);
+  __shared__ double A[kNB][kNB + 1], B[kNB][kNB + 1], S[kNB][kNB + 1];
+  const int tid = threadIdx.x, r = tid >> 3, c0 = (tid & 7) * 4;
+  for (int ib = jb + kNB; ib < n; ib += kNB) {
+    const int bi = min(kNB, n - ib);
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int kb = jb; kb < ib; kb += kNB) {
+      __syncthreads();
+      for (int e = tid; e < kNB * kNB; e += 256) {
+        const int rr = e / kNB, cc = e % kNB;
+        A[rr][cc] = rr < bi ? L[(size_t)(ib + rr) * n + kb + cc] : 0.0;            // kb + cc < ib <= n
+        B[rr][cc] = cc < bj ? X[(size_t)(kb + rr) * n + jb + cc] : 0.0;            // rows kb.. < ib: written earlier
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int q = 0; q < kNB; ++q) {
+        const double a = A[r][q];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] += a * B[q][c0 + u];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) S[r][c0 + u] = acc[u];
+    for (int e = tid; e < kNB * kNB; e += 256) {  // A <- X_ii (lower triangular, from k_tri_inv_diag)
+      const int rr = e / kNB, cc = e % kNB;
+      A[rr][cc] = (rr < bi && cc <= rr) ? X[(size_t)(ib + rr) * n + ib + cc] : 0.0;
+    }
+    __syncthreads();
+    double o[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int q = 0; q <= r; ++q) {
+      const double a = A[r][q];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) o[u] -= a * S[q][c0 + u];
+    }
+    if (r < bi)
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (c0 + u < bj) X[(size_t)(ib + r) * n + jb + c0 + u] = o[u];
+    __threadfence_block();
+  }
+}
+
+__global__ void k_transpose(const double *A, int n, double *At) {
+  __shared__ double T[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y)
+    T[r][threadIdx.x] = (by + r < n && bx + threadIdx.x < n) ? A[(size_t)(by + r) * n + bx + threadIdx.x] : 0.0;
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y)
+    if (bx + r < n && by + threadIdx.x < n) At[(size_t)(bx + r) * n + by + threadIdx.x] = T[threadIdx.x][r];
+}
+
+// rhs = Q^T d_special + d_rest of the coarse domain (domain.rs:405-416)
+__global__ void k_big_rhs(DomainTable t, const double *qpool, const double *res, double *rhs) {
+  const int rk = t.rank[0];
+  const int n = (int)(t.pt_ptr[1] - t.pt_ptr[0]), mm = n - rk;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= mm) return;
+  const int *idx = t.pt_idx + t.pt_ptr[0];
+  const double *Q = qpool + t.q_off[0];
+  double v = res[idx[rk + j]];
+  for (int a = 0; a < rk; ++a) v += Q[(size_t)a * mm + j] * res[idx[a]];
+  rhs[j] = v;
+}
+
+// y[r] = sum over the stored triangle of row r of M[r][c] v[c]: one warp per row, fixed summation order
+template <bool LOWER>
+__global__ void __launch_bounds__(256) k_tri_gemv(const double *M, int n, const double *v, double *y) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= n) return;
+  const double *row = M + (size_t)r * n;
+  const int lo = LOWER ? 0 : (r & ~31), hi = LOWER ? r + 1 : n;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int c = lo + lane;
+  for (; c + 96 < hi; c += 128) {
+    s0 += row[c] * v[c];
+    s1 += row[c + 32] * v[c + 32];
+    s2 += row[c + 64] * v[c + 64];
+    s3 += row[c + 96] * v[c + 96];
+  }
+  for (; c < hi; c += 32) s0 += row[c] * v[c];  // the upper case starts inside the zero part of the diagonal block
+  double sacc = (s0 + s1) + (s2 + s3);
+  for (int o = 16; o > 0; o >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, o);
+  if (lane == 0) y[r] = sacc;
+}
+
+// lambda_top = Q gamma, scatter, polynomial tail (the end of k_dom_solve for the coarse domain), one CTA
+__global__ void __launch_bounds__(1024) k_big_finish(DomainTable t, const double *qpool, const double *gamma,
+                                                     const double *res, double *out, int add_poly,
+                                                     const double *a_special, const double *sp_inv, size_t n_total) {
+  const int rk = t.rank[0];
+  const int n = (int)(t.pt_ptr[1] - t.pt_ptr[0]), mm = n - rk;
+  const int *idx = t.pt_idx + t.pt_ptr[0];
+  const double *Q = qpool + t.q_off[0];
+  __shared__ double top[16], red[16];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int a = warp; a < rk; a += 32) {
+    double sacc = 0.0;
+    for (int j = lane; j < mm; j += 32) sacc += Q[(size_t)a * mm + j] * gamma[j];
+    for (int o = 16; o > 0; o >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, o);
+    if (lane == 0) top[a] = sacc;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += 1024) out[idx[i]] = i < rk ? top[i] : gamma[i - rk];
+  if (add_poly && rk > 0 && a_special) {  // r = d_special - A_special lambda;  poly = sp_mono^-1 r  (domain.rs:446-463)
+    for (int a = warp; a < rk; a += 32) {
+      const double *row = a_special + (size_t)a * n;
+      double sacc = 0.0;
+      for (int i = lane; i < n; i += 32) sacc += row[i] * (i < rk ? top[i] : gamma[i - rk]);
+      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, o);
+      if (lane == 0) red[a] = res[idx[a]] - sacc;
+    }
+    __syncthreads();
+    if (tid < rk) {
+      double sacc = 0.0;
+      for (int b = 0; b < rk; ++b) sacc += sp_inv[tid * rk + b] * red[b];
+      out[n_total - rk + tid] = sacc;  // schwarz.rs:147-152: tail rows
+    }
+  }
+}
+
 // A[special, :] rows of the coarse domain (domain.rs:366)
 __global__ void k_special_rows(const int *idx, int n, int rk, const double *px, const double *py, const double *pz,
                                KParams kp, double nugget, double *out) {
@@ -517,6 +671,9 @@ struct LevelDev {
   DBuf<double> qpool, lpool;
   DBuf<uint8_t> use_inverse;  // all zero unless a domain needed the indefinite fallback
   int n_fallback = 0;
+  // one-domain level: X = L^-1 and its transpose (row-major mm x mm), vectors of the spread solve
+  bool big_inverse = false;
+  DBuf<double> linv, linv_t, big_v;
   DBuf<uint8_t> fail;         // per domain: Cholesky met a non-positive pivot
   std::vector<int> h_mms;     // order of every domain's Q^T A Q (host copy, for the fallback)
   std::vector<long long> h_l_off;
@@ -679,6 +836,17 @@ struct DeviceSolver {
           FB_LAUNCH(k_chol_big_update, grid, 256, smem, stream, lv.lpool.p, nn, kb);
         }
       }
+      // X = L^-1 and X^T for the spread solve (unused if the factorisation failed: factorise_finish then stores the
+      // explicit inverse and k_dom_solve serves the level)
+      lv.linv.reserve((size_t)nn * nn);
+      lv.linv_t.reserve((size_t)nn * nn);
+      lv.big_v.reserve(3 * (size_t)nn);
+      FB_CUDA(cudaMemsetAsync(lv.linv.p, 0, sizeof(double) * (size_t)nn * nn, stream));
+      const unsigned nblock = (unsigned)((nn + kNB - 1) / kNB);
+      FB_LAUNCH(k_tri_inv_diag, nblock, 32, 0, stream, lv.lpool.p, nn, lv.linv.p);
+      FB_LAUNCH(k_tri_inv_column, nblock, 256, 0, stream, lv.lpool.p, nn, lv.linv.p);
+      FB_LAUNCH(k_transpose, dim3(nblock, nblock), dim3(32, 8), 0, stream, lv.linv.p, nn, lv.linv_t.p);
+      lv.big_inverse = true;
     } else {
       FB_LAUNCH(k_cholesky, (unsigned)nd, 256, smem, stream, lv.tab, lv.lpool.p, lv.fail.p);
     }
@@ -857,6 +1025,16 @@ struct DeviceSolver {
   }
 
   void solve_level(const LevelDev &lv, const double *res, double *out, int mode, int add_poly, cudaStream_t stream) {
+    if (lv.big_inverse && lv.n_fallback == 0 && mode == 1) {  // the coarse domain, spread over the GPU
+      const int mm = (int)lv.max_mm;
+      double *rhs = lv.big_v.p, *y = rhs + mm, *gamma = y + mm;
+      FB_LAUNCH(k_big_rhs, nblk(mm, 256), 256, 0, stream, lv.tab, lv.qpool.p, res, rhs);
+      FB_LAUNCH((k_tri_gemv<true>), (unsigned)((mm + 7) / 8), 256, 0, stream, lv.linv.p, mm, rhs, y);
+      FB_LAUNCH((k_tri_gemv<false>), (unsigned)((mm + 7) / 8), 256, 0, stream, lv.linv_t.p, mm, y, gamma);
+      FB_LAUNCH(k_big_finish, 1, 1024, 0, stream, lv.tab, lv.qpool.p, gamma, res, out, add_poly,
+                lv.solve_for_poly ? lv.a_special.p : nullptr, lv.solve_for_poly ? lv.sp_inv.p : nullptr, nt);
+      return;
+    }
     const size_t smem = sizeof(double) * (lv.max_n + lv.max_mm + kSolveWarps * 32 + 32);
     // the gathered residual and the solution of a domain live in shared memory (227 KB per CTA on sm_100a)
     if (smem > 227 * 1024)
