@@ -19,8 +19,8 @@ One "step" = one matvec = set_weights(w) + evaluate(w, targets = sources) on a p
 * `sqrt_exact`: the same resident matvec with the third-order (~1 ulp) square root (fb_set_sqrt_mode(0)); the
              default is the second-order one (<= 1.3e-12 per kernel value, see include/ferreus_b200.h).
 N > 1: one process per GPU (torchrun), ONE shared 1M-point cloud partitioned by Morton-contiguous leaf ranges
-(csrc/comm.cu): owned-leaf upward pass, ncclAllReduce of the multipoles under the near-field pass, downward / leaf passes
-of the share (every kernel evaluation of the unpartitioned matvec is made by exactly one rank: the symmetric halves for
+(csrc/comm.cu): owned-leaf upward pass and ncclAllReduce of the multipoles with the near-field pass beside them on a
+low-priority stream, downward / leaf passes of the share (every kernel evaluation of the unpartitioned matvec is made by exactly one rank: the symmetric halves for
 foreign rows travel in the result), ncclAllReduce of the full-length result.  `value` = N / (device time of that step, max
 over ranks): strong scaling.  Every rank checks the partitioned result against the unpartitioned matvec on its own GPU.
 """
@@ -361,12 +361,12 @@ def main():
         med_r = {k: float(np.median([s_[k] for s_ in stage_ms])) for k in stage_ms[0]}
         a, b = tree.shard_rows(rank)
         kernel_keys = ["p2m", "m2m", "m2l", "wx", "l2l", "l2p", "leaf"]
-        mine = torch.tensor([float(b - a), med_r["near_field"], med_r["multipole_wait"], med_r["downward_leaf"],
+        mine = torch.tensor([float(b - a), med_r["upward_exchange"], med_r["downward"], med_r["near_field_join_l2p"],
                              med_r["result_allreduce"], partition_err] + [med_r["k_" + k] for k in kernel_keys],
                             dtype=torch.float64, device="cuda")
         allv = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allv, mine)
-        names = ["rows", "near_field_ms", "multipole_wait_ms", "downward_leaf_ms", "result_allreduce_ms",
+        names = ["rows", "upward_exchange_ms", "downward_ms", "near_field_join_l2p_ms", "result_allreduce_ms",
                  "rel_l2_vs_unpartitioned"] + ["kernel_" + k + "_ms" for k in kernel_keys]
         per_rank = [dict(zip(names, v.cpu().tolist())) for v in allv]
     total_ms_max, e2e_ms_max = [float(v) for v in tms.tolist()]
@@ -463,9 +463,10 @@ def main():
         if per_rank is not None:
             line["partition"] = {"per_rank": per_rank,
                                  "what": "device time per stage and per kernel on every rank (median over the timed steps); "
-                                         "near_field = weight sort + symmetric P2P of the owned chunks, with the owned-leaf "
-                                         "upward pass and the multipole all-reduce running beside it on a second stream; "
-                                         "multipole_wait = what is left of those two when the P2P is done"}
+                                         "upward_exchange = weight sort, owned-leaf upward pass and the multipole all-reduce on the "
+                                         "high-priority stream (the symmetric P2P of the owned chunks runs beside them and "
+                                         "beside the downward pass on a low-priority stream); near_field_join_l2p = what is "
+                                         "left of the P2P when the downward pass is done, plus L2P"}
         if world == 1 and not args.no_fit:
             line["fit"] = full_fit(n)
         if world == 1 and not args.no_cpu_baseline:

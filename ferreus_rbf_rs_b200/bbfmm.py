@@ -237,7 +237,7 @@ class FmmTree:
     def sharded_timing(self):
         ms = np.zeros(4)
         self._check(self._lib.fb_tree_sharded_timing(self._h, _lib.dptr(ms)))
-        return dict(zip(("near_field", "multipole_wait", "downward_leaf", "result_allreduce"), ms.tolist()))
+        return dict(zip(("upward_exchange", "downward", "near_field_join_l2p", "result_allreduce"), ms.tolist()))
 
     def sharded_download(self):
         out = _lib.pinned.empty((self._n, self._nrhs))

@@ -8,7 +8,8 @@
 //   upward      P2M over the OWNED leaves only, M2M over the cells that have owned descendants: every rank holds the
 //               exact multipoles of the cells inside its range and a partial sum for the cells that span ranks;
 //   exchange 1  ncclAllReduce(sum) of the multipole array completes the spanning cells and hands every rank the halo
-//               multipoles its V / W lists need, on a side stream UNDER the near-field pass (P2P needs no multipoles);
+//               multipoles its V / W lists need; upward pass and exchange run on the high-priority main stream, the
+//               near-field pass (it needs no multipoles) beside them on a low-priority one;
 //   near field  symmetric P2P (p2p_sym.cu) for the chunks of the owned range against ALL sources behind them: the
 //               source-side sums of rows another rank owns are added into this rank's copy of the full-length result;
 //   downward    M2L / L2L / L2P for the cells / targets of the share; the fused W/X kernel (p2l.cu) for the cells with
@@ -136,7 +137,7 @@ struct fb_shard {
   DBuf<unsigned long long> d_rows;
   std::vector<int> level_lo, level_hi;  // per level: the cells with owned targets are the ids [lo, hi)
   M2LItemTable *m2l_table = nullptr;    // M2L work items of that share
-  double last_ms[4] = {0, 0, 0, 0};   // near field, rest of upward pass + multipole all-reduce, downward + leaf, result all-reduce
+  double last_ms[4] = {0, 0, 0, 0};   // upward pass + multipole all-reduce, downward pass, (rest of the near field +) L2P, result all-reduce
   cudaEvent_t ev[5] = {};
   ~fb_shard() {
     for (auto &e : ev)
@@ -347,42 +348,36 @@ int fb_tree_matvec_sharded(fb_tree *t) {
     const size_t out_count = t->n * (size_t)t->nrhs;
     FB_CUDA(cudaEventRecord(sh.ev[0], s));
     t->sort_weights();
-    // The near-field pass needs the sorted weights and nothing else, so it runs on the main stream while the upward pass
-    // (P2M, then one small M2M launch per level: latency-bound on a rank's share) and exchange 1 run beside it on the
-    // communicator's stream.
+    // The near-field pass needs the sorted weights and nothing else: it goes to the tree's LOW-priority side stream, the
+    // upward pass (P2M, then one small M2M launch per level: latency-bound on a rank's share) and exchange 1 stay on the
+    // high-priority main stream, so their CTAs are placed ahead of the P2P kernel's pending ones.  (Two streams of equal
+    // priority measured 0.33 ms for the 0.08 ms M2M chain at 8 ranks: its launches queued behind the P2P grid.)
     const bool fuse = t->ht.adaptive && t->n_x_cells > 0;
     const size_t mult_count = nc * (size_t)t->nrhs * coef_stride(t->P);
-    FB_CUDA(cudaEventRecord(cm.ev_ready, s));
-    FB_CUDA(cudaStreamWaitEvent(cm.stream, cm.ev_ready, 0));
-    {
-      struct StreamSwap {  // fb_tree's passes launch on t->stream
-        fb_tree *t;
-        cudaStream_t saved;
-        StreamSwap(fb_tree *t_, cudaStream_t other) : t(t_), saved(t_->stream) { t->stream = other; }
-        ~StreamSwap() { t->stream = saved; }
-      } swap(t, cm.stream);
-      if (sh.full_upward) t->upward();
-      else t->upward(sh.d_owned_leaves.p, sh.n_owned_leaves, sh.ts.cell_flag);
-    }
+    cudaStream_t s2 = t->stream2;
+    FB_CUDA(cudaEventRecord(t->ev_fork, s));
+    FB_CUDA(cudaStreamWaitEvent(s2, t->ev_fork, 0));
+    // this rank's copy of the full-length result: owned rows + the symmetric halves it computes for foreign rows
+    t->d_out.zero(out_count, s2);
+    if (t->timing) FB_CUDA(cudaEventRecord(t->ev[10], s2));
+    t->launch_p2p(sh.ts, false, true, s2, true);  // U lists only; REDs: the fused W/X pass adds to the same rows
+    if (t->timing) FB_CUDA(cudaEventRecord(t->ev[11], s2));
+    FB_CUDA(cudaEventRecord(t->ev_join, s2));
+    if (sh.full_upward) t->upward();
+    else t->upward(sh.d_owned_leaves.p, sh.n_owned_leaves, sh.ts.cell_flag);
     if (cm.world > 1) {
-      FB_NCCL(nccl().AllReduce(t->d_mult.p, t->d_mult.p, mult_count, ncclDouble, ncclSum, cm.comm, cm.stream));
+      FB_NCCL(nccl().AllReduce(t->d_mult.p, t->d_mult.p, mult_count, ncclDouble, ncclSum, cm.comm, s));
       g_launches.fetch_add(1);
     }
-    FB_CUDA(cudaEventRecord(cm.ev_done, cm.stream));
-    // this rank's copy of the full-length result: owned rows + the symmetric halves it computes for foreign rows
-    t->d_out.zero(out_count, s);
-    if (t->timing) FB_CUDA(cudaEventRecord(t->ev[10], s));
-    t->launch_p2p(sh.ts, false, true, s, false);  // U lists only
-    if (t->timing) FB_CUDA(cudaEventRecord(t->ev[11], s));
     FB_CUDA(cudaEventRecord(sh.ev[1], s));
-    FB_CUDA(cudaStreamWaitEvent(s, cm.ev_done, 0));
-    FB_CUDA(cudaEventRecord(sh.ev[2], s));
     if (t->m2l_plan && (!sh.m2l_table || m2l_stream_table_nrhs(sh.m2l_table) != t->nrhs)) {
       if (sh.m2l_table) m2l_stream_table_free(sh.m2l_table);
       sh.m2l_table = nullptr;
       sh.m2l_table = m2l_stream_table_new(t->m2l_plan, t->nrhs, sh.level_lo.data(), sh.level_hi.data(), s);
     }
     t->downward(sh.ts.cell_flag, fuse ? &sh.ts : nullptr, true, false, sh.m2l_table);
+    FB_CUDA(cudaEventRecord(sh.ev[2], s));
+    FB_CUDA(cudaStreamWaitEvent(s, t->ev_join, 0));  // the near field joins in front of L2P (plain read-modify-write)
     if (t->timing) FB_CUDA(cudaEventRecord(t->ev[7], s));
     t->launch_l2p(sh.ts, false);
     if (t->timing) FB_CUDA(cudaEventRecord(t->ev[8], s));

@@ -1039,11 +1039,42 @@ TargetSet fb_tree::subset_target_set_dev(const unsigned long long *d_idx, size_t
   return ts;
 }
 
-// weights already in d_w_user: upward pass, downward pass restricted to the target set, leaf pass -> d_out
+// weights already in d_w_user: upward pass, downward pass restricted to the target set, leaf pass -> d_out.
+// The near-field pass (U lists) needs the sorted weights and nothing else: it is forked to the low-priority side stream
+// right away, so the upward pass — P2M plus one small, latency-bound M2M launch per level — runs beside it instead of in
+// front of it; the high-priority main stream's CTAs are placed ahead of the P2P kernel's pending ones.  Every writer of
+// the result rows adds with REDs until the two streams join in front of L2P.  On one GPU the whole matvec is bound by
+// the one FP64 pipe, so this only moves work around (measured 9.96 against 10.03 ms at the 1M-point headline) and it
+// blurs the per-stage times: opt-in with FB_NEAR_OVERLAP=1.  A rank's share of a partitioned tree (comm.cu), where the
+// upward pass is latency-bound and an all-reduce follows it, always runs this way.
 void fb_tree::matvec_dev(const TargetSet &ts) {
+  static const bool serial = [] {
+    const char *v = std::getenv("FB_NEAR_OVERLAP");
+    return !(v && v[0] == '1');
+  }();
   sort_weights();
+  if (serial) {
+    upward();
+    evaluate_sources_fused(ts);
+    return;
+  }
+  const bool fuse = ht.adaptive && n_x_cells > 0 && ts.row_of_pos != nullptr;
+  FB_CUDA(cudaEventRecord(ev_fork, stream));
+  FB_CUDA(cudaStreamWaitEvent(stream2, ev_fork, 0));
+  d_out.zero(ts.m * (size_t)nrhs, stream2);
+  if (timing) FB_CUDA(cudaEventRecord(ev[10], stream2));
+  launch_p2p(ts, false, true, stream2, true);  // U lists only
+  if (timing) FB_CUDA(cudaEventRecord(ev[11], stream2));
+  FB_CUDA(cudaEventRecord(ev_join, stream2));
   upward();
-  evaluate_sources_fused(ts);
+  downward(ts.cell_flag, fuse ? &ts : nullptr, true);
+  FB_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
+  if (timing) FB_CUDA(cudaEventRecord(ev[7], stream));
+  launch_l2p(ts, false);
+  if (timing) FB_CUDA(cudaEventRecord(ev[8], stream));
+  if (!fuse && n_w_entries > 0) launch_p2p(ts, false, false, stream, false, true);  // W lists on their own
+  if (timing) FB_CUDA(cudaEventRecord(ev[9], stream));
+  last_overlapped = true;
 }
 
 void fb_tree::fetch_output(size_t m, bool grads, double *out_vals, double *out_grads, ptrdiff_t o_rs,
@@ -1269,10 +1300,8 @@ int fb_tree_matvec_resident(fb_tree *t) {
     FB_CUDA(cudaSetDevice(t->device));
     FB_REQUIRE(t->d_w_user.cap >= t->n * (size_t)t->nrhs, "fb_tree_upload_weights must be called first");
     FB_CUDA(cudaEventRecord(t->ev_mv[0], t->stream));
-    t->sort_weights();
-    t->upward();
     TargetSet ts = t->have_subset ? t->ts_subset : t->source_target_set();
-    t->evaluate_sources_fused(ts);
+    t->matvec_dev(ts);
     t->last_out_rows = ts.m;
     FB_CUDA(cudaEventRecord(t->ev_mv[1], t->stream));
     FB_CUDA(cudaStreamSynchronize(t->stream));

@@ -1,4 +1,7 @@
-"""Multi-GPU sharding of one BBFMM tree by Morton-contiguous leaf ranges.
+"""Host-side sharding of one BBFMM tree by Morton-contiguous leaf ranges: the evaluate-a-subset variant
+driven from Python, kept for the CPU (gloo) tests of the cut and for callers without NCCL.  The production multi-GPU path
+is the library's own partition (csrc/comm.cu: FmmTree.shard / matvec_sharded, fb_comm_*), where no kernel evaluation is
+made twice and the exchanges are NCCL all-reduces on the device.
 
 Every rank holds the same tree (points and interaction lists are replicated; the upward pass, 2 % of a
 matvec, is recomputed locally).  The leaves, in Morton order, are cut into `world` contiguous ranges balanced
@@ -57,14 +60,17 @@ class ShardedMatvec:
             out[self.my_rows] = local
             return out
         import torch
+        # NCCL moves device memory only: stage the slices on this rank's GPU there, on the host for gloo / mpi
+        dev = (torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl"
+               else torch.device("cpu"))
         sizes = [r.size for r in self.rows]
         width = int(np.prod(local.shape[1:])) if local.ndim > 1 else 1
         pad = max(sizes) * width
-        buf = torch.zeros(pad, dtype=torch.float64)
-        buf[: local.size] = torch.from_numpy(np.ascontiguousarray(local).reshape(-1))
-        bufs = [torch.zeros(pad, dtype=torch.float64) for _ in range(self.world)]
+        buf = torch.zeros(pad, dtype=torch.float64, device=dev)
+        buf[: local.size] = torch.from_numpy(np.ascontiguousarray(local).reshape(-1)).to(dev)
+        bufs = [torch.zeros(pad, dtype=torch.float64, device=dev) for _ in range(self.world)]
         dist.all_gather(bufs, buf)
         out = np.zeros((self.n, width))
         for r in range(self.world):
-            out[self.rows[r]] = bufs[r][: sizes[r] * width].numpy().reshape(sizes[r], width)
+            out[self.rows[r]] = bufs[r][: sizes[r] * width].cpu().numpy().reshape(sizes[r], width)
         return out if local.ndim > 1 else out[:, 0]

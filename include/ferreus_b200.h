@@ -203,7 +203,7 @@ int fb_tree_shard(fb_tree *t, fb_comm *comm_or_null);            /* NULL drops t
 int fb_tree_shard_as(fb_tree *t, fb_comm *comm, int rank, int world, int exact);
 int fb_tree_shard_rows(const fb_tree *t, int rank, uint64_t *begin_pos, uint64_t *end_pos);  /* Morton positions  */
 int fb_tree_matvec_sharded(fb_tree *t);
-int fb_tree_sharded_timing(const fb_tree *t, double *ms_out4);   /* near field (upward pass + multipole all-reduce beside it), rest of those two, downward + leaf, result all-reduce */
+int fb_tree_sharded_timing(const fb_tree *t, double *ms_out4);   /* upward pass + multipole all-reduce, downward pass (near field beside both), rest of the near field + L2P, result all-reduce */
 int fb_tree_sharded_result_device(const fb_tree *t, const double **dev_ptr);
 int fb_tree_sharded_download(fb_tree *t, double *out_vals /* n x nrhs row-major */);
 /* the cut itself (host only): n_parts + 1 boundaries into the leaf sequence */

@@ -514,7 +514,7 @@ def test_nccl_partition_single_rank_matches_resident_matvec():
     got = np.array(pt.sharded_download()).reshape(n, 2)
     assert H.rel_l2(got, ref) <= 1e-13
     t = pt.sharded_timing()
-    assert all(v >= 0 for v in t.values()) and t["downward_leaf"] > 0
+    assert all(v >= 0 for v in t.values()) and t["downward"] > 0
     pt.shard(None)
     pt.matvec_resident()
     assert H.rel_l2(np.array(pt.download_result()).reshape(n, 2), ref) <= 1e-13

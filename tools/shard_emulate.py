@@ -46,7 +46,7 @@ def main():
             med = {k: float(np.median([a[k] for a in acc])) for k in acc[0]}
             a, b = tree.shard_rows(r)
             med["rows"] = b - a
-            med["step_ms"] = med["near_field"] + med["multipole_wait"] + med["downward_leaf"] + med["result_allreduce"]
+            med["step_ms"] = med["upward_exchange"] + med["downward"] + med["near_field_join_l2p"] + med["result_allreduce"]
             rows.append(med)
         out["worlds"][str(world)] = rows
         tree.shard(None)

@@ -88,8 +88,8 @@ def main():
         tree.matvec_resident()
         ref = np.array(tree.download_result())
         err = float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
-    mine = torch.tensor([dev_ms, 1e3 * float(np.median(walls)), med["near_field"], med["multipole_wait"],
-                         med["downward_leaf"], med["result_allreduce"], float(rows[rank][1] - rows[rank][0]),
+    mine = torch.tensor([dev_ms, 1e3 * float(np.median(walls)), med["upward_exchange"], med["downward"],
+                         med["near_field_join_l2p"], med["result_allreduce"], float(rows[rank][1] - rows[rank][0]),
                          err if err is not None else -1.0], dtype=torch.float64,
                         device="cuda" if world > 1 else "cpu")
     allv = [torch.zeros_like(mine) for _ in range(world)]
@@ -102,8 +102,8 @@ def main():
             "config": args.config, "n": n, "nrhs": int(w.shape[1]), "n_gpus": world, "tree_build_s": build_s,
             "ms_per_matvec_device_max_over_ranks": step_ms, "ms_per_matvec_wall_max_over_ranks": float(tab[:, 1].max()),
             "mpts_per_s": n / (step_ms * 1e-3) / 1e6,
-            "per_rank": [{"rank": r, "rows": int(tab[r, 6]), "device_ms": tab[r, 0], "near_field": tab[r, 2],
-                          "multipole_wait": tab[r, 3], "downward_leaf": tab[r, 4], "result_allreduce": tab[r, 5]}
+            "per_rank": [{"rank": r, "rows": int(tab[r, 6]), "device_ms": tab[r, 0], "upward_exchange": tab[r, 2],
+                          "downward": tab[r, 3], "near_field_join_l2p": tab[r, 4], "result_allreduce": tab[r, 5]}
                          for r in range(world)],
             "rel_l2_vs_unpartitioned": [float(v) for v in tab[:, 7]] if err is not None else None}), flush=True)
     dist.destroy_process_group()

@@ -4,4 +4,4 @@ print({k:round(v,3) for k,v in d['unpartitioned_ms'].items()})
 for W,rows in d['worlds'].items():
     print("world",W, "max step", round(max(r['step_ms'] for r in rows),3), "eff", round(d['unpartitioned_ms']['total']/int(W)/max(r['step_ms'] for r in rows),3))
     for r in rows:
-        print({k.replace('near_field','near').replace('multipole_wait','mwait').replace('downward_leaf','down').replace('result_allreduce','res'):round(v,3) for k,v in r.items()})
+        print({k.replace('upward_exchange','up').replace('near_field_join_l2p','join').replace('downward','down').replace('result_allreduce','res'):round(v,3) for k,v in r.items()})
