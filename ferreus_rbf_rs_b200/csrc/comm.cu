@@ -225,7 +225,7 @@ int fb_comm_world_size(const fb_comm *c) { return c ? c->world : -1; }
 // (calibrated on the 1M-point headline workload: symmetric P2P 1.16 ps, W/X 0.74 ps per evaluation, M2L 1.75 ns per entry
 // at P = 343): the P2P evaluations of a leaf are the pairs with the sources BEHIND it (one RHS: p2p_sym.cu) or all its
 // ordered pairs; a cell's X-list work and M2L entries are pushed down to its leaves.
-static void share_work(const fb_tree &t, uint64_t *leaf_ptr, double *work) {
+static void share_work(const fb_tree &t, int world, uint64_t *leaf_ptr, double *work) {
   const HostTree &ht = t.ht;
   const size_t nl = ht.leaves.size(), nc = ht.ncells();
   const bool sym = t.nrhs == 1;
@@ -237,6 +237,8 @@ static void share_work(const fb_tree &t, uint64_t *leaf_ptr, double *work) {
     const int nch = ht.child_ptr[c + 1] - ht.child_ptr[c];
     for (int k = ht.child_ptr[c]; k < ht.child_ptr[c + 1]; ++k) down[ht.child_idx[k]] += down[c] / nch;
   }
+  std::vector<double> near(nl, 0.0);
+  double near_total = 0.0;
   for (size_t l = 0; l < nl; ++l) {
     const int c = ht.leaves[l];
     leaf_ptr[l] = (uint64_t)ht.pt_begin[c];
@@ -246,10 +248,20 @@ static void share_work(const fb_tree &t, uint64_t *leaf_ptr, double *work) {
       const int u = ht.u_idx[e];
       if (!sym || ht.pt_begin[u] >= ht.pt_begin[c]) nsrc += ht.pt_end[u] - ht.pt_begin[u];
     }
+    near[l] = (sym ? 1.6 : 1.0) * nt * nsrc;
+    near_total += near[l];
     // (the M2P evaluations of the leaf's W list ride on the X-list evaluations of those cells)
-    work[l] = (sym ? 1.6 : 1.0) * nt * nsrc + down[c] + 0.3 * nt * t.P + 1.0;
+    work[l] = down[c] + 0.3 * nt * t.P + 1.0;
   }
   leaf_ptr[nl] = (uint64_t)t.n;
+  // The near field runs beside the upward pass and exchange 1, a chain of small launches and an all-reduce that takes
+  // about 0.35 ms however little it computes (measured at 8 ranks on the headline workload): that much P2P per rank costs
+  // nothing on the critical path, and a cut that counted it in full would leave the ranks with few direct pairs waiting
+  // on the ones with many far-field evaluations.  Only the part of the P2P beyond the slack is weighed.
+  const double unit_ms = 0.74e-9 * (1.0 + 0.15 * (t.nrhs - 1));  // one evaluation unit, B200, from the stage timings
+  const double near_ms = near_total * unit_ms;
+  const double alpha = near_ms > 0 ? std::min(1.0, std::max(0.25, 1.0 - 0.35 * world / near_ms)) : 1.0;
+  for (size_t l = 0; l < nl; ++l) work[l] += alpha * near[l];
 }
 
 // as_world > 0: take the share of rank `as_rank` of `as_world` ranks with a world-1 communicator — the per-rank kernel
@@ -280,7 +292,7 @@ static int shard_impl(fb_tree *t, fb_comm *comm, int as_rank, int as_world, int 
     const size_t nl = ht.leaves.size();
     std::vector<uint64_t> leaf_ptr(nl + 1);
     std::vector<double> work(nl);
-    share_work(*t, leaf_ptr.data(), work.data());
+    share_work(*t, world, leaf_ptr.data(), work.data());
     sh->leaf_bounds.resize(world + 1);
     partition_by_work(work.data(), nl, world, sh->leaf_bounds.data());
     sh->pos.resize(world + 1);

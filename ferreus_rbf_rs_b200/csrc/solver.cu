@@ -497,6 +497,173 @@ __global__ void __launch_bounds__(kSolveThreads) k_dom_solve(DomainTable t, cons
   }
 }
 
+// ---- Domain::solve, second form ------------------------------------------------------------------------------------
+// ncu on k_dom_solve at the 1M-point fit (2048 domains of ~980 points): 7.0 ms per launch for 15.7 GB of factor reads
+// (2.4 ms at the HBM peak).  The time went into what sits between the loads: per 32-row step a serial substitution with
+// 32 dependent divisions on one warp, and in the backward pass a column-block walk (256 B out of every 7.8 KB row).
+// This form removes both:
+//   * the 32 x 32 diagonal blocks of L are inverted in place once, at setup (k_inv_diag_inplace), so a block step is a
+//     32-lane dot product per row, all 32 warps at once, no division, no dependency chain;
+//   * the backward substitution is right-looking: as soon as the 32 values of a block are known, every thread subtracts
+//     their contribution from ITS column of the right-hand side — 32 independent, row-contiguous loads per thread — so
+//     both passes stream the lower triangle of L row block by row block.
+__global__ void k_inv_diag_inplace(DomainTable t, double *lpool) {
+  const int d = blockIdx.x;
+  const int mm = (int)(t.pt_ptr[d + 1] - t.pt_ptr[d]) - t.rank[d];
+  const int kb = blockIdx.y * kNB;
+  if (kb >= mm) return;
+  const int bs = min(kNB, mm - kb), lane = threadIdx.x;
+  double *L = lpool + t.l_off[d];
+  __shared__ double D[kNB][kNB + 1];
+  for (int r = 0; r < bs; ++r) D[r][lane] = (lane < bs && lane <= r) ? L[(size_t)(kb + r) * mm + kb + lane] : 0.0;
+  __syncwarp();
+  double x[kNB];
+#pragma unroll
+  for (int r = 0; r < kNB; ++r) x[r] = 0.0;
+  if (lane < bs) {  // column `lane` of the inverse by forward substitution
+#pragma unroll
+    for (int r = 0; r < kNB; ++r) {
+      if (r < bs && r >= lane) {
+        double v = r == lane ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < kNB; ++k)
+          if (k < r && k >= lane) v -= D[r][k] * x[k];
+        x[r] = v / D[r][r];
+      }
+    }
+  }
+  __syncwarp();
+  if (lane < bs)
+#pragma unroll
+    for (int r = 0; r < kNB; ++r)
+      if (r < bs && r >= lane) L[(size_t)(kb + r) * mm + kb + lane] = x[r];
+}
+
+__global__ void __launch_bounds__(kSolveThreads) k_dom_solve_v2(DomainTable t, const double *qpool, const double *lpool,
+                                                                const double *res, double *out, int mode, int add_poly,
+                                                                const double *a_special, const double *sp_inv,
+                                                                size_t n_total) {
+  const int d = blockIdx.x;
+  const int rk = t.rank[d];
+  const long long p0 = t.pt_ptr[d];
+  const int n = (int)(t.pt_ptr[d + 1] - p0), mm = n - rk;
+  const int *idx = t.pt_idx + p0;
+  const uint8_t *mask = t.pt_mask + p0;
+  const double *Q = qpool + t.q_off[d];
+  const double *L = lpool + t.l_off[d];
+  extern __shared__ double sm[];
+  double *dv = sm;        // n gathered residuals
+  double *x = dv + n;     // mm rhs / solution
+  double *red = x + mm;   // 32 partial sums
+  double *top = red + kSolveWarps * 32;  // rk
+  __shared__ double Dg[32][33];          // inverse of the diagonal block of the current step (lower triangle)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < n; i += kSolveThreads) dv[i] = res[idx[i]];
+  __syncthreads();
+  for (int j = tid; j < mm; j += kSolveThreads) {  // rhs = Q^T d_special + d_rest
+    double v = dv[rk + j];
+    for (int a = 0; a < rk; ++a) v += Q[(size_t)a * mm + j] * dv[a];
+    x[j] = v;
+  }
+  __syncthreads();
+  const bool inverse = t.use_inverse != nullptr && t.use_inverse[d] != 0;
+  if (inverse) {  // indefinite fallback: the slot holds the explicit inverse (see k_dom_solve)
+    for (int r = warp; r < mm; r += kSolveWarps) {
+      const double *row = L + (size_t)r * mm;
+      double sacc = 0.0;
+      for (int c = lane; c < mm; c += 32) sacc += row[c] * x[c];
+      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, o);
+      if (lane == 0) dv[rk + r] = sacc;
+    }
+    __syncthreads();
+    for (int j = tid; j < mm; j += kSolveThreads) x[j] = dv[rk + j];
+    __syncthreads();
+  }
+  // forward substitution L y = rhs, left-looking: row r of the block belongs to warp r
+  for (int kb = 0; !inverse && kb < mm; kb += 32) {
+    const int bs = min(32, mm - kb);
+    if (warp < bs) {
+      const double *row = L + (size_t)(kb + warp) * mm;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int c = lane;
+      for (; c + 96 < kb; c += 128) {
+        s0 += row[c] * x[c];
+        s1 += row[c + 32] * x[c + 32];
+        s2 += row[c + 64] * x[c + 64];
+        s3 += row[c + 96] * x[c + 96];
+      }
+      for (; c < kb; c += 32) s0 += row[c] * x[c];
+      Dg[warp][lane] = lane <= warp ? row[kb + lane] : 0.0;  // row `warp` of the inverted diagonal block
+      double sacc = (s0 + s1) + (s2 + s3);
+      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+      if (lane == 0) red[warp] = x[kb + warp] - sacc;
+    }
+    __syncthreads();
+    if (warp < bs) {  // y_r = sum_k Dinv[r][k] (rhs_k - partial_k)
+      double v = (lane <= warp) ? Dg[warp][lane] * red[lane] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) x[kb + warp] = v;
+    }
+    __syncthreads();
+  }
+  // backward substitution L^T gamma = y, right-looking
+  for (int kb = ((mm - 1) / 32) * 32; !inverse && kb >= 0; kb -= 32) {
+    const int bs = min(32, mm - kb);
+    if (warp < bs) Dg[warp][lane] = lane <= warp ? L[(size_t)(kb + warp) * mm + kb + lane] : 0.0;
+    if (tid < 32) red[tid] = tid < bs ? x[kb + tid] : 0.0;
+    __syncthreads();
+    if (warp < bs) {  // gamma_r = sum_{k >= r} Dinv[k][r] y_k
+      double v = (lane >= warp && lane < bs) ? Dg[lane][warp] * red[lane] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) x[kb + warp] = v;
+    }
+    __syncthreads();
+    for (int c = tid; c < kb; c += kSolveThreads) {  // y[c] -= sum_r L[kb + r][c] gamma[kb + r]
+      const double *col = L + (size_t)kb * mm + c;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int r = 0;
+      for (; r + 3 < bs; r += 4) {
+        a0 += col[(size_t)r * mm] * x[kb + r];
+        a1 += col[(size_t)(r + 1) * mm] * x[kb + r + 1];
+        a2 += col[(size_t)(r + 2) * mm] * x[kb + r + 2];
+        a3 += col[(size_t)(r + 3) * mm] * x[kb + r + 3];
+      }
+      for (; r < bs; ++r) a0 += col[(size_t)r * mm] * x[kb + r];
+      x[c] -= (a0 + a1) + (a2 + a3);
+    }
+    __syncthreads();
+  }
+  // lambda_top = Q gamma
+  for (int a = warp; a < rk; a += kSolveWarps) {
+    double sacc = 0.0;
+    for (int j = lane; j < mm; j += 32) sacc += Q[(size_t)a * mm + j] * x[j];
+    for (int o = 16; o > 0; o >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, o);
+    if (lane == 0) top[a] = sacc;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += kSolveThreads) {
+    const double lam = i < rk ? top[i] : x[i - rk];
+    if (mode == 1 || mask[i]) out[idx[i]] = lam;
+  }
+  if (mode == 1 && add_poly && rk > 0 && a_special) {
+    // r = d_special - A_special lambda;  poly = sp_mono^-1 r  (domain.rs:446-463)
+    __syncthreads();
+    for (int a = warp; a < rk; a += kSolveWarps) {
+      const double *row = a_special + (size_t)a * n;
+      double sacc = 0.0;
+      for (int i = lane; i < n; i += 32) sacc += row[i] * (i < rk ? top[i] : x[i - rk]);
+      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, o);
+      if (lane == 0) red[a] = dv[a] - sacc;
+    }
+    __syncthreads();
+    if (tid < rk) {
+      double sacc = 0.0;
+      for (int b = 0; b < rk; ++b) sacc += sp_inv[tid * rk + b] * red[b];
+      out[n_total - rk + tid] = sacc;  // schwarz.rs:147-152: tail rows
+    }
+  }
+}
+
 // ---- the single coarse domain (n ~ 2000) -----------------------------------------------------------------------------
 // k_dom_solve gives a domain one CTA: its two substitutions are chains of 2 x mm / 32 dependent steps, 3.5 ms for the
 // coarse domain of the 1M-point fit, three times per preconditioner cycle.  For a one-domain level the triangular factor
@@ -674,6 +841,7 @@ struct LevelDev {
   // one-domain level: X = L^-1 and its transpose (row-major mm x mm), vectors of the spread solve
   bool big_inverse = false;
   DBuf<double> linv, linv_t, big_v;
+  bool diag_inverted = false;  // the 32 x 32 diagonal blocks of every factor hold their inverses (k_dom_solve_v2)
   DBuf<uint8_t> fail;         // per domain: Cholesky met a non-positive pivot
   std::vector<int> h_mms;     // order of every domain's Q^T A Q (host copy, for the fallback)
   std::vector<long long> h_l_off;
@@ -849,6 +1017,9 @@ struct DeviceSolver {
       lv.big_inverse = true;
     } else {
       FB_LAUNCH(k_cholesky, (unsigned)nd, 256, smem, stream, lv.tab, lv.lpool.p, lv.fail.p);
+      FB_LAUNCH(k_inv_diag_inplace, dim3((unsigned)nd, (unsigned)((lv.max_mm + kNB - 1) / kNB)), 32, 0, stream, lv.tab,
+                lv.lpool.p);
+      lv.diag_inverted = true;
     }
   }
 
@@ -1042,6 +1213,14 @@ struct DeviceSolver {
                   "a subdomain of " + std::to_string(lv.max_n) + " points exceeds the shared-memory budget of the batched "
                   "subdomain solve (about 14300 points per domain): lower naive_solve_threshold / "
                   "DDMParams.coarse_threshold / DDMParams.leaf_threshold below that");
+    if (lv.diag_inverted) {
+      FB_CUDA(cudaFuncSetAttribute(k_dom_solve_v2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)std::max<size_t>(smem, 1024)));
+      FB_LAUNCH(k_dom_solve_v2, (unsigned)lv.n_domains, kSolveThreads, smem, stream, lv.tab, lv.qpool.p, lv.lpool.p, res,
+                out, mode, add_poly, lv.solve_for_poly ? lv.a_special.p : nullptr,
+                lv.solve_for_poly ? lv.sp_inv.p : nullptr, nt);
+      return;
+    }
     FB_CUDA(cudaFuncSetAttribute(k_dom_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
     FB_LAUNCH(k_dom_solve, (unsigned)lv.n_domains, kSolveThreads, smem, stream, lv.tab, lv.qpool.p, lv.lpool.p, res, out, mode,
               add_poly, lv.solve_for_poly ? lv.a_special.p : nullptr, lv.solve_for_poly ? lv.sp_inv.p : nullptr, nt,
