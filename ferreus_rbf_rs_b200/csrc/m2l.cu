@@ -270,7 +270,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_m2l_stream(const M2LStream
     const double *bp = st + (size_t)ar * Pc + kb * 4 + ak;
 #pragma unroll
     for (int q = 0; q < KSW; ++q) {
-      const double b0 = bp[q * 4], b1 = bp[(size_t)8 * Pc + q * 4];
+      // a slice one step short re-reads its last step (times a zero fragment) instead of the neighbour's first one, which
+      // that warp may already be overwriting with its partial sums (harmless for the product, but a genuine WAR race)
+      const int qq = q < kcnt ? q : kcnt - 1;
+      const double b0 = bp[qq * 4], b1 = bp[(size_t)8 * Pc + qq * 4];
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
         dmma(y[m][0][0], y[m][0][1], A1[m][q], b0);
@@ -460,20 +463,45 @@ M2LStreamPlan *m2l_stream_build(const HostTree &ht, const Operators &ops, int P,
   std::map<std::pair<int, int>, std::pair<long long, long long>> dense_off;  // (level, ref) -> (U, Vt)
   long long pool_size = 0;
   const int n_vec = (int)ops.ref_lookup.size();
-  for (int lvl = 2; lvl <= ht.depth; ++lvl) {
-    std::vector<std::vector<std::array<int, 2>>> per_t(n_vec);
-    for (int c = ht.level_ptr[lvl]; c < ht.level_ptr[lvl + 1]; ++c) {
-      uint32_t ac[3];
-      ht.anchor(c, ac);
-      for (long long e = ht.v_ptr[c]; e < ht.v_ptr[c + 1]; ++e) {
-        const int s = ht.v_idx[e];
-        uint32_t as[3];
-        ht.anchor(s, as);
-        int tix = 0;  // calculate_m2l_transfer_index, bbfmm.rs:989-998
-        for (int d = 0; d < dim; ++d) tix = tix * 7 + ((int)ac[d] - (int)as[d] + 3);
-        per_t[tix].push_back({c, s});
-      }
+  // transfer index of every V-list entry (calculate_m2l_transfer_index, bbfmm.rs:989-998), all cells at once
+  const size_t ncell = ht.ncells();
+  std::vector<uint32_t> anchors(3 * ncell);
+#pragma omp parallel for schedule(static)
+  for (long long c = 0; c < (long long)ncell; ++c) ht.anchor((int)c, &anchors[3 * (size_t)c]);
+  const long long n_v = ht.v_ptr[ncell];
+  std::vector<int> tix_of(n_v > 0 ? (size_t)n_v : 1);
+#pragma omp parallel for schedule(dynamic, 256)
+  for (long long c = 0; c < (long long)ncell; ++c) {
+    const uint32_t *ac = &anchors[3 * (size_t)c];
+    for (long long e = ht.v_ptr[c]; e < ht.v_ptr[c + 1]; ++e) {
+      const uint32_t *as = &anchors[3 * (size_t)ht.v_idx[e]];
+      int tix = 0;
+      for (int d = 0; d < dim; ++d) tix = tix * 7 + ((int)ac[d] - (int)as[d] + 3);
+      tix_of[e] = tix;
     }
+  }
+  for (int lvl = 2; lvl <= ht.depth; ++lvl) {
+    // counting sort of the level's entries by transfer index; cells are visited in ascending order, so the targets of a
+    // group come out ascending
+    std::vector<long long> start(n_vec + 1, 0);
+    for (int c = ht.level_ptr[lvl]; c < ht.level_ptr[lvl + 1]; ++c)
+      for (long long e = ht.v_ptr[c]; e < ht.v_ptr[c + 1]; ++e) ++start[tix_of[e] + 1];
+    for (int t = 0; t < n_vec; ++t) start[t + 1] += start[t];
+    std::vector<std::array<int, 2>> sorted((size_t)start[n_vec]);
+    {
+      std::vector<long long> fill(start.begin(), start.end() - 1);
+      for (int c = ht.level_ptr[lvl]; c < ht.level_ptr[lvl + 1]; ++c)
+        for (long long e = ht.v_ptr[c]; e < ht.v_ptr[c + 1]; ++e) sorted[(size_t)fill[tix_of[e]]++] = {c, ht.v_idx[e]};
+    }
+    struct Span {
+      const std::array<int, 2> *b, *e;
+      bool empty() const { return b == e; }
+      size_t size() const { return (size_t)(e - b); }
+      const std::array<int, 2> *begin() const { return b; }
+      const std::array<int, 2> *end() const { return e; }
+    };
+    std::vector<Span> per_t(n_vec);
+    for (int t = 0; t < n_vec; ++t) per_t[t] = {sorted.data() + start[t], sorted.data() + start[t + 1]};
     for (int tix = 0; tix < n_vec; ++tix) {
       if (per_t[tix].empty()) continue;
       const int ref = ops.ref_lookup[tix];
