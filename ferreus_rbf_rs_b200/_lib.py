@@ -137,6 +137,7 @@ SIGNATURES = {
     "fb_comm_world_size": (C.c_int, [C.c_void_p]),
     "fb_tree_shard": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fb_tree_shard_as": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "fb_tree_shard_fork_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "fb_tree_shard_rows": (C.c_int, [C.c_void_p, C.c_int, _u64p, _u64p]),
     "fb_tree_matvec_sharded": (C.c_int, [C.c_void_p]),
     "fb_tree_sharded_timing": (C.c_int, [C.c_void_p, _dp]),

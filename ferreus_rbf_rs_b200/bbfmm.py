@@ -226,6 +226,9 @@ class FmmTree:
         self._check(self._lib.fb_tree_shard_as(self._h, comm._h, rank, world, 1 if exact else 0))
         self._comm = comm
 
+    def shard_fork_mode(self, mode):
+        self._check(self._lib.fb_tree_shard_fork_mode(self._h, int(mode)))
+
     def shard_rows(self, rank):
         a, b = C.c_uint64(), C.c_uint64()
         self._check(self._lib.fb_tree_shard_rows(self._h, rank, C.byref(a), C.byref(b)))

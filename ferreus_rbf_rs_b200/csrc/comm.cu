@@ -126,6 +126,7 @@ struct fb_comm {
 // per-tree state of the partition (fb_tree::shard)
 struct fb_shard {
   fb_comm *comm = nullptr;
+  int fork_mode = 0;                  // where the near field forks off the main stream (fb_tree_shard_fork_mode)
   bool full_upward = false;           // emulated share with every multipole formed locally: the owned rows come out exact
   int rank = 0, world = 1;            // the share this process computes: the communicator's, or an emulated one (fb_tree_shard_as)
   std::vector<uint64_t> leaf_bounds;  // world + 1 boundaries into the Morton leaf sequence
@@ -340,6 +341,12 @@ int fb_tree_shard_as(fb_tree *t, fb_comm *comm, int rank, int world, int exact) 
   return shard_impl(t, comm, rank, world, exact);
 }
 
+int fb_tree_shard_fork_mode(fb_tree *t, int mode) {
+  if (!t || !t->shard || mode < 0 || mode > 1) return FB_ERR_INVALID_ARGUMENT;
+  t->shard->fork_mode = mode;
+  return FB_OK;
+}
+
 int fb_tree_shard_rows(const fb_tree *t, int rank, uint64_t *begin_pos, uint64_t *end_pos) {
   if (!t || !t->shard || rank < 0 || rank >= t->shard->world) return FB_ERR_INVALID_ARGUMENT;
   if (begin_pos) *begin_pos = (uint64_t)t->shard->pos[rank];
@@ -367,6 +374,12 @@ int fb_tree_matvec_sharded(fb_tree *t) {
     const bool fuse = t->ht.adaptive && t->n_x_cells > 0;
     const size_t mult_count = nc * (size_t)t->nrhs * coef_stride(t->P);
     cudaStream_t s2 = t->stream2;
+    // fork point of the near field: 0 = right after the weight sort (beside the upward pass too), 1 = after the upward
+    // pass (beside exchange 1 and the downward pass only: the upward pass then has the SMs to itself)
+    if (sh.fork_mode == 1) {
+      if (sh.full_upward) t->upward();
+      else t->upward(sh.d_owned_leaves.p, sh.n_owned_leaves, sh.ts.cell_flag);
+    }
     FB_CUDA(cudaEventRecord(t->ev_fork, s));
     FB_CUDA(cudaStreamWaitEvent(s2, t->ev_fork, 0));
     // this rank's copy of the full-length result: owned rows + the symmetric halves it computes for foreign rows
@@ -375,8 +388,10 @@ int fb_tree_matvec_sharded(fb_tree *t) {
     t->launch_p2p(sh.ts, false, true, s2, true);  // U lists only; REDs: the fused W/X pass adds to the same rows
     if (t->timing) FB_CUDA(cudaEventRecord(t->ev[11], s2));
     FB_CUDA(cudaEventRecord(t->ev_join, s2));
-    if (sh.full_upward) t->upward();
-    else t->upward(sh.d_owned_leaves.p, sh.n_owned_leaves, sh.ts.cell_flag);
+    if (sh.fork_mode != 1) {
+      if (sh.full_upward) t->upward();
+      else t->upward(sh.d_owned_leaves.p, sh.n_owned_leaves, sh.ts.cell_flag);
+    }
     if (cm.world > 1) {
       FB_NCCL(nccl().AllReduce(t->d_mult.p, t->d_mult.p, mult_count, ncclDouble, ncclSum, cm.comm, s));
       g_launches.fetch_add(1);

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--fork-mode", type=int, default=-1, help="near-field fork point (fb_tree_shard_fork_mode); -1 = library default")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -62,6 +63,8 @@ def main():
     comm = fb.Communicator.from_torch_distributed(dist)
     tree.upload_weights(w)  # before the cut: the work model depends on the number of right-hand sides
     tree.shard(comm)
+    if args.fork_mode >= 0:
+        tree.shard_fork_mode(args.fork_mode)
     rows = [tree.shard_rows(r) for r in range(world)]
 
     def barrier():
@@ -99,7 +102,7 @@ def main():
         step_ms = float(tab[:, 0].max())
         os.dup2(out_fd, 1)
         print(json.dumps({
-            "config": args.config, "n": n, "nrhs": int(w.shape[1]), "n_gpus": world, "tree_build_s": build_s,
+            "config": args.config, "fork_mode": args.fork_mode, "n": n, "nrhs": int(w.shape[1]), "n_gpus": world, "tree_build_s": build_s,
             "ms_per_matvec_device_max_over_ranks": step_ms, "ms_per_matvec_wall_max_over_ranks": float(tab[:, 1].max()),
             "mpts_per_s": n / (step_ms * 1e-3) / 1e6,
             "per_rank": [{"rank": r, "rows": int(tab[r, 6]), "device_ms": tab[r, 0], "upward_exchange": tab[r, 2],
