@@ -58,6 +58,7 @@ struct DirectArgs {  // leaf pass: P2P over U ranges + M2P over W cells (bbfmm.r
   const double *ccx, *ccy, *ccz, *chalf;
   const double *nodes;  // p Chebyshev nodes
   int p, dim, P, nrhs, rhs0;
+  int nrhs_pass;   // symmetric P2P: right-hand sides [rhs0, rhs0 + nrhs_pass) of this call
   int atomic_out;  // 1: results are added with RED (the kernel runs concurrently with other writers of `out`)
   int has_w;       // 1: some leaf owns a W list that this call must apply (M2P)
   int skip_p2p;    // 1: the U ranges were served by another kernel (p2p_sym.cu / p2p_mma.cu)

@@ -153,6 +153,42 @@ def test_p2p_symmetric_matches_full_lists(kernel, dim, adaptive, sparse, kind):
     assert H.rel_l2(sym, ot.evaluate(w, pts)) <= MATVEC_TOL
 
 
+@pytest.mark.parametrize("kernel,dim,nrhs,kind", [(0, 3, 2, "clustered"), (1, 2, 4, "uniform"), (3, 3, 3, "near"),
+                                                  (2, 3, 4, "clustered"), (7, 3, 2, "uniform"), (0, 3, 5, "uniform")])
+def test_p2p_symmetric_several_right_hand_sides(kernel, dim, nrhs, kind):
+    """2, 3 (= 2 + 1) and 4 right-hand sides take the symmetric kernel with NR columns per pass (16-source tiles, one
+    partial-sum matrix per column); 5 and more stay on the general kernel.  Same check as above: the same points in
+    another order take the every-ordered-pair path and must agree to summation round-off, column by column."""
+    rng = np.random.default_rng(199)
+    n = 6000
+    if kind == "near":
+        base = H.make_points(n // 2, dim, "clustered", seed=16)
+        pts = np.concatenate([base, base + rng.standard_normal(base.shape) * 10.0 ** rng.uniform(-9, -3, (len(base), 1))])
+        pts[-40:] = pts[:40]
+    else:
+        pts = H.make_points(n, dim, kind, seed=16)
+    pts = np.ascontiguousarray(pts)
+    n = len(pts)
+    w = rng.random((n, nrhs)) - 0.5
+    w[:, -1] *= 1e3  # columns of different magnitude: a column landing in another column's slot would show
+    pt = H.product_tree(pts, 5, kernel, True, True, 37, 0, 1e-8)
+    pt.set_weights(w)
+    sym = np.asarray(pt.evaluate(w, pts)).reshape(n, nrhs)
+    full = np.asarray(pt.evaluate(w, np.ascontiguousarray(pts[::-1]))).reshape(n, nrhs)[::-1]
+    for k in range(nrhs):
+        scale = np.abs(full[:, k]) + np.median(np.abs(full[:, k]))
+        assert (np.abs(sym[:, k] - full[:, k]) / scale).max() <= 1e-11, k
+        assert H.rel_l2(sym[:, k], full[:, k]) <= 1e-12, k
+    again = np.asarray(pt.evaluate_at_sources(w)).reshape(n, nrhs)
+    assert H.rel_l2(again, full) <= 1e-12
+    # one column at a time through the one-column kernel: the same numbers
+    for k in (0, nrhs - 1):
+        wk = np.ascontiguousarray(w[:, k:k + 1])
+        pt.set_weights(wk)
+        one = np.asarray(pt.evaluate(wk, pts)).reshape(n)
+        assert H.rel_l2(one, full[:, k]) <= 1e-12, k
+
+
 @pytest.mark.parametrize("kernel,dim,nrhs,kind", [(0, 3, 1, "near"), (0, 3, 3, "clustered"), (2, 3, 2, "uniform"),
                                                   (3, 3, 4, "clustered"), (0, 2, 1, "uniform"), (5, 3, 8, "near"),
                                                   (0, 3, 1, "offset")])
