@@ -28,11 +28,12 @@ constexpr int kSymWPC = 4;       // warps per CTA
 constexpr int kSymStride = 33;   // row stride of the partial-sum matrix (doubles)
 
 // NR right-hand sides per pass (1, 2 or 4): the kernel value of a pair is computed once and serves 2 NR accumulations.
-// The source-side partial sums need NR matrices, so tiles shrink to 16 sources for NR > 1 (shared memory per warp:
-// 10.5 / 11.4 / 20.9 KB for NR = 1 / 2 / 4).
+// The source-side partial sums need NR matrices, so tiles shrink to 16 / 8 sources for NR = 2 / 4 (shared memory per
+// warp: 10.5 / 11.4 / 12.5 KB; with 16-source tiles NR = 4 fitted two CTAs per SM and gained 9 % on the 2-D thin-plate
+// config where the model says 40 %).
 template <int NR>
 struct SymWarpSmem {
-  static constexpr int TS = NR == 1 ? 32 : 16;  // sources per tile
+  static constexpr int TS = NR == 1 ? 32 : (NR == 2 ? 16 : 8);  // sources per tile
   static constexpr int NV = 2 + NR / 2;         // double2 planes per source: {x, y}, {z, w0}, {w1, w2}, {w3, -}
   double2 st[2][NV][32];                        // double-buffered source tile (32 slots: the diagonal block uses them all)
   double part[NR * TS * kSymStride];            // part[r][j][l] = sum over the lane's targets of k(t, s_j) w_r[t]
@@ -214,7 +215,7 @@ __device__ __forceinline__ void p2p_sym_body(const DirectArgs &a, SymWarpSmem<NR
 }
 
 template <int FAM, bool FAST, int NR>
-__global__ void __launch_bounds__(kSymWPC * 32, NR == 1 ? 5 : (NR == 2 ? 4 : 2)) k_p2p_sym(const DirectArgs a, const int split) {
+__global__ void __launch_bounds__(kSymWPC * 32, NR == 1 ? 5 : (NR == 2 ? 4 : 3)) k_p2p_sym(const DirectArgs a, const int split) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long gw = (long long)blockIdx.x * kSymWPC + warp;
   const long long chunk = gw / split;
