@@ -8,8 +8,8 @@
 //   upward      P2M over the OWNED leaves only, M2M over the cells that have owned descendants: every rank holds the
 //               exact multipoles of the cells inside its range and a partial sum for the cells that span ranks;
 //   exchange 1  ncclAllReduce(sum) of the multipole array completes the spanning cells and hands every rank the halo
-//               multipoles its V / W lists need; upward pass and exchange run on the high-priority main stream, the
-//               near-field pass (it needs no multipoles) beside them on a low-priority one;
+//               multipoles its V / W lists need; the exchange and the downward pass run on the high-priority main
+//               stream, the near-field pass (it needs no multipoles) beside them on a low-priority one;
 //   near field  symmetric P2P (p2p_sym.cu) for the chunks of the owned range against ALL sources behind them: the
 //               source-side sums of rows another rank owns are added into this rank's copy of the full-length result;
 //   downward    M2L / L2L / L2P for the cells / targets of the share; the fused W/X kernel (p2l.cu) for the cells with
@@ -22,6 +22,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -126,7 +127,7 @@ struct fb_comm {
 // per-tree state of the partition (fb_tree::shard)
 struct fb_shard {
   fb_comm *comm = nullptr;
-  int fork_mode = 0;                  // where the near field forks off the main stream (fb_tree_shard_fork_mode)
+  int fork_mode = 0;                  // where the near field forks off the main stream: chosen in fb_tree_shard
   bool full_upward = false;           // emulated share with every multipole formed locally: the owned rows come out exact
   int rank = 0, world = 1;            // the share this process computes: the communicator's, or an emulated one (fb_tree_shard_as)
   std::vector<uint64_t> leaf_bounds;  // world + 1 boundaries into the Morton leaf sequence
@@ -226,7 +227,9 @@ int fb_comm_world_size(const fb_comm *c) { return c ? c->world : -1; }
 // (calibrated on the 1M-point headline workload: symmetric P2P 1.16 ps, W/X 0.74 ps per evaluation, M2L 1.75 ns per entry
 // at P = 343): the P2P evaluations of a leaf are the pairs with the sources BEHIND it (one RHS: p2p_sym.cu) or all its
 // ordered pairs; a cell's X-list work and M2L entries are pushed down to its leaves.
-static void share_work(const fb_tree &t, int world, uint64_t *leaf_ptr, double *work) {
+constexpr double kShortNearMs = 0.45;  // estimated near-field time of a rank below which it forks after the upward pass
+
+static double share_work(const fb_tree &t, int world, uint64_t *leaf_ptr, double *work) {
   const HostTree &ht = t.ht;
   const size_t nl = ht.leaves.size(), nc = ht.ncells();
   const bool sym = t.nrhs == 1;
@@ -255,14 +258,17 @@ static void share_work(const fb_tree &t, int world, uint64_t *leaf_ptr, double *
     work[l] = down[c] + 0.3 * nt * t.P + 1.0;
   }
   leaf_ptr[nl] = (uint64_t)t.n;
-  // The near field runs beside the upward pass and exchange 1, a chain of small launches and an all-reduce that takes
-  // about 0.35 ms however little it computes (measured at 8 ranks on the headline workload): that much P2P per rank costs
-  // nothing on the critical path, and a cut that counted it in full would leave the ranks with few direct pairs waiting
-  // on the ones with many far-field evaluations.  Only the part of the P2P beyond the slack is weighed.
+  // A SHORT near field (forked after the upward pass, see fb_tree_shard) runs beside exchange 1 and in the tails of the
+  // downward kernels: about 0.35 ms of it per rank cost nothing on the critical path at 8 ranks on the headline workload,
+  // and a cut that counted it in full left the ranks with few direct pairs waiting on the ones with many far-field
+  // evaluations.  Only the part beyond that slack is weighed.  A long near field (forked before the upward pass) is
+  // weighed in full: beside it the upward pass and the exchange stretch by about what it saves (measured at 2 / 4 ranks).
   const double unit_ms = 0.74e-9 * (1.0 + 0.15 * (t.nrhs - 1));  // one evaluation unit, B200, from the stage timings
   const double near_ms = near_total * unit_ms;
-  const double alpha = near_ms > 0 ? std::min(1.0, std::max(0.25, 1.0 - 0.35 * world / near_ms)) : 1.0;
+  const bool short_near = near_ms / world < kShortNearMs;
+  const double alpha = short_near && near_ms > 0 ? std::min(1.0, std::max(0.25, 1.0 - 0.35 * world / near_ms)) : 1.0;
   for (size_t l = 0; l < nl; ++l) work[l] += alpha * near[l];
+  return near_ms / world;  // estimated near-field time of a rank
 }
 
 // as_world > 0: take the share of rank `as_rank` of `as_world` ranks with a world-1 communicator — the per-rank kernel
@@ -293,7 +299,14 @@ static int shard_impl(fb_tree *t, fb_comm *comm, int as_rank, int as_world, int 
     const size_t nl = ht.leaves.size();
     std::vector<uint64_t> leaf_ptr(nl + 1);
     std::vector<double> work(nl);
-    share_work(*t, world, leaf_ptr.data(), work.data());
+    const double near_rank_ms = share_work(*t, world, leaf_ptr.data(), work.data());
+    // Fork point of the near field (see fb_tree_matvec_sharded).  The downward kernels fill the register file (M2L: one
+    // 384-thread CTA per SM, W/X: three CTAs per SM), so a P2P grid that is still running when they start only gets their
+    // tails: a LONG near field is better off starting beside the upward pass (2 / 4 ranks on the headline workload: 5.42
+    // / 2.78 ms against 5.56 / 2.91), a SHORT one after it, where it no longer stretches the latency-bound upward chain
+    // and the exchange behind it (8 ranks: 1.65 against 1.73 ms).
+    sh->fork_mode = near_rank_ms < kShortNearMs ? 1 : 0;
+    if (const char *v = std::getenv("FB_SHARD_FORK")) sh->fork_mode = v[0] == '1' ? 1 : 0;
     sh->leaf_bounds.resize(world + 1);
     partition_by_work(work.data(), nl, world, sh->leaf_bounds.data());
     sh->pos.resize(world + 1);
@@ -375,7 +388,8 @@ int fb_tree_matvec_sharded(fb_tree *t) {
     const size_t mult_count = nc * (size_t)t->nrhs * coef_stride(t->P);
     cudaStream_t s2 = t->stream2;
     // fork point of the near field: 0 = right after the weight sort (beside the upward pass too), 1 = after the upward
-    // pass (beside exchange 1 and the downward pass only: the upward pass then has the SMs to itself)
+    // pass (beside exchange 1 and the downward pass only: the upward pass then has the SMs to itself); chosen by
+    // fb_tree_shard from the estimated length of the near field (FB_SHARD_FORK / fb_tree_shard_fork_mode override it)
     if (sh.fork_mode == 1) {
       if (sh.full_upward) t->upward();
       else t->upward(sh.d_owned_leaves.p, sh.n_owned_leaves, sh.ts.cell_flag);

@@ -202,7 +202,8 @@ int fb_tree_shard(fb_tree *t, fb_comm *comm_or_null);            /* NULL drops t
  * multipoles only (faithful times, partial sums in the result), exact = 1 forms all of them (owned rows exact)       */
 int fb_tree_shard_as(fb_tree *t, fb_comm *comm, int rank, int world, int exact);
 /* where the near-field pass forks off: 0 = after the weight sort (beside the upward pass, exchange 1 and the downward
- * pass), 1 = after the upward pass (beside exchange 1 and the downward pass)                                        */
+ * pass), 1 = after the upward pass (beside exchange 1 and the downward pass).  fb_tree_shard picks one from the      *
+ * estimated length of the near field; this call overrides it                                                      */
 int fb_tree_shard_fork_mode(fb_tree *t, int mode);
 int fb_tree_shard_rows(const fb_tree *t, int rank, uint64_t *begin_pos, uint64_t *end_pos);  /* Morton positions  */
 int fb_tree_matvec_sharded(fb_tree *t);
