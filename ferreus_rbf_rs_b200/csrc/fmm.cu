@@ -134,15 +134,19 @@ int io_threads() {  // referenced from OpenMP clauses only (not static: the devi
 
 // bytewise equality of two host buffers, all host threads (24 MB in ~0.3 ms: cheaper than moving them over PCIe)
 static bool same_bytes(const void *a, const void *b, size_t bytes) {
+  // two different vectors differ in their first few values: settle that case before the thread team starts
+  const size_t head = std::min<size_t>(bytes, 4096);
+  if (std::memcmp(a, b, head) != 0) return false;
   const size_t chunk = 1 << 18;
   const long nchunks = (long)((bytes + chunk - 1) / chunk);
-  int differ = 0;
-#pragma omp parallel for schedule(static) reduction(| : differ) num_threads(io_threads())
+  std::atomic<int> differ{0};
+#pragma omp parallel for schedule(static) num_threads(io_threads())
   for (long c = 0; c < nchunks; ++c) {
+    if (differ.load(std::memory_order_relaxed)) continue;
     const size_t off = (size_t)c * chunk, len = std::min(chunk, bytes - off);
-    if (std::memcmp((const char *)a + off, (const char *)b + off, len) != 0) differ |= 1;
+    if (std::memcmp((const char *)a + off, (const char *)b + off, len) != 0) differ.store(1, std::memory_order_relaxed);
   }
-  return differ == 0;
+  return differ.load() == 0;
 }
 static void copy_bytes(void *dst, const void *src, size_t bytes) {
   const size_t chunk = 1 << 18;
@@ -573,7 +577,7 @@ void fb_tree::build(const double *points, size_t n_, int dim_, ptrdiff_t rs, ptr
 }
 
 // --------------------------------------------------------------------------------------- weights
-void fb_tree::upload_weights(const double *w, size_t n_rows, size_t nrhs_, ptrdiff_t rs, ptrdiff_t cs) {
+bool fb_tree::upload_weights(const double *w, size_t n_rows, size_t nrhs_, ptrdiff_t rs, ptrdiff_t cs) {
   FB_REQUIRE(w != nullptr, "weights required");
   FB_REQUIRE(n_rows >= n, "weights must have at least one row per source point");
   FB_REQUIRE(nrhs_ >= 1, "weights need at least one column");
@@ -583,7 +587,7 @@ void fb_tree::upload_weights(const double *w, size_t n_rows, size_t nrhs_, ptrdi
   // the second copy is recognised on the host and neither re-uploaded nor re-sorted.
   if (contiguous && w_cache_valid && (int)nrhs_ == nrhs && h_w_last_cnt == cnt && d_w.cap >= cnt &&
       same_bytes(w, h_w_last.p, cnt * sizeof(double)))
-    return;
+    return false;
   // fb_tree_set_weights returns without waiting for its transfer and upward pass: make sure nothing is still reading
   // the staging buffers before they are rewritten (or reallocated)
   FB_CUDA(cudaStreamSynchronize(stream));
@@ -591,9 +595,14 @@ void fb_tree::upload_weights(const double *w, size_t n_rows, size_t nrhs_, ptrdi
   if (contiguous) {
     // user memory is pageable: gather it into the pinned cache with all host threads and send it from there
     h_w_last.reserve(cnt);
-    copy_bytes(h_w_last.p, w, cnt * sizeof(double));
+    // in pieces: the transfer of one piece runs under the host copy of the next
+    const size_t piece = std::max<size_t>((cnt + 3) / 4, (size_t)1 << 17);
+    for (size_t off = 0; off < cnt; off += piece) {
+      const size_t len = std::min(piece, cnt - off);
+      copy_bytes(h_w_last.p + off, w + off, len * sizeof(double));
+      FB_CUDA(cudaMemcpyAsync(d_w_user.p + off, h_w_last.p + off, len * sizeof(double), cudaMemcpyHostToDevice, stream));
+    }
     h_w_last_cnt = cnt;
-    FB_CUDA(cudaMemcpyAsync(d_w_user.p, h_w_last.p, cnt * sizeof(double), cudaMemcpyHostToDevice, stream));
     w_cache_valid = true;
   } else {
     w_cache_valid = false;
@@ -604,6 +613,8 @@ void fb_tree::upload_weights(const double *w, size_t n_rows, size_t nrhs_, ptrdi
   }
   nrhs = (int)nrhs_;
   sort_weights();
+  last_w_ptr = contiguous ? w : nullptr;
+  return true;
 }
 
 void fb_tree::sort_weights() {
@@ -1242,9 +1253,25 @@ static int eval_common(fb_tree *t, const double *w, size_t n_rows, size_t nrhs, 
         FB_REQUIRE(t->have_weights, "set_weights must be called before evaluate");
         FB_REQUIRE((int)nrhs == t->nrhs, "weights must have the column count given to set_weights");
         if (leaves_only) FB_REQUIRE(t->have_locals, "set_local_coefficients must be called before evaluate_leaves");
+        // The solver's call (rbf.rs:1357-1364) hands over the vector it has just given to set_weights and the source
+        // points themselves, every time; both facts are established by comparing the caller's buffers with the library's
+        // copies on the host — 32 MB of memcmp at 1M points, longer than the upward pass it used to hide behind.  When
+        // the same two pointers arrive as in the last call that was confirmed to be that case, the device work is queued
+        // BEFORE the comparisons; if one of them fails after all, the call simply continues on the general path below
+        // (same stream: the speculative kernels finish first and their results are overwritten).
+        bool speculated = false;
+        if (!leaves_only && out_grads == nullptr && targets != nullptr && targets == t->spec_targets && w == t->last_w_ptr &&
+            m == t->n && t_cs == 1 && t_rs == (ptrdiff_t)t->dim && w_cs == 1 && w_rs == (ptrdiff_t)nrhs && t->w_cache_valid) {
+          t->evaluate_sources_fused(t->source_target_set());
+          speculated = true;
+        }
         TargetSet ts = t->bin_targets(targets, m, t_rs, t_cs, bad);  // before touching weights: errors leave state intact
-        t->upload_weights(w, n_rows, nrhs, w_rs, w_cs);
-        if (ts.all_sources && !leaves_only && out_grads == nullptr) {
+        const bool reuploaded = t->upload_weights(w, n_rows, nrhs, w_rs, w_cs);
+        const bool solver_call = ts.all_sources && !leaves_only && out_grads == nullptr;
+        t->spec_targets = (solver_call && !reuploaded) ? targets : nullptr;
+        if (speculated && solver_call && !reuploaded) {
+          // confirmed: the queued pass is the answer
+        } else if (solver_call) {
           t->evaluate_sources_fused(ts);
         } else {
           if (!leaves_only) t->downward(ts.cell_flag);

@@ -173,6 +173,8 @@ struct fb_tree {
   fb::PinnedBuf<double> h_w_last;             // pinned copy of the last contiguous upload (H2D source, duplicate test)
   size_t h_w_last_cnt = 0;
   bool w_cache_valid = false;                 // false once d_w_user was written on the device (solver)
+  const double *last_w_ptr = nullptr;         // caller's pointer of the last contiguous upload (never dereferenced)
+  const double *spec_targets = nullptr;       // caller's target pointer of the last evaluate confirmed to be the solver's call
   fb::DBuf<double> d_mult, d_loc;             // [cell][rhs][P]
   fb::DBuf<double> d_ccx, d_ccy, d_ccz, d_chalf;
   fb::DBuf<int> d_cell_parent, d_cell_slot, d_cell_ptb, d_cell_pte;
@@ -236,7 +238,8 @@ struct fb_tree {
   void build(const double *points, size_t n_, int dim_, ptrdiff_t rs, ptrdiff_t cs, int order_,
              const fb_kernel_params *k, int adaptive, int sparse, const double *extents,
              const fb_fmm_params *params);
-  void upload_weights(const double *w, size_t n_rows, size_t nrhs_, ptrdiff_t rs, ptrdiff_t cs);
+  // returns false when `w` is byte-identical to the last upload (nothing sent)
+  bool upload_weights(const double *w, size_t n_rows, size_t nrhs_, ptrdiff_t rs, ptrdiff_t cs);
   void sort_weights();
   // P2M over `leaves` (null = every leaf with sources) and M2M over the cells flagged in `cell_flag` (null = all)
   void upward(const int *leaves = nullptr, int n_leaves = 0, const uint8_t *cell_flag = nullptr);
