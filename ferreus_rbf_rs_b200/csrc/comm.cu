@@ -394,10 +394,12 @@ int fb_tree_matvec_sharded(fb_tree *t) {
       if (sh.full_upward) t->upward();
       else t->upward(sh.d_owned_leaves.p, sh.n_owned_leaves, sh.ts.cell_flag);
     }
+    // this rank's copy of the full-length result: owned rows + the symmetric halves it computes for foreign rows.  Zeroed
+    // on the main stream in front of the fork: both the near field (side stream) and the fused W/X pass (main stream) add
+    // into it
+    t->d_out.zero(out_count, s);
     FB_CUDA(cudaEventRecord(t->ev_fork, s));
     FB_CUDA(cudaStreamWaitEvent(s2, t->ev_fork, 0));
-    // this rank's copy of the full-length result: owned rows + the symmetric halves it computes for foreign rows
-    t->d_out.zero(out_count, s2);
     if (t->timing) FB_CUDA(cudaEventRecord(t->ev[10], s2));
     t->launch_p2p(sh.ts, false, true, s2, true);  // U lists only; REDs: the fused W/X pass adds to the same rows
     if (t->timing) FB_CUDA(cudaEventRecord(t->ev[11], s2));

@@ -1070,9 +1070,9 @@ void fb_tree::matvec_dev(const TargetSet &ts) {
     return;
   }
   const bool fuse = ht.adaptive && n_x_cells > 0 && ts.row_of_pos != nullptr;
+  d_out.zero(ts.m * (size_t)nrhs, stream);  // in front of the fork: both streams add into it
   FB_CUDA(cudaEventRecord(ev_fork, stream));
   FB_CUDA(cudaStreamWaitEvent(stream2, ev_fork, 0));
-  d_out.zero(ts.m * (size_t)nrhs, stream2);
   if (timing) FB_CUDA(cudaEventRecord(ev[10], stream2));
   launch_p2p(ts, false, true, stream2, true);  // U lists only
   if (timing) FB_CUDA(cudaEventRecord(ev[11], stream2));
