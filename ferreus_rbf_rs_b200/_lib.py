@@ -144,6 +144,11 @@ SIGNATURES = {
     "fb_tree_sharded_result_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "fb_tree_sharded_download": (C.c_int, [C.c_void_p, _dp]),
     "fb_partition_by_work": (C.c_int, [_dp, _sz, C.c_int, _u64p]),
+    "fb_host_tree_new": (C.c_int, [_dp, _sz, C.c_int, _pd, _pd, _dp, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "fb_host_tree_free": (None, [C.c_void_p]),
+    "fb_host_tree_counts": (C.c_int, [C.c_void_p, _u64p, _u64p, _i32p, _u64p]),
+    "fb_host_tree_dump_cells": (C.c_int, [C.c_void_p, _u64p, _u8p, _u64p, _u64p]),
+    "fb_host_tree_dump_list": (C.c_int, [C.c_void_p, C.c_int, _u64p, _u64p]),
     "fb_ops_new": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(FbKernelParams), C.c_int, C.c_double,
                              C.POINTER(C.c_void_p)]),
     "fb_ops_free": (None, [C.c_void_p]),

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <deque>
+#include <memory>
 #include <unordered_set>
 
 namespace fb {
@@ -16,13 +17,14 @@ inline void deinterleave(uint64_t pfx, int dim, uint32_t a[3]) {
     for (int j = 0; j < dim; ++j) a[j] |= (uint32_t)((pfx >> (bit * dim + j)) & 1ull) << bit;
 }
 
-inline uint64_t interleave(const uint32_t a[3], int dim) {
+}  // namespace
+uint64_t interleave(const uint32_t a[3], int dim) {
   uint64_t code = 0;
   for (int bit = 0; bit < 16; ++bit)
     for (int j = 0; j < dim; ++j) code |= (uint64_t)((a[j] >> bit) & 1u) << (bit * dim + j);
   return code;
 }
-
+namespace {
 struct LP {  // (level, prefix) pair: a cell position that may or may not exist in the tree
   int level;
   uint64_t prefix;
@@ -306,3 +308,122 @@ void HostTree::build_lists_regular() {
 }
 
 }  // namespace fb
+
+// ---- host-only tree + interaction lists (no GPU) ----------------------------------------------------------------------
+// The product path sorts the level-16 codes on the device (fmm.cu) and hands them to HostTree::build; this entry point
+// computes and sorts the same codes on the host, so the CPU test-suite can compare keys, leaf membership and the U / V /
+// W / X lists with the oracle bit for bit (morton.rs:29-373, linear_tree.rs:20-485) without a device.
+#include "../../include/ferreus_b200.h"
+
+struct fb_host_tree {
+  fb::HostTree ht;
+  std::vector<uint32_t> perm;  // sorted position -> source row (stable: equal codes keep their row order, like the radix sort)
+  size_t n = 0;
+};
+
+extern "C" {
+
+int fb_host_tree_new(const double *points, size_t n, int dim, ptrdiff_t row_stride, ptrdiff_t col_stride,
+                     const double *extents_or_null, uint64_t max_points_per_cell, int adaptive_tree, int sparse,
+                     fb_host_tree **out) {
+  if (!out) return FB_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  if (!points || n == 0 || dim < 1 || dim > 3 || max_points_per_cell == 0) return FB_ERR_INVALID_ARGUMENT;
+  try {
+    double ext[6];
+    if (extents_or_null) {
+      for (int d = 0; d < 2 * dim; ++d) ext[d] = extents_or_null[d];
+    } else {
+      for (int d = 0; d < dim; ++d) ext[d] = ext[dim + d] = points[(ptrdiff_t)d * col_stride];
+      for (size_t i = 0; i < n; ++i)
+        for (int d = 0; d < dim; ++d) {
+          const double v = points[(ptrdiff_t)i * row_stride + (ptrdiff_t)d * col_stride];
+          if (v < ext[d]) ext[d] = v;
+          if (v > ext[dim + d]) ext[dim + d] = v;
+        }
+    }
+    double center[3] = {0, 0, 0}, radius = -INFINITY;  // calculate_tree_center_and_radius, morton.rs:349-373
+    for (int d = 0; d < dim; ++d) {
+      const double lo = std::floor(ext[d]), hi = std::ceil(ext[dim + d]);
+      center[d] = (lo + hi) / 2.0;
+      radius = std::max(radius, (hi - lo) / 2.0 + 1e-3);
+    }
+    if (!(std::isfinite(radius) && radius > 0)) return FB_ERR_INVALID_ARGUMENT;
+    const double side16 = 2.0 * radius / 65536.0;  // morton.rs:29-32 at level 16
+    std::vector<uint64_t> codes(n);
+    for (size_t i = 0; i < n; ++i) {
+      uint32_t a[3] = {0, 0, 0};
+      for (int d = 0; d < dim; ++d) {
+        const double x = points[(ptrdiff_t)i * row_stride + (ptrdiff_t)d * col_stride];
+        const double q = std::floor((x - (center[d] - radius)) / side16);  // point_to_anchor, morton.rs:35-51
+        const uint64_t v = !(q >= 0.0) ? 0ull : (q >= 18446744073709551616.0 ? ~0ull : (uint64_t)q);
+        if (v >= 65536ull) return FB_ERR_INVALID_ARGUMENT;  // outside the given extents (fmm.cu rejects it the same way)
+        a[d] = (uint32_t)v;
+      }
+      codes[i] = fb::interleave(a, dim);
+    }
+    std::unique_ptr<fb_host_tree> t(new fb_host_tree());
+    t->n = n;
+    t->perm.resize(n);
+    for (size_t i = 0; i < n; ++i) t->perm[i] = (uint32_t)i;
+    std::stable_sort(t->perm.begin(), t->perm.end(), [&](uint32_t x, uint32_t y) { return codes[x] < codes[y]; });
+    std::vector<uint64_t> sorted(n);
+    for (size_t i = 0; i < n; ++i) sorted[i] = codes[t->perm[i]];
+    t->ht.build(sorted.data(), n, dim, center, radius, (size_t)max_points_per_cell, !sparse, adaptive_tree != 0);
+    *out = t.release();
+    return FB_OK;
+  } catch (...) {
+    return FB_ERR_INVALID_ARGUMENT;
+  }
+}
+
+void fb_host_tree_free(fb_host_tree *t) { delete t; }
+
+int fb_host_tree_counts(const fb_host_tree *t, uint64_t *n_cells, uint64_t *n_leaves, int32_t *depth, uint64_t *n_list4) {
+  if (!t) return FB_ERR_INVALID_ARGUMENT;
+  if (n_cells) *n_cells = t->ht.ncells();
+  if (n_leaves) *n_leaves = t->ht.leaves.size();
+  if (depth) *depth = t->ht.depth;
+  if (n_list4) {
+    n_list4[0] = t->ht.u_idx.size();
+    n_list4[1] = t->ht.v_idx.size();
+    n_list4[2] = t->ht.w_idx.size();
+    n_list4[3] = t->ht.x_idx.size();
+  }
+  return FB_OK;
+}
+
+int fb_host_tree_dump_cells(const fb_host_tree *t, uint64_t *keys, uint8_t *leaf_flags, uint64_t *leaf_ptr,
+                            uint64_t *leaf_idx) {
+  if (!t) return FB_ERR_INVALID_ARGUMENT;
+  const size_t nc = t->ht.ncells();
+  uint64_t off = 0;
+  for (size_t c = 0; c < nc; ++c) {
+    if (keys) keys[c] = t->ht.ref_key((int)c);
+    if (leaf_flags) leaf_flags[c] = t->ht.is_leaf[c];
+    if (leaf_ptr) leaf_ptr[c] = off;
+    if (t->ht.is_leaf[c]) {
+      const int b = t->ht.pt_begin[c], e = t->ht.pt_end[c];
+      if (leaf_idx) {
+        for (int i = b; i < e; ++i) leaf_idx[off + (i - b)] = t->perm[i];
+        std::sort(leaf_idx + off, leaf_idx + off + (e - b));
+      }
+      off += (uint64_t)(e - b);
+    }
+  }
+  if (leaf_ptr) leaf_ptr[nc] = off;
+  return FB_OK;
+}
+
+int fb_host_tree_dump_list(const fb_host_tree *t, int which, uint64_t *ptr, uint64_t *idx) {
+  if (!t || which < 0 || which > 3) return FB_ERR_INVALID_ARGUMENT;
+  const std::vector<int64_t> *p[4] = {&t->ht.u_ptr, &t->ht.v_ptr, &t->ht.w_ptr, &t->ht.x_ptr};
+  const std::vector<int32_t> *x[4] = {&t->ht.u_idx, &t->ht.v_idx, &t->ht.w_idx, &t->ht.x_idx};
+  if (ptr)
+    for (size_t i = 0; i < p[which]->size(); ++i) ptr[i] = (uint64_t)(*p[which])[i];
+  if (idx)
+    for (size_t i = 0; i < x[which]->size(); ++i) idx[i] = (uint64_t)(*x[which])[i];
+  return FB_OK;
+}
+
+}  // extern "C"

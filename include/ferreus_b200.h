@@ -213,6 +213,21 @@ int fb_tree_sharded_download(fb_tree *t, double *out_vals /* n x nrhs row-major 
 /* the cut itself (host only): n_parts + 1 boundaries into the leaf sequence */
 int fb_partition_by_work(const double *work, size_t n_leaves, int parts, uint64_t *bounds_out);
 
+/* ---- host-only tree + interaction lists (no GPU needed): the HostTree the device path builds (morton.rs:29-373,
+ * linear_tree.rs:20-485), from level-16 codes computed and sorted on the host instead of by the device radix sort; used
+ * by the CPU test-suite to compare keys, leaf membership and the U / V / W / X lists with the oracle bit for bit.
+ * dump_* have the layouts of fb_tree_dump_cells / fb_tree_dump_list.                                            ---- */
+typedef struct fb_host_tree fb_host_tree;
+int fb_host_tree_new(const double *points, size_t n, int dim, ptrdiff_t row_stride, ptrdiff_t col_stride,
+                     const double *extents_or_null, uint64_t max_points_per_cell, int adaptive_tree, int sparse,
+                     fb_host_tree **out);
+void fb_host_tree_free(fb_host_tree *t);
+int fb_host_tree_counts(const fb_host_tree *t, uint64_t *n_cells, uint64_t *n_leaves, int32_t *depth,
+                        uint64_t *n_list4 /* U, V, W, X entries */);
+int fb_host_tree_dump_cells(const fb_host_tree *t, uint64_t *keys, uint8_t *leaf_flags, uint64_t *leaf_ptr,
+                            uint64_t *leaf_idx);
+int fb_host_tree_dump_list(const fb_host_tree *t, int which, uint64_t *ptr, uint64_t *idx);
+
 /* ---- host-only operator precompute (no GPU needed): used by the CPU test-suite to check the
  * Chebyshev / ACA / SVD restatement (chebyshev.rs:650-814, aca.rs:23-247) against the oracle. ---- */
 typedef struct fb_ops fb_ops;
