@@ -179,6 +179,12 @@ SOLVER_SIGNATURES = {
     "fr_dense_spd_solve": (C.c_int, [_dp, C.c_int, _dp, C.c_int, _dp, _i32p]),
     "fr_evaluate_monomials": (C.c_int, [_dp, _sz, C.c_int, C.c_int, _dp, _dp, _dp, _i32p]),
     "fr_ddm_level": (C.c_int, [C.c_void_p, C.c_int, _u64p, _u64p, _u64p, _u64p, _u64p, _u8p]),
+    "fr_host_ddm_new": (C.c_int, [_dp, _sz, C.c_int, _pd, _pd, C.POINTER(FrSettings), C.POINTER(FrParams),
+                                  C.POINTER(C.c_void_p)]),
+    "fr_host_ddm_free": (None, [C.c_void_p]),
+    "fr_host_ddm_counts": (C.c_int, [C.c_void_p, _u64p, _u64p]),
+    "fr_host_ddm_kept": (C.c_int, [C.c_void_p, _u64p]),
+    "fr_host_ddm_level": (C.c_int, [C.c_void_p, C.c_int, _u64p, _u64p, _u64p, _u64p, _u64p, _u8p]),
 }
 
 

@@ -6,6 +6,7 @@
 #include <chrono>
 #include <cmath>
 #include <deque>
+#include <memory>
 #include <numeric>
 #include <string>
 
@@ -619,3 +620,89 @@ void thin_q_rowmajor(const double *a, size_t n, int m, double *q) {
 }
 
 }  // namespace fb
+
+// ---- host-only duplicate removal + DDM hierarchy (no GPU) --------------------------------------------------------------
+// What fr_fit does on the host before anything reaches the device (rbf.rs:341-359, domain_decomposition.rs:67-346), behind
+// plain entry points so that the CPU test-suite can compare the kept rows, the levels, the domains, their point order
+// (special points first) and the internal masks with the oracle.
+struct fr_host_ddm {
+  std::vector<int64_t> keep;
+  std::vector<fb::LevelHost> levels;
+};
+
+extern "C" {
+
+int fr_host_ddm_new(const double *points, size_t n, int dim, ptrdiff_t p_rs, ptrdiff_t p_cs, const fr_settings *settings,
+                    const fr_params *params_or_null, fr_host_ddm **out) {
+  if (!out) return FB_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  if (!points || !settings || n == 0 || dim < 1 || dim > 3) return FB_ERR_INVALID_ARGUMENT;
+  try {
+    fb::Settings st;
+    std::string err;
+    if (!fb::resolve_settings(*settings, dim, st, err)) return FB_ERR_INVALID_ARGUMENT;
+    fb::KParams kp;
+    if (!fb::make_kparams(st.kparams, kp)) return FB_ERR_INVALID_ARGUMENT;
+    fr_params params;
+    if (params_or_null) params = *params_or_null;
+    else fr_params_default(settings->kernel_type, &params);
+    std::vector<double> pts(n * dim);
+    for (size_t i = 0; i < n; ++i)
+      for (int d = 0; d < dim; ++d) pts[i * dim + d] = points[(ptrdiff_t)i * p_rs + (ptrdiff_t)d * p_cs];
+    std::unique_ptr<fr_host_ddm> h(new fr_host_ddm());
+    if (params.test_unique) {
+      h->keep = fb::remove_duplicates(pts.data(), n, dim, kp);
+    } else {
+      h->keep.resize(n);
+      for (size_t i = 0; i < n; ++i) h->keep[i] = (int64_t)i;
+    }
+    const size_t m = h->keep.size();
+    std::vector<double> kept(m * dim);
+    for (size_t k = 0; k < m; ++k) std::copy(&pts[h->keep[k] * dim], &pts[h->keep[k] * dim] + dim, &kept[k * dim]);
+    if (m > (size_t)params.naive_solve_threshold) h->levels = fb::build_ddm(kept.data(), m, dim, st, params);
+    *out = h.release();
+    return FB_OK;
+  } catch (...) {
+    return FB_ERR_INVALID_ARGUMENT;
+  }
+}
+
+void fr_host_ddm_free(fr_host_ddm *h) { delete h; }
+
+int fr_host_ddm_counts(const fr_host_ddm *h, uint64_t *n_kept, uint64_t *n_levels) {
+  if (!h) return FB_ERR_INVALID_ARGUMENT;
+  if (n_kept) *n_kept = h->keep.size();
+  if (n_levels) *n_levels = h->levels.size();
+  return FB_OK;
+}
+
+int fr_host_ddm_kept(const fr_host_ddm *h, uint64_t *rows) {
+  if (!h || !rows) return FB_ERR_INVALID_ARGUMENT;
+  for (size_t i = 0; i < h->keep.size(); ++i) rows[i] = (uint64_t)h->keep[i];
+  return FB_OK;
+}
+
+// same layout as fr_ddm_level
+int fr_host_ddm_level(const fr_host_ddm *h, int level, uint64_t *n_domains, uint64_t *n_level_points,
+                      uint64_t *level_points, uint64_t *dom_ptr, uint64_t *dom_idx, uint8_t *dom_internal) {
+  if (!h || level < 0 || level >= (int)h->levels.size()) return FB_ERR_INVALID_ARGUMENT;
+  const fb::LevelHost &lh = h->levels[level];
+  if (n_domains) *n_domains = lh.domains.size();
+  if (n_level_points) *n_level_points = lh.point_indices.size();
+  if (level_points)
+    for (size_t i = 0; i < lh.point_indices.size(); ++i) level_points[i] = (uint64_t)lh.point_indices[i];
+  uint64_t off = 0;
+  for (size_t d = 0; d < lh.domains.size(); ++d) {
+    if (dom_ptr) dom_ptr[d] = off;
+    const fb::DomainHost &dh = lh.domains[d];
+    for (size_t i = 0; i < dh.idx.size(); ++i) {
+      if (dom_idx) dom_idx[off + i] = (uint64_t)dh.idx[i];
+      if (dom_internal) dom_internal[off + i] = i < dh.mask.size() ? dh.mask[i] : 0;
+    }
+    off += dh.idx.size();
+  }
+  if (dom_ptr) dom_ptr[lh.domains.size()] = off;
+  return FB_OK;
+}
+
+}  // extern "C"

@@ -141,6 +141,19 @@ int fr_evaluate_targets(fr_model *m, const double *targets, size_t n_targets, pt
 int fr_ddm_level(const fr_model *m, int level, uint64_t *n_domains, uint64_t *n_level_points,
                  uint64_t *level_points, uint64_t *dom_ptr, uint64_t *dom_idx, uint8_t *dom_internal);
 
+/* ---- host-only duplicate removal + DDM hierarchy (no GPU needed): what fr_fit does on the host before anything reaches
+ * the device (rbf.rs:341-359, 1391-1467; domain_decomposition.rs:67-346; the host part of domain.rs:153-330), for the CPU
+ * test-suite.  No levels are built when the kept points do not exceed naive_solve_threshold (single dense domain).
+ * fr_host_ddm_level has the layout of fr_ddm_level.                                                             ---- */
+typedef struct fr_host_ddm fr_host_ddm;
+int fr_host_ddm_new(const double *points, size_t n, int dim, ptrdiff_t p_rs, ptrdiff_t p_cs, const fr_settings *settings,
+                    const fr_params *params_or_null, fr_host_ddm **out);
+void fr_host_ddm_free(fr_host_ddm *h);
+int fr_host_ddm_counts(const fr_host_ddm *h, uint64_t *n_kept, uint64_t *n_levels);
+int fr_host_ddm_kept(const fr_host_ddm *h, uint64_t *rows /* n_kept input rows that survive duplicate removal */);
+int fr_host_ddm_level(const fr_host_ddm *h, int level, uint64_t *n_domains, uint64_t *n_level_points,
+                      uint64_t *level_points, uint64_t *dom_ptr, uint64_t *dom_idx, uint8_t *dom_internal);
+
 /* ---- entry points of the reference's reproducible known-answer tests --------------------------------------------
  * fr_dense_spd_solve: x = A^-1 b for a dense symmetric n x n matrix (row-major) through the batched subdomain kernels
  * (blocked Cholesky with the DMMA trailing update, forward / backward substitution; an indefinite matrix takes the
