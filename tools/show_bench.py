@@ -1,3 +1,4 @@
+"""Print the headline numbers, stage times and (N > 1) the per-rank table of a bench.py JSON line:  python tools/show_bench.py FILE"""
 import json, sys
 d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 print("value", round(d['value'],2), "ms", round(d['ms_per_step'],4), "e2e", round(d['e2e']['value'],2), "gpus", d['n_gpus'], "clocks", d.get('clocks'))

@@ -1,3 +1,4 @@
+"""Print the per-rank table of a tools/shard_emulate.py JSON:  python tools/show_emul.py FILE"""
 import json, sys
 d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 print({k:round(v,3) for k,v in d['unpartitioned_ms'].items()})
