@@ -304,7 +304,7 @@ void fb_tree::build(const double *points, size_t n_, int dim_, ptrdiff_t rs, ptr
 
   lap("tree + lists (host)");
   // ---- host: operators
-  ops.build(order, dim, radius, ht.depth, kp, fparams.compression_type, fparams.epsilon);
+  ops.build_cached(order, dim, radius, ht.depth, kp, fparams.compression_type, fparams.epsilon);
   lap("operators (host)");
 
   // ---- upload cells
@@ -1638,7 +1638,7 @@ int fb_ops_new(int interpolation_order, int dim, double radius, int depth, const
   fb::KParams kp;
   if (!fb::make_kparams(*kernel, kp)) return FB_ERR_INVALID_ARGUMENT;
   fb_ops *o = new fb_ops();
-  o->ops.build(interpolation_order, dim, radius, depth, kp, compression_type, epsilon);
+  o->ops.build_cached(interpolation_order, dim, radius, depth, kp, compression_type, epsilon);
   *out = o;
   return FB_OK;
 }

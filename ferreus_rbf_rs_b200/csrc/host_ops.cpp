@@ -452,3 +452,68 @@ void Operators::build(int order, int dim_, double radius, int depth, const KPara
 }
 
 }  // namespace fb
+
+// ---------------------------------------------------------------------------------------- operator cache
+#include <cstring>
+#include <list>
+#include <mutex>
+
+namespace fb {
+
+size_t Operators::bytes() const {
+  size_t b = sizeof(double) * (nodes.size() + tnodes.size() + child_s.size()) +
+             sizeof(int32_t) * (perm.size() + inv_perm.size() + perm_lookup.size() + ref_lookup.size() + ref_vecs.size());
+  for (const auto &lv : m2l)
+    for (const auto &op : lv) b += sizeof(double) * (op.U.a.size() + op.Vt.a.size());
+  return b;
+}
+
+namespace {
+struct OpsKey {
+  int order, dim, depth, compression;
+  double radius, eps;
+  KParams kp;
+  bool operator==(const OpsKey &o) const {
+    return order == o.order && dim == o.dim && depth == o.depth && compression == o.compression &&
+           std::memcmp(&radius, &o.radius, sizeof(double)) == 0 && std::memcmp(&eps, &o.eps, sizeof(double)) == 0 &&
+           kp.fam == o.kp.fam && kp.pw == o.kp.pw && std::memcmp(&kp.s2, &o.kp.s2, sizeof(double)) == 0 &&
+           std::memcmp(&kp.ip2, &o.kp.ip2, sizeof(double)) == 0 &&
+           std::memcmp(&kp.near_slope, &o.kp.near_slope, sizeof(double)) == 0 &&
+           std::memcmp(&kp.far_coef, &o.kp.far_coef, sizeof(double)) == 0 &&
+           std::memcmp(&kp.total_sill, &o.kp.total_sill, sizeof(double)) == 0;
+  }
+};
+std::mutex g_ops_mutex;
+std::list<std::pair<OpsKey, Operators>> g_ops_cache;  // most recently used first
+constexpr size_t kOpsCacheEntries = 4;
+constexpr size_t kOpsCacheBytes = (size_t)768 << 20;
+}  // namespace
+
+bool Operators::build_cached(int order, int dim_, double radius, int depth, const KParams &kp, int compression,
+                             double eps) {
+  // kp.fast selects the square-root variant of the device loops only: the host operators do not depend on it
+  const OpsKey key{order, dim_, depth, compression, radius, eps, kp};
+  {
+    std::lock_guard<std::mutex> lock(g_ops_mutex);
+    for (auto it = g_ops_cache.begin(); it != g_ops_cache.end(); ++it)
+      if (it->first == key) {
+        *this = it->second;
+        g_ops_cache.splice(g_ops_cache.begin(), g_ops_cache, it);
+        return true;
+      }
+  }
+  build(order, dim_, radius, depth, kp, compression, eps);
+  if (bytes() <= kOpsCacheBytes / 2) {
+    std::lock_guard<std::mutex> lock(g_ops_mutex);
+    g_ops_cache.emplace_front(key, *this);
+    size_t total = 0;
+    for (const auto &e : g_ops_cache) total += e.second.bytes();
+    while (g_ops_cache.size() > kOpsCacheEntries || (total > kOpsCacheBytes && g_ops_cache.size() > 1)) {
+      total -= g_ops_cache.back().second.bytes();
+      g_ops_cache.pop_back();
+    }
+  }
+  return false;
+}
+
+}  // namespace fb

@@ -118,3 +118,27 @@ def test_singular_value_cutoff_rule():
     assert oc.calculate_singular_values_cutoff([1.0, 1e-3, 1e-6], 1e-2) == 1
     assert oc.calculate_singular_values_cutoff([1.0, 1e-3, 1e-6], 1e-4) == 2
     assert oc.calculate_singular_values_cutoff([1.0, 0.5, 0.25], 1e-8) == 3
+
+
+def test_operator_cache_returns_identical_operators():
+    """Operators::build_cached (host_ops.cpp): a second request with the same arguments is served from the process-wide
+    cache — bit-identical factors — and any changed argument (radius, epsilon, kernel parameter) misses it."""
+    L = _lib.lib()
+    P = 6 ** 3
+    a = host_ops(6, 3, 0.7310, 3, 3, 2, 1e-6, base_range=0.8)
+    b = host_ops(6, 3, 0.7310, 3, 3, 2, 1e-6, base_range=0.8)    # hit
+    c = host_ops(6, 3, 0.7310, 3, 3, 2, 1e-6, base_range=0.81)   # another kernel scale
+    d = host_ops(6, 3, 0.7311, 3, 3, 2, 1e-6, base_range=0.8)    # another radius
+    differs = {"c": False, "d": False}
+    for lvl in (2, 3):
+        for r in range(4):
+            ua, va = get_op(a, lvl, r, P, True)
+            ub, vb = get_op(b, lvl, r, P, True)
+            assert np.array_equal(ua, ub) and np.array_equal(va, vb)
+            for name, h in (("c", c), ("d", d)):
+                uo, _ = get_op(h, lvl, r, P, True)
+                if uo.shape != ua.shape or not np.array_equal(uo, ua):
+                    differs[name] = True
+    assert differs["c"] and differs["d"]
+    for h in (a, b, c, d):
+        L.fb_ops_free(h)
